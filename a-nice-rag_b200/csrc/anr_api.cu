@@ -1,0 +1,985 @@
+// C ABI (include/anr_b200.h): contexts, index objects, argument staging and the
+// kernel pipelines of each entry point.  No C++ exception crosses the boundary.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/anr_b200.h"
+#include "anr_internal.h"
+#include "anr_topk.cuh"
+
+using namespace anr;
+
+// ---------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* what, const char* detail = nullptr) {
+  g_last_error = what;
+  if (detail) {
+    g_last_error += ": ";
+    g_last_error += detail;
+  }
+  return code;
+}
+static int fail_cuda(const char* what, cudaError_t e) {
+  // leave the sticky error state readable but do not keep it queued for the next call
+  cudaGetLastError();
+  return fail(e == cudaErrorMemoryAllocation ? ANR_ERR_OOM : ANR_ERR_CUDA, what,
+              cudaGetErrorString(e));
+}
+#define ANR_CUDA(expr)                                       \
+  do {                                                       \
+    cudaError_t _e = (expr);                                 \
+    if (_e != cudaSuccess) return fail_cuda(#expr, _e);      \
+  } while (0)
+
+// ---------------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------------
+struct anr_ctx {
+  DeviceProps dp;
+  cudaStream_t stream = nullptr;
+  unsigned char* ws = nullptr;  // device scratch, grown on demand
+  size_t ws_bytes = 0;
+};
+
+struct anr_dense {
+  int device = 0;
+  float* emb = nullptr;
+  int64_t n = 0;
+  int32_t d = 0;
+  int32_t ld = 0;  // leading dimension in floats (d rounded up to a multiple of 4)
+  bool owned = true;
+};
+
+struct anr_bm25 {
+  int device = 0;
+  int64_t* term_ptr = nullptr;
+  int32_t* post_doc = nullptr;
+  float* post_w = nullptr;
+  float* idf = nullptr;
+  int32_t n_terms = 0;
+  int32_t n_docs = 0;
+  int64_t nnz = 0;
+};
+
+namespace {
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Bump allocator over the context's scratch buffer.
+struct Arena {
+  unsigned char* base;
+  size_t cap;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~static_cast<size_t>(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return p;
+  }
+};
+inline size_t padded(size_t bytes) { return (bytes + 255) & ~static_cast<size_t>(255); }
+
+int ws_reserve(anr_ctx* ctx, size_t bytes) {
+  bytes += 4096;
+  if (bytes <= ctx->ws_bytes) return ANR_OK;
+  // earlier work (on the context's stream or a caller's) may still be using the old buffer
+  ANR_CUDA(cudaDeviceSynchronize());
+  if (ctx->ws) cudaFree(ctx->ws);
+  ctx->ws = nullptr;
+  ctx->ws_bytes = 0;
+  size_t want = std::max(bytes, static_cast<size_t>(8) << 20);
+  want += want / 4;
+  ANR_CUDA(cudaMalloc(&ctx->ws, want));
+  ctx->ws_bytes = want;
+  return ANR_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+inline int pad_queries(int nq) { return nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : (nq + 7) / 8 * 8; }
+
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = static_cast<float>(in[i]);
+}
+__global__ void set_f64_pair_kernel(double* out, double a, double b) {
+  out[0] = a;
+  out[1] = b;
+}
+__global__ void set_i32_pair_kernel(int32_t* out, int32_t a, int32_t b) {
+  out[0] = a;
+  out[1] = b;
+}
+// BM25 results carry document ids in their own space: translate them to row ids of the
+// dense index' space before fusion (done by TopkOut::id_map), nothing else needed here.
+
+// Copy a [rows, d] fp32 matrix (host or device) into a [rows, ld] device matrix.
+cudaError_t copy_rows(float* dst, int ld, const float* src, int d, int64_t rows,
+                      cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if (ld == d)
+    return cudaMemcpyAsync(dst, src, static_cast<size_t>(rows) * d * 4, cudaMemcpyDefault, stream);
+  cudaError_t e = cudaMemsetAsync(dst, 0, static_cast<size_t>(rows) * ld * 4, stream);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy2DAsync(dst, static_cast<size_t>(ld) * 4, src, static_cast<size_t>(d) * 4,
+                           static_cast<size_t>(d) * 4, static_cast<size_t>(rows),
+                           cudaMemcpyDefault, stream);
+}
+
+// Host-or-device output: device pointers are written in place; host pointers get a
+// scratch twin that is copied back (and the call synchronises) at the end.
+template <typename T>
+struct OutBuf {
+  T* user = nullptr;
+  T* dev = nullptr;
+  size_t count = 0;
+  bool staged = false;
+};
+template <typename T>
+size_t out_need(const T* user, size_t count) {
+  return (user && !is_device_ptr(user)) ? padded(count * sizeof(T)) + 256 : 0;
+}
+template <typename T>
+OutBuf<T> out_make(Arena& a, T* user, size_t count) {
+  OutBuf<T> o;
+  o.user = user;
+  o.count = count;
+  if (!user) return o;
+  if (is_device_ptr(user)) {
+    o.dev = user;
+  } else {
+    o.dev = a.take<T>(count);
+    o.staged = true;
+  }
+  return o;
+}
+template <typename T>
+cudaError_t out_flush(const OutBuf<T>& o, cudaStream_t stream, bool* any_host) {
+  if (!o.staged) return cudaSuccess;
+  *any_host = true;
+  return cudaMemcpyAsync(o.user, o.dev, o.count * sizeof(T), cudaMemcpyDeviceToHost, stream);
+}
+
+// ---- dense top-k pipeline on device buffers -----------------------------------------
+// q_dev: [pad_queries(nq), ld].  Writes results through `out`.
+size_t dense_ws_bytes(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
+  const int nqp = pad_queries(nq);
+  if (k <= kMaxFusedK)
+    return padded(static_cast<size_t>(nqp) * dense_scan_max_grid(ctx->dp) * k * 8) + 256;
+  const int64_t n_pow2 = next_pow2(static_cast<int>(std::max<int64_t>(ix->n, 2)));
+  const int group = std::min(nqp, 8);
+  return padded(static_cast<size_t>(group) * n_pow2 * 8) + 256;
+}
+
+int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq, int k,
+                   const uint32_t* mask_dev, Arena& arena, const TopkOut& out,
+                   cudaStream_t stream) {
+  const int nqp = pad_queries(nq);
+  if (k <= kMaxFusedK) {
+    const int64_t stride = static_cast<int64_t>(dense_scan_max_grid(ctx->dp)) * k;
+    uint64_t* cand = arena.take<uint64_t>(static_cast<size_t>(nqp) * stride);
+    int grid = 0;
+    for (int q0 = 0; q0 < nqp; q0 += 8) {
+      const int g = std::min(8, nqp - q0);
+      ANR_CUDA(launch_dense_scan_topk(ctx->dp, ix->emb, ix->n, ix->ld,
+                                      q_dev + static_cast<size_t>(q0) * ix->ld, g, k, mask_dev,
+                                      cand + q0 * stride, stride, &grid, stream));
+    }
+    const int m = grid * k;
+    ANR_CUDA(launch_topk_final(cand, stride, m, m, 0, nq, k, out, stream));
+    return ANR_OK;
+  }
+  // k > kMaxFusedK: materialise every key, sort, emit (full-ranking path)
+  if (ix->n > (1ll << 30)) return fail(ANR_ERR_UNSUPPORTED, "k > 128 needs n <= 2^30");
+  const int64_t n_pow2 = next_pow2(static_cast<int>(std::max<int64_t>(ix->n, 2)));
+  const int group = std::min(nqp, 8);
+  uint64_t* keys = arena.take<uint64_t>(static_cast<size_t>(group) * n_pow2);
+  for (int q0 = 0; q0 < nq; q0 += group) {
+    const int real = std::min(group, nq - q0);
+    ANR_CUDA(launch_dense_scan_all(ctx->dp, ix->emb, ix->n, ix->ld,
+                                   q_dev + static_cast<size_t>(q0) * ix->ld, group, mask_dev, keys,
+                                   n_pow2, stream));
+    ANR_CUDA(launch_zero_tail(keys, n_pow2, ix->n, n_pow2, real, stream));
+    ANR_CUDA(launch_sort_desc(keys, n_pow2, n_pow2, real, stream));
+    TopkOut o = out;
+    if (o.keys) o.keys += q0 * out.stride_q;
+    if (o.scores) o.scores += q0 * out.stride_q;
+    if (o.ids) o.ids += q0 * out.stride_q;
+    if (o.counts) o.counts += q0 * out.count_stride;
+    ANR_CUDA(launch_emit_sorted(keys, n_pow2, n_pow2, real, k, o, stream));
+  }
+  return ANR_OK;
+}
+
+// ---- BM25 top-k pipeline on device buffers ---------------------------------------------
+size_t bm25_ws_bytes(const anr_ctx* ctx, const anr_bm25* ix, int nq, int k) {
+  if (k <= kMaxFusedK) {
+    const Bm25Plan plan = bm25_make_plan(ctx->dp, ix->n_docs, nq, k, false);
+    return padded(static_cast<size_t>(nq) * plan.n_tiles * k * 8) + 256;
+  }
+  const int64_t n_pow2 = next_pow2(std::max(ix->n_docs, 2));
+  return padded(static_cast<size_t>(std::min(nq, 8)) * n_pow2 * 8) + 256;
+}
+
+Bm25View bm25_view(const anr_bm25* ix) {
+  Bm25View v;
+  v.term_ptr = ix->term_ptr;
+  v.post_doc = ix->post_doc;
+  v.post_w = ix->post_w;
+  v.idf = ix->idf;
+  v.n_terms = ix->n_terms;
+  v.n_docs = ix->n_docs;
+  v.nnz = ix->nnz;
+  return v;
+}
+
+int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
+                  const int32_t* offsets_dev, int nq, int k, const uint32_t* mask_dev,
+                  Arena& arena, const TopkOut& out, cudaStream_t stream) {
+  const Bm25View v = bm25_view(ix);
+  if (k <= kMaxFusedK) {
+    const Bm25Plan plan = bm25_make_plan(ctx->dp, ix->n_docs, nq, k, false);
+    if (plan.smem_bytes > ctx->dp.max_smem_optin)
+      return fail(ANR_ERR_UNSUPPORTED, "bm25 tile does not fit in shared memory");
+    const int64_t stride = static_cast<int64_t>(plan.n_tiles) * k;
+    uint64_t* cand = arena.take<uint64_t>(static_cast<size_t>(nq) * stride);
+    ANR_CUDA(launch_bm25_score_topk(v, terms_dev, offsets_dev, nq, k, mask_dev, plan, cand, stride,
+                                    stream));
+    const int m = static_cast<int>(stride);
+    ANR_CUDA(launch_topk_final(cand, stride, m, m, 0, nq, k, out, stream));
+    return ANR_OK;
+  }
+  if (ix->n_docs > (1 << 30)) return fail(ANR_ERR_UNSUPPORTED, "k > 128 needs n_docs <= 2^30");
+  const int64_t n_pow2 = next_pow2(std::max(ix->n_docs, 2));
+  const int group = std::min(nq, 8);
+  uint64_t* keys = arena.take<uint64_t>(static_cast<size_t>(group) * n_pow2);
+  for (int q0 = 0; q0 < nq; q0 += group) {
+    const int real = std::min(group, nq - q0);
+    const Bm25Plan plan = bm25_make_plan(ctx->dp, ix->n_docs, real, 1, true);
+    ANR_CUDA(launch_bm25_score_all(v, terms_dev, offsets_dev + q0, real, mask_dev, plan, keys,
+                                   n_pow2, stream));
+    ANR_CUDA(launch_zero_tail(keys, n_pow2, ix->n_docs, n_pow2, real, stream));
+    ANR_CUDA(launch_sort_desc(keys, n_pow2, n_pow2, real, stream));
+    TopkOut o = out;
+    if (o.keys) o.keys += q0 * out.stride_q;
+    if (o.scores) o.scores += q0 * out.stride_q;
+    if (o.ids) o.ids += q0 * out.stride_q;
+    if (o.counts) o.counts += q0 * out.count_stride;
+    ANR_CUDA(launch_emit_sorted(keys, n_pow2, n_pow2, real, k, o, stream));
+  }
+  return ANR_OK;
+}
+
+// Stage the query matrix: returns a device [pad_queries(nq), ld] zero-padded copy.
+int stage_queries(const anr_dense* ix, const float* queries, int nq, Arena& arena,
+                  cudaStream_t stream, const float** q_dev) {
+  const int nqp = pad_queries(nq);
+  float* q = arena.take<float>(static_cast<size_t>(nqp) * ix->ld);
+  if (nqp != nq || ix->ld != ix->d)
+    ANR_CUDA(cudaMemsetAsync(q, 0, static_cast<size_t>(nqp) * ix->ld * 4, stream));
+  if (ix->ld == ix->d) {
+    ANR_CUDA(cudaMemcpyAsync(q, queries, static_cast<size_t>(nq) * ix->d * 4, cudaMemcpyDefault,
+                             stream));
+  } else {
+    ANR_CUDA(cudaMemcpy2DAsync(q, static_cast<size_t>(ix->ld) * 4, queries,
+                               static_cast<size_t>(ix->d) * 4, static_cast<size_t>(ix->d) * 4, nq,
+                               cudaMemcpyDefault, stream));
+  }
+  *q_dev = q;
+  return ANR_OK;
+}
+size_t stage_queries_bytes(const anr_dense* ix, int nq) {
+  return padded(static_cast<size_t>(pad_queries(nq)) * ix->ld * 4) + 256;
+}
+
+// Stage a bit mask ([ceil(n/32)] words) if it lives on the host.
+size_t stage_mask_bytes(const uint32_t* mask, int64_t n) {
+  return (mask && !is_device_ptr(mask)) ? padded(static_cast<size_t>((n + 31) / 32) * 4) + 256 : 0;
+}
+int stage_mask(const uint32_t* mask, int64_t n, Arena& arena, cudaStream_t stream,
+               const uint32_t** mask_dev) {
+  *mask_dev = mask;
+  if (!mask || is_device_ptr(mask)) return ANR_OK;
+  const size_t words = static_cast<size_t>((n + 31) / 32);
+  uint32_t* m = arena.take<uint32_t>(words);
+  ANR_CUDA(cudaMemcpyAsync(m, mask, words * 4, cudaMemcpyHostToDevice, stream));
+  *mask_dev = m;
+  return ANR_OK;
+}
+
+// Stage the CSR query terms.  Host arrays are copied; device arrays are used in place.
+struct QueryTerms {
+  const int32_t* terms = nullptr;
+  const int32_t* offsets = nullptr;
+};
+size_t stage_terms_bytes(const int32_t* q_terms, const int32_t* q_offsets, int nq) {
+  size_t need = 0;
+  if (!is_device_ptr(q_offsets)) {
+    need += padded(static_cast<size_t>(nq + 1) * 4) + 256;
+    if (!is_device_ptr(q_terms)) need += padded(static_cast<size_t>(std::max(q_offsets[nq], 1)) * 4) + 256;
+  }
+  return need;
+}
+int stage_terms(const int32_t* q_terms, const int32_t* q_offsets, int nq, Arena& arena,
+                cudaStream_t stream, QueryTerms* out) {
+  const bool off_dev = is_device_ptr(q_offsets), terms_dev = is_device_ptr(q_terms);
+  if (off_dev != terms_dev && q_terms)
+    return fail(ANR_ERR_INVALID, "q_terms and q_offsets must both be host or both be device");
+  out->terms = q_terms;
+  out->offsets = q_offsets;
+  if (off_dev) return ANR_OK;
+  if (q_offsets[0] != 0) return fail(ANR_ERR_INVALID, "q_offsets[0] must be 0");
+  for (int i = 0; i < nq; ++i)
+    if (q_offsets[i + 1] < q_offsets[i]) return fail(ANR_ERR_INVALID, "q_offsets must not decrease");
+  int32_t* off = arena.take<int32_t>(static_cast<size_t>(nq) + 1);
+  ANR_CUDA(cudaMemcpyAsync(off, q_offsets, (static_cast<size_t>(nq) + 1) * 4,
+                           cudaMemcpyHostToDevice, stream));
+  const int total = q_offsets[nq];
+  int32_t* t = arena.take<int32_t>(static_cast<size_t>(std::max(total, 1)));
+  if (total > 0)
+    ANR_CUDA(cudaMemcpyAsync(t, q_terms, static_cast<size_t>(total) * 4, cudaMemcpyHostToDevice,
+                             stream));
+  out->terms = t;
+  out->offsets = off;
+  return ANR_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------
+// ABI
+// ---------------------------------------------------------------------------------
+extern "C" {
+
+int anr_abi_version(void) { return ANR_ABI_VERSION; }
+const char* anr_last_error(void) { return g_last_error.c_str(); }
+
+int anr_ctx_create(int device, anr_ctx** out) {
+  if (!out) return fail(ANR_ERR_INVALID, "anr_ctx_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) {
+    cudaGetLastError();
+    return fail(ANR_ERR_NO_DEVICE, "no CUDA device: this library has no CPU implementation");
+  }
+  if (device < 0 || device >= count) return fail(ANR_ERR_INVALID, "device ordinal out of range");
+  cudaDeviceProp prop;
+  ANR_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    char msg[128];
+    snprintf(msg, sizeof msg, "device %d is sm_%d%d; the kernels are built for sm_100a only", device,
+             prop.major, prop.minor);
+    return fail(ANR_ERR_NO_DEVICE, msg);
+  }
+  anr_ctx* ctx = new (std::nothrow) anr_ctx;
+  if (!ctx) return fail(ANR_ERR_OOM, "host allocation failed");
+  ctx->dp.device = device;
+  ctx->dp.sm_count = prop.multiProcessorCount;
+  ctx->dp.max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+  DeviceGuard guard(device);
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return fail_cuda("cudaStreamCreate", e);
+  }
+  *out = ctx;
+  return ANR_OK;
+}
+
+int anr_ctx_destroy(anr_ctx* ctx) {
+  if (!ctx) return ANR_OK;
+  DeviceGuard guard(ctx->dp.device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ws) cudaFree(ctx->ws);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return ANR_OK;
+}
+
+int anr_ctx_sync(anr_ctx* ctx) {
+  if (!ctx) return fail(ANR_ERR_INVALID, "ctx is NULL");
+  DeviceGuard guard(ctx->dp.device);
+  ANR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ANR_OK;
+}
+
+int anr_ctx_info(anr_ctx* ctx, int32_t* sm_count, int64_t* hbm_total, int64_t* hbm_free) {
+  if (!ctx) return fail(ANR_ERR_INVALID, "ctx is NULL");
+  DeviceGuard guard(ctx->dp.device);
+  size_t f = 0, t = 0;
+  ANR_CUDA(cudaMemGetInfo(&f, &t));
+  if (sm_count) *sm_count = ctx->dp.sm_count;
+  if (hbm_total) *hbm_total = static_cast<int64_t>(t);
+  if (hbm_free) *hbm_free = static_cast<int64_t>(f);
+  return ANR_OK;
+}
+
+// ---- dense index --------------------------------------------------------------
+int anr_dense_create(anr_ctx* ctx, const float* emb, int64_t n, int32_t d, int32_t borrow,
+                     anr_dense** out) {
+  if (!ctx || !out) return fail(ANR_ERR_INVALID, "anr_dense_create: NULL argument");
+  *out = nullptr;
+  if (n < 0 || d < 1) return fail(ANR_ERR_INVALID, "anr_dense_create: bad shape");
+  if (n >= (1ll << 32) - 1) return fail(ANR_ERR_UNSUPPORTED, "more than 2^32-2 rows per index");
+  DeviceGuard guard(ctx->dp.device);
+  anr_dense* ix = new (std::nothrow) anr_dense;
+  if (!ix) return fail(ANR_ERR_OOM, "host allocation failed");
+  ix->device = ctx->dp.device;
+  ix->n = n;
+  ix->d = d;
+  ix->ld = (d + 3) / 4 * 4;
+  if (borrow) {
+    if (!emb || !is_device_ptr(emb) || ix->ld != d ||
+        (reinterpret_cast<uintptr_t>(emb) & 15) != 0) {
+      delete ix;
+      return fail(ANR_ERR_INVALID,
+                  "borrow needs a 16-byte aligned device pointer and d % 4 == 0");
+    }
+    ix->emb = const_cast<float*>(emb);
+    ix->owned = false;
+    *out = ix;
+    return ANR_OK;
+  }
+  const size_t bytes = std::max<size_t>(static_cast<size_t>(n) * ix->ld * 4, 16);
+  cudaError_t e = cudaMalloc(&ix->emb, bytes);
+  if (e != cudaSuccess) {
+    delete ix;
+    return fail_cuda("cudaMalloc(embedding matrix)", e);
+  }
+  if (emb && n > 0) {
+    e = copy_rows(ix->emb, ix->ld, emb, d, n, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      cudaFree(ix->emb);
+      delete ix;
+      return fail_cuda("upload of the embedding matrix", e);
+    }
+  }
+  *out = ix;
+  return ANR_OK;
+}
+
+int anr_dense_upload(anr_ctx* ctx, anr_dense* index, int64_t row0, const float* rows,
+                     int64_t n_rows) {
+  if (!ctx || !index || !rows) return fail(ANR_ERR_INVALID, "anr_dense_upload: NULL argument");
+  if (!index->owned) return fail(ANR_ERR_INVALID, "anr_dense_upload: borrowed index");
+  if (row0 < 0 || n_rows < 0 || row0 + n_rows > index->n)
+    return fail(ANR_ERR_INVALID, "anr_dense_upload: row range out of bounds");
+  DeviceGuard guard(ctx->dp.device);
+  ANR_CUDA(copy_rows(index->emb + static_cast<size_t>(row0) * index->ld, index->ld, rows, index->d,
+                     n_rows, ctx->stream));
+  // the source may be a pageable/pinned buffer the caller is about to reuse
+  ANR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ANR_OK;
+}
+
+int anr_dense_destroy(anr_dense* index) {
+  if (!index) return ANR_OK;
+  DeviceGuard guard(index->device);
+  if (index->owned && index->emb) cudaFree(index->emb);
+  delete index;
+  return ANR_OK;
+}
+
+int anr_dense_shape(const anr_dense* index, int64_t* n, int32_t* d) {
+  if (!index) return fail(ANR_ERR_INVALID, "index is NULL");
+  if (n) *n = index->n;
+  if (d) *d = index->d;
+  return ANR_OK;
+}
+
+static int dense_search_impl(anr_ctx* ctx, const anr_dense* index, const float* queries,
+                             int32_t nq, int32_t k, const uint32_t* row_mask, int64_t id_base,
+                             uint64_t* out_keys, float* out_scores, int32_t* out_rows,
+                             int32_t* out_counts, void* stream_v) {
+  if (!ctx || !index || !queries) return fail(ANR_ERR_INVALID, "dense search: NULL argument");
+  if (nq < 1 || k < 1) return fail(ANR_ERR_INVALID, "dense search: n_queries and k must be >= 1");
+  if (index->device != ctx->dp.device) return fail(ANR_ERR_INVALID, "index lives on another device");
+  DeviceGuard guard(ctx->dp.device);
+  cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  const size_t cells = static_cast<size_t>(nq) * k;
+  const size_t need = stage_queries_bytes(index, nq) + stage_mask_bytes(row_mask, index->n) +
+                      dense_ws_bytes(ctx, index, nq, k) + out_need(out_keys, cells) +
+                      out_need(out_scores, cells) + out_need(out_rows, cells) +
+                      out_need(out_counts, nq);
+  if (int rc = ws_reserve(ctx, need)) return rc;
+  Arena arena{ctx->ws, ctx->ws_bytes};
+  OutBuf<uint64_t> o_keys = out_make(arena, out_keys, cells);
+  OutBuf<float> o_scores = out_make(arena, out_scores, cells);
+  OutBuf<int32_t> o_rows = out_make(arena, out_rows, cells);
+  OutBuf<int32_t> o_counts = out_make(arena, out_counts, nq);
+  TopkOut out;
+  out.keys = o_keys.dev;
+  out.scores = o_scores.dev;
+  out.ids = o_rows.dev;
+  out.counts = o_counts.dev;
+  out.stride_q = k;
+  out.id_base = id_base;
+  if (index->n == 0) {
+    if (out.keys) ANR_CUDA(cudaMemsetAsync(out.keys, 0, cells * 8, stream));
+    if (out.scores) ANR_CUDA(cudaMemsetAsync(out.scores, 0, cells * 4, stream));
+    if (out.ids) ANR_CUDA(cudaMemsetAsync(out.ids, 0xff, cells * 4, stream));
+    if (out.counts) ANR_CUDA(cudaMemsetAsync(out.counts, 0, static_cast<size_t>(nq) * 4, stream));
+  } else {
+    const float* q_dev = nullptr;
+    const uint32_t* mask_dev = nullptr;
+    if (int rc = stage_queries(index, queries, nq, arena, stream, &q_dev)) return rc;
+    if (int rc = stage_mask(row_mask, index->n, arena, stream, &mask_dev)) return rc;
+    if (int rc = dense_pipeline(ctx, index, q_dev, nq, k, mask_dev, arena, out, stream)) return rc;
+  }
+  bool any_host = false;
+  ANR_CUDA(out_flush(o_keys, stream, &any_host));
+  ANR_CUDA(out_flush(o_scores, stream, &any_host));
+  ANR_CUDA(out_flush(o_rows, stream, &any_host));
+  ANR_CUDA(out_flush(o_counts, stream, &any_host));
+  if (any_host) ANR_CUDA(cudaStreamSynchronize(stream));
+  return ANR_OK;
+}
+
+int anr_dense_search(anr_ctx* ctx, const anr_dense* index, const float* queries,
+                     int32_t n_queries, int32_t k, const uint32_t* row_mask, int64_t id_base,
+                     float* out_scores, int32_t* out_rows, int32_t* out_counts, void* stream) {
+  return dense_search_impl(ctx, index, queries, n_queries, k, row_mask, id_base, nullptr,
+                           out_scores, out_rows, out_counts, stream);
+}
+
+int anr_dense_search_keys(anr_ctx* ctx, const anr_dense* index, const float* queries,
+                          int32_t n_queries, int32_t k, const uint32_t* row_mask, int64_t id_base,
+                          uint64_t* out_keys, void* stream) {
+  if (!out_keys) return fail(ANR_ERR_INVALID, "out_keys is NULL");
+  return dense_search_impl(ctx, index, queries, n_queries, k, row_mask, id_base, out_keys, nullptr,
+                           nullptr, nullptr, stream);
+}
+
+// ---- BM25 index ---------------------------------------------------------------------
+int anr_bm25_create(anr_ctx* ctx, const int64_t* term_ptr, const int32_t* post_doc,
+                    const int32_t* post_tf, const int32_t* doc_len, const double* idf,
+                    int32_t n_terms, int32_t n_docs, double k1, double b, double avgdl,
+                    anr_bm25** out) {
+  if (!ctx || !out) return fail(ANR_ERR_INVALID, "anr_bm25_create: NULL argument");
+  *out = nullptr;
+  if (n_terms < 0 || n_docs < 0) return fail(ANR_ERR_INVALID, "anr_bm25_create: bad shape");
+  if (!term_ptr || !idf || (n_docs > 0 && !doc_len))
+    return fail(ANR_ERR_INVALID, "anr_bm25_create: NULL array");
+  DeviceGuard guard(ctx->dp.device);
+  cudaStream_t stream = ctx->stream;
+  anr_bm25* ix = new (std::nothrow) anr_bm25;
+  if (!ix) return fail(ANR_ERR_OOM, "host allocation failed");
+  ix->device = ctx->dp.device;
+  ix->n_terms = n_terms;
+  ix->n_docs = n_docs;
+  int32_t* tf_dev = nullptr;
+  int32_t* dl_dev = nullptr;
+  double* idf64 = nullptr;
+  cudaError_t e = cudaSuccess;
+  auto cleanup = [&]() {
+    if (tf_dev) cudaFree(tf_dev);
+    if (dl_dev) cudaFree(dl_dev);
+    if (idf64) cudaFree(idf64);
+  };
+  auto bail = [&](const char* what) {
+    cleanup();
+    anr_bm25_destroy(ix);
+    return fail_cuda(what, e);
+  };
+  // term_ptr first: its last entry is the number of postings
+  if ((e = cudaMalloc(&ix->term_ptr, (static_cast<size_t>(n_terms) + 1) * 8)) != cudaSuccess)
+    return bail("cudaMalloc(term_ptr)");
+  if ((e = cudaMemcpyAsync(ix->term_ptr, term_ptr, (static_cast<size_t>(n_terms) + 1) * 8,
+                           cudaMemcpyDefault, stream)) != cudaSuccess)
+    return bail("copy(term_ptr)");
+  int64_t nnz = 0;
+  if ((e = cudaMemcpyAsync(&nnz, ix->term_ptr + n_terms, 8, cudaMemcpyDeviceToHost, stream)) !=
+          cudaSuccess ||
+      (e = cudaStreamSynchronize(stream)) != cudaSuccess)
+    return bail("read(nnz)");
+  if (nnz < 0 || (nnz > 0 && (!post_doc || !post_tf))) {
+    cleanup();
+    anr_bm25_destroy(ix);
+    return fail(ANR_ERR_INVALID, "anr_bm25_create: postings missing or term_ptr corrupt");
+  }
+  ix->nnz = nnz;
+  const size_t pn = static_cast<size_t>(std::max<int64_t>(nnz, 1));
+  if ((e = cudaMalloc(&ix->post_doc, pn * 4)) != cudaSuccess) return bail("cudaMalloc(post_doc)");
+  if ((e = cudaMalloc(&ix->post_w, pn * 4)) != cudaSuccess) return bail("cudaMalloc(post_w)");
+  if ((e = cudaMalloc(&ix->idf, std::max<size_t>(n_terms, 1) * 4)) != cudaSuccess)
+    return bail("cudaMalloc(idf)");
+  if ((e = cudaMalloc(&tf_dev, pn * 4)) != cudaSuccess) return bail("cudaMalloc(tf)");
+  if ((e = cudaMalloc(&dl_dev, std::max<size_t>(n_docs, 1) * 4)) != cudaSuccess)
+    return bail("cudaMalloc(doc_len)");
+  if ((e = cudaMalloc(&idf64, std::max<size_t>(n_terms, 1) * 8)) != cudaSuccess)
+    return bail("cudaMalloc(idf64)");
+  if (nnz > 0) {
+    if ((e = cudaMemcpyAsync(ix->post_doc, post_doc, pn * 4, cudaMemcpyDefault, stream)) !=
+        cudaSuccess)
+      return bail("copy(post_doc)");
+    if ((e = cudaMemcpyAsync(tf_dev, post_tf, pn * 4, cudaMemcpyDefault, stream)) != cudaSuccess)
+      return bail("copy(post_tf)");
+  }
+  if (n_docs > 0 &&
+      (e = cudaMemcpyAsync(dl_dev, doc_len, static_cast<size_t>(n_docs) * 4, cudaMemcpyDefault,
+                           stream)) != cudaSuccess)
+    return bail("copy(doc_len)");
+  if (n_terms > 0) {
+    if ((e = cudaMemcpyAsync(idf64, idf, static_cast<size_t>(n_terms) * 8, cudaMemcpyDefault,
+                             stream)) != cudaSuccess)
+      return bail("copy(idf)");
+    f64_to_f32_kernel<<<(n_terms + 255) / 256, 256, 0, stream>>>(idf64, ix->idf, n_terms);
+    if ((e = cudaGetLastError()) != cudaSuccess) return bail("idf conversion");
+  }
+  if ((e = launch_bm25_weights(ix->post_doc, tf_dev, dl_dev, nnz, k1, b, avgdl, ix->post_w,
+                               stream)) != cudaSuccess)
+    return bail("posting weights");
+  if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return bail("bm25 index build");
+  cleanup();
+  *out = ix;
+  return ANR_OK;
+}
+
+int anr_bm25_destroy(anr_bm25* index) {
+  if (!index) return ANR_OK;
+  DeviceGuard guard(index->device);
+  if (index->term_ptr) cudaFree(index->term_ptr);
+  if (index->post_doc) cudaFree(index->post_doc);
+  if (index->post_w) cudaFree(index->post_w);
+  if (index->idf) cudaFree(index->idf);
+  delete index;
+  return ANR_OK;
+}
+
+int anr_bm25_shape(const anr_bm25* index, int32_t* n_terms, int32_t* n_docs, int64_t* n_postings) {
+  if (!index) return fail(ANR_ERR_INVALID, "index is NULL");
+  if (n_terms) *n_terms = index->n_terms;
+  if (n_docs) *n_docs = index->n_docs;
+  if (n_postings) *n_postings = index->nnz;
+  return ANR_OK;
+}
+
+static int bm25_search_impl(anr_ctx* ctx, const anr_bm25* index, const int32_t* q_terms,
+                            const int32_t* q_offsets, int32_t nq, int32_t k,
+                            const uint32_t* doc_mask, const int32_t* doc_to_id, int64_t id_base,
+                            uint64_t* out_keys, float* out_scores, int32_t* out_docs,
+                            int32_t* out_counts, void* stream_v) {
+  if (!ctx || !index || !q_offsets) return fail(ANR_ERR_INVALID, "bm25 search: NULL argument");
+  if (nq < 1 || k < 1) return fail(ANR_ERR_INVALID, "bm25 search: n_queries and k must be >= 1");
+  if (index->device != ctx->dp.device) return fail(ANR_ERR_INVALID, "index lives on another device");
+  if (doc_to_id && !is_device_ptr(doc_to_id))
+    return fail(ANR_ERR_INVALID, "doc_to_id must be a device pointer (it is index-sized)");
+  DeviceGuard guard(ctx->dp.device);
+  cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  const size_t cells = static_cast<size_t>(nq) * k;
+  const size_t need = stage_terms_bytes(q_terms, q_offsets, nq) +
+                      stage_mask_bytes(doc_mask, index->n_docs) +
+                      bm25_ws_bytes(ctx, index, nq, k) + out_need(out_keys, cells) +
+                      out_need(out_scores, cells) + out_need(out_docs, cells) +
+                      out_need(out_counts, nq);
+  if (int rc = ws_reserve(ctx, need)) return rc;
+  Arena arena{ctx->ws, ctx->ws_bytes};
+  OutBuf<uint64_t> o_keys = out_make(arena, out_keys, cells);
+  OutBuf<float> o_scores = out_make(arena, out_scores, cells);
+  OutBuf<int32_t> o_docs = out_make(arena, out_docs, cells);
+  OutBuf<int32_t> o_counts = out_make(arena, out_counts, nq);
+  TopkOut out;
+  out.keys = o_keys.dev;
+  out.scores = o_scores.dev;
+  out.ids = o_docs.dev;
+  out.counts = o_counts.dev;
+  out.stride_q = k;
+  out.id_base = id_base;
+  out.id_map = doc_to_id;
+  if (index->n_docs == 0) {
+    if (out.keys) ANR_CUDA(cudaMemsetAsync(out.keys, 0, cells * 8, stream));
+    if (out.scores) ANR_CUDA(cudaMemsetAsync(out.scores, 0, cells * 4, stream));
+    if (out.ids) ANR_CUDA(cudaMemsetAsync(out.ids, 0xff, cells * 4, stream));
+    if (out.counts) ANR_CUDA(cudaMemsetAsync(out.counts, 0, static_cast<size_t>(nq) * 4, stream));
+  } else {
+    QueryTerms qt;
+    const uint32_t* mask_dev = nullptr;
+    if (int rc = stage_terms(q_terms, q_offsets, nq, arena, stream, &qt)) return rc;
+    if (int rc = stage_mask(doc_mask, index->n_docs, arena, stream, &mask_dev)) return rc;
+    if (int rc = bm25_pipeline(ctx, index, qt.terms, qt.offsets, nq, k, mask_dev, arena, out,
+                               stream))
+      return rc;
+  }
+  bool any_host = false;
+  ANR_CUDA(out_flush(o_keys, stream, &any_host));
+  ANR_CUDA(out_flush(o_scores, stream, &any_host));
+  ANR_CUDA(out_flush(o_docs, stream, &any_host));
+  ANR_CUDA(out_flush(o_counts, stream, &any_host));
+  if (any_host) ANR_CUDA(cudaStreamSynchronize(stream));
+  return ANR_OK;
+}
+
+int anr_bm25_search(anr_ctx* ctx, const anr_bm25* index, const int32_t* q_terms,
+                    const int32_t* q_offsets, int32_t n_queries, int32_t k,
+                    const uint32_t* doc_mask, const int32_t* doc_to_id, int64_t id_base,
+                    float* out_scores, int32_t* out_docs, int32_t* out_counts, void* stream) {
+  return bm25_search_impl(ctx, index, q_terms, q_offsets, n_queries, k, doc_mask, doc_to_id,
+                          id_base, nullptr, out_scores, out_docs, out_counts, stream);
+}
+
+int anr_bm25_search_keys(anr_ctx* ctx, const anr_bm25* index, const int32_t* q_terms,
+                         const int32_t* q_offsets, int32_t n_queries, int32_t k,
+                         const uint32_t* doc_mask, const int32_t* doc_to_id, int64_t id_base,
+                         uint64_t* out_keys, void* stream) {
+  if (!out_keys) return fail(ANR_ERR_INVALID, "out_keys is NULL");
+  return bm25_search_impl(ctx, index, q_terms, q_offsets, n_queries, k, doc_mask, doc_to_id,
+                          id_base, out_keys, nullptr, nullptr, nullptr, stream);
+}
+
+int anr_bm25_scores(anr_ctx* ctx, const anr_bm25* index, const int32_t* q_terms,
+                    int32_t n_q_terms, float* out_scores, void* stream_v) {
+  if (!ctx || !index || !out_scores || (n_q_terms > 0 && !q_terms))
+    return fail(ANR_ERR_INVALID, "anr_bm25_scores: NULL argument");
+  if (n_q_terms < 0) return fail(ANR_ERR_INVALID, "anr_bm25_scores: negative term count");
+  if (index->n_docs == 0) return ANR_OK;
+  DeviceGuard guard(ctx->dp.device);
+  cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  const size_t n = static_cast<size_t>(index->n_docs);
+  const size_t need = padded(n * 8) + padded(n * 4) +
+                      padded(static_cast<size_t>(n_q_terms + 1) * 4) + 2048;
+  if (int rc = ws_reserve(ctx, need)) return rc;
+  Arena arena{ctx->ws, ctx->ws_bytes};
+  uint64_t* keys = arena.take<uint64_t>(n);
+  OutBuf<float> o_scores = out_make(arena, out_scores, n);
+  int32_t* off = arena.take<int32_t>(2);
+  int32_t* terms = arena.take<int32_t>(static_cast<size_t>(std::max(n_q_terms, 1)));
+  set_i32_pair_kernel<<<1, 1, 0, stream>>>(off, 0, n_q_terms);
+  ANR_CUDA(cudaGetLastError());
+  if (n_q_terms > 0)
+    ANR_CUDA(cudaMemcpyAsync(terms, q_terms, static_cast<size_t>(n_q_terms) * 4, cudaMemcpyDefault,
+                             stream));
+  const Bm25Plan plan = bm25_make_plan(ctx->dp, index->n_docs, 1, 1, true);
+  ANR_CUDA(launch_bm25_score_all(bm25_view(index), terms, off, 1, nullptr, plan, keys,
+                                 static_cast<int64_t>(n), stream));
+  ANR_CUDA(launch_keys_to_scores(keys, static_cast<int64_t>(n), o_scores.dev, stream));
+  bool any_host = false;
+  ANR_CUDA(out_flush(o_scores, stream, &any_host));
+  if (any_host) ANR_CUDA(cudaStreamSynchronize(stream));
+  return ANR_OK;
+}
+
+// ---- fusion -------------------------------------------------------------------------
+int anr_wrrf_fuse(anr_ctx* ctx, const int32_t* ids, const int32_t* lens, const double* weights,
+                  int32_t n_lists, int32_t list_stride, int32_t n_queries, double rrf_k,
+                  int32_t top_n, int32_t* out_ids, double* out_scores, int32_t* out_counts,
+                  void* stream_v) {
+  if (!ctx || !ids || !lens || !weights || !out_ids || !out_scores)
+    return fail(ANR_ERR_INVALID, "anr_wrrf_fuse: NULL argument");
+  if (n_lists < 1 || n_lists > 64 || list_stride < 1 || n_queries < 1 || top_n < 1)
+    return fail(ANR_ERR_INVALID, "anr_wrrf_fuse: bad shape");
+  if (static_cast<int64_t>(n_lists) * list_stride > wrrf_max_entries())
+    return fail(ANR_ERR_UNSUPPORTED, "anr_wrrf_fuse: more than 8192 entries per query");
+  DeviceGuard guard(ctx->dp.device);
+  cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  const size_t n_ids = static_cast<size_t>(n_queries) * n_lists * list_stride;
+  const size_t n_lens = static_cast<size_t>(n_queries) * n_lists;
+  const size_t cells = static_cast<size_t>(n_queries) * top_n;
+  const bool ids_host = !is_device_ptr(ids), lens_host = !is_device_ptr(lens),
+             w_host = !is_device_ptr(weights);
+  const size_t need = (ids_host ? padded(n_ids * 4) + 256 : 0) +
+                      (lens_host ? padded(n_lens * 4) + 256 : 0) + (w_host ? 1024 : 0) +
+                      out_need(out_ids, cells) + out_need(out_scores, cells) +
+                      out_need(out_counts, n_queries);
+  if (int rc = ws_reserve(ctx, need)) return rc;
+  Arena arena{ctx->ws, ctx->ws_bytes};
+  const int32_t* ids_dev = ids;
+  const int32_t* lens_dev = lens;
+  const double* w_dev = weights;
+  if (ids_host) {
+    int32_t* p = arena.take<int32_t>(n_ids);
+    ANR_CUDA(cudaMemcpyAsync(p, ids, n_ids * 4, cudaMemcpyHostToDevice, stream));
+    ids_dev = p;
+  }
+  if (lens_host) {
+    int32_t* p = arena.take<int32_t>(n_lens);
+    ANR_CUDA(cudaMemcpyAsync(p, lens, n_lens * 4, cudaMemcpyHostToDevice, stream));
+    lens_dev = p;
+  }
+  if (w_host) {
+    double* p = arena.take<double>(n_lists);
+    ANR_CUDA(cudaMemcpyAsync(p, weights, static_cast<size_t>(n_lists) * 8, cudaMemcpyHostToDevice,
+                             stream));
+    w_dev = p;
+  }
+  OutBuf<int32_t> o_ids = out_make(arena, out_ids, cells);
+  OutBuf<double> o_scores = out_make(arena, out_scores, cells);
+  OutBuf<int32_t> o_counts = out_make(arena, out_counts, n_queries);
+  ANR_CUDA(launch_wrrf_fuse(ids_dev, lens_dev, w_dev, n_lists, list_stride, n_queries, rrf_k, top_n,
+                            o_ids.dev, o_scores.dev, o_counts.dev, stream));
+  bool any_host = false;
+  ANR_CUDA(out_flush(o_ids, stream, &any_host));
+  ANR_CUDA(out_flush(o_scores, stream, &any_host));
+  ANR_CUDA(out_flush(o_counts, stream, &any_host));
+  if (any_host) ANR_CUDA(cudaStreamSynchronize(stream));
+  return ANR_OK;
+}
+
+// ---- hybrid ---------------------------------------------------------------------------
+int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25,
+                      const float* queries, const int32_t* q_terms, const int32_t* q_offsets,
+                      int32_t nq, int32_t k_dense, int32_t k_bm25, const uint32_t* row_mask,
+                      const uint32_t* doc_mask, const int32_t* doc_to_id, int64_t id_base,
+                      double w_dense, double w_bm25, double rrf_k, int32_t top_n,
+                      int32_t* out_ids, double* out_scores, int32_t* out_counts,
+                      int32_t* out_dense_rows, float* out_dense_scores, int32_t* out_bm25_ids,
+                      float* out_bm25_scores, void* stream_v) {
+  if (!ctx || !dense || !bm25 || !queries || !q_offsets || !out_ids || !out_scores)
+    return fail(ANR_ERR_INVALID, "anr_hybrid_search: NULL argument");
+  if (nq < 1 || k_dense < 1 || k_bm25 < 1 || top_n < 1)
+    return fail(ANR_ERR_INVALID, "anr_hybrid_search: bad shape");
+  if (dense->device != ctx->dp.device || bm25->device != ctx->dp.device)
+    return fail(ANR_ERR_INVALID, "index lives on another device");
+  if (dense->n == 0 || bm25->n_docs == 0)
+    return fail(ANR_ERR_INVALID, "anr_hybrid_search: empty index");
+  if (doc_to_id && !is_device_ptr(doc_to_id))
+    return fail(ANR_ERR_INVALID, "doc_to_id must be a device pointer (it is index-sized)");
+  const int stride = std::max(k_dense, k_bm25);
+  if (2ll * stride > wrrf_max_entries())
+    return fail(ANR_ERR_UNSUPPORTED, "anr_hybrid_search: k_dense/k_bm25 above 4096");
+  DeviceGuard guard(ctx->dp.device);
+  cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+
+  const size_t fused_cells = static_cast<size_t>(nq) * top_n;
+  const size_t list_cells = static_cast<size_t>(nq) * 2 * stride;
+  const size_t need =
+      stage_queries_bytes(dense, nq) + stage_mask_bytes(row_mask, dense->n) +
+      stage_terms_bytes(q_terms, q_offsets, nq) + stage_mask_bytes(doc_mask, bm25->n_docs) +
+      dense_ws_bytes(ctx, dense, nq, k_dense) + bm25_ws_bytes(ctx, bm25, nq, k_bm25) +
+      padded(list_cells * 4) + padded(list_cells * 4) + padded(static_cast<size_t>(nq) * 2 * 4) +
+      2048 + out_need(out_ids, fused_cells) + out_need(out_scores, fused_cells) +
+      out_need(out_counts, nq) + out_need(out_dense_rows, static_cast<size_t>(nq) * k_dense) +
+      out_need(out_dense_scores, static_cast<size_t>(nq) * k_dense) +
+      out_need(out_bm25_ids, static_cast<size_t>(nq) * k_bm25) +
+      out_need(out_bm25_scores, static_cast<size_t>(nq) * k_bm25);
+  if (int rc = ws_reserve(ctx, need)) return rc;
+  Arena arena{ctx->ws, ctx->ws_bytes};
+
+  int32_t* lists = arena.take<int32_t>(list_cells);       // [nq][2][stride] ids
+  float* list_scores = arena.take<float>(list_cells);     // [nq][2][stride] scores
+  int32_t* lens = arena.take<int32_t>(static_cast<size_t>(nq) * 2);
+  double* w_dev = arena.take<double>(2);
+  OutBuf<int32_t> o_ids = out_make(arena, out_ids, fused_cells);
+  OutBuf<double> o_scores = out_make(arena, out_scores, fused_cells);
+  OutBuf<int32_t> o_counts = out_make(arena, out_counts, nq);
+
+  const float* q_dev = nullptr;
+  const uint32_t* row_mask_dev = nullptr;
+  const uint32_t* doc_mask_dev = nullptr;
+  QueryTerms qt;
+  if (int rc = stage_queries(dense, queries, nq, arena, stream, &q_dev)) return rc;
+  if (int rc = stage_mask(row_mask, dense->n, arena, stream, &row_mask_dev)) return rc;
+  if (int rc = stage_terms(q_terms, q_offsets, nq, arena, stream, &qt)) return rc;
+  if (int rc = stage_mask(doc_mask, bm25->n_docs, arena, stream, &doc_mask_dev)) return rc;
+  set_f64_pair_kernel<<<1, 1, 0, stream>>>(w_dev, w_dense, w_bm25);
+  ANR_CUDA(cudaGetLastError());
+
+  TopkOut od;
+  od.ids = lists;
+  od.scores = list_scores;
+  od.counts = lens;
+  od.stride_q = 2ll * stride;
+  od.count_stride = 2;
+  od.id_base = id_base;
+  if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k_dense, row_mask_dev, arena, od, stream))
+    return rc;
+  TopkOut ob = od;
+  ob.ids = lists + stride;
+  ob.scores = list_scores + stride;
+  ob.counts = lens + 1;
+  ob.id_map = doc_to_id;
+  if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k_bm25, doc_mask_dev, arena, ob,
+                             stream))
+    return rc;
+  ANR_CUDA(launch_wrrf_fuse(lists, lens, w_dev, 2, stride, nq, rrf_k, top_n, o_ids.dev,
+                            o_scores.dev, o_counts.dev, stream));
+
+  // optional per-retriever outputs: strided device -> user layout [nq, k]
+  auto copy_out = [&](void* user, const void* src, int k) -> cudaError_t {
+    if (!user) return cudaSuccess;
+    return cudaMemcpy2DAsync(user, static_cast<size_t>(k) * 4, src, static_cast<size_t>(stride) * 8,
+                             static_cast<size_t>(k) * 4, nq, cudaMemcpyDefault, stream);
+  };
+  bool any_host = false;
+  if (out_dense_rows) any_host |= !is_device_ptr(out_dense_rows);
+  if (out_dense_scores) any_host |= !is_device_ptr(out_dense_scores);
+  if (out_bm25_ids) any_host |= !is_device_ptr(out_bm25_ids);
+  if (out_bm25_scores) any_host |= !is_device_ptr(out_bm25_scores);
+  ANR_CUDA(copy_out(out_dense_rows, lists, k_dense));
+  ANR_CUDA(copy_out(out_dense_scores, list_scores, k_dense));
+  ANR_CUDA(copy_out(out_bm25_ids, lists + stride, k_bm25));
+  ANR_CUDA(copy_out(out_bm25_scores, list_scores + stride, k_bm25));
+  ANR_CUDA(out_flush(o_ids, stream, &any_host));
+  ANR_CUDA(out_flush(o_scores, stream, &any_host));
+  ANR_CUDA(out_flush(o_counts, stream, &any_host));
+  if (any_host) ANR_CUDA(cudaStreamSynchronize(stream));
+  return ANR_OK;
+}
+
+// ---- sharded merge ----------------------------------------------------------------------
+int anr_topk_merge(anr_ctx* ctx, const uint64_t* keys, int32_t n_parts, int32_t n_queries,
+                   int32_t k, float* out_scores, int32_t* out_ids, int32_t* out_counts,
+                   void* stream_v) {
+  if (!ctx || !keys) return fail(ANR_ERR_INVALID, "anr_topk_merge: NULL argument");
+  if (n_parts < 1 || n_queries < 1 || k < 1) return fail(ANR_ERR_INVALID, "anr_topk_merge: bad shape");
+  if (k > kMaxFusedK) return fail(ANR_ERR_UNSUPPORTED, "anr_topk_merge: k above 128");
+  DeviceGuard guard(ctx->dp.device);
+  cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  const size_t n_keys = static_cast<size_t>(n_parts) * n_queries * k;
+  const size_t cells = static_cast<size_t>(n_queries) * k;
+  const bool keys_host = !is_device_ptr(keys);
+  const size_t need = (keys_host ? padded(n_keys * 8) + 256 : 0) + out_need(out_scores, cells) +
+                      out_need(out_ids, cells) + out_need(out_counts, n_queries);
+  if (int rc = ws_reserve(ctx, need)) return rc;
+  Arena arena{ctx->ws, ctx->ws_bytes};
+  const uint64_t* keys_dev = keys;
+  if (keys_host) {
+    uint64_t* p = arena.take<uint64_t>(n_keys);
+    ANR_CUDA(cudaMemcpyAsync(p, keys, n_keys * 8, cudaMemcpyHostToDevice, stream));
+    keys_dev = p;
+  }
+  OutBuf<float> o_scores = out_make(arena, out_scores, cells);
+  OutBuf<int32_t> o_ids = out_make(arena, out_ids, cells);
+  OutBuf<int32_t> o_counts = out_make(arena, out_counts, n_queries);
+  TopkOut out;
+  out.scores = o_scores.dev;
+  out.ids = o_ids.dev;
+  out.counts = o_counts.dev;
+  out.stride_q = k;
+  ANR_CUDA(launch_topk_final(keys_dev, k, n_parts * k, k, static_cast<int64_t>(n_queries) * k,
+                             n_queries, k, out, stream));
+  bool any_host = false;
+  ANR_CUDA(out_flush(o_scores, stream, &any_host));
+  ANR_CUDA(out_flush(o_ids, stream, &any_host));
+  ANR_CUDA(out_flush(o_counts, stream, &any_host));
+  if (any_host) ANR_CUDA(cudaStreamSynchronize(stream));
+  return ANR_OK;
+}
+
+}  // extern "C"

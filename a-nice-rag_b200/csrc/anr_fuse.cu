@@ -1,0 +1,176 @@
+// Weighted reciprocal-rank fusion on device.
+//
+// Replaces SearchEngine.weighted_reciprocal_rank_fusion (src/search_engine.py:21-34):
+//     score[id] += weight[list] * (1 / (k + rank))        rank = 1, 2, ...
+// accumulated list after list in float64, then a STABLE sort by score descending
+// (ties keep first-insertion order: list 0's entries first, each list in rank order).
+// The device result is bit-identical to the Python loop: the reciprocal is an IEEE
+// float64 division, the product and the running sum are separate round-to-nearest
+// operations (no FMA contraction) and the sum runs in insertion order.
+//
+// One CTA per query, everything in shared memory:
+//   1. entries (id, position) with position = insertion index (list-major) are
+//      bitonic-sorted ascending by (id, position);
+//   2. the first entry of every id run ("head") walks its run in position order and
+//      accumulates the float64 score; its position is the id's first insertion;
+//   3. (orderable(score), first position) pairs are bitonic-sorted: score descending,
+//      position ascending -- exactly the order of Python's stable sorted(reverse=True);
+//   4. the first min(top_n, #ids) entries are written out.
+#include "anr_internal.h"
+#include "anr_common.cuh"
+
+namespace anr {
+
+constexpr int kWrrfThreads = 512;
+constexpr int kWrrfMaxEntries = 8192;  // padded (power of two) entries per query in smem
+
+int wrrf_max_entries() { return kWrrfMaxEntries; }
+
+__device__ __forceinline__ uint64_t f64_to_ord(double d) {
+  const uint64_t u = static_cast<uint64_t>(__double_as_longlong(d));
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ord_to_f64(uint64_t o) {
+  const uint64_t u = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
+  return __longlong_as_double(static_cast<long long>(u));
+}
+
+// a[] ascending (single 64-bit key)
+__device__ __forceinline__ void bitonic_asc_u64(uint64_t* a, int n_pow2) {
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int hi = lo + stride;
+        const bool asc = ((lo & size) == 0);
+        const uint64_t x = a[lo], y = a[hi];
+        if ((x > y) == asc) { a[lo] = y; a[hi] = x; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// pairs (s[], a[]): s descending, ties by low 32 bits of a ascending
+__device__ __forceinline__ bool pair_before(uint64_t s0, uint64_t a0, uint64_t s1, uint64_t a1) {
+  return s0 > s1 || (s0 == s1 && static_cast<uint32_t>(a0) < static_cast<uint32_t>(a1));
+}
+__device__ __forceinline__ void bitonic_pairs(uint64_t* s, uint64_t* a, int n_pow2) {
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const int hi = lo + stride;
+        const bool fwd = ((lo & size) == 0);
+        const uint64_t s0 = s[lo], a0 = a[lo], s1 = s[hi], a1 = a[hi];
+        // in a forward block the better pair must sit at lo
+        const bool hi_better = pair_before(s1, a1, s0, a0);
+        const bool lo_better = pair_before(s0, a0, s1, a1);
+        if (fwd ? hi_better : lo_better) { s[lo] = s1; a[lo] = a1; s[hi] = s0; a[hi] = a0; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kWrrfThreads)
+wrrf_fuse_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ lens,
+                 const double* __restrict__ weights, int n_lists, int list_stride, double rrf_k,
+                 int top_n, int n_pow2, int32_t* __restrict__ out_ids,
+                 double* __restrict__ out_scores, int32_t* __restrict__ out_counts) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* a = reinterpret_cast<uint64_t*>(smem);  // (id << 32) | position
+  uint64_t* s = a + n_pow2;                         // orderable score of heads, 0 otherwise
+  __shared__ int list_base[65];                     // insertion offset of each list (n_lists <= 64)
+  __shared__ int n_unique;
+
+  const int q = blockIdx.x;
+  const int32_t* qids = ids + static_cast<int64_t>(q) * n_lists * list_stride;
+  const int32_t* qlens = lens + static_cast<int64_t>(q) * n_lists;
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int l = 0; l < n_lists; ++l) {
+      list_base[l] = run;
+      int len = qlens[l];
+      len = len < 0 ? 0 : (len > list_stride ? list_stride : len);
+      run += len;
+    }
+    list_base[n_lists] = run;
+    n_unique = 0;
+  }
+  __syncthreads();
+  const int total = list_base[n_lists];
+
+  // 1. entries, padded with the largest key
+  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) a[i] = ~0ull;
+  __syncthreads();
+  for (int l = 0; l < n_lists; ++l) {
+    const int base = list_base[l], len = list_base[l + 1] - base;
+    for (int r = threadIdx.x; r < len; r += blockDim.x)
+      a[base + r] = (static_cast<uint64_t>(static_cast<uint32_t>(qids[l * list_stride + r])) << 32) |
+                    static_cast<uint32_t>(base + r);
+  }
+  bitonic_asc_u64(a, n_pow2);
+
+  // 2. heads accumulate their run in insertion order
+  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+    uint64_t sc = 0ull;
+    if (i < total) {
+      const uint32_t id = static_cast<uint32_t>(a[i] >> 32);
+      const bool head = (i == 0) || (static_cast<uint32_t>(a[i - 1] >> 32) != id);
+      if (head) {
+        double acc = 0.0;
+        for (int j = i; j < total && static_cast<uint32_t>(a[j] >> 32) == id; ++j) {
+          const int pos = static_cast<int>(static_cast<uint32_t>(a[j]));
+          int l = 0;
+          while (pos >= list_base[l + 1]) ++l;
+          const int rank = pos - list_base[l] + 1;
+          const double recip = __ddiv_rn(1.0, __dadd_rn(rrf_k, static_cast<double>(rank)));
+          acc = __dadd_rn(acc, __dmul_rn(weights[l], recip));
+        }
+        sc = f64_to_ord(acc);
+        atomicAdd(&n_unique, 1);
+      }
+    }
+    s[i] = sc;
+  }
+  // 3. order by (score desc, first position asc); non-heads (s == 0) sink to the end
+  bitonic_pairs(s, a, n_pow2);
+
+  // 4. emit
+  const int n_out = n_unique < top_n ? n_unique : top_n;
+  for (int i = threadIdx.x; i < top_n; i += blockDim.x) {
+    const int64_t o = static_cast<int64_t>(q) * top_n + i;
+    if (i < n_out) {
+      out_ids[o] = static_cast<int32_t>(static_cast<uint32_t>(a[i] >> 32));
+      out_scores[o] = ord_to_f64(s[i]);
+    } else {
+      out_ids[o] = -1;
+      out_scores[o] = 0.0;
+    }
+  }
+  if (threadIdx.x == 0 && out_counts) out_counts[q] = n_out;
+}
+
+cudaError_t launch_wrrf_fuse(const int32_t* ids, const int32_t* lens, const double* weights,
+                             int n_lists, int list_stride, int nq, double rrf_k, int top_n,
+                             int32_t* out_ids, double* out_scores, int32_t* out_counts,
+                             cudaStream_t stream) {
+  if (n_lists < 1 || n_lists > 64 || list_stride < 1 || top_n < 1) return cudaErrorInvalidValue;
+  const int64_t cap = static_cast<int64_t>(n_lists) * list_stride;
+  if (cap > kWrrfMaxEntries) return cudaErrorInvalidConfiguration;
+  const int n_pow2 = next_pow2(static_cast<int>(cap) < 2 ? 2 : static_cast<int>(cap));
+  const int smem = n_pow2 * 16;
+  cudaError_t e = cudaFuncSetAttribute(wrrf_fuse_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  if (nq < 1) return cudaSuccess;
+  wrrf_fuse_kernel<<<nq, kWrrfThreads, smem, stream>>>(ids, lens, weights, n_lists, list_stride,
+                                                       rrf_k, top_n, n_pow2, out_ids, out_scores,
+                                                       out_counts);
+  return cudaGetLastError();
+}
+
+}  // namespace anr

@@ -1,0 +1,99 @@
+// Internal launcher prototypes shared by the .cu translation units.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace anr {
+
+struct DeviceProps {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;  // bytes of dynamic shared memory one CTA may opt in to
+};
+
+// Where a top-k result goes.  Entry i of query q is written at q * stride_q + i of every
+// non-null array; counts[q * count_stride] = number of valid entries.  Ids are
+// id_map[id] when id_map is given, else id + id_base.  `keys` receives sortable keys
+// with the REMAPPED id (what the sharded merge consumes).
+struct TopkOut {
+  uint64_t* keys = nullptr;
+  float* scores = nullptr;
+  int32_t* ids = nullptr;
+  int32_t* counts = nullptr;
+  int64_t stride_q = 0;
+  int64_t count_stride = 1;
+  int64_t id_base = 0;
+  const int32_t* id_map = nullptr;
+};
+
+// ---- dense scan -------------------------------------------------------------
+// Scans rows [0, n) of emb (row-major, leading dimension ld floats, ld % 4 == 0)
+// against nq (1, 2, 4 or 8) queries staged at q_dev ([nq, ld], zero padded) and writes
+// per-CTA candidate keys cand[q * cand_stride_q + cta * k + i] (k <= kMaxFusedK).
+// Returns the number of CTAs launched through *grid_out (candidates per query = grid * k).
+cudaError_t launch_dense_scan_topk(const DeviceProps& dp, const float* emb, int64_t n, int ld,
+                                   const float* q_dev, int nq, int k, const uint32_t* mask,
+                                   uint64_t* cand, int64_t cand_stride_q, int* grid_out,
+                                   cudaStream_t stream);
+// Upper bound on the grid the scan will use (to size `cand`).
+int dense_scan_max_grid(const DeviceProps& dp);
+// Full materialisation: keys[q * keys_stride_q + row] for every row (0 for masked rows).
+cudaError_t launch_dense_scan_all(const DeviceProps& dp, const float* emb, int64_t n, int ld,
+                                  const float* q_dev, int nq, const uint32_t* mask,
+                                  uint64_t* keys, int64_t keys_stride_q, cudaStream_t stream);
+
+// ---- top-k ------------------------------------------------------------------
+// Per query: select the best k (<= kMaxFusedK) of m candidate keys, sorted best first.
+// Candidate i of query q is cand[q * cand_stride_q + (i / seg_len) * seg_stride + i % seg_len].
+cudaError_t launch_topk_final(const uint64_t* cand, int64_t cand_stride_q, int m, int seg_len,
+                              int64_t seg_stride, int nq, int k, const TopkOut& out,
+                              cudaStream_t stream);
+// Large-k path: sort keys[q][0..n_pow2) descending in place (global-memory bitonic).
+cudaError_t launch_sort_desc(uint64_t* keys, int64_t stride_q, int64_t n_pow2, int nq,
+                             cudaStream_t stream);
+cudaError_t launch_zero_tail(uint64_t* keys, int64_t stride_q, int64_t n, int64_t n_pow2, int nq,
+                             cudaStream_t stream);
+cudaError_t launch_emit_sorted(const uint64_t* keys, int64_t stride_q, int64_t n_avail, int nq,
+                               int k, const TopkOut& out, cudaStream_t stream);
+
+// ---- BM25 ---------------------------------------------------------------------
+struct Bm25View {
+  const int64_t* term_ptr;  // [n_terms + 1]
+  const int32_t* post_doc;  // [nnz]
+  const float* post_w;      // [nnz]
+  const float* idf;         // [n_terms]
+  int32_t n_terms;
+  int32_t n_docs;
+  int64_t nnz;
+};
+cudaError_t launch_bm25_weights(const int32_t* post_doc, const int32_t* post_tf,
+                                const int32_t* doc_len, int64_t nnz, double k1, double b,
+                                double avgdl, float* post_w, cudaStream_t stream);
+struct Bm25Plan {
+  int tile_docs;   // documents per shared-memory tile (multiple of 32)
+  int n_tiles;
+  int list_cap;
+  int smem_bytes;
+};
+Bm25Plan bm25_make_plan(const DeviceProps& dp, int n_docs, int nq, int k, bool emit_all);
+// cand[q * cand_stride_q + tile * k + i] candidate keys (ids = doc index)
+cudaError_t launch_bm25_score_topk(const Bm25View& ix, const int32_t* q_terms,
+                                   const int32_t* q_offsets, int nq, int k,
+                                   const uint32_t* doc_mask, const Bm25Plan& plan, uint64_t* cand,
+                                   int64_t cand_stride_q, cudaStream_t stream);
+// keys[q * keys_stride_q + doc] for every doc (0 for masked docs)
+cudaError_t launch_bm25_score_all(const Bm25View& ix, const int32_t* q_terms,
+                                  const int32_t* q_offsets, int nq, const uint32_t* doc_mask,
+                                  const Bm25Plan& plan, uint64_t* keys, int64_t keys_stride_q,
+                                  cudaStream_t stream);
+cudaError_t launch_keys_to_scores(const uint64_t* keys, int64_t n, float* scores,
+                                  cudaStream_t stream);
+
+// ---- fusion -------------------------------------------------------------------
+cudaError_t launch_wrrf_fuse(const int32_t* ids, const int32_t* lens, const double* weights,
+                             int n_lists, int list_stride, int nq, double rrf_k, int top_n,
+                             int32_t* out_ids, double* out_scores, int32_t* out_counts,
+                             cudaStream_t stream);
+int wrrf_max_entries();
+
+}  // namespace anr

@@ -1,0 +1,196 @@
+// Final top-k selection over candidate keys, and the large-k (full ranking) sort path.
+//
+// Small k (<= kMaxFusedK): one CTA per query; if the candidates fit in shared memory they
+// are bitonic-sorted directly, otherwise 32 warps first reduce them with threshold lists.
+// Large k (the evaluator's similarity_k = 12000 >= N case, src/retrieval_eval.py:142 ->
+// the `else: argsort()[::-1]` branches of src/search_engine.py:86-87,134-135,240-241):
+// all keys are materialised and sorted descending by a global-memory bitonic network whose
+// inner strides run in shared memory.
+#include "anr_internal.h"
+#include "anr_topk.cuh"
+
+namespace anr {
+
+__device__ __forceinline__ void emit_entry(uint64_t key, int64_t slot, const TopkOut& o) {
+  const bool valid = key != 0ull;
+  uint32_t id = key_id(key);
+  if (valid)
+    id = o.id_map ? static_cast<uint32_t>(o.id_map[id]) : static_cast<uint32_t>(id + o.id_base);
+  if (o.keys) o.keys[slot] = valid ? ((key & 0xffffffff00000000ull) | (0xffffffffu - id)) : 0ull;
+  if (o.scores) o.scores[slot] = valid ? key_score(key) : 0.f;
+  if (o.ids) o.ids[slot] = valid ? static_cast<int32_t>(id) : -1;
+}
+
+// Candidate i of a query lives at base[(i / seg_len) * seg_stride + (i % seg_len)]:
+// contiguous candidates use seg_len = m; the all-gathered [part][query][k] layout of
+// the sharded search uses seg_len = k, seg_stride = n_queries * k.
+__global__ void __launch_bounds__(kFinalThreads)
+topk_final_kernel(const uint64_t* __restrict__ cand, int64_t stride_q, int m, int seg_len,
+                  int64_t seg_stride, int k, TopkOut o) {
+  __shared__ uint64_t keys[kFinalSortCap];
+  const int q = blockIdx.x;
+  const uint64_t* c = cand + q * stride_q;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int p2;
+  if (m <= kFinalSortCap) {
+    p2 = next_pow2(m);
+    for (int i = threadIdx.x; i < p2; i += blockDim.x)
+      keys[i] = i < m ? c[(i / seg_len) * seg_stride + (i % seg_len)] : 0ull;
+  } else {
+    const int n_lists = kFinalThreads / 32;
+    p2 = next_pow2(n_lists * k);
+    for (int i = threadIdx.x; i < p2; i += blockDim.x) keys[i] = 0ull;
+    __syncthreads();
+    uint64_t thr = 0;
+    uint64_t* list = keys + warp * k;
+    for (int base = warp * 32; base < m; base += kFinalThreads) {
+      const int i = base + lane;
+      const uint64_t key = i < m ? c[(i / seg_len) * seg_stride + (i % seg_len)] : 0ull;
+      warp_list_offer(list, k, key, thr, lane);
+    }
+  }
+  block_bitonic_sort_desc(keys, p2);
+  uint64_t key = 0ull;
+  if (threadIdx.x < k) {
+    key = threadIdx.x < p2 ? keys[threadIdx.x] : 0ull;
+    emit_entry(key, q * o.stride_q + threadIdx.x, o);
+  }
+  const int cnt = __syncthreads_count(key != 0ull);
+  if (threadIdx.x == 0 && o.counts) o.counts[q * o.count_stride] = cnt;
+}
+
+cudaError_t launch_topk_final(const uint64_t* cand, int64_t cand_stride_q, int m, int seg_len,
+                              int64_t seg_stride, int nq, int k, const TopkOut& out,
+                              cudaStream_t stream) {
+  if (k < 1 || k > kMaxFusedK || m < 1 || seg_len < 1) return cudaErrorInvalidValue;
+  if (nq < 1) return cudaSuccess;
+  topk_final_kernel<<<nq, kFinalThreads, 0, stream>>>(cand, cand_stride_q, m, seg_len, seg_stride,
+                                                      k, out);
+  return cudaGetLastError();
+}
+
+// ---- large-k path: global bitonic sort, descending --------------------------------
+constexpr int kSortTile = 2048;  // keys per CTA in the shared-memory phases
+constexpr int kSortThreads = 1024;
+
+__device__ __forceinline__ void cmp_swap_desc(uint64_t& a, uint64_t& b, bool desc) {
+  if ((a < b) == desc) { uint64_t t = a; a = b; b = t; }
+}
+
+// All network steps with size <= kSortTile, entirely in shared memory.
+__global__ void __launch_bounds__(kSortThreads)
+bitonic_head_kernel(uint64_t* __restrict__ keys, int64_t stride_q, int64_t n_pow2) {
+  __shared__ uint64_t s[kSortTile];
+  uint64_t* base = keys + blockIdx.y * stride_q + static_cast<int64_t>(blockIdx.x) * kSortTile;
+  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * kSortTile;
+  const int tile = n_pow2 < kSortTile ? static_cast<int>(n_pow2) : kSortTile;
+  for (int i = threadIdx.x; i < tile; i += blockDim.x) s[i] = base[i];
+  for (int size = 2; size <= tile; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (tile >> 1); t += blockDim.x) {
+        const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        const bool desc = (((g0 + lo) & size) == 0);
+        cmp_swap_desc(s[lo], s[lo + stride], desc);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < tile; i += blockDim.x) base[i] = s[i];
+}
+
+// One (size, stride) step with stride >= kSortTile, in global memory.
+__global__ void __launch_bounds__(256)
+bitonic_global_step_kernel(uint64_t* __restrict__ keys, int64_t stride_q, int64_t n_pow2,
+                           int64_t size, int64_t stride) {
+  uint64_t* base = keys + blockIdx.y * stride_q;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= (n_pow2 >> 1)) return;
+  const int64_t lo = ((t / stride) * (stride << 1)) + (t % stride);
+  const bool desc = ((lo & size) == 0);
+  uint64_t a = base[lo], b = base[lo + stride];
+  if ((a < b) == desc) { base[lo] = b; base[lo + stride] = a; }
+}
+
+// The strides < kSortTile of one `size` (> kSortTile), in shared memory.
+__global__ void __launch_bounds__(kSortThreads)
+bitonic_tail_kernel(uint64_t* __restrict__ keys, int64_t stride_q, int64_t size) {
+  __shared__ uint64_t s[kSortTile];
+  uint64_t* base = keys + blockIdx.y * stride_q + static_cast<int64_t>(blockIdx.x) * kSortTile;
+  const int64_t g0 = static_cast<int64_t>(blockIdx.x) * kSortTile;
+  for (int i = threadIdx.x; i < kSortTile; i += blockDim.x) s[i] = base[i];
+  const bool desc = ((g0 & size) == 0);  // constant inside a tile since size > kSortTile
+  for (int stride = kSortTile >> 1; stride > 0; stride >>= 1) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < (kSortTile >> 1); t += blockDim.x) {
+      const int lo = ((t / stride) * (stride << 1)) + (t % stride);
+      cmp_swap_desc(s[lo], s[lo + stride], desc);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSortTile; i += blockDim.x) base[i] = s[i];
+}
+
+cudaError_t launch_sort_desc(uint64_t* keys, int64_t stride_q, int64_t n_pow2, int nq,
+                             cudaStream_t stream) {
+  if (n_pow2 < 1 || (n_pow2 & (n_pow2 - 1)) != 0) return cudaErrorInvalidValue;
+  if (n_pow2 == 1) return cudaSuccess;
+  const int64_t tiles = n_pow2 <= kSortTile ? 1 : n_pow2 / kSortTile;
+  dim3 grid_tiles(static_cast<unsigned>(tiles), nq);
+  bitonic_head_kernel<<<grid_tiles, kSortThreads, 0, stream>>>(keys, stride_q, n_pow2);
+  for (int64_t size = static_cast<int64_t>(kSortTile) * 2; size <= n_pow2; size <<= 1) {
+    for (int64_t stride = size >> 1; stride >= kSortTile; stride >>= 1) {
+      dim3 grid(static_cast<unsigned>(((n_pow2 >> 1) + 255) / 256), nq);
+      bitonic_global_step_kernel<<<grid, 256, 0, stream>>>(keys, stride_q, n_pow2, size, stride);
+    }
+    bitonic_tail_kernel<<<grid_tiles, kSortThreads, 0, stream>>>(keys, stride_q, size);
+  }
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256)
+emit_sorted_kernel(const uint64_t* __restrict__ keys, int64_t stride_q, int64_t n_avail, int k,
+                   TopkOut o) {
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  const int q = blockIdx.x;
+  int mine = 0;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const uint64_t key = i < n_avail ? keys[q * stride_q + i] : 0ull;
+    emit_entry(key, q * o.stride_q + i, o);
+    mine += key != 0ull;
+  }
+  if (mine) atomicAdd(&cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0 && o.counts) o.counts[q * o.count_stride] = cnt;
+}
+
+// keys[q][0 .. n_avail) sorted descending -> first k entries per query
+cudaError_t launch_emit_sorted(const uint64_t* keys, int64_t stride_q, int64_t n_avail, int nq,
+                               int k, const TopkOut& out, cudaStream_t stream) {
+  if (nq < 1) return cudaSuccess;
+  emit_sorted_kernel<<<nq, 256, 0, stream>>>(keys, stride_q, n_avail, k, out);
+  return cudaGetLastError();
+}
+
+// zero keys[q][n .. n_pow2) so the padding sorts last
+__global__ void __launch_bounds__(256)
+zero_tail_kernel(uint64_t* __restrict__ keys, int64_t stride_q, int64_t n, int64_t n_pow2) {
+  uint64_t* base = keys + blockIdx.y * stride_q;
+  for (int64_t i = n + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_pow2;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    base[i] = 0ull;
+}
+
+cudaError_t launch_zero_tail(uint64_t* keys, int64_t stride_q, int64_t n, int64_t n_pow2, int nq,
+                             cudaStream_t stream) {
+  if (n >= n_pow2 || nq < 1) return cudaSuccess;
+  int64_t blocks = (n_pow2 - n + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  dim3 grid(static_cast<unsigned>(blocks), nq);
+  zero_tail_kernel<<<grid, 256, 0, stream>>>(keys, stride_q, n, n_pow2);
+  return cudaGetLastError();
+}
+
+}  // namespace anr

@@ -1,0 +1,70 @@
+// Top-k building blocks on 64-bit sortable keys (anr_common.cuh):
+//   * a per-warp unsorted k-list in shared memory with a running threshold
+//     (almost every row is rejected by one register compare);
+//   * a block-wide bitonic sort (descending) in shared memory;
+//   * the final per-query selection kernel over a candidate array.
+#pragma once
+#include "anr_common.cuh"
+
+namespace anr {
+
+constexpr int kMaxFusedK = 128;      // fused (threshold-list) top-k handles k <= this
+constexpr int kFinalThreads = 1024;  // topk_final_kernel block size
+constexpr int kFinalSortCap = 4096;  // keys the final kernel sorts in shared memory
+
+// Replace the minimum of list[0..k) by `key` (caller guarantees key > current
+// minimum or the list has empty slots) and return the new minimum = the warp's
+// new acceptance threshold.  All 32 lanes call with the same arguments.
+__device__ __forceinline__ uint64_t warp_list_insert(uint64_t* list, int k, uint64_t key, int lane) {
+  uint64_t mn = ~0ull;
+  int mp = 0x7fffffff;
+  for (int i = lane; i < k; i += 32) {
+    uint64_t v = list[i];
+    if (v < mn) { mn = v; mp = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    uint64_t omn = __shfl_xor_sync(kFullMask, mn, o);
+    int omp = __shfl_xor_sync(kFullMask, mp, o);
+    if (omn < mn || (omn == mn && omp < mp)) { mn = omn; mp = omp; }
+  }
+  if (lane == 0) list[mp] = key;
+  __syncwarp();
+  uint64_t nm = ~0ull;
+  for (int i = lane; i < k; i += 32) {
+    uint64_t v = list[i];
+    nm = v < nm ? v : nm;
+  }
+  return warp_min_u64(nm);
+}
+
+// Lanes hold DIFFERENT candidate keys: insert every lane's key that beats thr.
+__device__ __forceinline__ void warp_list_offer(uint64_t* list, int k, uint64_t my_key,
+                                                uint64_t& thr, int lane) {
+  unsigned pending = __ballot_sync(kFullMask, my_key > thr);
+  while (pending) {
+    int src = __ffs(pending) - 1;
+    pending &= pending - 1;
+    uint64_t cand = __shfl_sync(kFullMask, my_key, src);
+    if (cand > thr) thr = warp_list_insert(list, k, cand, lane);
+  }
+}
+
+// Bitonic sort of keys[0..n_pow2) descending; every thread of the block calls.
+__device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* keys, int n_pow2) {
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
+        int lo = ((t / stride) * (stride << 1)) + (t % stride);
+        int hi = lo + stride;
+        bool desc = ((lo & size) == 0);
+        uint64_t a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+}  // namespace anr

@@ -1,0 +1,186 @@
+"""Drop-in ``DatabaseManager``: same contract as the reference's ``src/database_manager.py``
+(:14-99), plus a device-resident copy of what it loads.
+
+``load_embeddings_from_sql`` returns the same DataFrame (columns ``id, document, source,
+embedding, url``; ``embedding`` an object column of per-row fp32 arrays) -- the rows are
+views into ONE packed ``[N, D]`` matrix that is uploaded to HBM once, so searches never
+re-stack it (the reference's ``np.stack`` per query, search_engine.py:80).
+``load_bm25_from_pickle`` returns the same ``(bm25, sections, section_ids)`` tuple and
+attaches the CSR inverted index built from the unpickled ``BM25Okapi`` attributes.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import pickle
+import sqlite3
+import sys
+import threading
+import types
+from typing import Tuple
+
+import numpy as np
+import pandas as pd
+
+from . import native, registry
+
+
+def _no_device(exc: BaseException) -> bool:
+    return isinstance(exc, native.AnrError) and exc.code == 3
+
+
+class _AttrOnlyBM25Okapi:
+    """Stand-in for ``rank_bm25.BM25Okapi`` when that package is absent at unpickle time.
+
+    Real indices (written by src/processing/bm25_search.py:84-93) pickle an instance of
+    that class by reference; only its attributes are needed here.  ``get_scores`` is
+    served by the device index (fp32), there is no Python scoring loop behind it.
+    """
+
+    def get_scores(self, query):
+        entry = registry.resolve_bm25(self)
+        return entry.index.scores(entry.index.term_ids(query)).astype(np.float64)
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_anr_entry", None)   # device handles do not pickle
+        return state
+
+
+class _Document:
+    """Stand-in for ``langchain.schema.document.Document`` (page_content + metadata)."""
+
+    def __init__(self, page_content: str = "", metadata=None, **kwargs):
+        self.page_content = page_content
+        self.metadata = metadata if metadata is not None else {}
+        self.__dict__.update(kwargs)
+
+    def __setstate__(self, state):
+        # pydantic-based Documents pickle {"__dict__": {...}, ...}; plain ones pickle the dict
+        if isinstance(state, dict) and "__dict__" in state and isinstance(state["__dict__"], dict):
+            state = state["__dict__"]
+        self.__dict__.update(state)
+        self.__dict__.setdefault("page_content", "")
+        self.__dict__.setdefault("metadata", {})
+
+
+def _install_unpickle_shims() -> None:
+    """Make ``rank_bm25.BM25Okapi`` and langchain's ``Document`` resolvable for pickle.load
+    when those packages are not installed (they are not, offline)."""
+    try:
+        import rank_bm25  # noqa: F401
+    except ImportError:
+        mod = types.ModuleType("rank_bm25")
+        cls = type("BM25Okapi", (_AttrOnlyBM25Okapi,), {"__module__": "rank_bm25"})
+        mod.BM25Okapi = cls
+        sys.modules["rank_bm25"] = mod
+    for name in ("langchain.schema.document", "langchain_core.documents.base"):
+        try:
+            __import__(name)
+        except ImportError:
+            parts = name.split(".")
+            for i in range(1, len(parts) + 1):
+                sub = ".".join(parts[:i])
+                if sub not in sys.modules:
+                    sys.modules[sub] = types.ModuleType(sub)
+                    if i > 1:
+                        setattr(sys.modules[".".join(parts[:i - 1])], parts[i - 1], sys.modules[sub])
+            doc_cls = type("Document", (_Document,), {"__module__": name})
+            sys.modules[name].Document = doc_cls
+
+
+class DatabaseManager:
+
+    def __init__(self):
+        self._embeddings_cache = {}
+        self._bm25_cache = {}
+        self._lock = threading.Lock()
+        self.logger = logging.getLogger(__name__)
+
+    def load_embeddings_from_sql(self, db_path: str, model_name: str = None) -> pd.DataFrame:
+        """Load the ``chunks`` table into a DataFrame and pack + upload the embedding matrix."""
+        cache_key = f"{db_path}_{model_name}" if model_name else db_path
+        with self._lock:
+            if cache_key in self._embeddings_cache:
+                return self._embeddings_cache[cache_key]
+        try:
+            if not os.path.exists(db_path):
+                raise FileNotFoundError(f"Database not found: {db_path}")
+            conn = sqlite3.connect(db_path)
+            cursor = conn.cursor()
+            cursor.execute("SELECT id, content, source, embedding, url FROM chunks")
+            rows = cursor.fetchall()
+            if not rows:
+                self.logger.warning(f"No chunks found in {db_path}")
+                return pd.DataFrame()
+
+            # one packed [N, D] buffer; D is fixed by the first decodable row
+            ids, documents, sources, urls, blobs = [], [], [], [], []
+            for cid, content, source, blob, url in rows:
+                try:
+                    if len(memoryview(blob)) % 4 != 0:
+                        raise ValueError("buffer size must be a multiple of element size")
+                except (ValueError, TypeError) as e:
+                    self.logger.warning(f"Skipping invalid row {cid}: {e}")
+                    continue
+                ids.append(cid)
+                documents.append(content)
+                sources.append(source)
+                urls.append(url)
+                blobs.append(blob)
+            widths = {len(memoryview(b)) for b in blobs}
+            if len(widths) == 1:
+                d = widths.pop() // 4
+                packed = np.frombuffer(b"".join(blobs), dtype=np.float32).reshape(len(blobs), d)
+                embeddings = list(packed)            # N row views, like the per-row frombuffer
+            else:                                    # ragged widths: keep the reference's frame,
+                packed = None                        # searches will fail in np.stack like it does
+                embeddings = [np.frombuffer(b, dtype=np.float32) for b in blobs]
+            df = pd.DataFrame({
+                "id": ids, "document": documents, "source": sources,
+                "embedding": pd.Series(embeddings, dtype=object), "url": urls,
+            })
+            if packed is not None and len(df):
+                entry = registry.register_frame(df, packed)
+                try:
+                    entry.index()                    # upload now: queries must not pay for it
+                except Exception as e:
+                    if not _no_device(e):
+                        raise
+                    self.logger.warning(f"No B200 visible while loading {db_path}: "
+                                        "the index will be uploaded by the first search")
+            with self._lock:
+                self._embeddings_cache[cache_key] = df
+            return df
+        except Exception as e:
+            self.logger.error(f"Error loading embeddings from {db_path}: {e}")
+            raise
+        finally:
+            if "conn" in locals():
+                conn.close()
+
+    def load_bm25_from_pickle(self, filepath: str) -> Tuple:
+        """Unpickle ``{bm25, sections, section_ids}`` and build the device CSR index."""
+        with self._lock:
+            if filepath in self._bm25_cache:
+                return self._bm25_cache[filepath]
+        try:
+            if not os.path.exists(filepath):
+                raise FileNotFoundError(f"BM25 index not found: {filepath}")
+            _install_unpickle_shims()
+            with open(filepath, "rb") as f:
+                data = pickle.load(f)
+            result = (data["bm25"], data["sections"], data["section_ids"])
+            try:
+                registry.resolve_bm25(result[0])     # CSR inversion + upload, once
+            except Exception as e:
+                if not _no_device(e):
+                    raise
+                self.logger.warning(f"No B200 visible while loading {filepath}: "
+                                    "the index will be built by the first search")
+            with self._lock:
+                self._bm25_cache[filepath] = result
+            return result
+        except Exception as e:
+            self.logger.error(f"Error loading BM25 index from {filepath}: {e}")
+            raise

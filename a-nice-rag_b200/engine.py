@@ -1,0 +1,326 @@
+"""Device-resident indices and the calls on them (thin Python over the C ABI).
+
+Host-side work kept here, as SURVEY.md 8(b) assigns it: token string -> term id
+dictionary, doc index <-> id maps, the CSR inversion of a ``BM25Okapi``-shaped
+object, filter-string -> bit mask.  All scoring / selection / fusion runs in the
+CUDA library; nothing in this module computes a score on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+import weakref
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import native
+
+
+# ---------------------------------------------------------------------------------
+# contexts: one per (thread, device) -- a context owns scratch memory and a stream and
+# must not be shared by two threads (include/anr_b200.h)
+# ---------------------------------------------------------------------------------
+class Context:
+    def __init__(self, device: int = 0):
+        self.device = device
+        handle = C.c_void_p()
+        native.call("anr_ctx_create", device, C.byref(handle))
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, native.load().anr_ctx_destroy, handle)
+
+    def sync(self) -> None:
+        native.call("anr_ctx_sync", self.handle)
+
+    def info(self) -> Tuple[int, int, int]:
+        sm, total, free = C.c_int32(), C.c_int64(), C.c_int64()
+        native.call("anr_ctx_info", self.handle, C.byref(sm), C.byref(total), C.byref(free))
+        return sm.value, total.value, free.value
+
+
+_tls = threading.local()
+
+
+def current_device() -> int:
+    """The process' CUDA device: LOCAL_RANK-style selection goes through torch if it is loaded."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:  # pragma: no cover - torch is plumbing only
+        pass
+    return 0
+
+
+def context(device: Optional[int] = None) -> Context:
+    device = current_device() if device is None else device
+    cache = getattr(_tls, "contexts", None)
+    if cache is None:
+        cache = _tls.contexts = {}
+    ctx = cache.get(device)
+    if ctx is None:
+        ctx = cache[device] = Context(device)
+    return ctx
+
+
+# ---------------------------------------------------------------------------------
+# filters
+# ---------------------------------------------------------------------------------
+def parse_prefixes(filename_type_filter: str) -> Tuple[str, ...]:
+    """Same normalisation as src/search_engine.py:39 and :222."""
+    return tuple(p.strip().upper() for p in filename_type_filter.split(","))
+
+
+def prefix_mask(sources: Sequence[Optional[str]], filename_type_filter: str) -> np.ndarray:
+    """bool[n]: upper-cased source starts with any prefix (None / non-string -> False)."""
+    prefixes = parse_prefixes(filename_type_filter)
+    out = np.zeros(len(sources), dtype=bool)
+    for i, src in enumerate(sources):
+        if isinstance(src, str):
+            out[i] = src.upper().startswith(prefixes)
+    return out
+
+
+def pack_mask(mask: np.ndarray) -> np.ndarray:
+    """bool[n] -> uint32 words, bit (i & 31) of word (i >> 5) = mask[i] (the ABI's layout)."""
+    n = int(mask.shape[0])
+    words = (n + 31) // 32
+    padded = np.zeros(words * 32, dtype=np.uint8)
+    padded[:n] = mask
+    return np.packbits(padded.reshape(-1, 8), axis=1, bitorder="little").reshape(-1).view("<u4").copy()
+
+
+def _as_f32_matrix(x) -> np.ndarray:
+    a = np.asarray(x)
+    if a.ndim == 1:
+        a = a.reshape(1, -1)
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ---------------------------------------------------------------------------------
+# dense index
+# ---------------------------------------------------------------------------------
+class DenseIndex:
+    """Row-major [n, d] fp32 matrix resident in HBM (the chunk-embedding matrix)."""
+
+    def __init__(self, embeddings=None, n: Optional[int] = None, d: Optional[int] = None,
+                 device: Optional[int] = None, borrow: bool = False):
+        self.ctx_device = current_device() if device is None else device
+        ctx = context(self.ctx_device)
+        self._keepalive = None
+        if embeddings is not None:
+            if hasattr(embeddings, "data_ptr"):      # torch tensor, host or device
+                if embeddings.dim() != 2 or str(embeddings.dtype) != "torch.float32":
+                    raise ValueError("embeddings tensor must be 2-D float32")
+                embeddings = embeddings.contiguous()
+                n, d = int(embeddings.shape[0]), int(embeddings.shape[1])
+                if borrow:
+                    self._keepalive = embeddings
+            else:
+                embeddings = _as_f32_matrix(embeddings)
+                n, d = embeddings.shape
+                borrow = False
+        elif n is None or d is None:
+            raise ValueError("give embeddings or (n, d)")
+        handle = C.c_void_p()
+        native.call("anr_dense_create", ctx.handle, native.ptr(embeddings), int(n), int(d),
+                    1 if borrow else 0, C.byref(handle))
+        self.handle = handle
+        self.n, self.d = int(n), int(d)
+        self._masks: Dict[str, object] = {}
+        self._finalizer = weakref.finalize(self, native.load().anr_dense_destroy, handle)
+
+    def upload(self, row0: int, rows) -> None:
+        rows = rows if hasattr(rows, "data_ptr") else _as_f32_matrix(rows)
+        native.call("anr_dense_upload", context(self.ctx_device).handle, self.handle, int(row0),
+                    native.ptr(rows), int(rows.shape[0]))
+
+    def search(self, queries, k: int, row_mask: Optional[np.ndarray] = None, id_base: int = 0):
+        """-> (scores f32 [b, k], rows i32 [b, k], counts i32 [b]); rows = -1 past counts."""
+        q = _as_f32_matrix(queries)
+        if q.shape[1] != self.d:
+            raise ValueError(f"query width {q.shape[1]} != index width {self.d}")
+        b = q.shape[0]
+        scores = np.empty((b, k), dtype=np.float32)
+        rows = np.empty((b, k), dtype=np.int32)
+        counts = np.empty(b, dtype=np.int32)
+        native.call("anr_dense_search", context(self.ctx_device).handle, self.handle, native.ptr(q),
+                    b, int(k), native.ptr(row_mask), int(id_base), native.ptr(scores),
+                    native.ptr(rows), native.ptr(counts), None)
+        return scores, rows, counts
+
+
+# ---------------------------------------------------------------------------------
+# BM25 index
+# ---------------------------------------------------------------------------------
+def invert_okapi(bm25) -> Tuple[Dict[str, int], np.ndarray, np.ndarray, np.ndarray, np.ndarray,
+                                np.ndarray]:
+    """CSR inversion of a BM25Okapi-shaped object (attributes of rank_bm25.BM25Okapi).
+
+    Returns (vocab, term_ptr i64 [V+1], post_doc i32, post_tf i32, doc_len i32, idf f64 [V]).
+    Term ids follow the order of ``bm25.idf`` (the package's vocabulary order); postings of a
+    term are in ascending document order because documents are visited in order.
+    """
+    vocab = {tok: i for i, tok in enumerate(bm25.idf.keys())}
+    n_terms = len(vocab)
+    counts = np.zeros(n_terms, dtype=np.int64)
+    term_chunks: List[np.ndarray] = []
+    tf_chunks: List[np.ndarray] = []
+    doc_sizes = np.zeros(len(bm25.doc_freqs), dtype=np.int64)
+    get = vocab.__getitem__
+    for d, freqs in enumerate(bm25.doc_freqs):
+        m = len(freqs)
+        doc_sizes[d] = m
+        if m:
+            term_chunks.append(np.fromiter(map(get, freqs.keys()), dtype=np.int64, count=m))
+            tf_chunks.append(np.fromiter(freqs.values(), dtype=np.int64, count=m))
+    if term_chunks:
+        terms = np.concatenate(term_chunks)
+        tfs = np.concatenate(tf_chunks)
+    else:
+        terms = np.zeros(0, dtype=np.int64)
+        tfs = np.zeros(0, dtype=np.int64)
+    docs = np.repeat(np.arange(len(bm25.doc_freqs), dtype=np.int64), doc_sizes)
+    order = np.argsort(terms, kind="stable")      # stable: documents stay ascending per term
+    counts = np.bincount(terms, minlength=n_terms)
+    term_ptr = np.zeros(n_terms + 1, dtype=np.int64)
+    np.cumsum(counts, out=term_ptr[1:])
+    idf = np.fromiter((bm25.idf[t] for t in vocab), dtype=np.float64, count=n_terms)
+    return (vocab, term_ptr, docs[order].astype(np.int32), tfs[order].astype(np.int32),
+            np.asarray(bm25.doc_len, dtype=np.int32), idf)
+
+
+class Bm25Index:
+    """CSR inverted index in HBM with the BM25Okapi posting weights precomputed."""
+
+    def __init__(self, term_ptr, post_doc, post_tf, doc_len, idf, k1: float, b: float,
+                 avgdl: float, vocab: Optional[Dict[str, int]] = None,
+                 device: Optional[int] = None, n_terms: Optional[int] = None,
+                 n_docs: Optional[int] = None):
+        self.ctx_device = current_device() if device is None else device
+        ctx = context(self.ctx_device)
+
+        def prep(x, dtype):
+            if hasattr(x, "data_ptr"):
+                return x.contiguous()
+            return np.ascontiguousarray(x, dtype=dtype)
+
+        term_ptr, post_doc, post_tf = prep(term_ptr, np.int64), prep(post_doc, np.int32), prep(post_tf, np.int32)
+        doc_len, idf = prep(doc_len, np.int32), prep(idf, np.float64)
+        self.n_terms = int(term_ptr.shape[0]) - 1 if n_terms is None else int(n_terms)
+        self.n_docs = int(doc_len.shape[0]) if n_docs is None else int(n_docs)
+        handle = C.c_void_p()
+        native.call("anr_bm25_create", ctx.handle, native.ptr(term_ptr), native.ptr(post_doc),
+                    native.ptr(post_tf), native.ptr(doc_len), native.ptr(idf), self.n_terms,
+                    self.n_docs, float(k1), float(b), float(avgdl), C.byref(handle))
+        self.handle = handle
+        self.vocab = vocab
+        nnz = C.c_int64()
+        native.call("anr_bm25_shape", handle, None, None, C.byref(nnz))
+        self.n_postings = nnz.value
+        self._masks: Dict[str, object] = {}
+        self._finalizer = weakref.finalize(self, native.load().anr_bm25_destroy, handle)
+
+    @classmethod
+    def from_okapi(cls, bm25, device: Optional[int] = None) -> "Bm25Index":
+        vocab, term_ptr, post_doc, post_tf, doc_len, idf = invert_okapi(bm25)
+        return cls(term_ptr, post_doc, post_tf, doc_len, idf, bm25.k1, bm25.b, bm25.avgdl,
+                   vocab=vocab, device=device)
+
+    # -- queries --------------------------------------------------------------
+    def term_ids(self, tokens: Iterable[str]) -> np.ndarray:
+        """Token strings -> term ids in query order, -1 for tokens absent from the vocabulary."""
+        if self.vocab is None:
+            raise ValueError("index was built from term ids; pass term ids")
+        get = self.vocab.get
+        return np.fromiter((get(t, -1) for t in tokens), dtype=np.int32)
+
+    @staticmethod
+    def pack_queries(queries: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
+        offsets = np.zeros(len(queries) + 1, dtype=np.int32)
+        offsets[1:] = np.cumsum([len(q) for q in queries])
+        terms = (np.concatenate([np.asarray(q, dtype=np.int32) for q in queries])
+                 if offsets[-1] else np.zeros(0, dtype=np.int32))
+        return np.ascontiguousarray(terms, dtype=np.int32), offsets
+
+    def search(self, queries: Sequence[Sequence[int]], k: int,
+               doc_mask: Optional[np.ndarray] = None, id_base: int = 0):
+        """queries: term-id lists.  -> (scores f32 [b,k], docs i32 [b,k], counts i32 [b])."""
+        terms, offsets = self.pack_queries(queries)
+        b = len(queries)
+        scores = np.empty((b, k), dtype=np.float32)
+        docs = np.empty((b, k), dtype=np.int32)
+        counts = np.empty(b, dtype=np.int32)
+        native.call("anr_bm25_search", context(self.ctx_device).handle, self.handle,
+                    native.ptr(terms), native.ptr(offsets), b, int(k), native.ptr(doc_mask), None,
+                    int(id_base), native.ptr(scores), native.ptr(docs), native.ptr(counts), None)
+        return scores, docs, counts
+
+    def scores(self, term_ids: Sequence[int]) -> np.ndarray:
+        """fp32 score of every document for one query (BM25Okapi.get_scores on the device)."""
+        terms = np.ascontiguousarray(term_ids, dtype=np.int32)
+        out = np.zeros(self.n_docs, dtype=np.float32)
+        native.call("anr_bm25_scores", context(self.ctx_device).handle, self.handle,
+                    native.ptr(terms), int(terms.shape[0]), native.ptr(out), None)
+        return out
+
+
+# ---------------------------------------------------------------------------------
+# fusion
+# ---------------------------------------------------------------------------------
+WRRF_MAX_ENTRIES = 8192
+
+
+def wrrf_fuse(id_lists: Sequence[Sequence[int]], weights: Sequence[float], rrf_k: float,
+              top_n: Optional[int] = None, device: Optional[int] = None):
+    """Weighted RRF of integer-id ranked lists for ONE query -> (ids i32, scores f64)."""
+    n_lists = len(id_lists)
+    stride = max(1, max((len(l) for l in id_lists), default=1))
+    ids = np.full((1, n_lists, stride), -1, dtype=np.int32)
+    lens = np.zeros((1, n_lists), dtype=np.int32)
+    for i, l in enumerate(id_lists):
+        ids[0, i, :len(l)] = l
+        lens[0, i] = len(l)
+    total = int(lens.sum())
+    top_n = max(1, total if top_n is None else min(int(top_n), max(total, 1)))
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    out_ids = np.empty((1, top_n), dtype=np.int32)
+    out_scores = np.empty((1, top_n), dtype=np.float64)
+    out_counts = np.empty(1, dtype=np.int32)
+    native.call("anr_wrrf_fuse", context(device).handle, native.ptr(ids), native.ptr(lens),
+                native.ptr(w), n_lists, stride, 1, float(rrf_k), top_n, native.ptr(out_ids),
+                native.ptr(out_scores), native.ptr(out_counts), None)
+    c = int(out_counts[0])
+    return out_ids[0, :c], out_scores[0, :c]
+
+
+def hybrid_search(dense: DenseIndex, bm25: Bm25Index, queries, term_queries, k_dense: int,
+                  k_bm25: int, w_dense: float, w_bm25: float, rrf_k: float, top_n: int,
+                  row_mask=None, doc_mask=None, doc_to_id=None, id_base: int = 0,
+                  want_lists: bool = False):
+    """Batched dense + BM25 + WRRF (an extension: the reference is strictly batch-1).
+
+    -> dict(ids i32 [b, top_n], scores f64 [b, top_n], counts i32 [b] [, dense_rows,
+    dense_scores, bm25_ids, bm25_scores]).  ``doc_to_id`` must be a device int32 tensor
+    (BM25 doc index -> dense row id) or None when both indices share one id space.
+    """
+    q = _as_f32_matrix(queries)
+    b = q.shape[0]
+    terms, offsets = Bm25Index.pack_queries(term_queries)
+    ids = np.empty((b, top_n), dtype=np.int32)
+    scores = np.empty((b, top_n), dtype=np.float64)
+    counts = np.empty(b, dtype=np.int32)
+    extra = {}
+    if want_lists:
+        extra = dict(dense_rows=np.empty((b, k_dense), dtype=np.int32),
+                     dense_scores=np.empty((b, k_dense), dtype=np.float32),
+                     bm25_ids=np.empty((b, k_bm25), dtype=np.int32),
+                     bm25_scores=np.empty((b, k_bm25), dtype=np.float32))
+    native.call("anr_hybrid_search", context(dense.ctx_device).handle, dense.handle, bm25.handle,
+                native.ptr(q), native.ptr(terms), native.ptr(offsets), b, int(k_dense),
+                int(k_bm25), native.ptr(row_mask), native.ptr(doc_mask), native.ptr(doc_to_id),
+                int(id_base), float(w_dense), float(w_bm25), float(rrf_k), int(top_n),
+                native.ptr(ids), native.ptr(scores), native.ptr(counts),
+                native.ptr(extra.get("dense_rows")), native.ptr(extra.get("dense_scores")),
+                native.ptr(extra.get("bm25_ids")), native.ptr(extra.get("bm25_scores")), None)
+    return dict(ids=ids, scores=scores, counts=counts, **extra)

@@ -1,0 +1,171 @@
+"""Finding the device-resident index that belongs to a caller's Python object.
+
+The reference's callers keep the loaded ``DataFrame`` / ``BM25Okapi`` and hand it back
+into every search call (SURVEY.md 8(b) "Ownership"), so the HBM copy must be
+discoverable from that argument:
+  * DataFrames carry ``df.attrs["anr_dense_key"]``; pandas propagates ``attrs`` to frames
+    derived by masking/copying, which we recognise as row subsets of the original
+    (their index labels are the original row positions);
+  * BM25 objects get the index as an attribute (fallback: a registry keyed by ``id``).
+A frame / object we have never seen is packed and uploaded on first use and cached
+for as long as the Python object lives.
+"""
+from __future__ import annotations
+
+import itertools
+import logging
+import threading
+import weakref
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import pandas as pd
+
+from . import engine
+
+logger = logging.getLogger(__name__)
+ATTR_KEY = "anr_dense_key"
+_lock = threading.Lock()
+_next_key = itertools.count(1)
+
+
+class DenseEntry:
+    """Host-side companion of one DenseIndex: packed rows, ids, sources, cached masks."""
+
+    def __init__(self, packed: np.ndarray, ids: np.ndarray, sources: np.ndarray):
+        self.key = next(_next_key)
+        self.packed = packed            # [n, d] float32, C-contiguous (row i = df.iloc[i])
+        self.ids = ids                  # object array of chunk ids, for subset validation
+        self.sources = sources          # object array of `source` strings, for filters
+        self.n, self.d = packed.shape
+        self._index: Optional[engine.DenseIndex] = None
+        self._masks: Dict[str, Tuple[np.ndarray, object, int]] = {}
+        self._build_lock = threading.Lock()
+
+    def index(self) -> engine.DenseIndex:
+        with self._build_lock:
+            if self._index is None:
+                self._index = engine.DenseIndex(self.packed)
+            return self._index
+
+    def filter_mask(self, filename_type_filter: str):
+        """(bool[n], device words or None, eligible count), cached per filter string."""
+        hit = self._masks.get(filename_type_filter)
+        if hit is None:
+            mask = engine.prefix_mask(self.sources, filename_type_filter)
+            hit = (mask, device_words(engine.pack_mask(mask)), int(mask.sum()))
+            self._masks[filename_type_filter] = hit
+        return hit
+
+
+def device_words(words: np.ndarray):
+    """uint32 mask words -> resident device tensor (torch is the allocator here)."""
+    import torch
+    if not torch.cuda.is_available():
+        return None
+    return torch.from_numpy(words.view(np.int32)).to(f"cuda:{engine.current_device()}")
+
+
+_dense: Dict[int, DenseEntry] = {}
+
+
+def register_frame(df: pd.DataFrame, packed: np.ndarray) -> DenseEntry:
+    entry = DenseEntry(packed, df["id"].to_numpy(dtype=object), df["source"].to_numpy(dtype=object))
+    with _lock:
+        _dense[entry.key] = entry
+    df.attrs[ATTR_KEY] = entry.key
+    weakref.finalize(df, _dense.pop, entry.key, None)
+    return entry
+
+
+def resolve_frame(df: pd.DataFrame) -> Tuple[DenseEntry, Optional[np.ndarray]]:
+    """-> (entry, None) when ``df`` is a registered frame, (entry, row positions) when it is
+    a row subset derived from one; an unknown frame is packed, uploaded and remembered."""
+    entry = lookup_identity(df)
+    if entry is not None:
+        return entry, None
+    entry = _dense.get(df.attrs.get(ATTR_KEY, -1))
+    if entry is not None:
+        n = len(df)
+        labels = df.index
+        ids = df["id"].to_numpy(dtype=object) if "id" in df.columns else None
+        if ids is not None and n == entry.n and isinstance(labels, pd.RangeIndex) \
+                and labels.start == 0 and labels.step == 1:
+            if n == 0 or (ids[0] == entry.ids[0] and ids[n - 1] == entry.ids[n - 1]):
+                return entry, None
+        rows = np.asarray(labels)
+        if ids is not None and n and rows.dtype.kind in "iu" and rows.min() >= 0 \
+                and rows.max() < entry.n and labels.is_unique:
+            probe = np.unique(np.linspace(0, n - 1, num=min(n, 8)).astype(np.int64))
+            if all(ids[p] == entry.ids[rows[p]] for p in probe):
+                return entry, rows.astype(np.int64)
+    # unknown frame: pack and upload it (np.stack raises for ragged rows, like the reference)
+    packed = np.ascontiguousarray(np.stack(df["embedding"].values), dtype=np.float32)
+    if packed.ndim != 2:
+        raise ValueError("embedding column does not stack to a matrix")
+    n = len(df)
+    entry = DenseEntry(
+        packed,
+        df["id"].to_numpy(dtype=object) if "id" in df.columns else np.arange(n).astype(object),
+        df["source"].to_numpy(dtype=object) if "source" in df.columns
+        else np.full(n, None, dtype=object))
+    with _lock:
+        _dense[entry.key] = entry
+    # an unknown frame may carry arbitrary index labels: remember it by identity only
+    _by_identity[id(df)] = (weakref.ref(df), entry)
+    weakref.finalize(df, _forget_identity, id(df), entry.key)
+    return entry, None
+
+
+_by_identity: Dict[int, Tuple[weakref.ref, DenseEntry]] = {}
+
+
+def _forget_identity(obj_id: int, key: int) -> None:
+    _by_identity.pop(obj_id, None)
+    _dense.pop(key, None)
+
+
+def lookup_identity(df: pd.DataFrame) -> Optional[DenseEntry]:
+    hit = _by_identity.get(id(df))
+    if hit is not None and hit[0]() is df:
+        return hit[1]
+    return None
+
+
+# ---------------------------------------------------------------------------------
+class Bm25Entry:
+    def __init__(self, bm25):
+        self.index = engine.Bm25Index.from_okapi(bm25)
+        self._masks: Dict[Tuple[int, str], Tuple[object, object, int]] = {}
+
+    def filter_mask(self, sections, filename_type_filter: str):
+        """Mask over BM25 doc indices from each section's metadata["source"] (search_engine.py:224-231)."""
+        key = (id(sections), filename_type_filter)
+        hit = self._masks.get(key)
+        if hit is None:
+            sources = [s.metadata.get("source", "") for s in sections]
+            mask = engine.prefix_mask(sources, filename_type_filter)
+            if len(mask) != self.index.n_docs:
+                raise ValueError("bm25_sections does not match the BM25 index")
+            hit = (mask, device_words(engine.pack_mask(mask)), int(mask.sum()))
+            self._masks[key] = hit
+        return hit
+
+
+_bm25: Dict[int, Tuple[weakref.ref, Bm25Entry]] = {}
+
+
+def resolve_bm25(bm25) -> Bm25Entry:
+    entry = getattr(bm25, "_anr_entry", None)
+    if isinstance(entry, Bm25Entry):
+        return entry
+    hit = _bm25.get(id(bm25))
+    if hit is not None and hit[0]() is bm25:
+        return hit[1]
+    entry = Bm25Entry(bm25)
+    try:
+        bm25._anr_entry = entry
+    except AttributeError:  # __slots__ / frozen object
+        _bm25[id(bm25)] = (weakref.ref(bm25), entry)
+        weakref.finalize(bm25, _bm25.pop, id(bm25), None)
+    return entry
