@@ -41,11 +41,18 @@ static int fail_cuda(const char* what, cudaError_t e) {
 // ---------------------------------------------------------------------------------
 // objects
 // ---------------------------------------------------------------------------------
+struct EventPair {
+  cudaEvent_t start = nullptr, stop = nullptr;
+};
 struct anr_ctx {
   DeviceProps dp;
   cudaStream_t stream = nullptr;
   unsigned char* ws = nullptr;  // device scratch, grown on demand
   size_t ws_bytes = 0;
+  // profiling (anr_ctx_profile_*): event pairs recorded around the dominant kernels
+  bool profiling = false;
+  std::vector<EventPair> pool[2];  // created lazily, reused after every read
+  size_t used[2] = {0, 0};
 };
 
 struct anr_dense {
@@ -110,6 +117,31 @@ int ws_reserve(anr_ctx* ctx, size_t bytes) {
   return ANR_OK;
 }
 
+// Brackets one kernel launch with events when profiling is on.
+struct ProfileScope {
+  anr_ctx* ctx;
+  int kind;
+  cudaStream_t stream;
+  EventPair* ev = nullptr;
+  ProfileScope(anr_ctx* c, int k, cudaStream_t s) : ctx(c), kind(k), stream(s) {
+    if (!ctx->profiling) return;
+    if (ctx->used[kind] == ctx->pool[kind].size()) {
+      if (ctx->pool[kind].size() >= 65536) return;  // stop recording, keep running
+      EventPair p;
+      if (cudaEventCreate(&p.start) != cudaSuccess || cudaEventCreate(&p.stop) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+      }
+      ctx->pool[kind].push_back(p);
+    }
+    ev = &ctx->pool[kind][ctx->used[kind]++];
+    cudaEventRecord(ev->start, stream);
+  }
+  ~ProfileScope() {
+    if (ev) cudaEventRecord(ev->stop, stream);
+  }
+};
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) {
@@ -122,7 +154,20 @@ struct DeviceGuard {
   }
 };
 
-inline int pad_queries(int nq) { return nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : (nq + 7) / 8 * 8; }
+// Queries are scanned in groups of gmax (1, 2, 4 or 8); a short batch is one group of the next
+// power of two, a long one is padded to a multiple of gmax (pad rows are zero vectors).
+inline int pad_queries(int nq, int gmax) {
+  if (nq <= gmax) {
+    int p = 1;
+    while (p < nq) p <<= 1;
+    return p;
+  }
+  return (nq + gmax - 1) / gmax * gmax;
+}
+inline int dense_group(const anr_ctx* ctx, const anr_dense* ix, int k) {
+  const bool all = k > kMaxFusedK;
+  return dense_scan_max_queries(ctx->dp, ix->ld, all ? 1 : k, all);
+}
 
 __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int64_t n) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -189,24 +234,28 @@ cudaError_t out_flush(const OutBuf<T>& o, cudaStream_t stream, bool* any_host) {
 // ---- dense top-k pipeline on device buffers -----------------------------------------
 // q_dev: [pad_queries(nq), ld].  Writes results through `out`.
 size_t dense_ws_bytes(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
-  const int nqp = pad_queries(nq);
+  const int gmax = std::max(dense_group(ctx, ix, k), 1);
+  const int nqp = pad_queries(nq, gmax);
   if (k <= kMaxFusedK)
     return padded(static_cast<size_t>(nqp) * dense_scan_max_grid(ctx->dp) * k * 8) + 256;
   const int64_t n_pow2 = next_pow2(static_cast<int>(std::max<int64_t>(ix->n, 2)));
-  const int group = std::min(nqp, 8);
+  const int group = std::min(nqp, gmax);
   return padded(static_cast<size_t>(group) * n_pow2 * 8) + 256;
 }
 
 int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq, int k,
                    const uint32_t* mask_dev, Arena& arena, const TopkOut& out,
                    cudaStream_t stream) {
-  const int nqp = pad_queries(nq);
+  const int gmax = dense_group(ctx, ix, k);
+  if (gmax < 1) return fail(ANR_ERR_UNSUPPORTED, "embedding rows too long for the scan kernel");
+  const int nqp = pad_queries(nq, gmax);
   if (k <= kMaxFusedK) {
     const int64_t stride = static_cast<int64_t>(dense_scan_max_grid(ctx->dp)) * k;
     uint64_t* cand = arena.take<uint64_t>(static_cast<size_t>(nqp) * stride);
     int grid = 0;
-    for (int q0 = 0; q0 < nqp; q0 += 8) {
-      const int g = std::min(8, nqp - q0);
+    for (int q0 = 0; q0 < nqp; q0 += gmax) {
+      const int g = std::min(gmax, nqp - q0);
+      ProfileScope prof(ctx, 0, stream);
       ANR_CUDA(launch_dense_scan_topk(ctx->dp, ix->emb, ix->n, ix->ld,
                                       q_dev + static_cast<size_t>(q0) * ix->ld, g, k, mask_dev,
                                       cand + q0 * stride, stride, &grid, stream));
@@ -218,7 +267,7 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
   // k > kMaxFusedK: materialise every key, sort, emit (full-ranking path)
   if (ix->n > (1ll << 30)) return fail(ANR_ERR_UNSUPPORTED, "k > 128 needs n <= 2^30");
   const int64_t n_pow2 = next_pow2(static_cast<int>(std::max<int64_t>(ix->n, 2)));
-  const int group = std::min(nqp, 8);
+  const int group = std::min(nqp, gmax);
   uint64_t* keys = arena.take<uint64_t>(static_cast<size_t>(group) * n_pow2);
   for (int q0 = 0; q0 < nq; q0 += group) {
     const int real = std::min(group, nq - q0);
@@ -269,8 +318,11 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
       return fail(ANR_ERR_UNSUPPORTED, "bm25 tile does not fit in shared memory");
     const int64_t stride = static_cast<int64_t>(plan.n_tiles) * k;
     uint64_t* cand = arena.take<uint64_t>(static_cast<size_t>(nq) * stride);
-    ANR_CUDA(launch_bm25_score_topk(v, terms_dev, offsets_dev, nq, k, mask_dev, plan, cand, stride,
-                                    stream));
+    {
+      ProfileScope prof(ctx, 1, stream);
+      ANR_CUDA(launch_bm25_score_topk(v, terms_dev, offsets_dev, nq, k, mask_dev, plan, cand,
+                                      stride, stream));
+    }
     const int m = static_cast<int>(stride);
     ANR_CUDA(launch_topk_final(cand, stride, m, m, 0, nq, k, out, stream));
     return ANR_OK;
@@ -297,9 +349,9 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
 }
 
 // Stage the query matrix: returns a device [pad_queries(nq), ld] zero-padded copy.
-int stage_queries(const anr_dense* ix, const float* queries, int nq, Arena& arena,
+int stage_queries(const anr_dense* ix, const float* queries, int nq, int gmax, Arena& arena,
                   cudaStream_t stream, const float** q_dev) {
-  const int nqp = pad_queries(nq);
+  const int nqp = pad_queries(nq, std::max(gmax, 1));
   float* q = arena.take<float>(static_cast<size_t>(nqp) * ix->ld);
   if (nqp != nq || ix->ld != ix->d)
     ANR_CUDA(cudaMemsetAsync(q, 0, static_cast<size_t>(nqp) * ix->ld * 4, stream));
@@ -315,7 +367,7 @@ int stage_queries(const anr_dense* ix, const float* queries, int nq, Arena& aren
   return ANR_OK;
 }
 size_t stage_queries_bytes(const anr_dense* ix, int nq) {
-  return padded(static_cast<size_t>(pad_queries(nq)) * ix->ld * 4) + 256;
+  return padded(static_cast<size_t>(nq + 8) * ix->ld * 4) + 256;
 }
 
 // Stage a bit mask ([ceil(n/32)] words) if it lives on the host.
@@ -412,10 +464,37 @@ int anr_ctx_create(int device, anr_ctx** out) {
   return ANR_OK;
 }
 
+int anr_ctx_profile_enable(anr_ctx* ctx, int32_t on) {
+  if (!ctx) return fail(ANR_ERR_INVALID, "ctx is NULL");
+  ctx->profiling = on != 0;
+  return ANR_OK;
+}
+
+int anr_ctx_profile_read(anr_ctx* ctx, int32_t kind, double* total_ms, int64_t* launches) {
+  if (!ctx || kind < 0 || kind > 1) return fail(ANR_ERR_INVALID, "anr_ctx_profile_read: bad argument");
+  DeviceGuard guard(ctx->dp.device);
+  ANR_CUDA(cudaDeviceSynchronize());
+  double sum = 0.0;
+  for (size_t i = 0; i < ctx->used[kind]; ++i) {
+    float ms = 0.f;
+    ANR_CUDA(cudaEventElapsedTime(&ms, ctx->pool[kind][i].start, ctx->pool[kind][i].stop));
+    sum += ms;
+  }
+  if (total_ms) *total_ms = sum;
+  if (launches) *launches = static_cast<int64_t>(ctx->used[kind]);
+  ctx->used[kind] = 0;
+  return ANR_OK;
+}
+
 int anr_ctx_destroy(anr_ctx* ctx) {
   if (!ctx) return ANR_OK;
   DeviceGuard guard(ctx->dp.device);
   cudaStreamSynchronize(ctx->stream);
+  for (auto& pool : ctx->pool)
+    for (auto& p : pool) {
+      cudaEventDestroy(p.start);
+      cudaEventDestroy(p.stop);
+    }
   if (ctx->ws) cudaFree(ctx->ws);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -549,7 +628,7 @@ static int dense_search_impl(anr_ctx* ctx, const anr_dense* index, const float* 
   } else {
     const float* q_dev = nullptr;
     const uint32_t* mask_dev = nullptr;
-    if (int rc = stage_queries(index, queries, nq, arena, stream, &q_dev)) return rc;
+    if (int rc = stage_queries(index, queries, nq, dense_group(ctx, index, k), arena, stream, &q_dev)) return rc;
     if (int rc = stage_mask(row_mask, index->n, arena, stream, &mask_dev)) return rc;
     if (int rc = dense_pipeline(ctx, index, q_dev, nq, k, mask_dev, arena, out, stream)) return rc;
   }
@@ -893,7 +972,8 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
   const uint32_t* row_mask_dev = nullptr;
   const uint32_t* doc_mask_dev = nullptr;
   QueryTerms qt;
-  if (int rc = stage_queries(dense, queries, nq, arena, stream, &q_dev)) return rc;
+  if (int rc = stage_queries(dense, queries, nq, dense_group(ctx, dense, k_dense), arena, stream,
+                              &q_dev)) return rc;
   if (int rc = stage_mask(row_mask, dense->n, arena, stream, &row_mask_dev)) return rc;
   if (int rc = stage_terms(q_terms, q_offsets, nq, arena, stream, &qt)) return rc;
   if (int rc = stage_mask(doc_mask, bm25->n_docs, arena, stream, &doc_mask_dev)) return rc;
@@ -977,6 +1057,59 @@ int anr_topk_merge(anr_ctx* ctx, const uint64_t* keys, int32_t n_parts, int32_t 
   bool any_host = false;
   ANR_CUDA(out_flush(o_scores, stream, &any_host));
   ANR_CUDA(out_flush(o_ids, stream, &any_host));
+  ANR_CUDA(out_flush(o_counts, stream, &any_host));
+  if (any_host) ANR_CUDA(cudaStreamSynchronize(stream));
+  return ANR_OK;
+}
+
+int anr_sharded_fuse(anr_ctx* ctx, const uint64_t* gathered, int32_t n_parts, int32_t nq,
+                     int32_t k, double w_dense, double w_bm25, double rrf_k, int32_t top_n,
+                     int32_t* out_ids, double* out_scores, int32_t* out_counts, void* stream_v) {
+  if (!ctx || !gathered || !out_ids || !out_scores)
+    return fail(ANR_ERR_INVALID, "anr_sharded_fuse: NULL argument");
+  if (n_parts < 1 || nq < 1 || k < 1 || top_n < 1)
+    return fail(ANR_ERR_INVALID, "anr_sharded_fuse: bad shape");
+  if (k > kMaxFusedK) return fail(ANR_ERR_UNSUPPORTED, "anr_sharded_fuse: k above 128");
+  DeviceGuard guard(ctx->dp.device);
+  cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  const size_t n_keys = static_cast<size_t>(n_parts) * 2 * nq * k;
+  const size_t cells = static_cast<size_t>(nq) * top_n;
+  const size_t list_cells = static_cast<size_t>(nq) * 2 * k;
+  const bool keys_host = !is_device_ptr(gathered);
+  const size_t need = (keys_host ? padded(n_keys * 8) + 256 : 0) + padded(list_cells * 4) +
+                      padded(static_cast<size_t>(nq) * 2 * 4) + 2048 + out_need(out_ids, cells) +
+                      out_need(out_scores, cells) + out_need(out_counts, nq);
+  if (int rc = ws_reserve(ctx, need)) return rc;
+  Arena arena{ctx->ws, ctx->ws_bytes};
+  const uint64_t* keys_dev = gathered;
+  if (keys_host) {
+    uint64_t* p = arena.take<uint64_t>(n_keys);
+    ANR_CUDA(cudaMemcpyAsync(p, gathered, n_keys * 8, cudaMemcpyHostToDevice, stream));
+    keys_dev = p;
+  }
+  int32_t* lists = arena.take<int32_t>(list_cells);  // [nq][2][k]
+  int32_t* lens = arena.take<int32_t>(static_cast<size_t>(nq) * 2);
+  double* w_dev = arena.take<double>(2);
+  OutBuf<int32_t> o_ids = out_make(arena, out_ids, cells);
+  OutBuf<double> o_scores = out_make(arena, out_scores, cells);
+  OutBuf<int32_t> o_counts = out_make(arena, out_counts, nq);
+  set_f64_pair_kernel<<<1, 1, 0, stream>>>(w_dev, w_dense, w_bm25);
+  ANR_CUDA(cudaGetLastError());
+  const int64_t part_stride = 2ll * nq * k;
+  for (int which = 0; which < 2; ++which) {
+    TopkOut out;
+    out.ids = lists + which * k;
+    out.counts = lens + which;
+    out.stride_q = 2ll * k;
+    out.count_stride = 2;
+    ANR_CUDA(launch_topk_final(keys_dev + static_cast<int64_t>(which) * nq * k, k, n_parts * k, k,
+                               part_stride, nq, k, out, stream));
+  }
+  ANR_CUDA(launch_wrrf_fuse(lists, lens, w_dev, 2, k, nq, rrf_k, top_n, o_ids.dev, o_scores.dev,
+                            o_counts.dev, stream));
+  bool any_host = false;
+  ANR_CUDA(out_flush(o_ids, stream, &any_host));
+  ANR_CUDA(out_flush(o_scores, stream, &any_host));
   ANR_CUDA(out_flush(o_counts, stream, &any_host));
   if (any_host) ANR_CUDA(cudaStreamSynchronize(stream));
   return ANR_OK;

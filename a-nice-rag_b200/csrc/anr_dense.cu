@@ -6,7 +6,8 @@
 //     1-D bulk async copies (TMA engine, cp.async.bulk + mbarrier complete_tx) into a
 //     ring of up to 32 stages, so the bytes in flight per SM (~200 KB) are set by the
 //     ring and not by register pressure;
-//   * 8 consumer warps each own every 8th stage: a warp takes its RW rows, every lane
+//   * 8 consumer warps each own every 8th stage (a stage is always refilled for the same
+//     warp, so the mbarrier parity protocol can never be lapped): a warp takes its RW rows, every lane
 //     reads 128-bit words of the rows and of the staged queries (conflict-free
 //     LDS.128; the query words are reused by RW rows), fp32 FMA accumulation,
 //     xor-butterfly warp reduction;
@@ -28,6 +29,7 @@ constexpr int kScanMaxStages = 32;
 struct ScanLayout {
   int q_off, ring_off, list_off, bar_off, total_bytes;
   int stage_floats, n_stages, list_cap;
+  int n_cwarps;  // consumer warps that own stages (n_stages is a multiple of it)
 };
 
 template <int NQ, int RW, bool EMIT_ALL>
@@ -76,11 +78,11 @@ dense_scan_kernel(const float* __restrict__ emb, int64_t n, int ld, const float*
       }
     }
   } else {
-    // ---- consumers: warp w owns local tiles it = w, w + 8, ... ----
+    // ---- consumers: warp w owns local tiles it = w, w + n_cwarps, ... ----
     uint64_t thr[NQ];
 #pragma unroll
     for (int qi = 0; qi < NQ; ++qi) thr[qi] = 0;
-    for (int64_t it = warp; it < my_tiles; it += kScanConsumerWarps) {
+    for (int64_t it = warp; warp < L.n_cwarps && it < my_tiles; it += L.n_cwarps) {
       const int s = static_cast<int>(it % L.n_stages);
       const uint32_t ph = static_cast<uint32_t>(it / L.n_stages) & 1u;
       const float* tile = ring + static_cast<size_t>(s) * L.stage_floats;
@@ -184,6 +186,9 @@ static bool make_scan_layout(const DeviceProps& dp, int ld, int nq, int rw, int 
   int64_t n_stages = avail / stage_bytes;
   if (n_stages < 3) return false;
   if (n_stages > kScanMaxStages) n_stages = kScanMaxStages;
+  // stage s always serves consumer warp s % n_cwarps
+  L->n_cwarps = n_stages < kScanConsumerWarps ? static_cast<int>(n_stages) : kScanConsumerWarps;
+  n_stages = n_stages / L->n_cwarps * L->n_cwarps;
   L->stage_floats = rw * ld;
   L->n_stages = static_cast<int>(n_stages);
   L->list_off = align_up(L->ring_off + static_cast<int>(n_stages * stage_bytes), 16);
@@ -192,20 +197,36 @@ static bool make_scan_layout(const DeviceProps& dp, int ld, int nq, int rw, int 
   return L->total_bytes <= dp.max_smem_optin;
 }
 
+// Rows per stage: many queries want RW = 4 (each staged query word is reused by 4 rows, which
+// keeps shared-memory read traffic under the crossbar limit); few queries want whatever gives
+// the deepest ring (most bytes in flight).
+static int choose_rw(const DeviceProps& dp, int ld, int nq, int k, bool emit_all) {
+  int best = 0, best_score = -1;
+  for (int rw = 4; rw >= 1; rw >>= 1) {
+    ScanLayout L;
+    if (!make_scan_layout(dp, ld, nq, rw, k, emit_all, &L)) continue;
+    int score = L.n_stages >= 16 ? 2 : L.n_stages >= 8 ? 1 : 0;
+    if (nq >= 4 && rw == 4 && L.n_stages >= 8) score = 3;
+    if (score > best_score) { best_score = score; best = rw; }
+  }
+  return best;
+}
+
 int dense_scan_max_grid(const DeviceProps& dp) { return dp.sm_count; }
+
+int dense_scan_max_queries(const DeviceProps& dp, int ld, int k, bool emit_all) {
+  ScanLayout L;
+  for (int nq = 8; nq >= 1; nq >>= 1)
+    if (make_scan_layout(dp, ld, nq, 1, k, emit_all, &L)) return nq;
+  return 0;
+}
 
 template <int NQ, int RW, bool EMIT_ALL>
 static cudaError_t launch_scan_t(const DeviceProps& dp, const float* emb, int64_t n, int ld,
                                  const float* q_dev, int k, const uint32_t* mask, uint64_t* out,
                                  int64_t out_stride_q, int* grid_out, cudaStream_t stream) {
   ScanLayout L;
-  if (!make_scan_layout(dp, ld, NQ, RW, k, EMIT_ALL, &L)) {
-    // rows too long for RW rows per stage: fall back to fewer rows per stage
-    if (RW > 1)
-      return launch_scan_t<NQ, (RW > 1 ? RW / 2 : 1), EMIT_ALL>(dp, emb, n, ld, q_dev, k, mask, out,
-                                                               out_stride_q, grid_out, stream);
-    return cudaErrorInvalidConfiguration;
-  }
+  if (!make_scan_layout(dp, ld, NQ, RW, k, EMIT_ALL, &L)) return cudaErrorInvalidConfiguration;
   auto kern = dense_scan_kernel<NQ, RW, EMIT_ALL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        L.total_bytes);
@@ -219,16 +240,28 @@ static cudaError_t launch_scan_t(const DeviceProps& dp, const float* emb, int64_
   return cudaGetLastError();
 }
 
+template <int NQ, bool EMIT_ALL>
+static cudaError_t dispatch_rw(const DeviceProps& dp, const float* emb, int64_t n, int ld,
+                               const float* q_dev, int k, const uint32_t* mask, uint64_t* out,
+                               int64_t out_stride_q, int* grid_out, cudaStream_t stream) {
+  switch (choose_rw(dp, ld, NQ, k, EMIT_ALL)) {
+    case 4: return launch_scan_t<NQ, 4, EMIT_ALL>(dp, emb, n, ld, q_dev, k, mask, out, out_stride_q, grid_out, stream);
+    case 2: return launch_scan_t<NQ, 2, EMIT_ALL>(dp, emb, n, ld, q_dev, k, mask, out, out_stride_q, grid_out, stream);
+    case 1: return launch_scan_t<NQ, 1, EMIT_ALL>(dp, emb, n, ld, q_dev, k, mask, out, out_stride_q, grid_out, stream);
+    default: return cudaErrorInvalidConfiguration;
+  }
+}
+
 template <bool EMIT_ALL>
 static cudaError_t dispatch_scan(const DeviceProps& dp, const float* emb, int64_t n, int ld,
                                  const float* q_dev, int nq, int k, const uint32_t* mask,
                                  uint64_t* out, int64_t out_stride_q, int* grid_out,
                                  cudaStream_t stream) {
   switch (nq) {
-    case 1: return launch_scan_t<1, 4, EMIT_ALL>(dp, emb, n, ld, q_dev, k, mask, out, out_stride_q, grid_out, stream);
-    case 2: return launch_scan_t<2, 4, EMIT_ALL>(dp, emb, n, ld, q_dev, k, mask, out, out_stride_q, grid_out, stream);
-    case 4: return launch_scan_t<4, 4, EMIT_ALL>(dp, emb, n, ld, q_dev, k, mask, out, out_stride_q, grid_out, stream);
-    case 8: return launch_scan_t<8, 4, EMIT_ALL>(dp, emb, n, ld, q_dev, k, mask, out, out_stride_q, grid_out, stream);
+    case 1: return dispatch_rw<1, EMIT_ALL>(dp, emb, n, ld, q_dev, k, mask, out, out_stride_q, grid_out, stream);
+    case 2: return dispatch_rw<2, EMIT_ALL>(dp, emb, n, ld, q_dev, k, mask, out, out_stride_q, grid_out, stream);
+    case 4: return dispatch_rw<4, EMIT_ALL>(dp, emb, n, ld, q_dev, k, mask, out, out_stride_q, grid_out, stream);
+    case 8: return dispatch_rw<8, EMIT_ALL>(dp, emb, n, ld, q_dev, k, mask, out, out_stride_q, grid_out, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -37,6 +37,9 @@ cudaError_t launch_dense_scan_topk(const DeviceProps& dp, const float* emb, int6
                                    cudaStream_t stream);
 // Upper bound on the grid the scan will use (to size `cand`).
 int dense_scan_max_grid(const DeviceProps& dp);
+// Largest number of queries (8, 4, 2, 1; 0 = rows too long) one pass can stage in shared
+// memory next to a >= 3-stage row ring.
+int dense_scan_max_queries(const DeviceProps& dp, int ld, int k, bool emit_all);
 // Full materialisation: keys[q * keys_stride_q + row] for every row (0 for masked rows).
 cudaError_t launch_dense_scan_all(const DeviceProps& dp, const float* emb, int64_t n, int ld,
                                   const float* q_dev, int nq, const uint32_t* mask,

@@ -34,6 +34,8 @@ SIGNATURES = {
     "anr_ctx_destroy": [_P],
     "anr_ctx_sync": [_P],
     "anr_ctx_info": [_P, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_I64)],
+    "anr_ctx_profile_enable": [_P, _I32],
+    "anr_ctx_profile_read": [_P, _I32, C.POINTER(_F64), C.POINTER(_I64)],
     "anr_dense_create": [_P, _P, _I64, _I32, _I32, C.POINTER(_P)],
     "anr_dense_upload": [_P, _P, _I64, _P, _I64],
     "anr_dense_destroy": [_P],
@@ -50,6 +52,7 @@ SIGNATURES = {
     "anr_dense_search_keys": [_P, _P, _P, _I32, _I32, _P, _I64, _P, _P],
     "anr_bm25_search_keys": [_P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _P, _P],
     "anr_topk_merge": [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P],
+    "anr_sharded_fuse": [_P, _P, _I32, _I32, _I32, _F64, _F64, _F64, _I32, _P, _P, _P, _P],
 }
 EXPORTS = sorted(list(SIGNATURES) + ["anr_abi_version", "anr_last_error"])
 

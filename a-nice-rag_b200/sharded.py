@@ -1,0 +1,93 @@
+"""Corpus sharded by chunk across the GPUs of one box (one process per GPU).
+
+Rank r owns a contiguous range of embedding rows AND the same documents' postings; queries
+are replicated.  Every rank produces local top-k lists as sortable 64-bit keys (score in the
+high word, GLOBAL id in the low word), the lists are exchanged with ONE NCCL all-gather per
+retriever (``[B, k]`` keys per rank: latency-bound, a few hundred bytes at batch 1), every rank
+merges them on the device and runs the weighted RRF on the merged lists -- fusion needs global
+ranks, so it follows the merge.  BM25 shards score with GLOBAL statistics
+(N, avgdl, idf), so a sharded search returns what the unsharded one does.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import engine, native
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Rows [lo, hi) of rank ``rank``: contiguous, sizes differ by at most one."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def global_bm25_stats(nd_local, doc_len_sum_local: int, n_docs_local: int, group=None):
+    """All-reduce of the document frequencies, token count and document count: every shard
+    then derives the same idf table / avgdl as an unsharded index (run once at index build)."""
+    import torch
+    import torch.distributed as dist
+    nd = nd_local.clone() if hasattr(nd_local, "clone") else torch.as_tensor(np.asarray(nd_local))
+    extra = torch.tensor([doc_len_sum_local, n_docs_local], dtype=torch.int64, device=nd.device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(nd, group=group)
+        dist.all_reduce(extra, group=group)
+    tokens, n_docs = int(extra[0]), int(extra[1])
+    return nd, n_docs, tokens / max(n_docs, 1)
+
+
+class ShardedHybrid:
+    """Local indices of one rank + the exchange/merge/fusion of a sharded hybrid query."""
+
+    def __init__(self, dense: engine.DenseIndex, bm25: engine.Bm25Index, row_base: int,
+                 doc_base: Optional[int] = None, group=None):
+        import torch
+        self.torch = torch
+        self.dense, self.bm25 = dense, bm25
+        self.row_base = int(row_base)
+        self.doc_base = int(row_base if doc_base is None else doc_base)
+        self.group = group
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device("cuda", engine.current_device())
+        self._buf = {}
+
+    def _buffers(self, b: int, k: int, top_n: int):
+        key = (b, k, top_n)
+        if key not in self._buf:
+            t, dev = self.torch, self.device
+            self._buf[key] = dict(
+                local=t.empty((2, b, k), dtype=t.int64, device=dev),
+                gathered=t.empty((self.world, 2, b, k), dtype=t.int64, device=dev),
+                ids=t.empty((b, top_n), dtype=t.int32, device=dev),
+                scores=t.empty((b, top_n), dtype=t.float64, device=dev),
+                counts=t.empty((b,), dtype=t.int32, device=dev),
+            )
+        return self._buf[key]
+
+    def search(self, queries_dev, terms_dev, offsets_dev, b: int, k: int, w_dense: float,
+               w_bm25: float, rrf_k: float, top_n: int):
+        """queries [b, d] fp32, CSR term ids int32: device tensors.  Returns device tensors
+        (ids [b, top_n] int32 GLOBAL ids, scores f64, counts).  Everything is enqueued on
+        torch's current stream: 2 local searches, 1 all-gather, 1 merge+fuse call."""
+        t = self.torch
+        ctx = engine.context(self.device.index)
+        stream = t.cuda.current_stream().cuda_stream
+        buf = self._buffers(b, k, top_n)
+        local, gathered = buf["local"], buf["gathered"]
+        native.call("anr_dense_search_keys", ctx.handle, self.dense.handle, queries_dev.data_ptr(),
+                    b, k, None, self.row_base, local[0].data_ptr(), stream)
+        native.call("anr_bm25_search_keys", ctx.handle, self.bm25.handle, terms_dev.data_ptr(),
+                    offsets_dev.data_ptr(), b, k, None, None, self.doc_base, local[1].data_ptr(),
+                    stream)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=self.group)
+        else:
+            gathered = local
+        native.call("anr_sharded_fuse", ctx.handle, gathered.data_ptr(), self.world, b, k,
+                    float(w_dense), float(w_bm25), float(rrf_k), top_n, buf["ids"].data_ptr(),
+                    buf["scores"].data_ptr(), buf["counts"].data_ptr(), stream)
+        return buf["ids"], buf["scores"], buf["counts"]

@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""Headline benchmark: hybrid queries/s (dense top-10 + BM25 top-10 + weighted RRF -> top-10)
+over the BASELINE.json configs[1] corpus -- 1M chunks x 1024-d fp32 + a Zipf(1.1) BM25 corpus of
+1M documents (V=50k, 8-term queries) -- in batches of 64 queries, plus batch-1 latency.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  A step = one batch of B hybrid queries.
+  value     : queries/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e       : the same through the C-ABI with pinned HOST buffers (H2D of the queries and D2H
+              of the fused results inside the timed region)
+  roofline  : dense scan kernel, algorithmic bytes (rows x D x 4 per pass) / mean launch time,
+              against MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle port (numpy: BLAS dot + CSR BM25 + Python RRF, pre-stacked
+              matrix, i.e. WITHOUT the reference's per-query np.stack / pandas overhead) on a
+              bounded sample of the same batch, same corpus, on this box's host cores
+N > 1: the SAME 1M-chunk corpus is sharded by chunk over the ranks (strong scaling); local
+top-k keys are exchanged with one NCCL all-gather and merged + fused on every rank.
+--impl reference: only the CPU port is timed (rank 0), none of the CUDA library is loaded.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hybrid queries/sec (1M x 1024-d + BM25, top-10)"
+D = 1024
+VOCAB = 50_000
+ZIPF_S = 1.1
+K1, B_PARAM, EPS = 1.7, 0.83, 0.05
+W_DENSE, W_BM25, WRRF_K = 5.0, 1.0, 40.0
+TOPK = 10
+N_TERMS = 8
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunks", type=int, default=1_000_000, help="total corpus rows / BM25 docs")
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--cpu-queries", type=int, default=16, help="queries in the CPU sample")
+    ap.add_argument("--latency-iters", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------
+# synthetic workload (device generation; identical bytes are copied to the host for the CPU arm)
+# ---------------------------------------------------------------------------------------
+def make_queries(batch: int):
+    synth = importlib.import_module("a-nice-rag_b200.synth")
+    q = synth.unit_vectors(batch, D, seed=4321)
+    terms = synth.zipf_queries(batch, N_TERMS, VOCAB, ZIPF_S, seed=2025)
+    offsets = np.arange(0, (batch + 1) * N_TERMS, N_TERMS, dtype=np.int32)
+    return q, terms, offsets
+
+
+def make_shard(torch, device, lo: int, hi: int, shard_id: int):
+    synth = importlib.import_module("a-nice-rag_b200.synth")
+    emb = synth.unit_vectors_torch(hi - lo, D, 1234 + shard_id, device)
+    post = synth.zipf_postings_torch(hi - lo, VOCAB, ZIPF_S, 2024 + shard_id, device)
+    return emb, post
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arm: the oracle port, timed (and used as the checker of the GPU results)
+# ---------------------------------------------------------------------------------------
+def cpu_port_setup(emb_host, post_host, idf, avgdl):
+    from oracle import csr
+    return emb_host, csr.CsrIndex(
+        term_ptr=post_host["term_ptr"], post_doc=post_host["post_doc"],
+        post_tf=post_host["post_tf"], doc_len=post_host["doc_len"].astype(np.int64), idf=idf,
+        avgdl=avgdl, k1=K1, b=B_PARAM)
+
+
+def cpu_port_run(emb, index, queries, terms, n_queries: int):
+    """Runs n_queries hybrid queries on the CPU; returns (seconds, results)."""
+    from oracle import pipeline
+    weights = {"voyage-3-large": W_DENSE, "BM25": W_BM25}
+    results = []
+    t0 = time.perf_counter()
+    for q in range(n_queries):
+        results.append(pipeline.hybrid_query(queries[q], emb, index, [int(t) for t in terms[q]],
+                                             TOPK, TOPK, weights, WRRF_K, TOPK))
+    return time.perf_counter() - t0, results
+
+
+def check_against_cpu(results, got, queries_n: int):
+    """GPU fused output vs the oracle on the sampled queries (tie-aware on the two lists, exact
+    on the fusion given the lists).  Returns the number of queries checked."""
+    from oracle import pipeline, retrieval
+    for q in range(queries_n):
+        ref = results[q]
+        retrieval.assert_ranking_matches(
+            got["dense_rows"][q, :TOPK], got["dense_scores"][q, :TOPK], ref["dense_ids"],
+            ref["dense_scores"], all_scores=ref.get("dense_all"), rtol=1e-5, atol=1e-6,
+            what=f"bench dense q{q}")
+        b_all = ref["bm25_all"]
+        g_b = got["bm25_ids"][q, :TOPK]
+        s_g, s_w = b_all[g_b], b_all[ref["bm25_docs"]]
+        assert np.all(np.abs(s_g - s_w) <= 1e-5 * np.abs(s_w) + 1e-6), f"bench bm25 q{q}"
+        c = int(got["counts"][q])
+        pipeline.check_fused(got["ids"][q, :c], got["scores"][q, :c], got["dense_rows"][q, :TOPK],
+                             g_b, (W_DENSE, W_BM25), WRRF_K, TOPK)
+    return queries_n
+
+
+# ---------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the CPU port on this box's host cores; rank 0 only."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import torch
+    synth = importlib.import_module("a-nice-rag_b200.synth")
+    device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    emb, post = make_shard(torch, device, 0, args.chunks, 0)   # torch only generates the data
+    emb_host = emb.cpu().numpy()
+    post_host = {k: v.cpu().numpy() for k, v in post.items()}
+    del emb, post
+    idf = synth.idf_from_counts(args.chunks, post_host["nd"], EPS)
+    avgdl = float(post_host["doc_len"].astype(np.int64).sum() / args.chunks)
+    queries, terms, _ = make_queries(args.batch)
+    emb_h, index = cpu_port_setup(emb_host, post_host, idf, avgdl)
+    per_step = max(1, min(args.cpu_queries, args.batch) // 2)
+    for _ in range(args.warmup):
+        cpu_port_run(emb_h, index, queries, terms, 1)
+    total = 0.0
+    for _ in range(args.steps):
+        dt, _ = cpu_port_run(emb_h, index, queries, terms, per_step)
+        total += dt
+    qps = per_step * args.steps / total
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.chunks} chunks x {D}-d fp32 + BM25 {args.chunks} docs "
+                               f"V={VOCAB} Zipf {ZIPF_S}, {N_TERMS}-term queries, top-{TOPK} WRRF",
+                   "batch": per_step},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} queries per step over the full corpus; numpy "
+                                   "BLAS dot + CSR BM25 + Python RRF on a pre-stacked matrix"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    pkg = importlib.import_module("a-nice-rag_b200")
+    engine, native, synth = pkg.engine, pkg.native, importlib.import_module("a-nice-rag_b200.synth")
+    sharded = importlib.import_module("a-nice-rag_b200.sharded")
+    ctx = engine.context(local_rank)
+
+    # ---- corpus shard ------------------------------------------------------------------
+    lo, hi = sharded.shard_range(args.chunks, rank, world)
+    emb, post = make_shard(torch, device, lo, hi, rank)
+    nd, n_docs_total, avgdl = sharded.global_bm25_stats(
+        post["nd"], int(post["doc_len"].to(torch.int64).sum()), hi - lo)
+    idf = synth.idf_from_counts(n_docs_total, nd.cpu().numpy(), EPS)
+    dense = engine.DenseIndex(emb, borrow=True)
+    bm25 = engine.Bm25Index(post["term_ptr"], post["post_doc"], post["post_tf"], post["doc_len"],
+                            idf, K1, B_PARAM, avgdl, n_terms=VOCAB, n_docs=hi - lo)
+    n_postings = bm25.n_postings
+
+    # ---- queries -------------------------------------------------------------------------
+    B = args.batch
+    q_host, t_host, off_host = make_queries(B)
+    q_pin = torch.from_numpy(q_host).pin_memory()
+    t_pin = torch.from_numpy(t_host.reshape(-1).copy()).pin_memory()
+    off_pin = torch.from_numpy(off_host).pin_memory()
+    q_dev, t_dev, off_dev = q_pin.to(device), t_pin.to(device), off_pin.to(device)
+    out_ids = torch.empty((B, TOPK), dtype=torch.int32, device=device)
+    out_scores = torch.empty((B, TOPK), dtype=torch.float64, device=device)
+    out_counts = torch.empty((B,), dtype=torch.int32, device=device)
+    h_ids = torch.empty((B, TOPK), dtype=torch.int32).pin_memory()
+    h_scores = torch.empty((B, TOPK), dtype=torch.float64).pin_memory()
+    h_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
+    shard = sharded.ShardedHybrid(dense, bm25, row_base=lo) if world > 1 else None
+
+    def step_device(b=B):
+        stream = torch.cuda.current_stream().cuda_stream
+        if world > 1:
+            return shard.search(q_dev[:b], t_dev, off_dev, b, TOPK, W_DENSE, W_BM25, WRRF_K, TOPK)
+        native.call("anr_hybrid_search", ctx.handle, dense.handle, bm25.handle, q_dev.data_ptr(),
+                    t_dev.data_ptr(), off_dev.data_ptr(), b, TOPK, TOPK, None, None, None, 0,
+                    W_DENSE, W_BM25, WRRF_K, TOPK, out_ids.data_ptr(), out_scores.data_ptr(),
+                    out_counts.data_ptr(), None, None, None, None, stream)
+        return out_ids, out_scores, out_counts
+
+    def step_e2e(b=B):
+        """Host buffers in, host buffers out (the call synchronises before returning)."""
+        stream = torch.cuda.current_stream().cuda_stream
+        if world > 1:
+            qd = q_pin[:b].to(device, non_blocking=True)
+            td = t_pin.to(device, non_blocking=True)
+            od = off_pin.to(device, non_blocking=True)
+            ids, scores, counts = shard.search(qd, td, od, b, TOPK, W_DENSE, W_BM25, WRRF_K, TOPK)
+            h_ids[:b].copy_(ids, non_blocking=True)
+            h_scores[:b].copy_(scores, non_blocking=True)
+            h_counts[:b].copy_(counts, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return
+        native.call("anr_hybrid_search", ctx.handle, dense.handle, bm25.handle, q_pin.data_ptr(),
+                    t_pin.data_ptr(), off_pin.data_ptr(), b, TOPK, TOPK, None, None, None, 0,
+                    W_DENSE, W_BM25, WRRF_K, TOPK, h_ids.data_ptr(), h_scores.data_ptr(),
+                    h_counts.data_ptr(), None, None, None, None, stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """ms for `steps` calls: CUDA events on the launching stream, max over ranks."""
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        start.record()
+        for _ in range(steps):
+            fn()
+        stop.record()
+        barrier()
+        ms = torch.tensor([start.elapsed_time(stop)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # ---- warm-up, then the timed regions --------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+        step_e2e()
+    native.call("anr_ctx_profile_enable", ctx.handle, 1)
+    import ctypes as C
+    native.call("anr_ctx_profile_read", ctx.handle, 0, None, None)      # reset counters
+    native.call("anr_ctx_profile_read", ctx.handle, 1, None, None)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_dev = timed(step_device, args.steps)
+    scan_ms, scan_n, bm_ms, bm_n = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
+    native.call("anr_ctx_profile_read", ctx.handle, 0, C.byref(scan_ms), C.byref(scan_n))
+    native.call("anr_ctx_profile_read", ctx.handle, 1, C.byref(bm_ms), C.byref(bm_n))
+    native.call("anr_ctx_profile_enable", ctx.handle, 0)
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- batch-1 latency through the C-ABI with host buffers (p50 of wall-clock per call) -----
+    lat = []
+    if world == 1:
+        for i in range(args.latency_iters + 20):
+            t0 = time.perf_counter()
+            step_e2e(1)
+            if i >= 20:
+                lat.append(1e3 * (time.perf_counter() - t0))
+    ms_b1_dev = timed(lambda: step_device(1), max(args.steps, 50)) / max(args.steps, 50)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------
+    peak, peak_kind = load_peaks()
+    rows_local = hi - lo
+    scan_bytes = rows_local * D * 4
+    scan_avg_ms = scan_ms.value / max(scan_n.value, 1)
+    achieved = scan_bytes / (scan_avg_ms * 1e-3) / 1e9 if scan_avg_ms > 0 else 0.0
+    bm_avg_ms = bm_ms.value / max(bm_n.value, 1)
+
+    # ---- CPU baseline + parity of this very batch (N = 1) --------------------------------------
+    cpu = None
+    checked = 0
+    if world == 1 and not args.no_cpu_baseline:
+        emb_host = emb.cpu().numpy()
+        post_host = {k: v.cpu().numpy() for k, v in post.items()}
+        emb_h, index = cpu_port_setup(emb_host, post_host, idf, avgdl)
+        nq_cpu = min(args.cpu_queries, B)
+        cpu_port_run(emb_h, index, q_host, t_host, 1)                       # warm caches / BLAS
+        dt, results = cpu_port_run(emb_h, index, q_host, t_host, nq_cpu)
+        cpu = {"value": nq_cpu / dt, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{nq_cpu} of the batch's {B} queries over the full {args.chunks}-chunk "
+                         "corpus; numpy BLAS dot + CSR BM25 + Python RRF on a pre-stacked matrix "
+                         "(the reference's per-query np.stack and pandas work NOT included)"}
+        got = engine.hybrid_search(dense, bm25, q_host[:nq_cpu],
+                                   [list(map(int, t)) for t in t_host[:nq_cpu]], TOPK, TOPK,
+                                   W_DENSE, W_BM25, WRRF_K, TOPK, want_lists=True)
+        for r in results:   # full dense score vector only where ids differ is costly: recompute lazily
+            r["dense_all"] = None
+        for q in range(nq_cpu):
+            if not np.array_equal(got["dense_rows"][q], results[q]["dense_ids"]):
+                results[q]["dense_all"] = emb_h @ q_host[q]
+        checked = check_against_cpu(results, got, nq_cpu)
+
+    line = {
+        "metric": METRIC, "value": B * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.chunks} chunks x {D}-d fp32 + BM25 {args.chunks} docs "
+                               f"V={VOCAB} Zipf {ZIPF_S}, {N_TERMS}-term queries, top-{TOPK} WRRF "
+                               f"(w 5:1, k=40)", "batch": B, "sharding": f"chunks/{world}",
+                   "l2": "inputs larger than L2 (corpus shard >= 0.5 GB per GPU)",
+                   "bm25_postings_local": n_postings},
+        "e2e": {"value": B * args.steps / (ms_e2e * 1e-3), "unit": "queries/s",
+                "h2d_bytes_per_step": int(q_pin.numel() * 4 + t_pin.numel() * 4 + off_pin.numel() * 4),
+                "d2h_bytes_per_step": int(h_ids.numel() * 4 + h_scores.numel() * 8 + h_counts.numel() * 4)},
+        "gpu_launches": int((scan_n.value + bm_n.value) + 4 * args.steps),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                     "kernel": "dense_scan_kernel", "bytes_per_launch": scan_bytes,
+                     "avg_launch_ms": scan_avg_ms, "launches": int(scan_n.value),
+                     "share_of_step": scan_ms.value / ms_dev if ms_dev else None},
+        "bm25_kernel": {"avg_launch_ms": bm_avg_ms, "launches": int(bm_n.value),
+                        "share_of_step": bm_ms.value / ms_dev if ms_dev else None},
+        "batch1": {"device_ms": ms_b1_dev, "device_qps": 1e3 / ms_b1_dev if ms_b1_dev else None,
+                   "e2e_p50_ms": statistics.median(lat) if lat else None,
+                   "e2e_p95_ms": (sorted(lat)[int(0.95 * len(lat))] if lat else None)},
+        "clocks": clocks, "parity_checked_queries": checked,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,13 @@ int anr_ctx_sync(anr_ctx* ctx);
 /* sm count, total/free HBM bytes of the context's device (any pointer may be NULL) */
 int anr_ctx_info(anr_ctx* ctx, int32_t* sm_count, int64_t* hbm_total, int64_t* hbm_free);
 
+/* Per-kernel timing for roofline reports.  While enabled, every launch of the two dominant
+ * kernels (kind 0 = dense scan, kind 1 = BM25 score) is bracketed by CUDA events on the
+ * stream it is launched on.  anr_ctx_profile_read synchronises, returns the summed device
+ * time (ms) and launch count per kind since the last read, and resets the counters. */
+int anr_ctx_profile_enable(anr_ctx* ctx, int32_t on);
+int anr_ctx_profile_read(anr_ctx* ctx, int32_t kind, double* total_ms, int64_t* launches);
+
 /* ---- dense index: the chunk-embedding matrix ------------------------------
  * Replaces the per-query `np.stack(df["embedding"].values)` of
  * src/search_engine.py:80,128 with ONE row-major [n, d] fp32 matrix resident in
@@ -155,6 +162,15 @@ int anr_bm25_search_keys(anr_ctx* ctx, const anr_bm25* index, const int32_t* q_t
 int anr_topk_merge(anr_ctx* ctx, const uint64_t* keys, int32_t n_parts, int32_t n_queries,
                    int32_t k, float* out_scores, int32_t* out_ids, int32_t* out_counts,
                    void* stream);
+
+/* The consumer of the all-gathered buffer of a sharded hybrid query: gathered is
+ * [n_parts][2][n_queries][k] keys (per rank: dense keys, then BM25 keys, ids already global).
+ * Merges each retriever's n_parts lists to its global top-k and runs the weighted RRF on the
+ * two merged lists (fusion needs GLOBAL ranks, so it follows the merge) -> top_n fused.
+ * Same outputs as anr_hybrid_search. */
+int anr_sharded_fuse(anr_ctx* ctx, const uint64_t* gathered, int32_t n_parts, int32_t n_queries,
+                     int32_t k, double w_dense, double w_bm25, double rrf_k, int32_t top_n,
+                     int32_t* out_ids, double* out_scores, int32_t* out_counts, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,336 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the golden
+vectors the reference produced and against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): dense / BM25 scores within 1e-5 relative; top-k ids
+identical except inside groups of (near-)equal oracle score; fused float64 scores and order
+bit-identical given the ranked lists."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from helpers import (WEIGHTS, WRRF_K, check_ids_only, check_topk, csr_from_case, filter_mask,
+                     synth, tag)
+from oracle import csr, pipeline, retrieval
+
+pytestmark = pytest.mark.gpu
+
+engine = importlib.import_module("a-nice-rag_b200.engine")
+native = importlib.import_module("a-nice-rag_b200.native")
+
+FILTERS = (None, "CG,NG", "cg")
+KS = (10, 100, 3000)
+
+
+def term_ids_of(case, ix, q):
+    return [int(t) if t < ix.idf.shape[0] else -1 for t in case["term_queries"][q]]
+
+
+@pytest.fixture(scope="module")
+def small(small_case):
+    ix, okapi = csr_from_case(small_case)
+    dense = engine.DenseIndex(small_case["emb"])
+    bm25 = engine.Bm25Index(ix.term_ptr, ix.post_doc, ix.post_tf, ix.doc_len, ix.idf, ix.k1, ix.b,
+                            ix.avgdl)
+    return dict(case=small_case, ix=ix, okapi=okapi, dense=dense, bm25=bm25)
+
+
+# ---------------------------------------------------------------------------------------
+# dense
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flt", FILTERS)
+@pytest.mark.parametrize("k", KS)
+def test_dense_vs_golden(small, flt, k):
+    case = small["case"]
+    n = case["emb"].shape[0]
+    mask = None if flt is None else filter_mask(case, flt)
+    words = None if mask is None else engine.pack_mask(mask)
+    scores, rows, counts = small["dense"].search(case["queries"], k, row_mask=words)
+    for q in range(case["queries"].shape[0]):
+        want_n = int(case[f"dense_counts_{tag(flt)}_k{k}"][q])
+        assert counts[q] == want_n == min(k, n if mask is None else int(mask.sum()))
+        assert (rows[q, want_n:] == -1).all()
+        full = retrieval.dense_scores(case["queries"][q], case["emb"])
+        check_topk(rows[q, :want_n], scores[q, :want_n],
+                   case[f"dense_ids_{tag(flt)}_k{k}"][q, :want_n],
+                   case[f"dense_scores_{tag(flt)}_k{k}"][q, :want_n], full,
+                   f"dense q{q} {flt} k{k}")
+        if mask is not None:
+            assert mask[rows[q, :want_n]].all()
+
+
+def test_dense_empty_filter_and_single_query(small):
+    case = small["case"]
+    words = engine.pack_mask(np.zeros(case["emb"].shape[0], dtype=bool))
+    scores, rows, counts = small["dense"].search(case["queries"][0], 10, row_mask=words)
+    assert counts[0] == 0 and (rows == -1).all() and (scores == 0).all()
+
+
+@pytest.mark.parametrize("n,d", [(1, 8), (5, 50), (33, 4), (4097, 52), (3000, 1024), (700, 2048),
+                                 (257, 3072), (64, 8192)])
+@pytest.mark.parametrize("nq", [1, 2, 3, 8, 9])
+def test_dense_shapes_vs_oracle(n, d, nq):
+    emb = synth.unit_vectors(n, d, seed=100 + n)
+    queries = synth.unit_vectors(nq, d, seed=200 + d)
+    index = engine.DenseIndex(emb)
+    for k in (1, 7, 128, 129):
+        scores, rows, counts = index.search(queries, k)
+        for q in range(nq):
+            c = min(k, n)
+            assert counts[q] == c
+            want_rows, want_scores = retrieval.dense_topk(queries[q], emb, k)
+            check_topk(rows[q, :c], scores[q, :c], want_rows, want_scores,
+                       retrieval.dense_scores(queries[q], emb), f"dense n{n} d{d} q{q} k{k}")
+
+
+def test_dense_exact_ties_prefer_lower_row():
+    """All-equal scores: the documented tie rule (higher score, then lower row) decides."""
+    emb = np.tile(synth.unit_vectors(1, 64, seed=5), (1000, 1))
+    index = engine.DenseIndex(emb)
+    scores, rows, counts = index.search(emb[0], 16)
+    assert rows[0].tolist() == list(range(16)) and counts[0] == 16
+    assert np.all(scores[0] == scores[0, 0])
+
+
+def test_dense_upload_in_slabs_and_id_base():
+    emb = synth.unit_vectors(5000, 128, seed=9)
+    index = engine.DenseIndex(n=5000, d=128)
+    for r0 in range(0, 5000, 1024):
+        index.upload(r0, emb[r0:r0 + 1024])
+    q = synth.unit_vectors(1, 128, seed=10)
+    scores, rows, _ = index.search(q, 10, id_base=1_000_000)
+    want_rows, want_scores = retrieval.dense_topk(q[0], emb, 10)
+    check_topk(rows[0] - 1_000_000, scores[0], want_rows, want_scores,
+               retrieval.dense_scores(q[0], emb), "slab upload")
+
+
+def test_dense_200k_rows_property():
+    """A size the fused scan runs many tiles per CTA on: compare with the slab-wise oracle."""
+    import torch
+    n, d = 200_000, 1024
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    emb = torch.randn(n, d, generator=g, device="cuda", dtype=torch.float32)
+    emb /= emb.norm(dim=1, keepdim=True)
+    index = engine.DenseIndex(emb, borrow=True)
+    queries = synth.unit_vectors(3, d, seed=4321)
+    scores, rows, counts = index.search(queries, 10)
+    host = emb.cpu().numpy()
+    for q in range(3):
+        want_rows, want_scores = retrieval.dense_topk(queries[q], host, 10)
+        check_topk(rows[q], scores[q], want_rows, want_scores,
+                   retrieval.dense_scores(queries[q], host), f"200k q{q}")
+
+
+# ---------------------------------------------------------------------------------------
+# BM25
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flt", FILTERS)
+@pytest.mark.parametrize("k", KS)
+def test_bm25_vs_golden(small, flt, k):
+    case, ix = small["case"], small["ix"]
+    nq = case["term_queries"].shape[0]
+    mask = None if flt is None else filter_mask(case, flt)
+    words = None if mask is None else engine.pack_mask(mask)
+    queries = [term_ids_of(case, ix, q) for q in range(nq)]
+    scores, docs, counts = small["bm25"].search(queries, k, doc_mask=words)
+    for q in range(nq):
+        want_n = int(case[f"bm25_counts_{tag(flt)}_k{k}"][q])
+        assert counts[q] == want_n
+        want = case[f"bm25_ids_{tag(flt)}_k{k}"][q, :want_n]
+        all_scores = case["bm25_all_scores"][q]
+        got = docs[q, :want_n]
+        if flt:
+            # the reference's filtered branch is a stable sort: ascending doc index among exact
+            # ties -- the kernel's tie rule; near-ties (fp32 vs float64) stay tolerance-checked
+            check_ids_only(got, want, all_scores, f"bm25 q{q} {flt} k{k}")
+            assert mask[got].all()
+        else:
+            check_ids_only(got, want, all_scores, f"bm25 q{q} k{k}")
+        np.testing.assert_allclose(scores[q, :want_n], all_scores[got], rtol=1e-5, atol=1e-6)
+
+
+def test_bm25_filtered_exact_ties_are_stable(small):
+    """Planted duplicate documents 39/40/41/1500: equal scores must come out in ascending doc
+    order, as the reference's stable sort leaves them (search_engine.py:233)."""
+    case, ix = small["case"], small["ix"]
+    mask = np.ones(case["emb"].shape[0], dtype=bool)
+    scores, docs, counts = small["bm25"].search([term_ids_of(case, ix, 6)], 50,
+                                                doc_mask=engine.pack_mask(mask))
+    got = docs[0, :counts[0]].tolist()
+    pos = [got.index(d) for d in (39, 40, 41, 1500)]
+    assert pos == sorted(pos) and pos[-1] - pos[0] == 3
+    assert len({float(scores[0, p]) for p in pos}) == 1
+
+
+def test_bm25_get_scores_vs_oracle(small):
+    case, ix = small["case"], small["ix"]
+    for q in range(case["term_queries"].shape[0]):
+        got = small["bm25"].scores(term_ids_of(case, ix, q))
+        np.testing.assert_allclose(got, case["bm25_all_scores"][q], rtol=1e-5, atol=1e-6)
+
+
+def test_bm25_long_query_and_many_tiles():
+    """70 terms (> one staged chunk of 64) over 60k documents (many tiles)."""
+    n, vocab = 60_000, 5000
+    doc_ptr, tokens = synth.zipf_corpus(n, vocab, 1.1, seed=31, len_lo=30, len_hi=80)
+    ix = csr.from_token_ids(doc_ptr, tokens, vocab, 1.7, 0.83, 0.05)
+    index = engine.Bm25Index(ix.term_ptr, ix.post_doc, ix.post_tf, ix.doc_len, ix.idf, ix.k1,
+                             ix.b, ix.avgdl)
+    tq = synth.zipf_queries(5, 70, vocab, 1.1, seed=32)
+    for k in (10, 128, 500):
+        scores, docs, counts = index.search([list(map(int, t)) for t in tq], k)
+        for q in range(5):
+            all_scores = csr.scores(ix, [int(t) for t in tq[q]])
+            want = retrieval.bm25_topk(all_scores, k)
+            check_ids_only(docs[q, :counts[q]], want, all_scores, f"bm25 60k q{q} k{k}")
+            np.testing.assert_allclose(scores[q, :counts[q]], all_scores[docs[q, :counts[q]]],
+                                       rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------
+# fusion
+# ---------------------------------------------------------------------------------------
+def test_wrrf_bit_exact_random_lists():
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        n_lists = int(rng.integers(1, 6))
+        lists = [rng.permutation(200)[:rng.integers(0, 60)].tolist() for _ in range(n_lists)]
+        weights = [float(w) for w in rng.choice([0.5, 1.0, 1.0, 5.0, 2.5], size=n_lists)]
+        rrf_k = float(rng.choice([40, 50, 60]))
+        want = retrieval.weighted_rrf([(l, str(i)) for i, l in enumerate(lists)],
+                                      {str(i): w for i, w in enumerate(weights)}, rrf_k)
+        ids, scores = engine.wrrf_fuse(lists, weights, rrf_k)
+        assert ids.tolist() == [i for i, _ in want], trial
+        assert scores.tolist() == [s for _, s in want], trial
+
+
+def test_wrrf_equal_weight_ties_keep_insertion_order():
+    a, b = [10, 11, 12, 13], [20, 21, 22, 23]
+    ids, scores = engine.wrrf_fuse([a, b], [1.0, 1.0], 40.0)
+    assert ids.tolist() == [10, 20, 11, 21, 12, 22, 13, 23]
+    ids, _ = engine.wrrf_fuse([a, b], [1.0, 1.0], 40.0, top_n=3)
+    assert ids.tolist() == [10, 20, 11]
+
+
+def test_wrrf_large_lists():
+    rng = np.random.default_rng(4)
+    lists = [rng.permutation(5000)[:4000].tolist(), rng.permutation(5000)[:4000].tolist()]
+    want = retrieval.weighted_rrf([(lists[0], "a"), (lists[1], "b")], {"a": 5.0, "b": 1.0}, 40)
+    ids, scores = engine.wrrf_fuse(lists, [5.0, 1.0], 40.0)
+    assert ids.tolist() == [i for i, _ in want]
+    assert scores.tolist() == [s for _, s in want]
+
+
+# ---------------------------------------------------------------------------------------
+# hybrid + sharded merge
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flt", (None, "CG,NG"))
+def test_hybrid_vs_golden(small, flt):
+    case, ix = small["case"], small["ix"]
+    nq, k = case["queries"].shape[0], 10
+    mask = None if flt is None else filter_mask(case, flt)
+    words = None if mask is None else engine.pack_mask(mask)
+    queries = [term_ids_of(case, ix, q) for q in range(nq)]
+    res = engine.hybrid_search(small["dense"], small["bm25"], case["queries"], queries, k, k,
+                               5.0, 1.0, WRRF_K, 2 * k, row_mask=words, doc_mask=words,
+                               want_lists=True)
+    for q in range(nq):
+        full = retrieval.dense_scores(case["queries"][q], case["emb"])
+        dn = int(case[f"dense_counts_{tag(flt)}_k{k}"][q])
+        check_topk(res["dense_rows"][q, :dn], res["dense_scores"][q, :dn],
+                   case[f"dense_ids_{tag(flt)}_k{k}"][q, :dn],
+                   case[f"dense_scores_{tag(flt)}_k{k}"][q, :dn], full, f"hybrid dense q{q}")
+        bn = int(case[f"bm25_counts_{tag(flt)}_k{k}"][q])
+        check_ids_only(res["bm25_ids"][q, :bn], case[f"bm25_ids_{tag(flt)}_k{k}"][q, :bn],
+                       case["bm25_all_scores"][q], f"hybrid bm25 q{q}")
+        c = int(res["counts"][q])
+        pipeline.check_fused(res["ids"][q, :c], res["scores"][q, :c], res["dense_rows"][q, :dn],
+                             res["bm25_ids"][q, :bn], (5.0, 1.0), WRRF_K, 2 * k)
+        # and against the reference's fused list wherever its two lists had no tie choice
+        if (res["dense_rows"][q, :dn] == case[f"dense_ids_{tag(flt)}_k{k}"][q, :dn]).all() and \
+                (res["bm25_ids"][q, :bn] == case[f"bm25_ids_{tag(flt)}_k{k}"][q, :bn]).all():
+            fn = int(case[f"fused_counts_{tag(flt)}_k{k}"][q])
+            assert res["ids"][q, :c].tolist() == case[f"fused_ids_{tag(flt)}_k{k}"][q, :fn].tolist()
+            assert res["scores"][q, :c].tolist() == \
+                case[f"fused_scores_{tag(flt)}_k{k}"][q, :fn].tolist()
+
+
+def test_sharded_keys_merge_equals_unsharded(small):
+    """3 row shards searched separately, keys concatenated as an all-gather would, merged."""
+    import ctypes as C
+    case = small["case"]
+    emb, queries = case["emb"], case["queries"]
+    nq, k = queries.shape[0], 10
+    bounds = [0, 700, 1400, emb.shape[0]]
+    ctx = engine.context()
+    keys = np.zeros((3, nq, k), dtype=np.uint64)
+    for s in range(3):
+        shard = engine.DenseIndex(emb[bounds[s]:bounds[s + 1]])
+        native.call("anr_dense_search_keys", ctx.handle, shard.handle, native.ptr(queries), nq, k,
+                    None, bounds[s], native.ptr(keys[s]), None)
+    scores = np.empty((nq, k), dtype=np.float32)
+    ids = np.empty((nq, k), dtype=np.int32)
+    counts = np.empty(nq, dtype=np.int32)
+    native.call("anr_topk_merge", ctx.handle, native.ptr(keys), 3, nq, k, native.ptr(scores),
+                native.ptr(ids), native.ptr(counts), None)
+    u_scores, u_rows, _ = small["dense"].search(queries, k)
+    assert np.array_equal(ids, u_rows) and np.array_equal(scores, u_scores)
+    assert (counts == k).all()
+
+
+# ---------------------------------------------------------------------------------------
+# the drop-in classes on the reference's own CPU-runnable case (BASELINE configs[0])
+# ---------------------------------------------------------------------------------------
+def test_dropin_config0_vs_reference_golden(config0_golden, tmp_path):
+    from oracle import make_golden
+    pkg = importlib.import_module("a-nice-rag_b200")
+    case = make_golden.config0_inputs()
+    assert np.allclose(make_golden.checksum(case), config0_golden["input_checksum"], rtol=1e-12)
+    n = case["emb"].shape[0]
+    srcs = list(case["sources"])
+    ids = synth.chunk_ids(n, srcs)
+    contents = [f"content {i}" for i in range(n)]
+    ix, okapi = csr_from_case(case)
+    db, pkl = str(tmp_path / "chunks.db"), str(tmp_path / "bm25.pkl")
+    synth.write_chunks_db(db, ids, contents, srcs, case["emb"])
+    synth.write_bm25_pickle(pkl, okapi, contents, ids, srcs)
+
+    dm = pkg.DatabaseManager()
+    df = dm.load_embeddings_from_sql(db, "voyage-3-large")
+    bm25, sections, section_ids = dm.load_bm25_from_pickle(pkl)
+    assert list(df.columns) == ["id", "document", "source", "embedding", "url"]
+    assert dm.load_embeddings_from_sql(db, "voyage-3-large") is df
+    se = pkg.SearchEngine(None, None)
+    row_of = {c: i for i, c in enumerate(ids)}
+    for flt, t in ((None, "none"), ("CG, NG", "CG_NG")):
+        for q in range(0, 100, 3):
+            res = se.similarity_search_with_embedding(case["queries"][q], df, "voyage-3-large", 10, flt)
+            full = retrieval.dense_scores(case["queries"][q], case["emb"])
+            check_topk([row_of[c] for c in res["id"]], res["similarity"].to_numpy(),
+                       config0_golden[f"dense_ids_{t}_k10"][q], config0_golden[f"dense_scores_{t}_k10"][q],
+                       full, f"dropin dense q{q} {flt}")
+            assert list(res.columns) == ["id", "document", "source", "embedding", "url", "similarity"]
+            toks = synth.token_strings(case["term_queries"][q])
+            hits = se.bm25_search_preprocessed(toks, bm25, sections, section_ids, 10, flt)
+            all_scores = csr.scores(ix, [int(x) for x in case["term_queries"][q]])
+            check_ids_only([row_of[c] for c in hits], config0_golden[f"bm25_ids_{t}_k10"][q],
+                           all_scores, f"dropin bm25 q{q} {flt}")
+            fused = se.weighted_reciprocal_rank_fusion(
+                [(res["id"].tolist(), "voyage-3-large"), (hits, "BM25")], WEIGHTS, WRRF_K)
+            want = retrieval.weighted_rrf(
+                [(res["id"].tolist(), "voyage-3-large"), (hits, "BM25")], WEIGHTS, WRRF_K)
+            assert fused == want
+    # batched extension == per-query calls
+    qs = list(range(0, 16))
+    batch = se.hybrid_search_batch(case["queries"][qs],
+                                   [synth.token_strings(case["term_queries"][q]) for q in qs],
+                                   df, bm25, sections, section_ids, WEIGHTS, "voyage-3-large",
+                                   10, 10, WRRF_K)
+    for j, q in enumerate(qs):
+        res = se.similarity_search_with_embedding(case["queries"][q], df, "voyage-3-large", 10)
+        hits = se.bm25_search_preprocessed(synth.token_strings(case["term_queries"][q]), bm25,
+                                           sections, section_ids, 10)
+        want = retrieval.weighted_rrf([(res["id"].tolist(), "voyage-3-large"), (hits, "BM25")],
+                                      WEIGHTS, WRRF_K)[:10]
+        assert batch[j] == want

@@ -1,0 +1,189 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls: there is no GPU here)."""
+import ctypes
+import importlib
+import os
+import re
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from helpers import ROOT, csr_from_case, synth
+from oracle import csr, retrieval
+
+engine = importlib.import_module("a-nice-rag_b200.engine")
+native = importlib.import_module("a-nice-rag_b200.native")
+registry = importlib.import_module("a-nice-rag_b200.registry")
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "anr_b200.h")).read()
+    declared = set(re.findall(r"\b(anr_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
+    lib = native.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.anr_abi_version() == 1
+
+
+def test_no_device_is_a_loud_error_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    handle = ctypes.c_void_p()
+    rc = native.load().anr_ctx_create(0, ctypes.byref(handle))
+    assert rc == 3 and b"no CPU implementation" in native.load().anr_last_error()
+    with pytest.raises(native.AnrError):
+        engine.DenseIndex(np.zeros((4, 8), dtype=np.float32))
+
+
+def test_pack_mask_layout():
+    rng = np.random.default_rng(0)
+    for n in (1, 31, 32, 33, 1000):
+        mask = rng.random(n) < 0.4
+        words = engine.pack_mask(mask)
+        assert words.dtype == np.uint32 and len(words) == (n + 31) // 32
+        for i in range(n):
+            assert bool((words[i >> 5] >> (i & 31)) & 1) == bool(mask[i])
+
+
+def test_prefix_mask_matches_reference_semantics():
+    srcs = ["CG12", "cg7", "NG1", "PH2", None, "", "XCG1", " ng3", float("nan")]
+    for flt in ("CG, ng", "cg", "ZZ", "C"):
+        assert engine.prefix_mask(srcs, flt).tolist() == retrieval.filter_mask(srcs, flt).tolist()
+
+
+def test_invert_okapi_equals_oracle_inversion(small_case):
+    ix, okapi = csr_from_case(small_case)
+    vocab, term_ptr, post_doc, post_tf, doc_len, idf = engine.invert_okapi(okapi)
+    want = csr.from_okapi(okapi)
+    assert vocab == want.vocab
+    assert np.array_equal(term_ptr, want.term_ptr) and np.array_equal(post_doc, want.post_doc)
+    assert np.array_equal(post_tf, want.post_tf) and np.array_equal(idf, want.idf)
+    assert np.array_equal(doc_len, want.doc_len)
+    for t in range(len(term_ptr) - 1):          # ascending documents inside every term
+        seg = post_doc[term_ptr[t]:term_ptr[t + 1]]
+        assert np.all(np.diff(seg) > 0)
+
+
+def test_pack_queries_csr():
+    terms, offsets = engine.Bm25Index.pack_queries([[3, 3, -1], [], [7]])
+    assert terms.tolist() == [3, 3, -1, 7] and offsets.tolist() == [0, 3, 3, 4]
+
+
+def test_database_manager_contract_without_gpu(tmp_path, caplog):
+    pkg = importlib.import_module("a-nice-rag_b200")
+    n, d = 50, 12
+    emb = synth.unit_vectors(n, d, seed=1)
+    srcs = synth.sources(n, seed=2)
+    ids = synth.chunk_ids(n, srcs)
+    db = str(tmp_path / "c.db")
+    bad = [("bad1", "x", "CG1", b"\x00\x01\x02", "u"), ("bad2", "x", "CG1", None, "u")]
+    synth.write_chunks_db(db, ids, [f"doc {i}" for i in range(n)], srcs, emb, extra_rows=bad)
+    dm = pkg.DatabaseManager()
+    df = dm.load_embeddings_from_sql(db, "m")
+    assert list(df.columns) == ["id", "document", "source", "embedding", "url"]
+    assert len(df) == n and list(df["id"]) == ids            # invalid rows skipped
+    assert all(isinstance(e, np.ndarray) and e.dtype == np.float32 for e in df["embedding"])
+    assert np.array_equal(np.stack(df["embedding"].values), emb)
+    assert df["url"][0] == "https://www.nice.org.uk/guidance/" + srcs[0].lower()
+    assert dm.load_embeddings_from_sql(db, "m") is df        # cached
+    with pytest.raises(FileNotFoundError):
+        dm.load_embeddings_from_sql(str(tmp_path / "missing.db"))
+    with pytest.raises(FileNotFoundError):
+        dm.load_bm25_from_pickle(str(tmp_path / "missing.pkl"))
+    # derived frames are recognised as row subsets of the registered one
+    entry, subset = registry.resolve_frame(df)
+    assert subset is None and entry.n == n
+    sub = df[df["source"].str.startswith("CG")].copy()
+    e2, rows = registry.resolve_frame(sub)
+    assert e2 is entry and rows.tolist() == sub.index.tolist()
+    empty_db = str(tmp_path / "e.db")
+    synth.write_chunks_db(empty_db, [], [], [], np.zeros((0, 4), dtype=np.float32))
+    assert dm.load_embeddings_from_sql(empty_db).empty
+
+
+def test_bm25_pickle_roundtrip_with_shims(tmp_path, small_case):
+    pkg = importlib.import_module("a-nice-rag_b200")
+    _, okapi = csr_from_case(small_case)
+    n = len(okapi.doc_freqs)
+    srcs = list(small_case["sources"])
+    ids = synth.chunk_ids(n, srcs)
+    pkl = str(tmp_path / "b.pkl")
+    synth.write_bm25_pickle(pkl, okapi, [""] * n, ids, srcs)
+    assert "rank_bm25" not in sys.modules or hasattr(sys.modules["rank_bm25"], "__file__")
+    bm25, sections, section_ids = pkg.DatabaseManager().load_bm25_from_pickle(pkl)
+    assert type(bm25).__name__ == "BM25Okapi" and type(bm25).__module__ == "rank_bm25"
+    assert bm25.idf == okapi.idf and bm25.doc_len == okapi.doc_len and bm25.avgdl == okapi.avgdl
+    assert section_ids == ids and sections[3].metadata == {"id": ids[3], "source": srcs[3]}
+
+
+def test_reference_named_modules_resolve_to_the_product():
+    src = os.path.join(ROOT, "a-nice-rag_b200", "src")
+    saved = {k: sys.modules.pop(k, None) for k in ("search_engine", "database_manager", "config",
+                                                   "processing", "processing.preprocess_bm25")}
+    sys.path.insert(0, src)
+    try:
+        se = importlib.import_module("search_engine")
+        dm = importlib.import_module("database_manager")
+        cfg = importlib.import_module("config")
+        pp = importlib.import_module("processing.preprocess_bm25")
+        pkg = importlib.import_module("a-nice-rag_b200")
+        assert se.SearchEngine is pkg.SearchEngine and dm.DatabaseManager is pkg.DatabaseManager
+        assert cfg.Config.DEFAULT_MODEL_WEIGHTS == {"voyage-3-large": 5.0, "BM25": 1.0,
+                                                    "text-embedding-3-large": 0.0,
+                                                    "voyage-3.5": 0.0, "Qwen3": 0.0}
+        assert pp.preprocess_text("The 12 patients with Hypertension!") == ["patients", "hypertension"]
+        with pytest.raises(ValueError):
+            cfg.Config.get_source_config("nope")
+        assert cfg.Config.get_source_config("NICE").voyage_db_path.endswith("2048.db")
+    finally:
+        sys.path.remove(src)
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
+
+
+def test_signatures_match_the_reference():
+    import inspect
+    pkg = importlib.import_module("a-nice-rag_b200")
+    se = pkg.SearchEngine
+    want = {
+        "similarity_search_with_embedding": ["self", "query_embedding", "df", "model_name",
+                                             "similarity_k", "filename_type_filter"],
+        "similarity_search": ["self", "query_text", "df", "model_name", "similarity_k",
+                              "filename_type_filter", "query_embedding"],
+        "bm25_search": ["self", "query_text", "bm25", "bm25_sections", "bm25_section_ids",
+                        "similarity_k", "filename_type_filter", "use_lemmatized"],
+        "bm25_search_preprocessed": ["self", "query_tokens", "bm25", "bm25_sections",
+                                     "bm25_section_ids", "similarity_k", "filename_type_filter"],
+        "weighted_reciprocal_rank_fusion": ["self", "ranked_lists", "model_weights", "k"],
+        "rerank_documents": ["self", "query_text", "documents", "reranker_model", "reranker_top_k"],
+    }
+    for name, params in want.items():
+        sig = inspect.signature(getattr(se, name))
+        assert list(sig.parameters) == params, name
+    assert inspect.signature(se.weighted_reciprocal_rank_fusion).parameters["k"].default == 50
+    assert inspect.signature(se.similarity_search).parameters["similarity_k"].default == 25
+    assert se(None, None).bm25_search_preprocessed([], None, None, None) == []
+    assert se(None, None).weighted_reciprocal_rank_fusion([], {}) == []
+
+
+def test_shard_ranges_cover_without_overlap():
+    sharded = importlib.import_module("a-nice-rag_b200.sharded")
+    for n in (0, 1, 7, 1_000_000, 100_000_003):
+        for world in (1, 2, 3, 8):
+            spans = [sharded.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_idf_from_counts_matches_okapi(small_case):
+    ix, okapi = csr_from_case(small_case)
+    nd = np.diff(ix.term_ptr)
+    idf = synth.idf_from_counts(len(okapi.doc_freqs), nd, 0.05)
+    np.testing.assert_allclose(idf, ix.idf, rtol=1e-12, atol=1e-15)
