@@ -17,6 +17,8 @@
 //   * at the end the CTA bitonic-sorts its 8 lists per query and writes k
 //     candidates per query; topk_final_kernel (anr_topk.cu) merges the CTAs.
 // Algorithmic HBM bytes: n * ld * 4 per pass (each row read exactly once).
+#include <cstdlib>
+
 #include "anr_internal.h"
 #include "anr_topk.cuh"
 
@@ -201,6 +203,12 @@ static bool make_scan_layout(const DeviceProps& dp, int ld, int nq, int rw, int 
 // keeps shared-memory read traffic under the crossbar limit); few queries want whatever gives
 // the deepest ring (most bytes in flight).
 static int choose_rw(const DeviceProps& dp, int ld, int nq, int k, bool emit_all) {
+  if (const char* force = getenv("ANR_SCAN_RW")) {  // tuning knob for profiling runs
+    const int rw = atoi(force);
+    ScanLayout L;
+    if ((rw == 1 || rw == 2 || rw == 4) && make_scan_layout(dp, ld, nq, rw, k, emit_all, &L))
+      return rw;
+  }
   int best = 0, best_score = -1;
   for (int rw = 4; rw >= 1; rw >>= 1) {
     ScanLayout L;

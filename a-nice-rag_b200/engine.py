@@ -52,6 +52,14 @@ def current_device() -> int:
     return 0
 
 
+def torch_stream_ptr() -> int:
+    """torch's current stream as the ABI's ``stream`` argument.  torch's default stream is the
+    legacy default stream, whose handle is 0 -- which the ABI reads as "use the context's own
+    stream" -- so it is passed as cudaStreamLegacy (0x1) instead."""
+    import torch
+    return torch.cuda.current_stream().cuda_stream or 1
+
+
 def context(device: Optional[int] = None) -> Context:
     device = current_device() if device is None else device
     cache = getattr(_tls, "contexts", None)

@@ -75,7 +75,7 @@ class ShardedHybrid:
         torch's current stream: 2 local searches, 1 all-gather, 1 merge+fuse call."""
         t = self.torch
         ctx = engine.context(self.device.index)
-        stream = t.cuda.current_stream().cuda_stream
+        stream = engine.torch_stream_ptr()
         buf = self._buffers(b, k, top_n)
         local, gathered = buf["local"], buf["gathered"]
         native.call("anr_dense_search_keys", ctx.handle, self.dense.handle, queries_dev.data_ptr(),

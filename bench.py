@@ -267,7 +267,7 @@ def run_ours(args):
     shard = sharded.ShardedHybrid(dense, bm25, row_base=lo) if world > 1 else None
 
     def step_device(b=B):
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = engine.torch_stream_ptr()
         if world > 1:
             return shard.search(q_dev[:b], t_dev, off_dev, b, TOPK, W_DENSE, W_BM25, WRRF_K, TOPK)
         native.call("anr_hybrid_search", ctx.handle, dense.handle, bm25.handle, q_dev.data_ptr(),
@@ -278,7 +278,7 @@ def run_ours(args):
 
     def step_e2e(b=B):
         """Host buffers in, host buffers out (the call synchronises before returning)."""
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = engine.torch_stream_ptr()
         if world > 1:
             qd = q_pin[:b].to(device, non_blocking=True)
             td = t_pin.to(device, non_blocking=True)
