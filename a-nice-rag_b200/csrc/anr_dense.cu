@@ -67,9 +67,9 @@ dense_scan_kernel(const float* __restrict__ emb, int64_t n, int ld, const float*
   if (warp == kScanConsumerWarps) {
     // ---- producer: one lane feeds the ring ----
     if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
       for (int64_t it = 0; it < my_tiles; ++it) {
-        const int s = static_cast<int>(it % L.n_stages);
-        const uint32_t ph = static_cast<uint32_t>(it / L.n_stages) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
         const int64_t row0 = (blockIdx.x + it * gridDim.x) * RW;
         const int64_t left = n - row0;
@@ -77,16 +77,19 @@ dense_scan_kernel(const float* __restrict__ emb, int64_t n, int ld, const float*
         const uint32_t bytes = static_cast<uint32_t>(rows) * ld * 4u;
         mbar_arrive_expect_tx(&full[s], bytes);
         bulk_g2s(ring + static_cast<size_t>(s) * L.stage_floats, emb + row0 * ld, bytes, &full[s]);
+        if (++s == L.n_stages) { s = 0; ph ^= 1u; }
       }
     }
   } else {
     // ---- consumers: warp w owns local tiles it = w, w + n_cwarps, ... ----
-    uint64_t thr[NQ];
-#pragma unroll
-    for (int qi = 0; qi < NQ; ++qi) thr[qi] = 0;
+    uint64_t thr = 0;  // this warp's k-th best key so far for THIS LANE's query (see below)
+    // stage of local tile it is it % n_stages; n_stages is a multiple of n_cwarps, so warp w
+    // only ever sees stages w, w + n_cwarps, ... and the parity flips when that walk wraps
+    int s = warp - L.n_cwarps;
+    uint32_t ph = 0;
     for (int64_t it = warp; warp < L.n_cwarps && it < my_tiles; it += L.n_cwarps) {
-      const int s = static_cast<int>(it % L.n_stages);
-      const uint32_t ph = static_cast<uint32_t>(it / L.n_stages) & 1u;
+      s += L.n_cwarps;
+      if (s >= L.n_stages) { s -= L.n_stages; ph ^= 1u; }
       const float* tile = ring + static_cast<size_t>(s) * L.stage_floats;
       const int64_t row0 = (blockIdx.x + it * gridDim.x) * RW;
       const int64_t left = n - row0;
@@ -124,36 +127,36 @@ dense_scan_kernel(const float* __restrict__ emb, int64_t n, int ld, const float*
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
 
-#pragma unroll
-      for (int r = 0; r < RW; ++r)
-#pragma unroll
-        for (int qi = 0; qi < NQ; ++qi) acc[r][qi] = warp_sum(acc[r][qi]);  // same value in all lanes
-
-#pragma unroll
-      for (int r = 0; r < RW; ++r) {
-        if (r >= rows) continue;
-        const int64_t gi = row0 + r;
-        if (EMIT_ALL) {
+      // V = RW * NQ partial sums per lane -> ONE finished score per lane: lane l ends up with
+      // the warp total of (row r, query qi) = divmod(l / G, NQ), replicated over G = 32 / V lanes
+      constexpr int V = RW * NQ;
+      constexpr int G = 32 / V;
+      const float total = warp_transpose_reduce<V>(&acc[0][0], lane);
+      const int idx = lane / G;
+      const int r = idx / NQ, qi = idx % NQ;
+      const int64_t gi = row0 + r;
+      const bool leader = (lane % G) == 0 && r < rows;
+      if (EMIT_ALL) {
+        if (leader) {
           bool ok = true;
           if (mask) ok = (__ldg(mask + (gi >> 5)) >> (gi & 31)) & 1u;
-          if (lane == 0) {
-#pragma unroll
-            for (int qi = 0; qi < NQ; ++qi)
-              out[qi * out_stride_q + gi] =
-                  ok ? make_key(acc[r][qi], static_cast<uint32_t>(gi)) : 0ull;
-          }
-        } else {
-          int eligible = -1;  // -1 unknown, 0 masked out, 1 eligible
-#pragma unroll
-          for (int qi = 0; qi < NQ; ++qi) {
-            const uint64_t key = make_key(acc[r][qi], static_cast<uint32_t>(gi));
-            if (key > thr[qi]) {  // warp-uniform
-              if (eligible < 0)
-                eligible = mask ? static_cast<int>((__ldg(mask + (gi >> 5)) >> (gi & 31)) & 1u) : 1;
-              if (eligible)
-                thr[qi] = warp_list_insert(lists + qi * L.list_cap + warp * k, k, key, lane);
-            }
-          }
+          out[qi * out_stride_q + gi] = ok ? make_key(total, static_cast<uint32_t>(gi)) : 0ull;
+        }
+      } else {
+        const uint64_t key = leader ? make_key(total, static_cast<uint32_t>(gi)) : 0ull;
+        unsigned pending = __ballot_sync(kFullMask, key > thr);
+        while (pending) {  // rare: almost every score is rejected by the compare above
+          const int src = __ffs(pending) - 1;
+          pending &= pending - 1;
+          const uint64_t cand = __shfl_sync(kFullMask, key, src);
+          const uint64_t cur = __shfl_sync(kFullMask, thr, src);
+          if (cand <= cur) continue;  // an earlier insert of this pass raised the bar
+          const uint32_t row = key_id(cand);
+          if (mask && !((__ldg(mask + (row >> 5)) >> (row & 31)) & 1u)) continue;
+          const int sq = (src / G) % NQ;
+          const uint64_t nt =
+              warp_list_insert_cold(lists + sq * L.list_cap + warp * k, k, cand, lane);
+          if (qi == sq) thr = nt;
         }
       }
     }
@@ -199,9 +202,7 @@ static bool make_scan_layout(const DeviceProps& dp, int ld, int nq, int rw, int 
   return L->total_bytes <= dp.max_smem_optin;
 }
 
-// Rows per stage: many queries want RW = 4 (each staged query word is reused by 4 rows, which
-// keeps shared-memory read traffic under the crossbar limit); few queries want whatever gives
-// the deepest ring (most bytes in flight).
+// Rows per stage.
 static int choose_rw(const DeviceProps& dp, int ld, int nq, int k, bool emit_all) {
   if (const char* force = getenv("ANR_SCAN_RW")) {  // tuning knob for profiling runs
     const int rw = atoi(force);
@@ -209,24 +210,17 @@ static int choose_rw(const DeviceProps& dp, int ld, int nq, int k, bool emit_all
     if ((rw == 1 || rw == 2 || rw == 4) && make_scan_layout(dp, ld, nq, rw, k, emit_all, &L))
       return rw;
   }
-  int best = 0, best_score = -1;
+  // measured on B200 (profiles/): 16 KB bulk copies (RW = 4 at D = 1024) with 8 stages reach
+  // 7.1 TB/s, 8 KB copies with 24 stages 5.9 TB/s, 4 KB copies 3.0 TB/s -> largest RW that
+  // still leaves one stage per consumer warp
+  int fallback = 0;
   for (int rw = 4; rw >= 1; rw >>= 1) {
     ScanLayout L;
     if (!make_scan_layout(dp, ld, nq, rw, k, emit_all, &L)) continue;
-    int score = L.n_stages >= 16 ? 2 : L.n_stages >= 8 ? 1 : 0;
-    if (nq >= 4 && rw == 4 && L.n_stages >= 8) score = 3;
-    if (score > best_score) { best_score = score; best = rw; }
+    if (L.n_stages >= kScanConsumerWarps) return rw;
+    if (!fallback) fallback = rw;
   }
-  return best;
-}
-
-int dense_scan_max_grid(const DeviceProps& dp) { return dp.sm_count; }
-
-int dense_scan_max_queries(const DeviceProps& dp, int ld, int k, bool emit_all) {
-  ScanLayout L;
-  for (int nq = 8; nq >= 1; nq >>= 1)
-    if (make_scan_layout(dp, ld, nq, 1, k, emit_all, &L)) return nq;
-  return 0;
+  return fallback;
 }
 
 template <int NQ, int RW, bool EMIT_ALL>

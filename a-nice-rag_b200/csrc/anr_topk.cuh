@@ -38,6 +38,36 @@ __device__ __forceinline__ uint64_t warp_list_insert(uint64_t* list, int k, uint
   return warp_min_u64(nm);
 }
 
+// Out-of-line copy for hot loops: keeps the rarely taken insert path out of the instruction
+// stream of the scan (32 inlined copies made the dense scan I-cache bound, see profiles/).
+static __device__ __noinline__ uint64_t warp_list_insert_cold(uint64_t* list, int k, uint64_t key,
+                                                       int lane) {
+  return warp_list_insert(list, k, key, lane);
+}
+
+// V partial sums per lane -> one warp total per lane: after log2(V) exchange stages lane l
+// holds the total of element l / (32 / V) (V - 1 shuffles instead of 5 * V), the remaining
+// stages are a plain butterfly inside each group of 32 / V lanes.
+template <int V>
+__device__ __forceinline__ float warp_transpose_reduce(float* v, int lane) {
+  static_assert(V == 1 || V == 2 || V == 4 || V == 8 || V == 16 || V == 32, "V must divide 32");
+  int o = 16;
+#pragma unroll
+  for (int c = V; c > 1; c >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < c / 2; ++j) {
+      const float send = upper ? v[j] : v[j + c / 2];
+      const float keep = upper ? v[j + c / 2] : v[j];
+      v[j] = keep + __shfl_xor_sync(kFullMask, send, o);
+    }
+    o >>= 1;
+  }
+  float total = v[0];
+  for (; o > 0; o >>= 1) total += __shfl_xor_sync(kFullMask, total, o);
+  return total;
+}
+
 // Lanes hold DIFFERENT candidate keys: insert every lane's key that beats thr.
 __device__ __forceinline__ void warp_list_offer(uint64_t* list, int k, uint64_t my_key,
                                                 uint64_t& thr, int lane) {
