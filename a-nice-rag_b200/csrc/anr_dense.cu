@@ -223,6 +223,15 @@ static int choose_rw(const DeviceProps& dp, int ld, int nq, int k, bool emit_all
   return fallback;
 }
 
+int dense_scan_max_grid(const DeviceProps& dp) { return dp.sm_count; }
+
+int dense_scan_max_queries(const DeviceProps& dp, int ld, int k, bool emit_all) {
+  ScanLayout L;
+  for (int nq = 8; nq >= 1; nq >>= 1)
+    if (make_scan_layout(dp, ld, nq, 1, k, emit_all, &L)) return nq;
+  return 0;
+}
+
 template <int NQ, int RW, bool EMIT_ALL>
 static cudaError_t launch_scan_t(const DeviceProps& dp, const float* emb, int64_t n, int ld,
                                  const float* q_dev, int k, const uint32_t* mask, uint64_t* out,
