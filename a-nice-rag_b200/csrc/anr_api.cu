@@ -62,6 +62,9 @@ struct anr_dense {
   int32_t d = 0;
   int32_t ld = 0;  // leading dimension in floats (d rounded up to a multiple of 4)
   bool owned = true;
+  // max row norm, for the tf32 error bound of the tensor-core scan (computed on first need)
+  mutable float norm_max = 0.f;
+  mutable bool norm_valid = false;
 };
 
 struct anr_bm25 {
@@ -233,9 +236,25 @@ cudaError_t out_flush(const OutBuf<T>& o, cudaStream_t stream, bool* any_host) {
 
 // ---- dense top-k pipeline on device buffers -----------------------------------------
 // q_dev: [pad_queries(nq), ld].  Writes results through `out`.
+// More queries than one pass of the CUDA-core scan takes -> tensor-core scan (when the shape
+// fits it): 32 queries per pass over the corpus instead of 8.
+inline bool dense_use_tc(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
+  return nq > 8 && k <= kMaxFusedK && dense_tc_supported(ctx->dp, ix->n, ix->ld, k);
+}
+inline int dense_padded_queries(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
+  if (dense_use_tc(ctx, ix, nq, k)) {
+    const int p = dense_tc_queries_per_pass();
+    return (nq + p - 1) / p * p;
+  }
+  return pad_queries(nq, std::max(dense_group(ctx, ix, k), 1));
+}
+
 size_t dense_ws_bytes(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
   const int gmax = std::max(dense_group(ctx, ix, k), 1);
   const int nqp = pad_queries(nq, gmax);
+  if (dense_use_tc(ctx, ix, nq, k))
+    return padded(dense_tc_cand_keys(ctx->dp, k) * 8) + padded(static_cast<size_t>(nq) * 4) +
+           padded(static_cast<size_t>(dense_scan_max_grid(ctx->dp)) * k * 8) + 1024;
   if (k <= kMaxFusedK)
     return padded(static_cast<size_t>(nqp) * dense_scan_max_grid(ctx->dp) * k * 8) + 256;
   const int64_t n_pow2 = next_pow2(static_cast<int>(std::max<int64_t>(ix->n, 2)));
@@ -248,6 +267,51 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
                    cudaStream_t stream) {
   const int gmax = dense_group(ctx, ix, k);
   if (gmax < 1) return fail(ANR_ERR_UNSUPPORTED, "embedding rows too long for the scan kernel");
+  if (dense_use_tc(ctx, ix, nq, k)) {
+    if (!ix->norm_valid) {  // once per index: the error bound needs max |row|
+      float* d_norm = arena.take<float>(1);
+      ANR_CUDA(launch_row_norm_max(ix->emb, ix->n, ix->ld, d_norm, stream));
+      ANR_CUDA(cudaMemcpyAsync(&ix->norm_max, d_norm, 4, cudaMemcpyDeviceToHost, stream));
+      ANR_CUDA(cudaStreamSynchronize(stream));
+      ix->norm_valid = true;
+    }
+    const int per = dense_tc_queries_per_pass();
+    uint64_t* tc_cand = arena.take<uint64_t>(dense_tc_cand_keys(ctx->dp, k));
+    int32_t* flags = arena.take<int32_t>(static_cast<size_t>(nq));
+    for (int q0 = 0; q0 < nq; q0 += per) {
+      TopkOut o = out;
+      if (o.keys) o.keys += q0 * out.stride_q;
+      if (o.scores) o.scores += q0 * out.stride_q;
+      if (o.ids) o.ids += q0 * out.stride_q;
+      if (o.counts) o.counts += q0 * out.count_stride;
+      ProfileScope prof(ctx, 0, stream);
+      ANR_CUDA(launch_dense_tc(ctx->dp, ix->emb, ix->n, ix->ld,
+                               q_dev + static_cast<size_t>(q0) * ix->ld, std::min(per, nq - q0), k,
+                               mask_dev, ix->norm_max, tc_cand, o, flags + q0, stream));
+    }
+    // queries whose candidate lists could not prove exactness go through the exact scan
+    std::vector<int32_t> host_flags(static_cast<size_t>(nq));
+    ANR_CUDA(cudaMemcpyAsync(host_flags.data(), flags, static_cast<size_t>(nq) * 4,
+                             cudaMemcpyDeviceToHost, stream));
+    ANR_CUDA(cudaStreamSynchronize(stream));
+    const int64_t stride = static_cast<int64_t>(dense_scan_max_grid(ctx->dp)) * k;
+    uint64_t* cand = nullptr;
+    for (int q = 0; q < nq; ++q) {
+      if (!host_flags[q]) continue;
+      if (!cand) cand = arena.take<uint64_t>(static_cast<size_t>(stride));
+      int grid = 0;
+      ANR_CUDA(launch_dense_scan_topk(ctx->dp, ix->emb, ix->n, ix->ld,
+                                      q_dev + static_cast<size_t>(q) * ix->ld, 1, k, mask_dev, cand,
+                                      stride, &grid, stream));
+      TopkOut o = out;
+      if (o.keys) o.keys += q * out.stride_q;
+      if (o.scores) o.scores += q * out.stride_q;
+      if (o.ids) o.ids += q * out.stride_q;
+      if (o.counts) o.counts += q * out.count_stride;
+      ANR_CUDA(launch_topk_final(cand, stride, grid * k, grid * k, 0, 1, k, o, stream));
+    }
+    return ANR_OK;
+  }
   const int nqp = pad_queries(nq, gmax);
   if (k <= kMaxFusedK) {
     const int64_t stride = static_cast<int64_t>(dense_scan_max_grid(ctx->dp)) * k;
@@ -349,9 +413,8 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
 }
 
 // Stage the query matrix: returns a device [pad_queries(nq), ld] zero-padded copy.
-int stage_queries(const anr_dense* ix, const float* queries, int nq, int gmax, Arena& arena,
+int stage_queries(const anr_dense* ix, const float* queries, int nq, int nqp, Arena& arena,
                   cudaStream_t stream, const float** q_dev) {
-  const int nqp = pad_queries(nq, std::max(gmax, 1));
   float* q = arena.take<float>(static_cast<size_t>(nqp) * ix->ld);
   if (nqp != nq || ix->ld != ix->d)
     ANR_CUDA(cudaMemsetAsync(q, 0, static_cast<size_t>(nqp) * ix->ld * 4, stream));
@@ -367,7 +430,7 @@ int stage_queries(const anr_dense* ix, const float* queries, int nq, int gmax, A
   return ANR_OK;
 }
 size_t stage_queries_bytes(const anr_dense* ix, int nq) {
-  return padded(static_cast<size_t>(nq + 8) * ix->ld * 4) + 256;
+  return padded(static_cast<size_t>(nq + 32) * ix->ld * 4) + 256;
 }
 
 // Stage a bit mask ([ceil(n/32)] words) if it lives on the host.
@@ -571,6 +634,7 @@ int anr_dense_upload(anr_ctx* ctx, anr_dense* index, int64_t row0, const float* 
   if (row0 < 0 || n_rows < 0 || row0 + n_rows > index->n)
     return fail(ANR_ERR_INVALID, "anr_dense_upload: row range out of bounds");
   DeviceGuard guard(ctx->dp.device);
+  index->norm_valid = false;
   ANR_CUDA(copy_rows(index->emb + static_cast<size_t>(row0) * index->ld, index->ld, rows, index->d,
                      n_rows, ctx->stream));
   // the source may be a pageable/pinned buffer the caller is about to reuse
@@ -628,7 +692,8 @@ static int dense_search_impl(anr_ctx* ctx, const anr_dense* index, const float* 
   } else {
     const float* q_dev = nullptr;
     const uint32_t* mask_dev = nullptr;
-    if (int rc = stage_queries(index, queries, nq, dense_group(ctx, index, k), arena, stream, &q_dev)) return rc;
+    if (int rc = stage_queries(index, queries, nq, dense_padded_queries(ctx, index, nq, k), arena, stream,
+                              &q_dev)) return rc;
     if (int rc = stage_mask(row_mask, index->n, arena, stream, &mask_dev)) return rc;
     if (int rc = dense_pipeline(ctx, index, q_dev, nq, k, mask_dev, arena, out, stream)) return rc;
   }
@@ -972,8 +1037,8 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
   const uint32_t* row_mask_dev = nullptr;
   const uint32_t* doc_mask_dev = nullptr;
   QueryTerms qt;
-  if (int rc = stage_queries(dense, queries, nq, dense_group(ctx, dense, k_dense), arena, stream,
-                              &q_dev)) return rc;
+  if (int rc = stage_queries(dense, queries, nq, dense_padded_queries(ctx, dense, nq, k_dense),
+                              arena, stream, &q_dev)) return rc;
   if (int rc = stage_mask(row_mask, dense->n, arena, stream, &row_mask_dev)) return rc;
   if (int rc = stage_terms(q_terms, q_offsets, nq, arena, stream, &qt)) return rc;
   if (int rc = stage_mask(doc_mask, bm25->n_docs, arena, stream, &doc_mask_dev)) return rc;

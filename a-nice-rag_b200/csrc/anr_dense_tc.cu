@@ -1,0 +1,497 @@
+// Dense inner-product scan for LARGE query batches on the 5th-generation tensor cores.
+//
+// At more than a few queries per pass the scan stops being a memory-bound matrix-vector
+// product (anr_dense.cu) and becomes a dense contraction  S[rows, queries] = E · Qᵀ.  This
+// kernel computes it with tcgen05.mma.kind::tf32 directly on the fp32 corpus -- the tensor
+// core reads the fp32 words as tf32 (10-bit mantissa), so no shadow copy of the corpus is
+// needed and HBM traffic stays at rows x D x 4 bytes per pass of 32 queries -- and never
+// writes the score matrix: the epilogue reads the accumulator tile from TMEM, rejects almost
+// every score with one compare against a running per-(warp, query) threshold and keeps a short
+// candidate list per query.  tf32 scores are only used to NOMINATE candidates: the rescoring
+// kernel below recomputes every candidate within a rigorous error margin of the k-th best in
+// exact fp32 and ranks on those scores, and flags a query for the exact scan when a candidate
+// list could have dropped a row inside the margin (so results equal the exact path's).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0    TMA producer: 2-D tensor-map loads (SWIZZLE_128B) of [128 rows x 32 floats] corpus
+//             boxes into a ring; the 32 x D query block is loaded once and stays resident
+//   warp 1    allocates TMEM, then one elected lane issues 4 x (M=128, N=32, K=8) MMAs per box
+//             and commits them to the ring's "empty" barriers / the accumulator "full" barrier
+//   warps 2-5 epilogue: tcgen05.ld of the finished accumulator (lane = corpus row, column =
+//             query), candidate selection; two accumulators so tile t+1 runs under it
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "anr_internal.h"
+#include "anr_topk.cuh"
+
+namespace anr {
+
+constexpr int kTcRows = 128;        // corpus rows per tile = UMMA M
+constexpr int kTcQueries = 32;      // queries per pass = UMMA N
+constexpr int kTcSlab = 32;         // floats per K slab = one 128-byte swizzle row
+constexpr int kTcThreads = 192;     // producer warp, MMA warp, 4 epilogue warps
+constexpr int kTcEpiWarps = 4;
+constexpr int kTcMaxStages = 8;
+constexpr int kTcABytes = kTcRows * kTcSlab * 4;      // 16 KB per stage
+constexpr int kTcBSlabBytes = kTcQueries * kTcSlab * 4;  // 4 KB per query slab
+
+// instruction descriptor: D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both
+// K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28
+constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) |
+                              (static_cast<uint32_t>(kTcQueries >> 3) << 17) |
+                              (static_cast<uint32_t>(kTcRows >> 4) << 24);
+
+struct TcLayout {
+  int b_off, ring_off, list_off, bar_off, total_bytes;
+  int n_stages, n_slabs, kl;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+      "{%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: start >> 4 | LBO (unused, 1) << 16 |
+// SBO (8 rows x 128 B = 1024 B) >> 4 << 32 | version 1 << 46 | layout SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) |
+         (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(kTcIdesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// ---- the scan --------------------------------------------------------------------------
+// cand: [kTcQueries][grid][kTcEpiWarps][kl] keys with tf32 scores (0 = empty slot)
+__global__ void __launch_bounds__(kTcThreads, 1)
+dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                int64_t n, const uint32_t* __restrict__ mask, uint64_t* __restrict__ cand,
+                TcLayout L) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* b_smem = smem + L.b_off;       // n_slabs x [32 queries x 128 B], swizzled
+  unsigned char* ring = smem + L.ring_off;      // n_stages x [128 rows x 128 B], swizzled
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + L.list_off);  // [4 warps][32 queries][kl]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* empty = full + kTcMaxStages;
+  uint64_t* b_full = empty + kTcMaxStages;
+  uint64_t* acc_full = b_full + 1;              // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (n + kTcRows - 1) / kTcRows;
+  const int64_t my_tiles =
+      n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  for (int i = threadIdx.x; i < kTcEpiWarps * kTcQueries * L.kl; i += blockDim.x) lists[i] = 0ull;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < L.n_stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(b_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], kTcEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {  // 64 TMEM columns: two 128 x 32 fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(64)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- TMA producer ----
+    if (lane == 0) {
+      mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(L.n_slabs) * kTcBSlabBytes);
+      for (int kb = 0; kb < L.n_slabs; ++kb)
+        tma_load_2d(b_smem + static_cast<size_t>(kb) * kTcBSlabBytes, &map_b, kb * kTcSlab, 0,
+                    b_full);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int row0 = static_cast<int>((blockIdx.x + it * gridDim.x) * kTcRows);
+        for (int kb = 0; kb < L.n_slabs; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], kTcABytes);
+          tma_load_2d(ring + static_cast<size_t>(s) * kTcABytes, &map_a, kb * kTcSlab, row0,
+                      &full[s]);
+          if (++s == L.n_stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ----
+    if (lane == 0) {
+      mbar_wait(b_full, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int a = static_cast<int>(it & 1);
+        const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+        mbar_wait(&acc_empty[a], aph ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(a * kTcQueries);
+        for (int kb = 0; kb < L.n_slabs; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t da = tc_smem_desc(smem_u32(ring + static_cast<size_t>(s) * kTcABytes));
+          const uint64_t db = tc_smem_desc(smem_u32(b_smem + static_cast<size_t>(kb) * kTcBSlabBytes));
+#pragma unroll
+          for (int kk = 0; kk < kTcSlab / 8; ++kk)  // K = 8 tf32 = 32 bytes per MMA
+            tc_mma_tf32(tmem_d, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2),
+                        (kb | kk) != 0 ? 1u : 0u);
+          tc_commit(&empty[s]);  // stage reusable once these MMAs have read it
+          if (++s == L.n_stages) { s = 0; ph ^= 1u; }
+        }
+        tc_commit(&acc_full[a]);  // accumulator complete
+      }
+    }
+  } else {
+    // ---- epilogue: TMEM lane = corpus row, column = query ----
+    const int ew = warp - 2;               // list owner index
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may read
+    uint64_t* my_lists = lists + static_cast<size_t>(ew) * kTcQueries * L.kl;
+    uint64_t thr[kTcQueries];
+#pragma unroll
+    for (int j = 0; j < kTcQueries; ++j) thr[j] = 0ull;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int a = static_cast<int>(it & 1);
+      const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+      mbar_wait(&acc_full[a], aph);
+      tc_fence_after();
+      uint32_t v[32];
+      tc_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                      static_cast<uint32_t>(a * kTcQueries),
+                  v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);
+
+      const int64_t row = (blockIdx.x + it * gridDim.x) * kTcRows + quad * 32 + lane;
+      bool ok = row < n;
+      if (ok && mask) ok = (__ldg(mask + (row >> 5)) >> (row & 31)) & 1u;
+#pragma unroll
+      for (int j = 0; j < kTcQueries; ++j) {
+        const uint64_t key = ok ? make_key(__uint_as_float(v[j]), static_cast<uint32_t>(row)) : 0ull;
+        unsigned pending = __ballot_sync(kFullMask, key > thr[j]);
+        while (pending) {  // rare
+          const int src = __ffs(pending) - 1;
+          pending &= pending - 1;
+          const uint64_t c = __shfl_sync(kFullMask, key, src);
+          if (c > thr[j]) thr[j] = warp_list_insert_cold(my_lists + j * L.kl, L.kl, c, lane);
+        }
+      }
+    }
+    __syncwarp();
+    // lists -> global: cand[q][cta][warp][kl]
+    for (int i = lane; i < kTcQueries * L.kl; i += 32) {
+      const int q = i / L.kl, e = i % L.kl;
+      cand[((static_cast<int64_t>(q) * gridDim.x + blockIdx.x) * kTcEpiWarps + ew) * L.kl + e] =
+          my_lists[i];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64)
+                 : "memory");
+  }
+}
+
+// ---- exact rescoring -----------------------------------------------------------------
+// One CTA per query.  Among the m = grid * 4 * kl nominated candidates: T = k-th best tf32
+// score; every candidate with tf32 score >= T - 2*eps is rescored in exact fp32 (eps bounds
+// |tf32 score - exact score|), the exact top-k is emitted.  flags[q] = 1 when exactness cannot be
+// guaranteed from the lists (a full list whose minimum lies inside the margin may have dropped
+// a relevant row, or more than kTcRescoreCap candidates fall inside the margin): the caller
+// then reruns that query through the exact scan.
+constexpr int kTcRescoreCap = 2048;
+constexpr int kTcRescoreThreads = 512;
+
+__global__ void __launch_bounds__(kTcRescoreThreads)
+dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
+                        const float* __restrict__ emb, int ld, const float* __restrict__ q_dev,
+                        int k, float emb_norm_max, TopkOut o, int32_t* __restrict__ flags) {
+  __shared__ uint64_t top[1024];                 // warp lists for the tf32 top-k (32 warps x k<=32)
+  __shared__ uint64_t sel[kTcRescoreCap];        // candidates inside the margin, then exact keys
+  __shared__ int n_sel, bad;
+  __shared__ float q_norm2;
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_warps = kTcRescoreThreads / 32;
+  const uint64_t* c = cand + static_cast<int64_t>(q) * n_lists * kl;
+  const int m = n_lists * kl;
+  const float* qv = q_dev + static_cast<size_t>(q) * ld;
+
+  if (threadIdx.x == 0) { n_sel = 0; bad = 0; q_norm2 = 0.f; }
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) top[i] = 0ull;
+  __syncthreads();
+  // |q|^2
+  float part = 0.f;
+  for (int i = threadIdx.x; i < ld; i += blockDim.x) part = fmaf(qv[i], qv[i], part);
+  part = warp_sum(part);
+  if (lane == 0) atomicAdd(&q_norm2, part);
+  // tf32 top-k over all candidates (threshold lists per warp, then one sort)
+  {
+    uint64_t thr = 0;
+    uint64_t* list = top + warp * k;
+    for (int base = warp * 32; base < m; base += kTcRescoreThreads) {
+      const int i = base + lane;
+      warp_list_offer(list, k, i < m ? c[i] : 0ull, thr, lane);
+    }
+  }
+  const int p2 = next_pow2(n_warps * k);
+  block_bitonic_sort_desc(top, p2);   // top[0..k) = best k by tf32 score
+  const uint64_t kth = top[k - 1];
+  // error bound of a tf32 product sum: each operand loses < 2^-10 relative (13 mantissa bits
+  // dropped), accumulation noise D * 2^-22 -> |err| <= 2.5e-3 * |q| * |e| (Cauchy-Schwarz)
+  const float eps = 2.5e-3f * sqrtf(q_norm2) * emb_norm_max;
+  // fewer than k candidates exist at all: everything nominated is rescored
+  const float cut = kth ? key_score(kth) - 2.f * eps : -INFINITY;
+  __syncthreads();
+  for (int l = threadIdx.x; l < n_lists; l += blockDim.x) {   // could a list have dropped a row?
+    uint64_t mn = ~0ull;
+    for (int e = 0; e < kl; ++e) {
+      const uint64_t v = c[static_cast<int64_t>(l) * kl + e];
+      mn = v < mn ? v : mn;
+    }
+    if (mn != 0ull && key_score(mn) >= cut) bad = 1;
+  }
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const uint64_t v = c[i];
+    if (v != 0ull && key_score(v) >= cut) {
+      const int slot = atomicAdd(&n_sel, 1);
+      if (slot < kTcRescoreCap) sel[slot] = v;
+    }
+  }
+  __syncthreads();
+  int ns = n_sel;
+  if (ns > kTcRescoreCap) {
+    if (threadIdx.x == 0) bad = 1;
+    ns = kTcRescoreCap;
+  }
+  // exact fp32 inner products, one warp per candidate
+  for (int i = warp; i < ns; i += n_warps) {
+    const uint32_t row = key_id(sel[i]);
+    const float* e = emb + static_cast<size_t>(row) * ld;
+    float acc = 0.f;
+    for (int col = lane * 4; col < ld; col += 128) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(e + col));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(qv + col));
+      acc = fmaf(a.x, b.x, acc);
+      acc = fmaf(a.y, b.y, acc);
+      acc = fmaf(a.z, b.z, acc);
+      acc = fmaf(a.w, b.w, acc);
+    }
+    acc = warp_sum(acc);
+    __syncwarp();
+    if (lane == 0) sel[i] = make_key(acc, row);
+  }
+  __syncthreads();
+  const int sp2 = next_pow2(ns < 2 ? 2 : ns);
+  for (int i = ns + threadIdx.x; i < sp2; i += blockDim.x) sel[i] = 0ull;
+  block_bitonic_sort_desc(sel, sp2);
+  uint64_t key = 0ull;
+  if (threadIdx.x < k) {
+    key = threadIdx.x < ns ? sel[threadIdx.x] : 0ull;
+    const int64_t slot = q * o.stride_q + threadIdx.x;
+    const bool valid = key != 0ull;
+    const uint32_t id = key_id(key);
+    const uint32_t out_id =
+        valid ? (o.id_map ? static_cast<uint32_t>(o.id_map[id]) : static_cast<uint32_t>(id + o.id_base))
+              : 0u;
+    if (o.keys) o.keys[slot] = valid ? ((key & 0xffffffff00000000ull) | (0xffffffffu - out_id)) : 0ull;
+    if (o.scores) o.scores[slot] = valid ? key_score(key) : 0.f;
+    if (o.ids) o.ids[slot] = valid ? static_cast<int32_t>(out_id) : -1;
+  }
+  const int cnt = __syncthreads_count(key != 0ull);
+  if (threadIdx.x == 0) {
+    if (o.counts) o.counts[q * o.count_stride] = cnt;
+    flags[q] = bad;
+  }
+}
+
+// max |row| over the corpus (for the error bound); result in *out (must be zeroed first)
+__global__ void __launch_bounds__(256)
+row_norm_max_kernel(const float* __restrict__ emb, int64_t n, int ld, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float best = 0.f;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < n;
+       row += static_cast<int64_t>(gridDim.x) * 8) {
+    const float* e = emb + row * ld;
+    float acc = 0.f;
+    for (int col = lane * 4; col < ld; col += 128) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(e + col));
+      acc = fmaf(a.x, a.x, acc);
+      acc = fmaf(a.y, a.y, acc);
+      acc = fmaf(a.z, a.z, acc);
+      acc = fmaf(a.w, a.w, acc);
+    }
+    acc = warp_sum(acc);
+    best = fmaxf(best, acc);
+  }
+  // non-negative floats order like their bit patterns
+  if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(best)));
+}
+
+cudaError_t launch_row_norm_max(const float* emb, int64_t n, int ld, float* out,
+                                cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(out, 0, 4, stream);
+  if (e != cudaSuccess || n <= 0) return e;
+  int64_t blocks = (n + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  row_norm_max_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(emb, n, ld, out);
+  return cudaGetLastError();
+}
+
+// ---- host side ---------------------------------------------------------------------------
+static inline int tc_align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+static int tc_list_len(int k) {
+  int kl = 16;
+  while (kl < k + 6) kl <<= 1;
+  return kl;
+}
+
+static bool make_tc_layout(const DeviceProps& dp, int ld, int k, TcLayout* L) {
+  if (ld % kTcSlab != 0 || k < 1 || k > 26) return false;
+  L->n_slabs = ld / kTcSlab;
+  L->kl = tc_list_len(k);
+  L->b_off = 0;
+  L->ring_off = tc_align_up(L->n_slabs * kTcBSlabBytes, 1024);
+  const int list_bytes = kTcEpiWarps * kTcQueries * L->kl * 8;
+  const int bar_bytes = (2 * kTcMaxStages + 1 + 4) * 8 + 16;
+  const int avail = dp.max_smem_optin - 1024 /* alignment slack */ - L->ring_off - list_bytes -
+                    bar_bytes - 256;
+  int n_stages = avail / kTcABytes;
+  if (n_stages < 3) return false;
+  if (n_stages > kTcMaxStages) n_stages = kTcMaxStages;
+  L->n_stages = n_stages;
+  L->list_off = L->ring_off + n_stages * kTcABytes;
+  L->bar_off = tc_align_up(L->list_off + list_bytes, 16);
+  L->total_bytes = L->bar_off + bar_bytes;
+  return true;
+}
+
+bool dense_tc_supported(const DeviceProps& dp, int64_t n, int ld, int k) {
+  if (getenv("ANR_DISABLE_TC")) return false;
+  TcLayout L;
+  return n >= kTcRows && n < (1ll << 31) && make_tc_layout(dp, ld, k, &L);
+}
+
+int dense_tc_queries_per_pass() { return kTcQueries; }
+
+size_t dense_tc_cand_keys(const DeviceProps& dp, int k) {
+  return static_cast<size_t>(kTcQueries) * dp.sm_count * kTcEpiWarps * tc_list_len(k);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) ==
+            cudaSuccess &&
+        st == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, ld] (row-major), box [box_rows, 32 floats], 128-byte swizzle.
+static bool encode_map(CUtensorMap* map, const float* base, int64_t rows, int ld, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  const cuuint32_t box[2] = {kTcSlab, static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
+            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// One pass: the 32 queries at q_dev ([32, ld], zero rows for padding) against the whole corpus.
+// Writes candidates to cand (dense_tc_cand_keys keys) and the exact top-k of the first
+// n_real queries through `out` (already offset to the first query), flags[0..n_real).
+cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, int ld,
+                            const float* q_dev, int n_real, int k, const uint32_t* mask,
+                            float emb_norm_max, uint64_t* cand, const TopkOut& out, int32_t* flags,
+                            cudaStream_t stream) {
+  TcLayout L;
+  if (!make_tc_layout(dp, ld, k, &L)) return cudaErrorInvalidConfiguration;
+  CUtensorMap map_a, map_b;
+  if (!encode_map(&map_a, emb, n, ld, kTcRows) || !encode_map(&map_b, q_dev, kTcQueries, ld, kTcQueries))
+    return cudaErrorInvalidValue;
+  const int smem = L.total_bytes + 1024;  // room to align the dynamic base to 1024 bytes
+  cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       smem);
+  if (e != cudaSuccess) return e;
+  const int64_t n_tiles = (n + kTcRows - 1) / kTcRows;
+  const int grid = static_cast<int>(n_tiles < dp.sm_count ? n_tiles : dp.sm_count);
+  // cand is indexed with gridDim.x: clear the slots of CTAs that do not exist
+  dense_tc_kernel<<<grid, kTcThreads, smem, stream>>>(map_a, map_b, n, mask, cand, L);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  dense_tc_rescore_kernel<<<n_real, kTcRescoreThreads, 0, stream>>>(
+      cand, grid * kTcEpiWarps, L.kl, emb, ld, q_dev, k, emb_norm_max, out, flags);
+  return cudaGetLastError();
+}
+
+}  // namespace anr

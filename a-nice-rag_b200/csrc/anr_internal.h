@@ -45,6 +45,20 @@ cudaError_t launch_dense_scan_all(const DeviceProps& dp, const float* emb, int64
                                   const float* q_dev, int nq, const uint32_t* mask,
                                   uint64_t* keys, int64_t keys_stride_q, cudaStream_t stream);
 
+// ---- dense scan on the tensor cores (anr_dense_tc.cu) ---------------------------------------
+// tcgen05 tf32 scan of 32 queries per pass + exact fp32 rescoring of the nominated candidates.
+bool dense_tc_supported(const DeviceProps& dp, int64_t n, int ld, int k);
+int dense_tc_queries_per_pass();
+size_t dense_tc_cand_keys(const DeviceProps& dp, int k);  // scratch keys one pass needs
+cudaError_t launch_row_norm_max(const float* emb, int64_t n, int ld, float* out,
+                                cudaStream_t stream);
+// q_dev: [32, ld] (zero rows pad a short group); results of the first n_real queries go through
+// `out` (positioned at the group's first query); flags[q] = 1 -> rerun q through the exact scan.
+cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, int ld,
+                            const float* q_dev, int n_real, int k, const uint32_t* mask,
+                            float emb_norm_max, uint64_t* cand, const TopkOut& out, int32_t* flags,
+                            cudaStream_t stream);
+
 // ---- top-k ------------------------------------------------------------------
 // Per query: select the best k (<= kMaxFusedK) of m candidate keys, sorted best first.
 // Candidate i of query q is cand[q * cand_stride_q + (i / seg_len) * seg_stride + i % seg_len].

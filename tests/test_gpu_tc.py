@@ -1,0 +1,75 @@
+"""GPU: the tensor-core (tcgen05 tf32 + exact fp32 rescoring) scan used for query batches > 8
+must return what the exact scan returns: same ids up to oracle-score ties, fp32-accurate scores."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from helpers import check_topk, synth
+from oracle import retrieval
+
+pytestmark = pytest.mark.gpu
+engine = importlib.import_module("a-nice-rag_b200.engine")
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    emb = synth.unit_vectors(20_000, 1024, seed=1234)
+    return emb, engine.DenseIndex(emb)
+
+
+@pytest.mark.parametrize("nq", [9, 32, 33, 64, 70])
+@pytest.mark.parametrize("k", [1, 10, 26])
+def test_tc_batches_vs_oracle(corpus, nq, k):
+    emb, index = corpus
+    queries = synth.unit_vectors(nq, 1024, seed=4321 + nq)
+    scores, rows, counts = index.search(queries, k)
+    full = queries @ emb.T
+    for q in range(nq):
+        assert counts[q] == k
+        want_rows, want_scores = retrieval.dense_topk(queries[q], emb, k)
+        check_topk(rows[q], scores[q], want_rows, want_scores, full[q], f"tc nq{nq} k{k} q{q}")
+
+
+def test_tc_with_mask_and_unnormalised_rows():
+    rng = np.random.default_rng(7)
+    emb = (synth.unit_vectors(9_000, 512, seed=3) * rng.uniform(0.2, 6.0, size=(9_000, 1))).astype(np.float32)
+    index = engine.DenseIndex(emb)
+    mask = rng.random(9_000) < 0.6
+    queries = (synth.unit_vectors(40, 512, seed=4) * 3.0).astype(np.float32)
+    scores, rows, counts = index.search(queries, 10, row_mask=engine.pack_mask(mask))
+    for q in range(40):
+        want_rows, want_scores = retrieval.dense_topk(queries[q], emb, 10, mask)
+        check_topk(rows[q], scores[q], want_rows, want_scores, queries[q] @ emb.T, f"tc mask q{q}")
+        assert mask[rows[q]].all()
+
+
+def test_tc_duplicate_cluster_takes_the_exact_fallback():
+    """60 identical adjacent rows overflow one warp's candidate list: the query must be flagged
+    and rerun through the exact scan, whose tie rule (lower row first) decides."""
+    emb = synth.unit_vectors(30_000, 1024, seed=11)
+    emb[5000:5060] = emb[5000]
+    index = engine.DenseIndex(emb)
+    queries = synth.unit_vectors(16, 1024, seed=12)
+    queries[5] = emb[5000]
+    scores, rows, counts = index.search(queries, 10)
+    assert rows[5].tolist() == list(range(5000, 5010))
+    for q in range(16):
+        want_rows, want_scores = retrieval.dense_topk(queries[q], emb, 10)
+        check_topk(rows[q], scores[q], want_rows, want_scores, queries[q] @ emb.T, f"tc dup q{q}")
+
+
+def test_tc_and_scan_paths_agree(corpus):
+    emb, index = corpus
+    queries = synth.unit_vectors(48, 1024, seed=99)
+    s_tc, r_tc, _ = index.search(queries, 10)
+    os.environ["ANR_DISABLE_TC"] = "1"
+    try:
+        s_sc, r_sc, _ = index.search(queries, 10)
+    finally:
+        del os.environ["ANR_DISABLE_TC"]
+    full = queries @ emb.T
+    for q in range(48):
+        check_topk(r_tc[q], s_tc[q], r_sc[q], s_sc[q], full[q], f"tc vs scan q{q}")
+    assert (r_tc == r_sc).mean() > 0.99
