@@ -105,8 +105,8 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
 // cand: [kTcQueries][grid][kTcEpiWarps][kl] keys with tf32 scores (0 = empty slot)
 __global__ void __launch_bounds__(kTcThreads, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                int64_t n, const uint32_t* __restrict__ mask, uint64_t* __restrict__ cand,
-                TcLayout L) {
+                int64_t n, const uint32_t* __restrict__ mask, const uint64_t* __restrict__ thr0,
+                uint64_t* __restrict__ cand, TcLayout L) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* b_smem = smem + L.b_off;       // n_slabs x [32 queries x 128 B], swizzled
   unsigned char* ring = smem + L.ring_off;      // n_stages x [128 rows x 128 B], swizzled
@@ -200,9 +200,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int ew = warp - 2;               // list owner index
     const int quad = warp & 3;             // TMEM lane quadrant this warp may read
     uint64_t* my_lists = lists + static_cast<size_t>(ew) * kTcQueries * L.kl;
+    // starting thresholds from the sample pre-pass (a lower bound of every query's global
+    // kl-th best): without them each warp would insert ~kl * ln(rows / kl) rows per query
     uint64_t thr[kTcQueries];
 #pragma unroll
-    for (int j = 0; j < kTcQueries; ++j) thr[j] = 0ull;
+    for (int j = 0; j < kTcQueries; ++j) thr[j] = thr0 ? thr0[j] : 0ull;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int a = static_cast<int>(it & 1);
       const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
@@ -259,10 +261,37 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 constexpr int kTcRescoreCap = 2048;
 constexpr int kTcRescoreThreads = 512;
 
+// Sample pre-pass: thr0[q] = key that rejects every score <= the kl-th best tf32 score among the
+// sample's candidates.  The kl-th best of a subset never exceeds the kl-th best of the whole
+// corpus, so rows at or below it cannot be among the global top-kl.
+__global__ void __launch_bounds__(kTcRescoreThreads)
+dense_tc_thr_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
+                    uint64_t* __restrict__ thr0) {
+  __shared__ uint64_t top[1024];
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint64_t* c = cand + static_cast<int64_t>(q) * n_lists * kl;
+  const int m = n_lists * kl;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) top[i] = 0ull;
+  __syncthreads();
+  uint64_t thr = 0;
+  uint64_t* list = top + warp * kl;
+  for (int base = warp * 32; base < m; base += kTcRescoreThreads) {
+    const int i = base + lane;
+    warp_list_offer(list, kl, i < m ? c[i] : 0ull, thr, lane);
+  }
+  block_bitonic_sort_desc(top, next_pow2((kTcRescoreThreads / 32) * kl));
+  if (threadIdx.x == 0) {
+    const uint64_t kth = top[kl - 1];
+    thr0[q] = kth ? (kth | 0xffffffffull) : 0ull;
+  }
+}
+
 __global__ void __launch_bounds__(kTcRescoreThreads)
 dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
                         const float* __restrict__ emb, int ld, const float* __restrict__ q_dev,
-                        int k, float emb_norm_max, TopkOut o, int32_t* __restrict__ flags) {
+                        int k, float emb_norm_max, const uint64_t* __restrict__ thr0, TopkOut o,
+                        int32_t* __restrict__ flags) {
   __shared__ uint64_t top[1024];                 // warp lists for the tf32 top-k (32 warps x k<=32)
   __shared__ uint64_t sel[kTcRescoreCap];        // candidates inside the margin, then exact keys
   __shared__ int n_sel, bad;
@@ -300,6 +329,8 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
   // fewer than k candidates exist at all: everything nominated is rescored
   const float cut = kth ? key_score(kth) - 2.f * eps : -INFINITY;
   __syncthreads();
+  // rows rejected by the pre-pass threshold are safe only if that threshold lies below the margin
+  if (threadIdx.x == 0 && thr0 && thr0[q] != 0ull && key_score(thr0[q]) >= cut) bad = 1;
   for (int l = threadIdx.x; l < n_lists; l += blockDim.x) {   // could a list have dropped a row?
     uint64_t mn = ~0ull;
     for (int e = 0; e < kl; ++e) {
@@ -432,8 +463,10 @@ bool dense_tc_supported(const DeviceProps& dp, int64_t n, int ld, int k) {
 
 int dense_tc_queries_per_pass() { return kTcQueries; }
 
+// scratch one pass needs: candidates of the main pass + of the sample pre-pass + thresholds
 size_t dense_tc_cand_keys(const DeviceProps& dp, int k) {
-  return static_cast<size_t>(kTcQueries) * dp.sm_count * kTcEpiWarps * tc_list_len(k);
+  return 2 * static_cast<size_t>(kTcQueries) * dp.sm_count * kTcEpiWarps * tc_list_len(k) +
+         kTcQueries;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -485,12 +518,23 @@ cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, 
   if (e != cudaSuccess) return e;
   const int64_t n_tiles = (n + kTcRows - 1) / kTcRows;
   const int grid = static_cast<int>(n_tiles < dp.sm_count ? n_tiles : dp.sm_count);
-  // cand is indexed with gridDim.x: clear the slots of CTAs that do not exist
-  dense_tc_kernel<<<grid, kTcThreads, smem, stream>>>(map_a, map_b, n, mask, cand, L);
+  const size_t pass_keys = static_cast<size_t>(kTcQueries) * dp.sm_count * kTcEpiWarps * L.kl;
+  uint64_t* cand_sample = cand + pass_keys;
+  uint64_t* thr0 = nullptr;
+  // sample pre-pass over the first tile of every CTA (worth it from ~8 tiles per CTA on)
+  const int64_t n_sample = static_cast<int64_t>(dp.sm_count) * kTcRows;
+  if (n >= 8 * n_sample) {
+    thr0 = cand_sample + pass_keys;
+    dense_tc_kernel<<<dp.sm_count, kTcThreads, smem, stream>>>(map_a, map_b, n_sample, mask,
+                                                               nullptr, cand_sample, L);
+    dense_tc_thr_kernel<<<kTcQueries, kTcRescoreThreads, 0, stream>>>(
+        cand_sample, dp.sm_count * kTcEpiWarps, L.kl, thr0);
+  }
+  dense_tc_kernel<<<grid, kTcThreads, smem, stream>>>(map_a, map_b, n, mask, thr0, cand, L);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dense_tc_rescore_kernel<<<n_real, kTcRescoreThreads, 0, stream>>>(
-      cand, grid * kTcEpiWarps, L.kl, emb, ld, q_dev, k, emb_norm_max, out, flags);
+      cand, grid * kTcEpiWarps, L.kl, emb, ld, q_dev, k, emb_norm_max, thr0, out, flags);
   return cudaGetLastError();
 }
 
