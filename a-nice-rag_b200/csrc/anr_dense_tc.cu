@@ -102,7 +102,10 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // ---- the scan --------------------------------------------------------------------------
-// cand: [kTcQueries][grid][kTcEpiWarps][kl] keys with tf32 scores (0 = empty slot)
+// EMIT = false: cand is [kTcQueries][grid][kTcEpiWarps][kl] candidate keys with tf32 scores
+//               (0 = empty slot), selected above the starting thresholds thr0 (nullable)
+// EMIT = true : cand is [kTcQueries][n] keys of EVERY row (0 = masked), used on a small sample
+template <bool EMIT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 int64_t n, const uint32_t* __restrict__ mask, const uint64_t* __restrict__ thr0,
@@ -224,22 +227,31 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
       for (int j = 0; j < kTcQueries; ++j) {
         const uint64_t key = ok ? make_key(__uint_as_float(v[j]), static_cast<uint32_t>(row)) : 0ull;
+        if (EMIT) {
+          if (row < n) cand[static_cast<int64_t>(j) * n + row] = key;
+          continue;
+        }
         unsigned pending = __ballot_sync(kFullMask, key > thr[j]);
         while (pending) {  // rare
           const int src = __ffs(pending) - 1;
           pending &= pending - 1;
           const uint64_t c = __shfl_sync(kFullMask, key, src);
-          if (c > thr[j]) thr[j] = warp_list_insert_cold(my_lists + j * L.kl, L.kl, c, lane);
+          if (c > thr[j]) {
+            // the list minimum is 0 until the list is full: never let it lower the bar
+            const uint64_t nm = warp_list_insert_cold(my_lists + j * L.kl, L.kl, c, lane);
+            thr[j] = nm > thr[j] ? nm : thr[j];
+          }
         }
       }
     }
     __syncwarp();
     // lists -> global: cand[q][cta][warp][kl]
-    for (int i = lane; i < kTcQueries * L.kl; i += 32) {
-      const int q = i / L.kl, e = i % L.kl;
-      cand[((static_cast<int64_t>(q) * gridDim.x + blockIdx.x) * kTcEpiWarps + ew) * L.kl + e] =
-          my_lists[i];
-    }
+    if (!EMIT)
+      for (int i = lane; i < kTcQueries * L.kl; i += 32) {
+        const int q = i / L.kl, e = i % L.kl;
+        cand[((static_cast<int64_t>(q) * gridDim.x + blockIdx.x) * kTcEpiWarps + ew) * L.kl + e] =
+            my_lists[i];
+      }
   }
 
   tc_fence_before();
@@ -265,13 +277,12 @@ constexpr int kTcRescoreThreads = 512;
 // sample's candidates.  The kl-th best of a subset never exceeds the kl-th best of the whole
 // corpus, so rows at or below it cannot be among the global top-kl.
 __global__ void __launch_bounds__(kTcRescoreThreads)
-dense_tc_thr_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
+dense_tc_thr_kernel(const uint64_t* __restrict__ cand, int m, int kl,
                     uint64_t* __restrict__ thr0) {
   __shared__ uint64_t top[1024];
   const int q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint64_t* c = cand + static_cast<int64_t>(q) * n_lists * kl;
-  const int m = n_lists * kl;
+  const uint64_t* c = cand + static_cast<int64_t>(q) * m;
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) top[i] = 0ull;
   __syncthreads();
   uint64_t thr = 0;
@@ -465,8 +476,8 @@ int dense_tc_queries_per_pass() { return kTcQueries; }
 
 // scratch one pass needs: candidates of the main pass + of the sample pre-pass + thresholds
 size_t dense_tc_cand_keys(const DeviceProps& dp, int k) {
-  return 2 * static_cast<size_t>(kTcQueries) * dp.sm_count * kTcEpiWarps * tc_list_len(k) +
-         kTcQueries;
+  return static_cast<size_t>(kTcQueries) * dp.sm_count * kTcEpiWarps * tc_list_len(k) +
+         static_cast<size_t>(kTcQueries) * dp.sm_count * kTcRows + kTcQueries;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -513,8 +524,11 @@ cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, 
   if (!encode_map(&map_a, emb, n, ld, kTcRows) || !encode_map(&map_b, q_dev, kTcQueries, ld, kTcQueries))
     return cudaErrorInvalidValue;
   const int smem = L.total_bytes + 1024;  // room to align the dynamic base to 1024 bytes
-  cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       smem);
+  cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel<false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(dense_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem);
   if (e != cudaSuccess) return e;
   const int64_t n_tiles = (n + kTcRows - 1) / kTcRows;
   const int grid = static_cast<int>(n_tiles < dp.sm_count ? n_tiles : dp.sm_count);
@@ -524,13 +538,13 @@ cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, 
   // sample pre-pass over the first tile of every CTA (worth it from ~8 tiles per CTA on)
   const int64_t n_sample = static_cast<int64_t>(dp.sm_count) * kTcRows;
   if (n >= 8 * n_sample) {
-    thr0 = cand_sample + pass_keys;
-    dense_tc_kernel<<<dp.sm_count, kTcThreads, smem, stream>>>(map_a, map_b, n_sample, mask,
-                                                               nullptr, cand_sample, L);
+    thr0 = cand_sample + static_cast<size_t>(kTcQueries) * n_sample;
+    dense_tc_kernel<true><<<dp.sm_count, kTcThreads, smem, stream>>>(map_a, map_b, n_sample, mask,
+                                                                     nullptr, cand_sample, L);
     dense_tc_thr_kernel<<<kTcQueries, kTcRescoreThreads, 0, stream>>>(
-        cand_sample, dp.sm_count * kTcEpiWarps, L.kl, thr0);
+        cand_sample, static_cast<int>(n_sample), L.kl, thr0);
   }
-  dense_tc_kernel<<<grid, kTcThreads, smem, stream>>>(map_a, map_b, n, mask, thr0, cand, L);
+  dense_tc_kernel<false><<<grid, kTcThreads, smem, stream>>>(map_a, map_b, n, mask, thr0, cand, L);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dense_tc_rescore_kernel<<<n_real, kTcRescoreThreads, 0, stream>>>(
