@@ -11,9 +11,12 @@
 // most once per term, so within one term the scatter `acc[doc - d0] += idf * w` is
 // conflict-free WITHOUT atomics; terms are processed one after another (query order,
 // duplicates repeated -- the accumulation order of the reference loop) with a CTA
-// barrier between them.  The tile's accumulators are then scanned once through the
-// same threshold-list top-k used by the dense scan; zero-score documents are
-// ordinary candidates (the reference returns them when fewer than k documents match).
+// barrier between them.  Tile top-k without per-row list maintenance: every thread takes the
+// best key of its own documents, the k-th largest of those 256 thread-bests is a lower bound
+// of the tile's k-th best (k distinct documents reach it), a second sweep collects the few
+// documents at or above it (at most k threads can hold any) and one small sort ranks them.
+// Zero-score documents are ordinary candidates (the reference returns them when fewer than k
+// documents match); keys are unique (score, then lower document first), so ties are exact.
 //
 // Algorithmic HBM bytes per query: 8 B per posting of every query-term occurrence
 // (4 B doc id + 4 B precomputed weight) + k*8 B of candidates per tile.
@@ -23,7 +26,6 @@
 namespace anr {
 
 constexpr int kBm25Threads = 256;
-constexpr int kBm25Warps = kBm25Threads / 32;
 constexpr int kBm25TermChunk = 64;  // query terms whose slice bounds are staged at once
 
 // weight[p] = tf*(k1+1) / (tf + k1*(1 - b + b*doc_len/avgdl)), evaluated in float64 in the
@@ -63,10 +65,17 @@ Bm25Plan bm25_make_plan(const DeviceProps& dp, int n_docs, int nq, int k, bool e
   int64_t tile = (static_cast<int64_t>(n_docs) + tiles_wanted - 1) / tiles_wanted;
   if (tile < 1024) tile = 1024;
   if (tile > 12288) tile = 12288;
+  // the collect buffer holds k * ceil(tile / 256) keys at most: keep it <= 2048 entries
+  if (!emit_all && k > 0) {
+    const int64_t per_thread = 2048 / k > 1 ? 2048 / k : 1;
+    if (tile > per_thread * kBm25Threads) tile = per_thread * kBm25Threads;
+  }
   tile = (tile + 31) / 32 * 32;
   p.tile_docs = static_cast<int>(tile);
   p.n_tiles = n_docs > 0 ? static_cast<int>((n_docs + tile - 1) / tile) : 0;
-  p.list_cap = emit_all ? 0 : next_pow2(kBm25Warps * k);
+  const int per_thread = (p.tile_docs + kBm25Threads - 1) / kBm25Threads;
+  p.list_cap = emit_all ? 0 : next_pow2(k * per_thread < 2 * kBm25Threads ? 2 * kBm25Threads
+                                                                           : k * per_thread);
   p.smem_bytes = p.tile_docs * 4 + p.list_cap * 8 + kBm25TermChunk * (8 + 8 + 4);
   return p;
 }
@@ -85,15 +94,12 @@ bm25_score_kernel(Bm25View ix, const int32_t* __restrict__ q_terms,
   float* s_idf = reinterpret_cast<float*>(s_hi + kBm25TermChunk);
 
   const int tile = blockIdx.x, q = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d0 = tile * tile_docs;
   const int d1 = min(ix.n_docs, d0 + tile_docs);
   const int nd = d1 - d0;
   const int t_begin = q_offsets[q], t_end = q_offsets[q + 1];
 
   for (int i = threadIdx.x; i < nd; i += blockDim.x) acc[i] = 0.f;
-  if (!EMIT_ALL)
-    for (int i = threadIdx.x; i < list_cap; i += blockDim.x) lists[i] = 0ull;
 
   for (int c0 = t_begin; c0 < t_end; c0 += kBm25TermChunk) {
     const int nc = min(kBm25TermChunk, t_end - c0);
@@ -153,23 +159,40 @@ bm25_score_kernel(Bm25View ix, const int32_t* __restrict__ q_terms,
     }
     return;
   }
-  uint64_t thr = 0;
-  uint64_t* list = lists + warp * k;
-  for (int base = warp * 32; base < nd; base += kBm25Threads) {
-    const int i = base + lane;
-    uint64_t key = 0ull;
-    if (i < nd) {
-      const int doc = d0 + i;
-      bool ok = true;
-      if (doc_mask) ok = (__ldg(doc_mask + (doc >> 5)) >> (doc & 31)) & 1u;
-      if (ok) key = make_key(acc[i], static_cast<uint32_t>(doc));
+  // ---- tile top-k ----
+  __shared__ int n_sel;
+  uint64_t* tbest = lists;                 // [256] thread-bests, sorted in place
+  uint64_t* sel = lists + kBm25Threads;    // collected keys (list_cap - 256 slots)
+  const int sel_cap = list_cap - kBm25Threads;
+  auto key_of = [&](int i) -> uint64_t {
+    const int doc = d0 + i;
+    if (doc_mask && !((__ldg(doc_mask + (doc >> 5)) >> (doc & 31)) & 1u)) return 0ull;
+    return make_key(acc[i], static_cast<uint32_t>(doc));
+  };
+  uint64_t best = 0ull;
+  for (int i = threadIdx.x; i < nd; i += kBm25Threads) {
+    const uint64_t key = key_of(i);
+    best = key > best ? key : best;
+  }
+  tbest[threadIdx.x] = best;
+  if (threadIdx.x == 0) n_sel = 0;
+  block_bitonic_sort_desc(tbest, kBm25Threads);
+  const uint64_t thr = k <= kBm25Threads ? tbest[k - 1] : 0ull;   // 0: fewer than k threads hold a document
+  __syncthreads();
+  for (int i = threadIdx.x; i < sel_cap; i += kBm25Threads) sel[i] = 0ull;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nd; i += kBm25Threads) {
+    const uint64_t key = key_of(i);
+    if (key != 0ull && key >= thr) {
+      const int slot = atomicAdd(&n_sel, 1);
+      if (slot < sel_cap) sel[slot] = key;   // cannot overflow: <= k threads x ceil(tile / 256) docs
     }
-    warp_list_offer(list, k, key, thr, lane);
   }
   __syncthreads();
-  block_bitonic_sort_desc(lists, list_cap);
+  const int ns = n_sel < sel_cap ? n_sel : sel_cap;
+  block_bitonic_sort_desc(sel, next_pow2(ns < 2 ? 2 : ns));
   for (int i = threadIdx.x; i < k; i += blockDim.x)
-    out[q * out_stride_q + static_cast<int64_t>(tile) * k + i] = lists[i];
+    out[q * out_stride_q + static_cast<int64_t>(tile) * k + i] = i < ns ? sel[i] : 0ull;
 }
 
 template <bool EMIT_ALL>
