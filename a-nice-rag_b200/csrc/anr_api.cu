@@ -243,7 +243,7 @@ inline bool dense_use_tc(const anr_ctx* ctx, const anr_dense* ix, int nq, int k)
 }
 inline int dense_padded_queries(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
   if (dense_use_tc(ctx, ix, nq, k)) {
-    const int p = dense_tc_queries_per_pass();
+    const int p = 2 * dense_tc_queries_per_pass();   // the pair pass reads 64 query rows
     return (nq + p - 1) / p * p;
   }
   return pad_queries(nq, std::max(dense_group(ctx, ix, k), 1));
@@ -278,16 +278,26 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
     const int per = dense_tc_queries_per_pass();
     uint64_t* tc_cand = arena.take<uint64_t>(dense_tc_cand_keys(ctx->dp, k));
     int32_t* flags = arena.take<int32_t>(static_cast<size_t>(nq));
-    for (int q0 = 0; q0 < nq; q0 += per) {
+    const bool pair = dense_tc_pair_enabled() && (ctx->dp.sm_count % 2) == 0;
+    for (int q0 = 0; q0 < nq;) {
       TopkOut o = out;
       if (o.keys) o.keys += q0 * out.stride_q;
       if (o.scores) o.scores += q0 * out.stride_q;
       if (o.ids) o.ids += q0 * out.stride_q;
       if (o.counts) o.counts += q0 * out.count_stride;
       ProfileScope prof(ctx, 0, stream);
-      ANR_CUDA(launch_dense_tc(ctx->dp, ix->emb, ix->n, ix->ld,
-                               q_dev + static_cast<size_t>(q0) * ix->ld, std::min(per, nq - q0), k,
-                               mask_dev, ix->norm_max, tc_cand, o, flags + q0, stream));
+      if (pair && nq - q0 > per) {   // 33..64 queries left: one pass of the CTA-pair kernel
+        ANR_CUDA(launch_dense_tc_pair(ctx->dp, ix->emb, ix->n, ix->ld,
+                                      q_dev + static_cast<size_t>(q0) * ix->ld,
+                                      std::min(2 * per, nq - q0), k, mask_dev, ix->norm_max,
+                                      tc_cand, o, flags + q0, stream));
+        q0 += 2 * per;
+      } else {
+        ANR_CUDA(launch_dense_tc(ctx->dp, ix->emb, ix->n, ix->ld,
+                                 q_dev + static_cast<size_t>(q0) * ix->ld, std::min(per, nq - q0),
+                                 k, mask_dev, ix->norm_max, tc_cand, o, flags + q0, stream));
+        q0 += per;
+      }
     }
     // queries whose candidate lists could not prove exactness go through the exact scan
     std::vector<int32_t> host_flags(static_cast<size_t>(nq));
@@ -430,7 +440,7 @@ int stage_queries(const anr_dense* ix, const float* queries, int nq, int nqp, Ar
   return ANR_OK;
 }
 size_t stage_queries_bytes(const anr_dense* ix, int nq) {
-  return padded(static_cast<size_t>(nq + 32) * ix->ld * 4) + 256;
+  return padded(static_cast<size_t>(nq + 64) * ix->ld * 4) + 256;
 }
 
 // Stage a bit mask ([ceil(n/32)] words) if it lives on the host.
@@ -938,8 +948,8 @@ int anr_wrrf_fuse(anr_ctx* ctx, const int32_t* ids, const int32_t* lens, const d
     return fail(ANR_ERR_INVALID, "anr_wrrf_fuse: NULL argument");
   if (n_lists < 1 || n_lists > 64 || list_stride < 1 || n_queries < 1 || top_n < 1)
     return fail(ANR_ERR_INVALID, "anr_wrrf_fuse: bad shape");
-  if (static_cast<int64_t>(n_lists) * list_stride > wrrf_max_entries())
-    return fail(ANR_ERR_UNSUPPORTED, "anr_wrrf_fuse: more than 8192 entries per query");
+  if (static_cast<int64_t>(n_lists) * list_stride > (1 << 22))
+    return fail(ANR_ERR_UNSUPPORTED, "anr_wrrf_fuse: more than 2^22 entries per query");
   DeviceGuard guard(ctx->dp.device);
   cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
   const size_t n_ids = static_cast<size_t>(n_queries) * n_lists * list_stride;
@@ -947,7 +957,8 @@ int anr_wrrf_fuse(anr_ctx* ctx, const int32_t* ids, const int32_t* lens, const d
   const size_t cells = static_cast<size_t>(n_queries) * top_n;
   const bool ids_host = !is_device_ptr(ids), lens_host = !is_device_ptr(lens),
              w_host = !is_device_ptr(weights);
-  const size_t need = (ids_host ? padded(n_ids * 4) + 256 : 0) +
+  const size_t scratch_keys = wrrf_scratch_keys(n_lists, list_stride, n_queries);
+  const size_t need = (ids_host ? padded(n_ids * 4) + 256 : 0) + padded(scratch_keys * 8) + 256 +
                       (lens_host ? padded(n_lens * 4) + 256 : 0) + (w_host ? 1024 : 0) +
                       out_need(out_ids, cells) + out_need(out_scores, cells) +
                       out_need(out_counts, n_queries);
@@ -975,8 +986,9 @@ int anr_wrrf_fuse(anr_ctx* ctx, const int32_t* ids, const int32_t* lens, const d
   OutBuf<int32_t> o_ids = out_make(arena, out_ids, cells);
   OutBuf<double> o_scores = out_make(arena, out_scores, cells);
   OutBuf<int32_t> o_counts = out_make(arena, out_counts, n_queries);
+  uint64_t* scratch = scratch_keys ? arena.take<uint64_t>(scratch_keys) : nullptr;
   ANR_CUDA(launch_wrrf_fuse(ids_dev, lens_dev, w_dev, n_lists, list_stride, n_queries, rrf_k, top_n,
-                            o_ids.dev, o_scores.dev, o_counts.dev, stream));
+                            scratch, o_ids.dev, o_scores.dev, o_counts.dev, stream));
   bool any_host = false;
   ANR_CUDA(out_flush(o_ids, stream, &any_host));
   ANR_CUDA(out_flush(o_scores, stream, &any_host));
@@ -1062,7 +1074,7 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
   if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k_bm25, doc_mask_dev, arena, ob,
                              stream))
     return rc;
-  ANR_CUDA(launch_wrrf_fuse(lists, lens, w_dev, 2, stride, nq, rrf_k, top_n, o_ids.dev,
+  ANR_CUDA(launch_wrrf_fuse(lists, lens, w_dev, 2, stride, nq, rrf_k, top_n, nullptr, o_ids.dev,
                             o_scores.dev, o_counts.dev, stream));
 
   // optional per-retriever outputs: strided device -> user layout [nq, k]
@@ -1170,8 +1182,8 @@ int anr_sharded_fuse(anr_ctx* ctx, const uint64_t* gathered, int32_t n_parts, in
     ANR_CUDA(launch_topk_final(keys_dev + static_cast<int64_t>(which) * nq * k, k, n_parts * k, k,
                                part_stride, nq, k, out, stream));
   }
-  ANR_CUDA(launch_wrrf_fuse(lists, lens, w_dev, 2, k, nq, rrf_k, top_n, o_ids.dev, o_scores.dev,
-                            o_counts.dev, stream));
+  ANR_CUDA(launch_wrrf_fuse(lists, lens, w_dev, 2, k, nq, rrf_k, top_n, nullptr, o_ids.dev,
+                            o_scores.dev, o_counts.dev, stream));
   bool any_host = false;
   ANR_CUDA(out_flush(o_ids, stream, &any_host));
   ANR_CUDA(out_flush(o_scores, stream, &any_host));

@@ -263,6 +263,189 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
 }
 
+// ---- 64 queries per pass: a CTA pair shares every corpus tile --------------------------------
+// Cluster of 2 CTAs.  Rank r keeps queries [32r, 32r + 32) resident and runs its own MMAs,
+// accumulators and epilogue exactly like dense_tc_kernel, but each corpus box is fetched from
+// HBM ONCE per pair: rank r loads rows [64r, 64r + 64) of the box and the TMA multicasts them
+// into BOTH CTAs' rings, so HBM traffic per query halves.  A stage may be refilled only after
+// both CTAs' MMAs have read it: every commit arrives on the "empty" barrier of both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* map, int c0,
+                                                  int c1, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
+// map_a: box [64 rows x 32 floats]; map_b: [64 queries, ld], box [32 x 32].
+// cand: [64 queries][n_clusters][kTcEpiWarps][kl]
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+dense_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a,
+                     const __grid_constant__ CUtensorMap map_b, int64_t n,
+                     const uint32_t* __restrict__ mask, const uint64_t* __restrict__ thr0,
+                     uint64_t* __restrict__ cand, TcLayout L) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* b_smem = smem + L.b_off;
+  unsigned char* ring = smem + L.ring_off;
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + L.list_off);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* empty = full + kTcMaxStages;
+  uint64_t* b_full = empty + kTcMaxStages;
+  uint64_t* acc_full = b_full + 1;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int64_t n_tiles = (n + kTcRows - 1) / kTcRows;
+  const int64_t my_tiles =
+      n_tiles > cluster ? (n_tiles - cluster + n_clusters - 1) / n_clusters : 0;
+
+  for (int i = threadIdx.x; i < kTcEpiWarps * kTcQueries * L.kl; i += blockDim.x) lists[i] = 0ull;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < L.n_stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 2);   // one commit from each CTA of the pair
+    }
+    mbar_init(b_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], kTcEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(64)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(L.n_slabs) * kTcBSlabBytes);
+      for (int kb = 0; kb < L.n_slabs; ++kb)
+        tma_load_2d(b_smem + static_cast<size_t>(kb) * kTcBSlabBytes, &map_b, kb * kTcSlab,
+                    rank * kTcQueries, b_full);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int row0 = static_cast<int>((cluster + it * n_clusters) * kTcRows);
+        for (int kb = 0; kb < L.n_slabs; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], kTcABytes);   // own half + the peer's half
+          tma_load_2d_mcast(ring + static_cast<size_t>(s) * kTcABytes + rank * (kTcABytes / 2),
+                            &map_a, kb * kTcSlab, row0 + rank * (kTcRows / 2), &full[s], 0x3);
+          if (++s == L.n_stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(b_full, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int a = static_cast<int>(it & 1);
+        const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+        mbar_wait(&acc_empty[a], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(a * kTcQueries);
+        for (int kb = 0; kb < L.n_slabs; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t da = tc_smem_desc(smem_u32(ring + static_cast<size_t>(s) * kTcABytes));
+          const uint64_t db = tc_smem_desc(smem_u32(b_smem + static_cast<size_t>(kb) * kTcBSlabBytes));
+#pragma unroll
+          for (int kk = 0; kk < kTcSlab / 8; ++kk)
+            tc_mma_tf32(tmem_d, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2),
+                        (kb | kk) != 0 ? 1u : 0u);
+          tc_commit_mcast(&empty[s], 0x3);
+          if (++s == L.n_stages) { s = 0; ph ^= 1u; }
+        }
+        tc_commit(&acc_full[a]);
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    uint64_t* my_lists = lists + static_cast<size_t>(ew) * kTcQueries * L.kl;
+    uint64_t thr[kTcQueries];
+#pragma unroll
+    for (int j = 0; j < kTcQueries; ++j) thr[j] = thr0 ? thr0[rank * kTcQueries + j] : 0ull;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int a = static_cast<int>(it & 1);
+      const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+      mbar_wait(&acc_full[a], aph);
+      tc_fence_after();
+      uint32_t v[32];
+      tc_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                      static_cast<uint32_t>(a * kTcQueries),
+                  v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);
+
+      const int64_t row = (cluster + it * n_clusters) * kTcRows + quad * 32 + lane;
+      bool ok = row < n;
+      if (ok && mask) ok = (__ldg(mask + (row >> 5)) >> (row & 31)) & 1u;
+#pragma unroll
+      for (int j = 0; j < kTcQueries; ++j) {
+        const uint64_t key = ok ? make_key(__uint_as_float(v[j]), static_cast<uint32_t>(row)) : 0ull;
+        unsigned pending = __ballot_sync(kFullMask, key > thr[j]);
+        while (pending) {
+          const int src = __ffs(pending) - 1;
+          pending &= pending - 1;
+          const uint64_t c = __shfl_sync(kFullMask, key, src);
+          if (c > thr[j]) {
+            const uint64_t nm = warp_list_insert_cold(my_lists + j * L.kl, L.kl, c, lane);
+            thr[j] = nm > thr[j] ? nm : thr[j];
+          }
+        }
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < kTcQueries * L.kl; i += 32) {
+      const int q = rank * kTcQueries + i / L.kl, e = i % L.kl;
+      cand[((static_cast<int64_t>(q) * n_clusters + cluster) * kTcEpiWarps + ew) * L.kl + e] =
+          my_lists[i];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64)
+                 : "memory");
+  }
+}
+
 // ---- exact rescoring -----------------------------------------------------------------
 // One CTA per query.  Among the m = grid * 4 * kl nominated candidates: T = k-th best tf32
 // score; every candidate with tf32 score >= T - 2*eps is rescored in exact fp32 (eps bounds
@@ -279,21 +462,20 @@ constexpr int kTcRescoreThreads = 512;
 __global__ void __launch_bounds__(kTcRescoreThreads)
 dense_tc_thr_kernel(const uint64_t* __restrict__ cand, int m, int kl,
                     uint64_t* __restrict__ thr0) {
-  __shared__ uint64_t top[1024];
+  // kl-th largest of the 512 per-thread bests: kl distinct rows reach it, so it is a lower
+  // bound of the sample's (hence the corpus') kl-th best -- all a starting threshold needs
+  __shared__ uint64_t best[kTcRescoreThreads];
   const int q = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint64_t* c = cand + static_cast<int64_t>(q) * m;
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) top[i] = 0ull;
-  __syncthreads();
-  uint64_t thr = 0;
-  uint64_t* list = top + warp * kl;
-  for (int base = warp * 32; base < m; base += kTcRescoreThreads) {
-    const int i = base + lane;
-    warp_list_offer(list, kl, i < m ? c[i] : 0ull, thr, lane);
+  uint64_t b = 0ull;
+  for (int i = threadIdx.x; i < m; i += kTcRescoreThreads) {
+    const uint64_t v = c[i];
+    b = v > b ? v : b;
   }
-  block_bitonic_sort_desc(top, next_pow2((kTcRescoreThreads / 32) * kl));
+  best[threadIdx.x] = b;
+  block_bitonic_sort_desc(best, kTcRescoreThreads);
   if (threadIdx.x == 0) {
-    const uint64_t kth = top[kl - 1];
+    const uint64_t kth = best[kl - 1];
     thr0[q] = kth ? (kth | 0xffffffffull) : 0ull;
   }
 }
@@ -476,8 +658,9 @@ int dense_tc_queries_per_pass() { return kTcQueries; }
 
 // scratch one pass needs: candidates of the main pass + of the sample pre-pass + thresholds
 size_t dense_tc_cand_keys(const DeviceProps& dp, int k) {
-  return static_cast<size_t>(kTcQueries) * dp.sm_count * kTcEpiWarps * tc_list_len(k) +
-         static_cast<size_t>(kTcQueries) * dp.sm_count * kTcRows + kTcQueries;
+  // sized for the 64-query pair pass (the 32-query pass needs half of it)
+  return 2 * (static_cast<size_t>(kTcQueries) * dp.sm_count * kTcEpiWarps * tc_list_len(k) +
+              static_cast<size_t>(kTcQueries) * dp.sm_count * kTcRows + kTcQueries);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -551,5 +734,51 @@ cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, 
       cand, grid * kTcEpiWarps, L.kl, emb, ld, q_dev, k, emb_norm_max, thr0, out, flags);
   return cudaGetLastError();
 }
+
+// One pass over the corpus for 64 queries at q_dev ([64, ld]) with the CTA-pair kernel.
+cudaError_t launch_dense_tc_pair(const DeviceProps& dp, const float* emb, int64_t n, int ld,
+                                 const float* q_dev, int n_real, int k, const uint32_t* mask,
+                                 float emb_norm_max, uint64_t* cand, const TopkOut& out,
+                                 int32_t* flags, cudaStream_t stream) {
+  TcLayout L;
+  if (!make_tc_layout(dp, ld, k, &L)) return cudaErrorInvalidConfiguration;
+  CUtensorMap map_a_half, map_a, map_b64, map_b0, map_b1;
+  if (!encode_map(&map_a_half, emb, n, ld, kTcRows / 2) || !encode_map(&map_a, emb, n, ld, kTcRows) ||
+      !encode_map(&map_b64, q_dev, 2 * kTcQueries, ld, kTcQueries) ||
+      !encode_map(&map_b0, q_dev, kTcQueries, ld, kTcQueries) ||
+      !encode_map(&map_b1, q_dev + static_cast<size_t>(kTcQueries) * ld, kTcQueries, ld, kTcQueries))
+    return cudaErrorInvalidValue;
+  const int smem = L.total_bytes + 1024;
+  cudaError_t e = cudaFuncSetAttribute(dense_tc_pair_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(dense_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem);
+  if (e != cudaSuccess) return e;
+  const int n_clusters = dp.sm_count / 2;
+  const size_t pass_keys = 2 * static_cast<size_t>(kTcQueries) * n_clusters * kTcEpiWarps * L.kl;
+  uint64_t* cand_sample = cand + pass_keys;
+  uint64_t* thr0 = nullptr;
+  const int64_t n_sample = static_cast<int64_t>(dp.sm_count) * kTcRows;
+  if (n >= 8 * n_sample) {   // two 32-query sample pre-passes (emit mode), one threshold kernel
+    thr0 = cand_sample + 2 * static_cast<size_t>(kTcQueries) * n_sample;
+    dense_tc_kernel<true><<<dp.sm_count, kTcThreads, smem, stream>>>(map_a, map_b0, n_sample, mask,
+                                                                     nullptr, cand_sample, L);
+    dense_tc_kernel<true><<<dp.sm_count, kTcThreads, smem, stream>>>(
+        map_a, map_b1, n_sample, mask, nullptr,
+        cand_sample + static_cast<size_t>(kTcQueries) * n_sample, L);
+    dense_tc_thr_kernel<<<2 * kTcQueries, kTcRescoreThreads, 0, stream>>>(
+        cand_sample, static_cast<int>(n_sample), L.kl, thr0);
+  }
+  dense_tc_pair_kernel<<<2 * n_clusters, kTcThreads, smem, stream>>>(map_a_half, map_b64, n, mask,
+                                                                     thr0, cand, L);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  dense_tc_rescore_kernel<<<n_real, kTcRescoreThreads, 0, stream>>>(
+      cand, n_clusters * kTcEpiWarps, L.kl, emb, ld, q_dev, k, emb_norm_max, thr0, out, flags);
+  return cudaGetLastError();
+}
+
+bool dense_tc_pair_enabled() { return getenv("ANR_DISABLE_TC_PAIR") == nullptr; }
 
 }  // namespace anr

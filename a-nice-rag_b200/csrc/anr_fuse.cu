@@ -8,7 +8,9 @@
 // float64 division, the product and the running sum are separate round-to-nearest
 // operations (no FMA contraction) and the sum runs in insertion order.
 //
-// One CTA per query, everything in shared memory:
+// One CTA per query; the working arrays live in shared memory up to 8192 entries per query and
+// in an L2-resident global scratch beyond that (the evaluator fuses up to 5 lists x 12 000 ids,
+// src/retrieval_eval.py:142-143):
 //   1. entries (id, position) with position = insertion index (list-major) are
 //      bitonic-sorted ascending by (id, position);
 //   2. the first entry of every id run ("head") walks its run in position order and
@@ -78,11 +80,14 @@ __device__ __forceinline__ void bitonic_pairs(uint64_t* s, uint64_t* a, int n_po
 __global__ void __launch_bounds__(kWrrfThreads)
 wrrf_fuse_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ lens,
                  const double* __restrict__ weights, int n_lists, int list_stride, double rrf_k,
-                 int top_n, int n_pow2, int32_t* __restrict__ out_ids,
-                 double* __restrict__ out_scores, int32_t* __restrict__ out_counts) {
+                 int top_n, int n_pow2, uint64_t* __restrict__ scratch,
+                 int32_t* __restrict__ out_ids, double* __restrict__ out_scores,
+                 int32_t* __restrict__ out_counts) {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint64_t* a = reinterpret_cast<uint64_t*>(smem);  // (id << 32) | position
-  uint64_t* s = a + n_pow2;                         // orderable score of heads, 0 otherwise
+  // (id << 32) | position, then orderable score of heads (0 otherwise)
+  uint64_t* a = scratch ? scratch + static_cast<size_t>(blockIdx.x) * 2 * n_pow2
+                        : reinterpret_cast<uint64_t*>(smem);
+  uint64_t* s = a + n_pow2;
   __shared__ int list_base[65];                     // insertion offset of each list (n_lists <= 64)
   __shared__ int n_unique;
 
@@ -154,22 +159,31 @@ wrrf_fuse_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ le
   if (threadIdx.x == 0 && out_counts) out_counts[q] = n_out;
 }
 
+size_t wrrf_scratch_keys(int n_lists, int list_stride, int nq) {
+  const int64_t cap = static_cast<int64_t>(n_lists) * list_stride;
+  if (cap <= kWrrfMaxEntries) return 0;
+  return static_cast<size_t>(nq) * 2 * next_pow2(static_cast<int>(cap));
+}
+
 cudaError_t launch_wrrf_fuse(const int32_t* ids, const int32_t* lens, const double* weights,
                              int n_lists, int list_stride, int nq, double rrf_k, int top_n,
-                             int32_t* out_ids, double* out_scores, int32_t* out_counts,
-                             cudaStream_t stream) {
+                             uint64_t* scratch, int32_t* out_ids, double* out_scores,
+                             int32_t* out_counts, cudaStream_t stream) {
   if (n_lists < 1 || n_lists > 64 || list_stride < 1 || top_n < 1) return cudaErrorInvalidValue;
   const int64_t cap = static_cast<int64_t>(n_lists) * list_stride;
-  if (cap > kWrrfMaxEntries) return cudaErrorInvalidConfiguration;
+  if (cap > (1 << 22)) return cudaErrorInvalidConfiguration;
   const int n_pow2 = next_pow2(static_cast<int>(cap) < 2 ? 2 : static_cast<int>(cap));
-  const int smem = n_pow2 * 16;
+  const bool in_smem = cap <= kWrrfMaxEntries;
+  if (!in_smem && !scratch) return cudaErrorInvalidValue;
+  const int smem = in_smem ? n_pow2 * 16 : 0;
   cudaError_t e = cudaFuncSetAttribute(wrrf_fuse_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kWrrfMaxEntries * 16);
   if (e != cudaSuccess) return e;
   if (nq < 1) return cudaSuccess;
   wrrf_fuse_kernel<<<nq, kWrrfThreads, smem, stream>>>(ids, lens, weights, n_lists, list_stride,
-                                                       rrf_k, top_n, n_pow2, out_ids, out_scores,
-                                                       out_counts);
+                                                       rrf_k, top_n, n_pow2,
+                                                       in_smem ? nullptr : scratch, out_ids,
+                                                       out_scores, out_counts);
   return cudaGetLastError();
 }
 

@@ -59,6 +59,13 @@ cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, 
                             float emb_norm_max, uint64_t* cand, const TopkOut& out, int32_t* flags,
                             cudaStream_t stream);
 
+// Same for 64 queries at q_dev ([64, ld]) in ONE pass: a CTA pair shares each corpus tile.
+cudaError_t launch_dense_tc_pair(const DeviceProps& dp, const float* emb, int64_t n, int ld,
+                                 const float* q_dev, int n_real, int k, const uint32_t* mask,
+                                 float emb_norm_max, uint64_t* cand, const TopkOut& out,
+                                 int32_t* flags, cudaStream_t stream);
+bool dense_tc_pair_enabled();
+
 // ---- top-k ------------------------------------------------------------------
 // Per query: select the best k (<= kMaxFusedK) of m candidate keys, sorted best first.
 // Candidate i of query q is cand[q * cand_stride_q + (i / seg_len) * seg_stride + i % seg_len].
@@ -107,10 +114,12 @@ cudaError_t launch_keys_to_scores(const uint64_t* keys, int64_t n, float* scores
                                   cudaStream_t stream);
 
 // ---- fusion -------------------------------------------------------------------
+// scratch: wrrf_scratch_keys() 64-bit words (0 when the union fits in shared memory)
 cudaError_t launch_wrrf_fuse(const int32_t* ids, const int32_t* lens, const double* weights,
                              int n_lists, int list_stride, int nq, double rrf_k, int top_n,
-                             int32_t* out_ids, double* out_scores, int32_t* out_counts,
-                             cudaStream_t stream);
+                             uint64_t* scratch, int32_t* out_ids, double* out_scores,
+                             int32_t* out_counts, cudaStream_t stream);
+size_t wrrf_scratch_keys(int n_lists, int list_stride, int nq);
 int wrrf_max_entries();
 
 }  // namespace anr

@@ -59,11 +59,60 @@ topk_final_kernel(const uint64_t* __restrict__ cand, int64_t stride_q, int m, in
   if (threadIdx.x == 0 && o.counts) o.counts[q * o.count_stride] = cnt;
 }
 
+// Small candidate sets (k * ceil(m / 256) <= kSmallCap): the k-th largest of the 256 per-thread
+// bests bounds the k-th best from below; one sweep collects the few keys at or above it and one
+// short sort ranks them -- an order of magnitude fewer barriers than sorting all m keys.
+constexpr int kSmallThreads = 256;
+constexpr int kSmallCap = 2048;
+
+__global__ void __launch_bounds__(kSmallThreads)
+topk_final_small_kernel(const uint64_t* __restrict__ cand, int64_t stride_q, int m, int seg_len,
+                        int64_t seg_stride, int k, TopkOut o) {
+  __shared__ uint64_t best[kSmallThreads];
+  __shared__ uint64_t sel[kSmallCap];
+  __shared__ int n_sel;
+  const int q = blockIdx.x;
+  const uint64_t* c = cand + q * stride_q;
+  uint64_t b = 0ull;
+  for (int i = threadIdx.x; i < m; i += kSmallThreads) {
+    const uint64_t v = c[(i / seg_len) * seg_stride + (i % seg_len)];
+    b = v > b ? v : b;
+  }
+  best[threadIdx.x] = b;
+  if (threadIdx.x == 0) n_sel = 0;
+  block_bitonic_sort_desc(best, kSmallThreads);
+  const uint64_t thr = k <= kSmallThreads ? best[k - 1] : 0ull;
+  const int cap = next_pow2(k * ((m + kSmallThreads - 1) / kSmallThreads));
+  for (int i = threadIdx.x; i < cap; i += kSmallThreads) sel[i] = 0ull;
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += kSmallThreads) {
+    const uint64_t v = c[(i / seg_len) * seg_stride + (i % seg_len)];
+    if (v != 0ull && v >= thr) {
+      const int slot = atomicAdd(&n_sel, 1);
+      if (slot < cap) sel[slot] = v;
+    }
+  }
+  __syncthreads();
+  const int ns = n_sel < cap ? n_sel : cap;
+  block_bitonic_sort_desc(sel, next_pow2(ns < 2 ? 2 : ns));
+  uint64_t key = 0ull;
+  for (int i = threadIdx.x; i < k; i += kSmallThreads) {
+    key = i < ns ? sel[i] : 0ull;
+    emit_entry(key, q * o.stride_q + i, o);
+  }
+  if (threadIdx.x == 0 && o.counts) o.counts[q * o.count_stride] = ns < k ? ns : k;
+}
+
 cudaError_t launch_topk_final(const uint64_t* cand, int64_t cand_stride_q, int m, int seg_len,
                               int64_t seg_stride, int nq, int k, const TopkOut& out,
                               cudaStream_t stream) {
   if (k < 1 || k > kMaxFusedK || m < 1 || seg_len < 1) return cudaErrorInvalidValue;
   if (nq < 1) return cudaSuccess;
+  if (static_cast<int64_t>(k) * ((m + kSmallThreads - 1) / kSmallThreads) <= kSmallCap) {
+    topk_final_small_kernel<<<nq, kSmallThreads, 0, stream>>>(cand, cand_stride_q, m, seg_len,
+                                                              seg_stride, k, out);
+    return cudaGetLastError();
+  }
   topk_final_kernel<<<nq, kFinalThreads, 0, stream>>>(cand, cand_stride_q, m, seg_len, seg_stride,
                                                       k, out);
   return cudaGetLastError();

@@ -276,7 +276,7 @@ class Bm25Index:
 # ---------------------------------------------------------------------------------
 # fusion
 # ---------------------------------------------------------------------------------
-WRRF_MAX_ENTRIES = 8192
+WRRF_MAX_ENTRIES = 1 << 22
 
 
 def wrrf_fuse(id_lists: Sequence[Sequence[int]], weights: Sequence[float], rrf_k: float,

@@ -349,6 +349,12 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel -----------------------------------------------------
     peak, peak_kind = load_peaks()
+    traffic = None        # dram bytes per launch of the dominant kernel, from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and args.chunks == 1_000_000 and world == 1:
+        with open(tpath) as fh:
+            traffic = json.load(fh)["bytes_per_launch"].get(
+                "dense_tc_kernel<0>" if B > 8 else "dense_scan_kernel<1, 4, 0>")
     rows_local = hi - lo
     scan_bytes = rows_local * D * 4
     scan_avg_ms = scan_ms.value / max(scan_n.value, 1)
@@ -394,8 +400,9 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(h_ids.numel() * 4 + h_scores.numel() * 8 + h_counts.numel() * 4)},
         "gpu_launches": int((scan_n.value + bm_n.value) + 4 * args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
-                     "kernel": "dense_scan_kernel", "bytes_per_launch": scan_bytes,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
+                     "kernel": "dense_tc_kernel (+ sample pre-pass, rescoring)" if B > 8
+                               else "dense_scan_kernel", "bytes_per_launch": scan_bytes,
                      "avg_launch_ms": scan_avg_ms, "launches": int(scan_n.value),
                      "share_of_step": scan_ms.value / ms_dev if ms_dev else None},
         "bm25_kernel": {"avg_launch_ms": bm_avg_ms, "launches": int(bm_n.value),

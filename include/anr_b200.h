@@ -123,7 +123,8 @@ int anr_bm25_scores(anr_ctx* ctx, const anr_bm25* index, const int32_t* q_terms,
  * float64 with the reference's operation order (bit-identical scores); output
  * sorted by score descending, ties in first-insertion order (list 0 first).
  * ids is [n_queries, n_lists, list_stride], lens is [n_queries, n_lists].
- * Writes the first min(top_n, |union|) fused entries per query. */
+ * Writes the first min(top_n, |union|) fused entries per query.  Up to 2^22 entries per query
+ * (n_lists * list_stride); unions above 8192 entries use an L2-resident scratch. */
 int anr_wrrf_fuse(anr_ctx* ctx, const int32_t* ids, const int32_t* lens, const double* weights,
                   int32_t n_lists, int32_t list_stride, int32_t n_queries, double rrf_k,
                   int32_t top_n, int32_t* out_ids, double* out_scores, int32_t* out_counts,

@@ -334,3 +334,51 @@ def test_dropin_config0_vs_reference_golden(config0_golden, tmp_path):
         want = retrieval.weighted_rrf([(res["id"].tolist(), "voyage-3-large"), (hits, "BM25")],
                                       WEIGHTS, WRRF_K)[:10]
         assert batch[j] == want
+
+
+def test_wrrf_evaluator_sized_union_bit_exact():
+    """5 ranked lists x 12 000 ids (retrieval_eval.py:142-143: similarity_k = 12000): the union
+    does not fit in shared memory and runs through the global scratch."""
+    rng = np.random.default_rng(8)
+    lists = [rng.permutation(15000)[:12000].tolist() for _ in range(5)]
+    weights = [5.0, 0.7, 1.3, 2.0, 1.0]
+    want = retrieval.weighted_rrf([(l, str(i)) for i, l in enumerate(lists)],
+                                  {str(i): w for i, w in enumerate(weights)}, 40)
+    ids, scores = engine.wrrf_fuse(lists, weights, 40.0)
+    assert ids.tolist() == [i for i, _ in want]
+    assert scores.tolist() == [s for _, s in want]
+
+
+def test_sharded_fuse_equals_unsharded_hybrid(small):
+    """Three shards (dense rows AND the same documents' postings, global BM25 statistics) searched
+    separately; their keys, laid out as the NCCL all-gather would leave them, go through
+    anr_sharded_fuse and must reproduce the unsharded anr_hybrid_search bit for bit."""
+    case, ix = small["case"], small["ix"]
+    emb, queries = case["emb"], case["queries"]
+    nq, k = queries.shape[0], 10
+    term_queries = [term_ids_of(case, ix, q) for q in range(nq)]
+    terms, offsets = engine.Bm25Index.pack_queries(term_queries)
+    bounds = [0, 700, 1400, emb.shape[0]]
+    ctx = engine.context()
+    gathered = np.zeros((3, 2, nq, k), dtype=np.uint64)
+    for s in range(3):
+        lo, hi = bounds[s], bounds[s + 1]
+        d_shard = engine.DenseIndex(emb[lo:hi])
+        local = csr.from_token_ids(case["doc_ptr"][lo:hi + 1] - case["doc_ptr"][lo],
+                                   case["tokens"][case["doc_ptr"][lo]:case["doc_ptr"][hi]],
+                                   int(case["vocab"]), ix.k1, ix.b, 0.05)
+        b_shard = engine.Bm25Index(local.term_ptr, local.post_doc, local.post_tf, local.doc_len,
+                                   ix.idf, ix.k1, ix.b, ix.avgdl)      # GLOBAL idf / avgdl
+        native.call("anr_dense_search_keys", ctx.handle, d_shard.handle, native.ptr(queries), nq,
+                    k, None, lo, native.ptr(gathered[s, 0]), None)
+        native.call("anr_bm25_search_keys", ctx.handle, b_shard.handle, native.ptr(terms),
+                    native.ptr(offsets), nq, k, None, None, lo, native.ptr(gathered[s, 1]), None)
+    ids = np.empty((nq, 2 * k), dtype=np.int32)
+    scores = np.empty((nq, 2 * k), dtype=np.float64)
+    counts = np.empty(nq, dtype=np.int32)
+    native.call("anr_sharded_fuse", ctx.handle, native.ptr(gathered), 3, nq, k, 5.0, 1.0,
+                float(WRRF_K), 2 * k, native.ptr(ids), native.ptr(scores), native.ptr(counts), None)
+    res = engine.hybrid_search(small["dense"], small["bm25"], queries, term_queries, k, k, 5.0, 1.0,
+                               WRRF_K, 2 * k)
+    assert np.array_equal(counts, res["counts"])
+    assert np.array_equal(ids, res["ids"]) and np.array_equal(scores, res["scores"])

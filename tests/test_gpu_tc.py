@@ -45,19 +45,34 @@ def test_tc_with_mask_and_unnormalised_rows():
         assert mask[rows[q]].all()
 
 
-def test_tc_duplicate_cluster_takes_the_exact_fallback():
+@pytest.mark.parametrize("nq", [16, 48])
+def test_tc_duplicate_cluster_takes_the_exact_fallback(nq):
     """60 identical adjacent rows overflow one warp's candidate list: the query must be flagged
     and rerun through the exact scan, whose tie rule (lower row first) decides."""
     emb = synth.unit_vectors(30_000, 1024, seed=11)
     emb[5000:5060] = emb[5000]
     index = engine.DenseIndex(emb)
-    queries = synth.unit_vectors(16, 1024, seed=12)
+    queries = synth.unit_vectors(nq, 1024, seed=12)
     queries[5] = emb[5000]
+    queries[nq - 3] = emb[5001]
     scores, rows, counts = index.search(queries, 10)
     assert rows[5].tolist() == list(range(5000, 5010))
-    for q in range(16):
+    assert rows[nq - 3].tolist() == list(range(5000, 5010))
+    for q in range(nq):
         want_rows, want_scores = retrieval.dense_topk(queries[q], emb, 10)
         check_topk(rows[q], scores[q], want_rows, want_scores, queries[q] @ emb.T, f"tc dup q{q}")
+
+
+def test_tc_pair_and_single_pass_agree(corpus):
+    emb, index = corpus
+    queries = synth.unit_vectors(64, 1024, seed=77)
+    s_pair, r_pair, _ = index.search(queries, 10)
+    os.environ["ANR_DISABLE_TC_PAIR"] = "1"
+    try:
+        s_one, r_one, _ = index.search(queries, 10)
+    finally:
+        del os.environ["ANR_DISABLE_TC_PAIR"]
+    assert np.array_equal(r_pair, r_one) and np.array_equal(s_pair, s_one)
 
 
 def test_tc_and_scan_paths_agree(corpus):
