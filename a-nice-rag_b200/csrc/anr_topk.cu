@@ -82,7 +82,8 @@ topk_final_small_kernel(const uint64_t* __restrict__ cand, int64_t stride_q, int
   if (threadIdx.x == 0) n_sel = 0;
   block_bitonic_sort_desc(best, kSmallThreads);
   const uint64_t thr = k <= kSmallThreads ? best[k - 1] : 0ull;
-  const int cap = next_pow2(k * ((m + kSmallThreads - 1) / kSmallThreads));
+  const int want = k * ((m + kSmallThreads - 1) / kSmallThreads);
+  const int cap = next_pow2(want < 2 ? 2 : want);
   for (int i = threadIdx.x; i < cap; i += kSmallThreads) sel[i] = 0ull;
   __syncthreads();
   for (int i = threadIdx.x; i < m; i += kSmallThreads) {
