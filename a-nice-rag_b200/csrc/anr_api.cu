@@ -47,6 +47,9 @@ struct EventPair {
 struct anr_ctx {
   DeviceProps dp;
   cudaStream_t stream = nullptr;
+  // BM25 of a hybrid query runs on `side` under the dense scan (fork/join through the events)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   unsigned char* ws = nullptr;  // device scratch, grown on demand
   size_t ws_bytes = 0;
   // profiling (anr_ctx_profile_*): event pairs recorded around the dominant kernels
@@ -529,9 +532,12 @@ int anr_ctx_create(int device, anr_ctx** out) {
   ctx->dp.max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
   DeviceGuard guard(device);
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) {
-    delete ctx;
-    return fail_cuda("cudaStreamCreate", e);
+    anr_ctx_destroy(ctx);
+    return fail_cuda("stream/event creation", e);
   }
   *out = ctx;
   return ANR_OK;
@@ -562,14 +568,18 @@ int anr_ctx_profile_read(anr_ctx* ctx, int32_t kind, double* total_ms, int64_t* 
 int anr_ctx_destroy(anr_ctx* ctx) {
   if (!ctx) return ANR_OK;
   DeviceGuard guard(ctx->dp.device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->side) cudaStreamSynchronize(ctx->side);
   for (auto& pool : ctx->pool)
     for (auto& p : pool) {
       cudaEventDestroy(p.start);
       cudaEventDestroy(p.stop);
     }
   if (ctx->ws) cudaFree(ctx->ws);
-  cudaStreamDestroy(ctx->stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ANR_OK;
 }
@@ -1064,16 +1074,27 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
   od.stride_q = 2ll * stride;
   od.count_stride = 2;
   od.id_base = id_base;
-  if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k_dense, row_mask_dev, arena, od, stream))
-    return rc;
   TopkOut ob = od;
   ob.ids = lists + stride;
   ob.scores = list_scores + stride;
   ob.counts = lens + 1;
   ob.id_map = doc_to_id;
+  // The CUDA-core scan leaves ~90 KB of shared memory per SM free: BM25 CTAs co-reside with it,
+  // so for small batches BM25 runs on the side stream underneath the scan.  The tensor-core
+  // scan fills the SM, there the two run back to back on one stream.
+  const bool overlap = !dense_use_tc(ctx, dense, nq, k_dense);
+  cudaStream_t bm25_stream = overlap ? ctx->side : stream;
+  if (overlap) {
+    ANR_CUDA(cudaEventRecord(ctx->ev_fork, stream));
+    ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  }
   if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k_bm25, doc_mask_dev, arena, ob,
-                             stream))
+                             bm25_stream))
     return rc;
+  if (overlap) ANR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+  if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k_dense, row_mask_dev, arena, od, stream))
+    return rc;
+  if (overlap) ANR_CUDA(cudaStreamWaitEvent(stream, ctx->ev_join, 0));
   ANR_CUDA(launch_wrrf_fuse(lists, lens, w_dev, 2, stride, nq, rrf_k, top_n, nullptr, o_ids.dev,
                             o_scores.dev, o_counts.dev, stream));
 

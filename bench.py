@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunks", type=int, default=1_000_000, help="total corpus rows / BM25 docs")
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--vocab", type=int, default=VOCAB)
     ap.add_argument("--cpu-queries", type=int, default=16, help="queries in the CPU sample")
     ap.add_argument("--latency-iters", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -129,7 +130,7 @@ class ClockSampler:
 def make_queries(batch: int):
     synth = importlib.import_module("a-nice-rag_b200.synth")
     q = synth.unit_vectors(batch, D, seed=4321)
-    terms = synth.zipf_queries(batch, N_TERMS, VOCAB, ZIPF_S, seed=2025)
+    terms = synth.zipf_queries(batch, N_TERMS, VOCAB, ZIPF_S, seed=2025)   # VOCAB = --vocab
     offsets = np.arange(0, (batch + 1) * N_TERMS, N_TERMS, dtype=np.int32)
     return q, terms, offsets
 
@@ -249,6 +250,7 @@ def run_ours(args):
     dense = engine.DenseIndex(emb, borrow=True)
     bm25 = engine.Bm25Index(post["term_ptr"], post["post_doc"], post["post_tf"], post["doc_len"],
                             idf, K1, B_PARAM, avgdl, n_terms=VOCAB, n_docs=hi - lo)
+    del post["post_tf"]
     n_postings = bm25.n_postings
 
     # ---- queries -------------------------------------------------------------------------
@@ -421,7 +423,9 @@ def run_ours(args):
 
 
 def main():
+    global VOCAB
     args = parse_args()
+    VOCAB = args.vocab
     if args.impl == "reference":
         run_reference(args)
     else:
