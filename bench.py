@@ -250,7 +250,6 @@ def run_ours(args):
     dense = engine.DenseIndex(emb, borrow=True)
     bm25 = engine.Bm25Index(post["term_ptr"], post["post_doc"], post["post_tf"], post["doc_len"],
                             idf, K1, B_PARAM, avgdl, n_terms=VOCAB, n_docs=hi - lo)
-    del post["post_tf"]
     n_postings = bm25.n_postings
 
     # ---- queries -------------------------------------------------------------------------
