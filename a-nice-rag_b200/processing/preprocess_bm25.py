@@ -44,6 +44,11 @@ wouldn't
 """.split())
 
 _PUNCT_TABLE = str.maketrans("", "", string.punctuation)
+_UNICODE_QUOTES = str.maketrans({c: " " for c in "\u2018\u2019\u201c\u201d\u00ab\u00bb"})
+# the Treebank tokenizer behind word_tokenize splits these contractions (the ones that survive
+# punctuation stripping); both halves are then ordinary tokens ("cannot" -> "can", "not")
+_TREEBANK_SPLITS = {"cannot": ("can", "not"), "gimme": ("gim", "me"), "gonna": ("gon", "na"),
+                    "gotta": ("got", "ta"), "lemme": ("lem", "me"), "wanna": ("wan", "na")}
 _warned = False
 
 
@@ -55,7 +60,10 @@ def preprocess_text(text: str, use_lemmatization: bool = False) -> List[str]:
         tokens = _word_tokenize(text)
         stop = set(_nltk_stopwords.words("english"))
     else:
-        tokens = text.split()
+        tokens = []
+        # word_tokenize isolates typographic quotes (string.punctuation is ASCII only)
+        for tok in text.translate(_UNICODE_QUOTES).split():
+            tokens.extend(_TREEBANK_SPLITS.get(tok, (tok,)))
         stop = ENGLISH_STOPWORDS
     tokens = [t for t in tokens if t not in stop and not t.isnumeric() and len(t) > 1]
     if use_lemmatization:

@@ -86,7 +86,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={index}", f"--query-gpu={self.QUERY}",
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -316,6 +316,9 @@ def run_ours(args):
         return float(ms)
 
     # ---- warm-up, then the timed regions --------------------------------------------------
+    # clocks are sampled from the warm-up to the end of the latency loop (the timed regions
+    # alone can be shorter than one nvidia-smi sampling period)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_device()
         step_e2e()
@@ -323,14 +326,12 @@ def run_ours(args):
     import ctypes as C
     native.call("anr_ctx_profile_read", ctx.handle, 0, None, None)      # reset counters
     native.call("anr_ctx_profile_read", ctx.handle, 1, None, None)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_dev = timed(step_device, args.steps)
     scan_ms, scan_n, bm_ms, bm_n = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
     native.call("anr_ctx_profile_read", ctx.handle, 0, C.byref(scan_ms), C.byref(scan_n))
     native.call("anr_ctx_profile_read", ctx.handle, 1, C.byref(bm_ms), C.byref(bm_n))
     native.call("anr_ctx_profile_enable", ctx.handle, 0)
     ms_e2e = timed(step_e2e, args.steps)
-    clocks = sampler.stop() if sampler else None
 
     # ---- batch-1 latency through the C-ABI with host buffers (p50 of wall-clock per call) -----
     lat = []
@@ -341,6 +342,12 @@ def run_ours(args):
             if i >= 20:
                 lat.append(1e3 * (time.perf_counter() - t0))
     ms_b1_dev = timed(lambda: step_device(1), max(args.steps, 50)) / max(args.steps, 50)
+    # keep the GPU under the same load until at least a few clock samples exist
+    t_end = time.perf_counter() + 1.0
+    while time.perf_counter() < t_end:
+        step_device()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
 
     if rank != 0:
         if world > 1:

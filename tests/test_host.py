@@ -187,3 +187,29 @@ def test_idf_from_counts_matches_okapi(small_case):
     nd = np.diff(ix.term_ptr)
     idf = synth.idf_from_counts(len(okapi.doc_freqs), nd, 0.05)
     np.testing.assert_allclose(idf, ix.idf, rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/data/test_queries_bm25.csv"),
+                    reason="reference tokeniser goldens not mounted")
+def test_offline_tokeniser_reproduces_the_reference_goldens():
+    """The only input->output goldens the reference ships: 9 609 + 8 168
+    (query, tokens_regular) rows written by its NLTK pipeline (preprocess_bm25.py:33-52).  The
+    offline tokeniser must reproduce every one of them (lemmatised tokens need WordNet)."""
+    import ast
+    pp = importlib.import_module("a-nice-rag_b200.processing.preprocess_bm25")
+    for name in ("suggested_queries_bm25_preprocessed.csv", "test_queries_bm25.csv"):
+        df = pd.read_csv(os.path.join("/root/reference/data", name))
+        bad = [q for q, t in zip(df["query"], df["tokens_regular"])
+               if pp.preprocess_text(q) != ast.literal_eval(t)]
+        assert not bad, (name, len(bad), bad[:3])
+
+
+def test_offline_tokeniser_on_frozen_golden_sample():
+    import ast
+    import json
+    pp = importlib.import_module("a-nice-rag_b200.processing.preprocess_bm25")
+    with open(os.path.join(ROOT, "tests", "golden", "tokeniser_sample.json")) as fh:
+        rows = json.load(fh)["rows"]
+    assert len(rows) == 60
+    for row in rows:
+        assert pp.preprocess_text(row["query"]) == ast.literal_eval(row["tokens_regular"]), row
