@@ -343,8 +343,9 @@ def run_ours(args):
                 lat.append(1e3 * (time.perf_counter() - t0))
     ms_b1_dev = timed(lambda: step_device(1), max(args.steps, 50)) / max(args.steps, 50)
     # keep the GPU under the same load until at least a few clock samples exist
-    t_end = time.perf_counter() + 1.0
-    while time.perf_counter() < t_end:
+    # (a fixed count derived from the max-reduced step time: every rank runs the same number
+    # of collectives)
+    for _ in range(int(min(2000, max(10, 1000.0 / max(ms_dev / args.steps, 1e-3))))):
         step_device()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
