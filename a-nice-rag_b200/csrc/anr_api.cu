@@ -256,7 +256,7 @@ size_t dense_ws_bytes(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
   const int gmax = std::max(dense_group(ctx, ix, k), 1);
   const int nqp = pad_queries(nq, gmax);
   if (dense_use_tc(ctx, ix, nq, k))
-    return padded(dense_tc_cand_keys(ctx->dp, k) * 8) + padded(static_cast<size_t>(nq) * 4) +
+    return padded(dense_tc_cand_keys(ctx->dp, ix->n, k) * 8) + padded(static_cast<size_t>(nq) * 4) +
            padded(static_cast<size_t>(dense_scan_max_grid(ctx->dp)) * k * 8) + 1024;
   if (k <= kMaxFusedK)
     return padded(static_cast<size_t>(nqp) * dense_scan_max_grid(ctx->dp) * k * 8) + 256;
@@ -279,7 +279,7 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
       ix->norm_valid = true;
     }
     const int per = dense_tc_queries_per_pass();
-    uint64_t* tc_cand = arena.take<uint64_t>(dense_tc_cand_keys(ctx->dp, k));
+    uint64_t* tc_cand = arena.take<uint64_t>(dense_tc_cand_keys(ctx->dp, ix->n, k));
     int32_t* flags = arena.take<int32_t>(static_cast<size_t>(nq));
     const bool pair = dense_tc_pair_enabled() && (ctx->dp.sm_count % 2) == 0;
     for (int q0 = 0; q0 < nq;) {

@@ -462,6 +462,7 @@ constexpr int kTcRescoreThreads = 512;
 __global__ void __launch_bounds__(kTcRescoreThreads)
 dense_tc_thr_kernel(const uint64_t* __restrict__ cand, int m, int kl,
                     uint64_t* __restrict__ thr0) {
+  // (kl = the rank asked for, <= 512)
   // kl-th largest of the 512 per-thread bests: kl distinct rows reach it, so it is a lower
   // bound of the sample's (hence the corpus') kl-th best -- all a starting threshold needs
   __shared__ uint64_t best[kTcRescoreThreads];
@@ -485,7 +486,7 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
                         const float* __restrict__ emb, int ld, const float* __restrict__ q_dev,
                         int k, float emb_norm_max, const uint64_t* __restrict__ thr0, TopkOut o,
                         int32_t* __restrict__ flags) {
-  __shared__ uint64_t top[1024];                 // warp lists for the tf32 top-k (32 warps x k<=32)
+  __shared__ uint64_t top[2048];                 // warp lists for the tf32 top-k (16 warps x k<=128)
   __shared__ uint64_t sel[kTcRescoreCap];        // candidates inside the margin, then exact keys
   __shared__ int n_sel, bad;
   __shared__ float q_norm2;
@@ -497,7 +498,7 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
   const float* qv = q_dev + static_cast<size_t>(q) * ld;
 
   if (threadIdx.x == 0) { n_sel = 0; bad = 0; q_norm2 = 0.f; }
-  for (int i = threadIdx.x; i < 1024; i += blockDim.x) top[i] = 0ull;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) top[i] = 0ull;
   __syncthreads();
   // |q|^2
   float part = 0.f;
@@ -622,14 +623,23 @@ cudaError_t launch_row_norm_max(const float* emb, int64_t n, int ld, float* out,
 // ---- host side ---------------------------------------------------------------------------
 static inline int tc_align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-static int tc_list_len(int k) {
-  int kl = 16;
-  while (kl < k + 6) kl <<= 1;
-  return kl;
+// Per-(warp, query) candidate list length.  With the pre-pass threshold only a handful of rows
+// per list survive (see tc_sample_rows), so the lists stay short whatever k is; a list that does
+// fill up inside the margin flags the query for the exact scan.
+static int tc_list_len(int k) { return k <= 10 ? 16 : 32; }
+
+// Rank of the sample's score used as starting threshold, and the sample size that leaves
+// about rank * n / sample <= 4096 rows per query above it (~7 per list).
+static int tc_thr_rank(int k) { return k <= 10 ? 16 : k + 32; }
+static int64_t tc_sample_rows(const DeviceProps& dp, int64_t n, int k) {
+  const int64_t wave = static_cast<int64_t>(dp.sm_count) * kTcRows;
+  int64_t want = (static_cast<int64_t>(tc_thr_rank(k)) * n + 4095) / 4096;
+  if (want < wave) want = wave;
+  return (want + wave - 1) / wave * wave;
 }
 
 static bool make_tc_layout(const DeviceProps& dp, int ld, int k, TcLayout* L) {
-  if (ld % kTcSlab != 0 || k < 1 || k > 26) return false;
+  if (ld % kTcSlab != 0 || k < 1 || k > 128) return false;
   L->n_slabs = ld / kTcSlab;
   L->kl = tc_list_len(k);
   L->b_off = 0;
@@ -657,10 +667,10 @@ bool dense_tc_supported(const DeviceProps& dp, int64_t n, int ld, int k) {
 int dense_tc_queries_per_pass() { return kTcQueries; }
 
 // scratch one pass needs: candidates of the main pass + of the sample pre-pass + thresholds
-size_t dense_tc_cand_keys(const DeviceProps& dp, int k) {
+size_t dense_tc_cand_keys(const DeviceProps& dp, int64_t n, int k) {
   // sized for the 64-query pair pass (the 32-query pass needs half of it)
   return 2 * (static_cast<size_t>(kTcQueries) * dp.sm_count * kTcEpiWarps * tc_list_len(k) +
-              static_cast<size_t>(kTcQueries) * dp.sm_count * kTcRows + kTcQueries);
+              static_cast<size_t>(kTcQueries) * tc_sample_rows(dp, n, k) + kTcQueries);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -719,13 +729,13 @@ cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, 
   uint64_t* cand_sample = cand + pass_keys;
   uint64_t* thr0 = nullptr;
   // sample pre-pass over the first tile of every CTA (worth it from ~8 tiles per CTA on)
-  const int64_t n_sample = static_cast<int64_t>(dp.sm_count) * kTcRows;
+  const int64_t n_sample = tc_sample_rows(dp, n, k);
   if (n >= 8 * n_sample) {
     thr0 = cand_sample + static_cast<size_t>(kTcQueries) * n_sample;
     dense_tc_kernel<true><<<dp.sm_count, kTcThreads, smem, stream>>>(map_a, map_b, n_sample, mask,
                                                                      nullptr, cand_sample, L);
     dense_tc_thr_kernel<<<kTcQueries, kTcRescoreThreads, 0, stream>>>(
-        cand_sample, static_cast<int>(n_sample), L.kl, thr0);
+        cand_sample, static_cast<int>(n_sample), tc_thr_rank(k), thr0);
   }
   dense_tc_kernel<false><<<grid, kTcThreads, smem, stream>>>(map_a, map_b, n, mask, thr0, cand, L);
   e = cudaGetLastError();
@@ -759,7 +769,7 @@ cudaError_t launch_dense_tc_pair(const DeviceProps& dp, const float* emb, int64_
   const size_t pass_keys = 2 * static_cast<size_t>(kTcQueries) * n_clusters * kTcEpiWarps * L.kl;
   uint64_t* cand_sample = cand + pass_keys;
   uint64_t* thr0 = nullptr;
-  const int64_t n_sample = static_cast<int64_t>(dp.sm_count) * kTcRows;
+  const int64_t n_sample = tc_sample_rows(dp, n, k);
   if (n >= 8 * n_sample) {   // two 32-query sample pre-passes (emit mode), one threshold kernel
     thr0 = cand_sample + 2 * static_cast<size_t>(kTcQueries) * n_sample;
     dense_tc_kernel<true><<<dp.sm_count, kTcThreads, smem, stream>>>(map_a, map_b0, n_sample, mask,
@@ -768,7 +778,7 @@ cudaError_t launch_dense_tc_pair(const DeviceProps& dp, const float* emb, int64_
         map_a, map_b1, n_sample, mask, nullptr,
         cand_sample + static_cast<size_t>(kTcQueries) * n_sample, L);
     dense_tc_thr_kernel<<<2 * kTcQueries, kTcRescoreThreads, 0, stream>>>(
-        cand_sample, static_cast<int>(n_sample), L.kl, thr0);
+        cand_sample, static_cast<int>(n_sample), tc_thr_rank(k), thr0);
   }
   dense_tc_pair_kernel<<<2 * n_clusters, kTcThreads, smem, stream>>>(map_a_half, map_b64, n, mask,
                                                                      thr0, cand, L);

@@ -49,7 +49,7 @@ cudaError_t launch_dense_scan_all(const DeviceProps& dp, const float* emb, int64
 // tcgen05 tf32 scan of 32 queries per pass + exact fp32 rescoring of the nominated candidates.
 bool dense_tc_supported(const DeviceProps& dp, int64_t n, int ld, int k);
 int dense_tc_queries_per_pass();
-size_t dense_tc_cand_keys(const DeviceProps& dp, int k);  // scratch keys one pass needs
+size_t dense_tc_cand_keys(const DeviceProps& dp, int64_t n, int k);  // scratch keys one pass needs
 cudaError_t launch_row_norm_max(const float* emb, int64_t n, int ld, float* out,
                                 cudaStream_t stream);
 // q_dev: [32, ld] (zero rows pad a short group); results of the first n_real queries go through

@@ -88,3 +88,23 @@ def test_tc_and_scan_paths_agree(corpus):
     for q in range(48):
         check_topk(r_tc[q], s_tc[q], r_sc[q], s_sc[q], full[q], f"tc vs scan q{q}")
     assert (r_tc == r_sc).mean() > 0.99
+
+
+@pytest.mark.parametrize("k", [50, 100, 128])
+def test_tc_large_k_on_200k_rows(k):
+    """top-100-style requests (BASELINE configs[2]) through the tensor-core path: the sample
+    pre-pass scales with k, lists stay short, rescoring ranks on exact fp32 scores."""
+    import torch
+    n, d, nq = 200_000, 1024, 40
+    g = torch.Generator(device="cuda").manual_seed(99)
+    emb_dev = torch.randn(n, d, generator=g, device="cuda", dtype=torch.float32)
+    emb_dev /= emb_dev.norm(dim=1, keepdim=True)
+    index = engine.DenseIndex(emb_dev, borrow=True)
+    emb = emb_dev.cpu().numpy()
+    queries = synth.unit_vectors(nq, d, seed=5)
+    scores, rows, counts = index.search(queries, k)
+    full = queries @ emb.T
+    for q in range(nq):
+        assert counts[q] == k
+        want_rows, want_scores = retrieval.dense_topk(queries[q], emb, k)
+        check_topk(rows[q], scores[q], want_rows, want_scores, full[q], f"tc k{k} q{q}")
