@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--chunks", type=int, default=1_000_000, help="total corpus rows / BM25 docs")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--vocab", type=int, default=VOCAB)
+    ap.add_argument("--chunks-per-gpu", type=int, default=0,
+                    help="weak scaling: total corpus = this x world size (overrides --chunks)")
     ap.add_argument("--cpu-queries", type=int, default=16, help="queries in the CPU sample")
     ap.add_argument("--latency-iters", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -397,7 +399,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": B * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong",
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak" if args.chunks_per_gpu else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.chunks} chunks x {D}-d fp32 + BM25 {args.chunks} docs "
                                f"V={VOCAB} Zipf {ZIPF_S}, {N_TERMS}-term queries, top-{TOPK} WRRF "
@@ -433,6 +436,8 @@ def main():
     global VOCAB
     args = parse_args()
     VOCAB = args.vocab
+    if args.chunks_per_gpu:
+        args.chunks = args.chunks_per_gpu * dist_env()[2]
     if args.impl == "reference":
         run_reference(args)
     else:
