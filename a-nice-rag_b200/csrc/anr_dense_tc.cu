@@ -21,6 +21,7 @@
 //             query), candidate selection; two accumulators so tile t+1 runs under it
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "anr_internal.h"
@@ -621,6 +622,15 @@ cudaError_t launch_row_norm_max(const float* emb, int64_t n, int ld, float* out,
 }
 
 // ---- host side ---------------------------------------------------------------------------
+static int64_t tc_sample_rows(const DeviceProps& dp, int64_t n, int k);
+// Rows of the sample pre-pass: the planned sample, shrunk to a quarter of a small corpus;
+// 0 = corpus too small for a pre-pass to pay off.
+static int64_t tc_prepass_rows(const DeviceProps& dp, int64_t n, int k) {
+  int64_t rows = tc_sample_rows(dp, n, k);
+  if (n < 4 * rows) rows = n / 4 / kTcRows * kTcRows;
+  return rows >= 8 * kTcRows ? rows : 0;
+}
+
 static inline int tc_align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 // Per-(warp, query) candidate list length.  With the pre-pass threshold only a handful of rows
@@ -729,11 +739,12 @@ cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, 
   uint64_t* cand_sample = cand + pass_keys;
   uint64_t* thr0 = nullptr;
   // sample pre-pass over the first tile of every CTA (worth it from ~8 tiles per CTA on)
-  const int64_t n_sample = tc_sample_rows(dp, n, k);
-  if (n >= 8 * n_sample) {
+  const int64_t n_sample = tc_prepass_rows(dp, n, k);
+  if (n_sample > 0) {
     thr0 = cand_sample + static_cast<size_t>(kTcQueries) * n_sample;
-    dense_tc_kernel<true><<<dp.sm_count, kTcThreads, smem, stream>>>(map_a, map_b, n_sample, mask,
-                                                                     nullptr, cand_sample, L);
+    const int grid_s = static_cast<int>(std::min<int64_t>(dp.sm_count, n_sample / kTcRows));
+    dense_tc_kernel<true><<<grid_s, kTcThreads, smem, stream>>>(map_a, map_b, n_sample, mask,
+                                                                nullptr, cand_sample, L);
     dense_tc_thr_kernel<<<kTcQueries, kTcRescoreThreads, 0, stream>>>(
         cand_sample, static_cast<int>(n_sample), tc_thr_rank(k), thr0);
   }
@@ -769,12 +780,13 @@ cudaError_t launch_dense_tc_pair(const DeviceProps& dp, const float* emb, int64_
   const size_t pass_keys = 2 * static_cast<size_t>(kTcQueries) * n_clusters * kTcEpiWarps * L.kl;
   uint64_t* cand_sample = cand + pass_keys;
   uint64_t* thr0 = nullptr;
-  const int64_t n_sample = tc_sample_rows(dp, n, k);
-  if (n >= 8 * n_sample) {   // two 32-query sample pre-passes (emit mode), one threshold kernel
+  const int64_t n_sample = tc_prepass_rows(dp, n, k);
+  if (n_sample > 0) {   // two 32-query sample pre-passes (emit mode), one threshold kernel
     thr0 = cand_sample + 2 * static_cast<size_t>(kTcQueries) * n_sample;
-    dense_tc_kernel<true><<<dp.sm_count, kTcThreads, smem, stream>>>(map_a, map_b0, n_sample, mask,
-                                                                     nullptr, cand_sample, L);
-    dense_tc_kernel<true><<<dp.sm_count, kTcThreads, smem, stream>>>(
+    const int grid_s = static_cast<int>(std::min<int64_t>(dp.sm_count, n_sample / kTcRows));
+    dense_tc_kernel<true><<<grid_s, kTcThreads, smem, stream>>>(map_a, map_b0, n_sample, mask,
+                                                                nullptr, cand_sample, L);
+    dense_tc_kernel<true><<<grid_s, kTcThreads, smem, stream>>>(
         map_a, map_b1, n_sample, mask, nullptr,
         cand_sample + static_cast<size_t>(kTcQueries) * n_sample, L);
     dense_tc_thr_kernel<<<2 * kTcQueries, kTcRescoreThreads, 0, stream>>>(

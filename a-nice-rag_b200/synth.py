@@ -183,31 +183,49 @@ def unit_vectors_torch(n: int, d: int, seed: int, device):
 def zipf_postings_torch(n_docs: int, vocab: int, s: float, seed: int, device,
                         len_lo: int = 100, len_hi: int = 300):
     """Zipf corpus inverted on ``device``.  -> dict(term_ptr i64 [V+1], post_doc i32, post_tf
-    i32, doc_len i32 [n_docs], nd i64 [V]); postings sorted by (term, doc)."""
+    i32, doc_len i32 [n_docs], nd i64 [V]); postings sorted by (term, doc).
+
+    Built slab by slab (2^17 documents each: torch.unique handles < 2^31 keys): a slab's
+    (term, doc, tf) triples come out sorted by (term, doc), slabs are in document order, so the
+    postings of term t from slab j land at term_ptr[t] + (postings of t in slabs < j) + rank."""
     import torch
     g = torch.Generator(device=device).manual_seed(seed)
     lens = torch.randint(len_lo, len_hi, (n_docs,), generator=g, device=device)
     cdf = torch.cumsum(torch.from_numpy(zipf_probs(vocab, s)).to(device), 0)
-    keys = []
-    step = 1 << 17                              # documents per slab: bounds the temporaries
+    step = 1 << 17
+    slabs = []                                   # (term i32, doc i32, tf i32, nd_slab i64)
+    nd = torch.zeros(vocab, dtype=torch.int64, device=device)
     for d0 in range(0, n_docs, step):
         l = lens[d0:d0 + step]
         total = int(l.sum())
         u = torch.rand(total, generator=g, device=device, dtype=torch.float64)
         tok = torch.searchsorted(cdf, u, right=True).clamp_(max=vocab - 1)
-        doc = torch.repeat_interleave(torch.arange(d0, d0 + l.numel(), device=device), l)
-        keys.append(tok * n_docs + doc)
+        doc = torch.repeat_interleave(torch.arange(l.numel(), device=device), l)
+        uniq, tf = torch.unique(tok * l.numel() + doc, return_counts=True)   # sorted (term, doc)
         del u, tok, doc
-    key = torch.cat(keys)
-    del keys
-    uniq, tf = torch.unique(key, return_counts=True)     # sorted by (term, doc)
-    del key
-    term = torch.div(uniq, n_docs, rounding_mode="floor")
-    nd = torch.bincount(term, minlength=vocab)
+        term = torch.div(uniq, l.numel(), rounding_mode="floor")
+        nd_slab = torch.bincount(term, minlength=vocab)
+        slabs.append((term.to(torch.int32), (uniq - term * l.numel() + d0).to(torch.int32),
+                      tf.to(torch.int32), nd_slab))
+        nd += nd_slab
+        del uniq, term
     term_ptr = torch.zeros(vocab + 1, dtype=torch.int64, device=device)
     term_ptr[1:] = torch.cumsum(nd, 0)
-    return dict(term_ptr=term_ptr, post_doc=(uniq - term * n_docs).to(torch.int32),
-                post_tf=tf.to(torch.int32), doc_len=lens.to(torch.int32), nd=nd)
+    nnz = int(term_ptr[-1])
+    post_doc = torch.empty(nnz, dtype=torch.int32, device=device)
+    post_tf = torch.empty(nnz, dtype=torch.int32, device=device)
+    base = term_ptr[:-1].clone()                 # next free slot of every term
+    for term, doc, tf, nd_slab in slabs:
+        start = torch.cumsum(nd_slab, 0) - nd_slab           # first index of each term in the slab
+        t = term.long()
+        dest = base[t] + (torch.arange(t.numel(), device=device) - start[t])
+        post_doc[dest] = doc
+        post_tf[dest] = tf
+        base += nd_slab
+        del dest, t
+    del slabs
+    return dict(term_ptr=term_ptr, post_doc=post_doc, post_tf=post_tf,
+                doc_len=lens.to(torch.int32), nd=nd)
 
 
 def idf_from_counts(n_docs_total: int, nd: np.ndarray, epsilon: float) -> np.ndarray:
