@@ -54,8 +54,10 @@ struct anr_ctx {
   size_t ws_bytes = 0;
   // profiling (anr_ctx_profile_*): event pairs recorded around the dominant kernels
   bool profiling = false;
-  std::vector<EventPair> pool[2];  // created lazily, reused after every read
-  size_t used[2] = {0, 0};
+  // kind 0 = dense scan kernel, 1 = BM25 score kernel, 2 = a whole tensor-core pass
+  // (sample pre-pass + threshold + scan + rescoring)
+  std::vector<EventPair> pool[3];  // created lazily, reused after every read
+  size_t used[3] = {0, 0, 0};
 };
 
 struct anr_dense {
@@ -147,6 +149,21 @@ struct ProfileScope {
     if (ev) cudaEventRecord(ev->stop, stream);
   }
 };
+
+// An event pair the callee records itself (around one kernel inside a multi-kernel launcher).
+EventPair* profile_take(anr_ctx* ctx, int kind) {
+  if (!ctx->profiling) return nullptr;
+  if (ctx->used[kind] == ctx->pool[kind].size()) {
+    if (ctx->pool[kind].size() >= 65536) return nullptr;
+    EventPair p;
+    if (cudaEventCreate(&p.start) != cudaSuccess || cudaEventCreate(&p.stop) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    ctx->pool[kind].push_back(p);
+  }
+  return &ctx->pool[kind][ctx->used[kind]++];
+}
 
 struct DeviceGuard {
   int prev = -1;
@@ -288,17 +305,20 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
       if (o.scores) o.scores += q0 * out.stride_q;
       if (o.ids) o.ids += q0 * out.stride_q;
       if (o.counts) o.counts += q0 * out.count_stride;
-      ProfileScope prof(ctx, 0, stream);
+      ProfileScope prof(ctx, 2, stream);
+      EventPair* ev = profile_take(ctx, 0);
       if (pair && nq - q0 > per) {   // 33..64 queries left: one pass of the CTA-pair kernel
         ANR_CUDA(launch_dense_tc_pair(ctx->dp, ix->emb, ix->n, ix->ld,
                                       q_dev + static_cast<size_t>(q0) * ix->ld,
                                       std::min(2 * per, nq - q0), k, mask_dev, ix->norm_max,
-                                      tc_cand, o, flags + q0, stream));
+                                      tc_cand, o, flags + q0, ev ? ev->start : nullptr,
+                                      ev ? ev->stop : nullptr, stream));
         q0 += 2 * per;
       } else {
         ANR_CUDA(launch_dense_tc(ctx->dp, ix->emb, ix->n, ix->ld,
                                  q_dev + static_cast<size_t>(q0) * ix->ld, std::min(per, nq - q0),
-                                 k, mask_dev, ix->norm_max, tc_cand, o, flags + q0, stream));
+                                 k, mask_dev, ix->norm_max, tc_cand, o, flags + q0,
+                                 ev ? ev->start : nullptr, ev ? ev->stop : nullptr, stream));
         q0 += per;
       }
     }
@@ -550,7 +570,7 @@ int anr_ctx_profile_enable(anr_ctx* ctx, int32_t on) {
 }
 
 int anr_ctx_profile_read(anr_ctx* ctx, int32_t kind, double* total_ms, int64_t* launches) {
-  if (!ctx || kind < 0 || kind > 1) return fail(ANR_ERR_INVALID, "anr_ctx_profile_read: bad argument");
+  if (!ctx || kind < 0 || kind > 2) return fail(ANR_ERR_INVALID, "anr_ctx_profile_read: bad argument");
   DeviceGuard guard(ctx->dp.device);
   ANR_CUDA(cudaDeviceSynchronize());
   double sum = 0.0;

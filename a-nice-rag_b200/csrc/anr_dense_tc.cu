@@ -720,7 +720,7 @@ static bool encode_map(CUtensorMap* map, const float* base, int64_t rows, int ld
 cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, int ld,
                             const float* q_dev, int n_real, int k, const uint32_t* mask,
                             float emb_norm_max, uint64_t* cand, const TopkOut& out, int32_t* flags,
-                            cudaStream_t stream) {
+                            cudaEvent_t ev_start, cudaEvent_t ev_stop, cudaStream_t stream) {
   TcLayout L;
   if (!make_tc_layout(dp, ld, k, &L)) return cudaErrorInvalidConfiguration;
   CUtensorMap map_a, map_b;
@@ -748,7 +748,9 @@ cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, 
     dense_tc_thr_kernel<<<kTcQueries, kTcRescoreThreads, 0, stream>>>(
         cand_sample, static_cast<int>(n_sample), tc_thr_rank(k), thr0);
   }
+  if (ev_start) cudaEventRecord(ev_start, stream);   // brackets the main scan kernel only
   dense_tc_kernel<false><<<grid, kTcThreads, smem, stream>>>(map_a, map_b, n, mask, thr0, cand, L);
+  if (ev_stop) cudaEventRecord(ev_stop, stream);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dense_tc_rescore_kernel<<<n_real, kTcRescoreThreads, 0, stream>>>(
@@ -760,7 +762,8 @@ cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, 
 cudaError_t launch_dense_tc_pair(const DeviceProps& dp, const float* emb, int64_t n, int ld,
                                  const float* q_dev, int n_real, int k, const uint32_t* mask,
                                  float emb_norm_max, uint64_t* cand, const TopkOut& out,
-                                 int32_t* flags, cudaStream_t stream) {
+                                 int32_t* flags, cudaEvent_t ev_start, cudaEvent_t ev_stop,
+                                 cudaStream_t stream) {
   TcLayout L;
   if (!make_tc_layout(dp, ld, k, &L)) return cudaErrorInvalidConfiguration;
   CUtensorMap map_a_half, map_a, map_b64, map_b0, map_b1;
@@ -792,8 +795,10 @@ cudaError_t launch_dense_tc_pair(const DeviceProps& dp, const float* emb, int64_
     dense_tc_thr_kernel<<<2 * kTcQueries, kTcRescoreThreads, 0, stream>>>(
         cand_sample, static_cast<int>(n_sample), tc_thr_rank(k), thr0);
   }
+  if (ev_start) cudaEventRecord(ev_start, stream);
   dense_tc_pair_kernel<<<2 * n_clusters, kTcThreads, smem, stream>>>(map_a_half, map_b64, n, mask,
                                                                      thr0, cand, L);
+  if (ev_stop) cudaEventRecord(ev_stop, stream);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dense_tc_rescore_kernel<<<n_real, kTcRescoreThreads, 0, stream>>>(

@@ -52,18 +52,20 @@ int dense_tc_queries_per_pass();
 size_t dense_tc_cand_keys(const DeviceProps& dp, int64_t n, int k);  // scratch keys one pass needs
 cudaError_t launch_row_norm_max(const float* emb, int64_t n, int ld, float* out,
                                 cudaStream_t stream);
+// ev_start / ev_stop (nullable) are recorded around the main scan kernel only.
 // q_dev: [32, ld] (zero rows pad a short group); results of the first n_real queries go through
 // `out` (positioned at the group's first query); flags[q] = 1 -> rerun q through the exact scan.
 cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, int ld,
                             const float* q_dev, int n_real, int k, const uint32_t* mask,
                             float emb_norm_max, uint64_t* cand, const TopkOut& out, int32_t* flags,
-                            cudaStream_t stream);
+                            cudaEvent_t ev_start, cudaEvent_t ev_stop, cudaStream_t stream);
 
 // Same for 64 queries at q_dev ([64, ld]) in ONE pass: a CTA pair shares each corpus tile.
 cudaError_t launch_dense_tc_pair(const DeviceProps& dp, const float* emb, int64_t n, int ld,
                                  const float* q_dev, int n_real, int k, const uint32_t* mask,
                                  float emb_norm_max, uint64_t* cand, const TopkOut& out,
-                                 int32_t* flags, cudaStream_t stream);
+                                 int32_t* flags, cudaEvent_t ev_start, cudaEvent_t ev_stop,
+                                 cudaStream_t stream);
 bool dense_tc_pair_enabled();
 
 // ---- top-k ------------------------------------------------------------------

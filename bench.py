@@ -326,12 +326,14 @@ def run_ours(args):
         step_e2e()
     native.call("anr_ctx_profile_enable", ctx.handle, 1)
     import ctypes as C
-    native.call("anr_ctx_profile_read", ctx.handle, 0, None, None)      # reset counters
-    native.call("anr_ctx_profile_read", ctx.handle, 1, None, None)
+    for kind in (0, 1, 2):
+        native.call("anr_ctx_profile_read", ctx.handle, kind, None, None)   # reset counters
     ms_dev = timed(step_device, args.steps)
     scan_ms, scan_n, bm_ms, bm_n = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
+    pass_ms, pass_n = C.c_double(), C.c_int64()
     native.call("anr_ctx_profile_read", ctx.handle, 0, C.byref(scan_ms), C.byref(scan_n))
     native.call("anr_ctx_profile_read", ctx.handle, 1, C.byref(bm_ms), C.byref(bm_n))
+    native.call("anr_ctx_profile_read", ctx.handle, 2, C.byref(pass_ms), C.byref(pass_n))
     native.call("anr_ctx_profile_enable", ctx.handle, 0)
     ms_e2e = timed(step_e2e, args.steps)
 
@@ -365,7 +367,8 @@ def run_ours(args):
     if os.path.exists(tpath) and args.chunks == 1_000_000 and world == 1:
         with open(tpath) as fh:
             traffic = json.load(fh)["bytes_per_launch"].get(
-                "dense_tc_kernel<0>" if B > 8 else "dense_scan_kernel<1, 4, 0>")
+                ("dense_tc_pair_kernel" if B > 32 else "dense_tc_kernel<0>") if B > 8
+                else "dense_scan_kernel<1, 4, 0>")
     rows_local = hi - lo
     scan_bytes = rows_local * D * 4
     scan_avg_ms = scan_ms.value / max(scan_n.value, 1)
@@ -413,10 +416,13 @@ def run_ours(args):
         "gpu_launches": int((scan_n.value + bm_n.value) + 4 * args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
-                     "kernel": "dense_tc_kernel (+ sample pre-pass, rescoring)" if B > 8
+                     "kernel": ("dense_tc_pair_kernel" if B > 32 else "dense_tc_kernel") if B > 8
                                else "dense_scan_kernel", "bytes_per_launch": scan_bytes,
                      "avg_launch_ms": scan_avg_ms, "launches": int(scan_n.value),
                      "share_of_step": scan_ms.value / ms_dev if ms_dev else None},
+        "dense_tc_pass": {"what": "sample pre-pass + threshold + scan + exact rescoring",
+                          "avg_ms": pass_ms.value / max(pass_n.value, 1), "passes": int(pass_n.value),
+                          "share_of_step": pass_ms.value / ms_dev if ms_dev else None},
         "bm25_kernel": {"avg_launch_ms": bm_avg_ms, "launches": int(bm_n.value),
                         "share_of_step": bm_ms.value / ms_dev if ms_dev else None},
         "batch1": {"device_ms": ms_b1_dev, "device_qps": 1e3 / ms_b1_dev if ms_b1_dev else None,

@@ -50,9 +50,10 @@ int anr_ctx_sync(anr_ctx* ctx);
 /* sm count, total/free HBM bytes of the context's device (any pointer may be NULL) */
 int anr_ctx_info(anr_ctx* ctx, int32_t* sm_count, int64_t* hbm_total, int64_t* hbm_free);
 
-/* Per-kernel timing for roofline reports.  While enabled, every launch of the two dominant
- * kernels (kind 0 = dense scan, kind 1 = BM25 score) is bracketed by CUDA events on the
- * stream it is launched on.  anr_ctx_profile_read synchronises, returns the summed device
+/* Per-kernel timing for roofline reports.  While enabled, every launch of the dominant
+ * kernels (kind 0 = dense scan kernel -- CUDA-core, tcgen05 or tcgen05 CTA-pair variant --,
+ * kind 1 = BM25 score kernel, kind 2 = a whole tensor-core pass: sample pre-pass + threshold +
+ * scan + rescoring) is bracketed by CUDA events on the stream it is launched on.  anr_ctx_profile_read synchronises, returns the summed device
  * time (ms) and launch count per kind since the last read, and resets the counters. */
 int anr_ctx_profile_enable(anr_ctx* ctx, int32_t on);
 int anr_ctx_profile_read(anr_ctx* ctx, int32_t kind, double* total_ms, int64_t* launches);

@@ -29,10 +29,14 @@ for nq in nqs:
     for it in range(iters + 3):
         if it == 3:
             native.call("anr_ctx_profile_read", ctx.handle, 0, None, None)
+            native.call("anr_ctx_profile_read", ctx.handle, 2, None, None)
         native.call("anr_dense_search", ctx.handle, index.handle, q.data_ptr(), nq, k, None, 0,
                     scores.data_ptr(), rows.data_ptr(), counts.data_ptr(), None)
     ms, cnt = C.c_double(), C.c_int64()
     native.call("anr_ctx_profile_read", ctx.handle, 0, C.byref(ms), C.byref(cnt))
     avg = ms.value / max(cnt.value, 1)
-    print(f"nq={nq} rw={os.environ.get('ANR_SCAN_RW', 'auto')} scan avg {avg:.4f} ms over {cnt.value} launches "
-          f"-> {n * d * 4 / avg / 1e6:.1f} GB/s", flush=True)
+    pms, pcnt = C.c_double(), C.c_int64()
+    native.call("anr_ctx_profile_read", ctx.handle, 2, C.byref(pms), C.byref(pcnt))
+    extra = f"; whole tensor-core pass {pms.value / pcnt.value:.4f} ms" if pcnt.value else ""
+    print(f"nq={nq} rw={os.environ.get('ANR_SCAN_RW', 'auto')} scan kernel avg {avg:.4f} ms over {cnt.value} launches "
+          f"-> {n * d * 4 / avg / 1e6:.1f} GB/s{extra}", flush=True)
