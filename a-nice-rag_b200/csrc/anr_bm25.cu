@@ -101,13 +101,13 @@ bm25_score_kernel(Bm25View ix, const int32_t* __restrict__ q_terms,
 
   for (int i = threadIdx.x; i < nd; i += blockDim.x) acc[i] = 0.f;
 
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int c0 = t_begin; c0 < t_end; c0 += kBm25TermChunk) {
     const int nc = min(kBm25TermChunk, t_end - c0);
     __syncthreads();  // previous chunk's bounds are no longer read; acc zeroing is visible
-    // ---- slice bounds: thread j -> lower bound of d0, thread nc + j -> lower bound of d1 ----
-    if (threadIdx.x < 2 * nc) {
-      const int j = threadIdx.x < nc ? threadIdx.x : threadIdx.x - nc;
-      const int target = threadIdx.x < nc ? d0 : d1;
+    // ---- first posting of every term inside the tile: one WARP per term, 32-ary search
+    //      (5 dependent loads for 2^23 postings instead of 23 for a binary search) ----
+    for (int j = warp; j < nc; j += kBm25Threads / 32) {
       const int term = q_terms[c0 + j];
       int64_t lo = 0, hi = 0;
       float idf = 0.f;
@@ -116,35 +116,64 @@ bm25_score_kernel(Bm25View ix, const int32_t* __restrict__ q_terms,
         if (idf != 0.f) {  // `idf.get(q) or 0`: a zero idf contributes nothing
           lo = ix.term_ptr[term];
           hi = ix.term_ptr[term + 1];
-          while (lo < hi) {
-            const int64_t mid = lo + ((hi - lo) >> 1);
-            if (__ldg(ix.post_doc + mid) < target) lo = mid + 1; else hi = mid;
-          }
         }
       }
-      if (threadIdx.x < nc) { s_lo[j] = lo; s_idf[j] = idf; } else { s_hi[j] = lo; }
+      const int64_t term_end = hi;
+      while (hi > lo) {   // invariant: the answer (first index with doc >= d0) lies in [lo, hi]
+        const int64_t len = hi - lo;
+        if (len <= 32) {
+          const int64_t pos = lo + lane;
+          const bool below = pos < hi && __ldg(ix.post_doc + pos) < d0;
+          lo += __popc(__ballot_sync(kFullMask, below));
+          break;
+        }
+        const int64_t step = (len + 32) / 33;
+        const int64_t pos = lo + (lane + 1) * step - 1;
+        const bool below = pos < hi && __ldg(ix.post_doc + pos) < d0;
+        const int cnt = __popc(__ballot_sync(kFullMask, below));
+        const int64_t nlo = lo + cnt * step;
+        const int64_t nhi = lo + (cnt + 1) * step - 1;
+        lo = nlo;
+        hi = nhi < hi ? nhi : hi;
+      }
+      if (lane == 0) { s_lo[j] = lo; s_hi[j] = term_end; s_idf[j] = idf; }
     }
     __syncthreads();
-    // ---- scatter-accumulate, one term after another ----
-    for (int j = 0; j < nc; ++j) {
-      const int64_t lo = s_lo[j], hi = s_hi[j];
-      const float idf = s_idf[j];
-      int64_t p = lo + threadIdx.x;
-      // 4 postings in flight per thread
-      for (; p + 3 * kBm25Threads < hi; p += 4 * kBm25Threads) {
-        int dd[4];
-        float ww[4];
+    // ---- scatter-accumulate, one term after another.  A thread walks p = lo + tid, + 256, ...
+    //      and stops at its first posting at or beyond the tile end (documents ascend), so no
+    //      second search is needed; the first loads of term j+1 are issued BEFORE the barrier
+    //      that closes term j, so their latency is not paid after it. ----
+    struct Item { int d[4]; float w[4]; };
+    const int kInvalid = 0x7fffffff;
+    auto load_item = [&](int64_t p, int64_t end) {
+      Item it;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          dd[u] = __ldg(ix.post_doc + p + u * kBm25Threads);
-          ww[u] = __ldg(ix.post_w + p + u * kBm25Threads);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[dd[u] - d0] += idf * ww[u];
+      for (int u = 0; u < 4; ++u) {
+        const int64_t pp = p + u * kBm25Threads;
+        const bool in = pp < end;
+        it.d[u] = in ? __ldg(ix.post_doc + pp) : kInvalid;
+        it.w[u] = in ? __ldg(ix.post_w + pp) : 0.f;
       }
-      for (; p < hi; p += kBm25Threads)
-        acc[__ldg(ix.post_doc + p) - d0] += idf * __ldg(ix.post_w + p);
-      if (lo < hi) __syncthreads();  // lo/hi are CTA-uniform
+      return it;
+    };
+    Item pre = load_item(s_lo[0] + threadIdx.x, s_hi[0]);
+    for (int j = 0; j < nc; ++j) {
+      const int64_t end = s_hi[j];
+      const float idf = s_idf[j];
+      int64_t p = s_lo[j] + threadIdx.x;
+      Item cur = pre;
+      while (true) {
+        const bool more = cur.d[3] < d1;   // the 4th posting is the furthest: still inside?
+        Item nxt;
+        if (more) { p += 4 * kBm25Threads; nxt = load_item(p, end); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (cur.d[u] < d1) acc[cur.d[u] - d0] += idf * cur.w[u];
+        if (!more) break;
+        cur = nxt;
+      }
+      if (j + 1 < nc) pre = load_item(s_lo[j + 1] + threadIdx.x, s_hi[j + 1]);
+      __syncthreads();
     }
   }
   __syncthreads();
@@ -174,11 +203,48 @@ bm25_score_kernel(Bm25View ix, const int32_t* __restrict__ q_terms,
     const uint64_t key = key_of(i);
     best = key > best ? key : best;
   }
-  tbest[threadIdx.x] = best;
   if (threadIdx.x == 0) n_sel = 0;
-  block_bitonic_sort_desc(tbest, kBm25Threads);
-  const uint64_t thr = k <= kBm25Threads ? tbest[k - 1] : 0ull;   // 0: fewer than k threads hold a document
-  __syncthreads();
+  __shared__ uint64_t s_thr;
+  if (k <= 32) {
+    // k-th largest of the 256 thread-bests without a block-wide sort: every warp sorts its 32
+    // keys in registers (shuffles, no barrier), warp 0 then pops the largest head k times
+    uint64_t v = best;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const uint64_t other = __shfl_xor_sync(kFullMask, v, stride);
+        const bool keep_max = ((lane & stride) == 0) == ((lane & size) == 0);
+        v = keep_max ? (v > other ? v : other) : (v < other ? v : other);
+      }
+    tbest[threadIdx.x] = v;   // warp w's keys, descending, at tbest[32 w ..]
+    __syncthreads();
+    if (warp == 0) {
+      int head = 0;   // lanes 0..7: read position in warp `lane`'s sorted run
+      uint64_t kth = 0ull;
+      for (int it = 0; it < k; ++it) {
+        const uint64_t c = (lane < kBm25Threads / 32 && head < 32) ? tbest[lane * 32 + head] : 0ull;
+        uint64_t m = c;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+          const uint64_t other = __shfl_xor_sync(kFullMask, m, o);
+          m = other > m ? other : m;
+        }
+        m = __shfl_sync(kFullMask, m, 0);   // max over lanes 0..7
+        kth = m;
+        if (m == 0ull) break;               // fewer than k threads hold a document
+        if (c == m) ++head;                 // keys are unique: exactly one lane advances
+      }
+      if (lane == 0) s_thr = kth;
+    }
+    __syncthreads();
+  } else {
+    tbest[threadIdx.x] = best;
+    block_bitonic_sort_desc(tbest, kBm25Threads);
+    if (threadIdx.x == 0) s_thr = k <= kBm25Threads ? tbest[k - 1] : 0ull;
+    __syncthreads();
+  }
+  const uint64_t thr = s_thr;   // 0: fewer than k threads hold a document -> everything passes
   for (int i = threadIdx.x; i < sel_cap; i += kBm25Threads) sel[i] = 0ull;
   __syncthreads();
   for (int i = threadIdx.x; i < nd; i += kBm25Threads) {
@@ -190,9 +256,21 @@ bm25_score_kernel(Bm25View ix, const int32_t* __restrict__ q_terms,
   }
   __syncthreads();
   const int ns = n_sel < sel_cap ? n_sel : sel_cap;
-  block_bitonic_sort_desc(sel, next_pow2(ns < 2 ? 2 : ns));
-  for (int i = threadIdx.x; i < k; i += blockDim.x)
-    out[q * out_stride_q + static_cast<int64_t>(tile) * k + i] = i < ns ? sel[i] : 0ull;
+  uint64_t* o = out + q * out_stride_q + static_cast<int64_t>(tile) * k;
+  if (ns <= kBm25Threads) {
+    // rank by counting (keys are unique): one pass, no sort
+    for (int i = threadIdx.x; i < k; i += kBm25Threads)
+      if (i >= ns) o[i] = 0ull;
+    if (threadIdx.x < ns) {
+      const uint64_t key = sel[threadIdx.x];
+      int rank = 0;
+      for (int j = 0; j < ns; ++j) rank += sel[j] > key;
+      if (rank < k) o[rank] = key;
+    }
+  } else {
+    block_bitonic_sort_desc(sel, next_pow2(ns));
+    for (int i = threadIdx.x; i < k; i += blockDim.x) o[i] = i < ns ? sel[i] : 0ull;
+  }
 }
 
 template <bool EMIT_ALL>

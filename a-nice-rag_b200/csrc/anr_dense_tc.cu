@@ -487,7 +487,7 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
                         const float* __restrict__ emb, int ld, const float* __restrict__ q_dev,
                         int k, float emb_norm_max, const uint64_t* __restrict__ thr0, TopkOut o,
                         int32_t* __restrict__ flags) {
-  __shared__ uint64_t top[2048];                 // warp lists for the tf32 top-k (16 warps x k<=128)
+  __shared__ uint64_t top[kTcRescoreThreads];    // per-thread best tf32 keys
   __shared__ uint64_t sel[kTcRescoreCap];        // candidates inside the margin, then exact keys
   __shared__ int n_sel, bad;
   __shared__ float q_norm2;
@@ -499,24 +499,24 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
   const float* qv = q_dev + static_cast<size_t>(q) * ld;
 
   if (threadIdx.x == 0) { n_sel = 0; bad = 0; q_norm2 = 0.f; }
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) top[i] = 0ull;
   __syncthreads();
   // |q|^2
   float part = 0.f;
   for (int i = threadIdx.x; i < ld; i += blockDim.x) part = fmaf(qv[i], qv[i], part);
   part = warp_sum(part);
   if (lane == 0) atomicAdd(&q_norm2, part);
-  // tf32 top-k over all candidates (threshold lists per warp, then one sort)
+  // T = k-th largest of the 512 per-thread bests: a lower bound of the k-th best tf32 score
+  // (k distinct candidates reach it).  A lower T only widens the rescored margin, so exactness
+  // is unaffected and no list of candidates has to be maintained here.
   {
-    uint64_t thr = 0;
-    uint64_t* list = top + warp * k;
-    for (int base = warp * 32; base < m; base += kTcRescoreThreads) {
-      const int i = base + lane;
-      warp_list_offer(list, k, i < m ? c[i] : 0ull, thr, lane);
+    uint64_t b = 0ull;
+    for (int i = threadIdx.x; i < m; i += kTcRescoreThreads) {
+      const uint64_t v = c[i];
+      b = v > b ? v : b;
     }
+    top[threadIdx.x] = b;
   }
-  const int p2 = next_pow2(n_warps * k);
-  block_bitonic_sort_desc(top, p2);   // top[0..k) = best k by tf32 score
+  block_bitonic_sort_desc(top, kTcRescoreThreads);
   const uint64_t kth = top[k - 1];
   // error bound of a tf32 product sum: each operand loses < 2^-10 relative (13 mantissa bits
   // dropped), accumulation noise D * 2^-22 -> |err| <= 2.5e-3 * |q| * |e| (Cauchy-Schwarz)
