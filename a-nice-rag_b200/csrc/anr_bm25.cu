@@ -74,8 +74,10 @@ Bm25Plan bm25_make_plan(const DeviceProps& dp, int n_docs, int nq, int k, bool e
   p.tile_docs = static_cast<int>(tile);
   p.n_tiles = n_docs > 0 ? static_cast<int>((n_docs + tile - 1) / tile) : 0;
   const int per_thread = (p.tile_docs + kBm25Threads - 1) / kBm25Threads;
-  p.list_cap = emit_all ? 0 : next_pow2(k * per_thread < 2 * kBm25Threads ? 2 * kBm25Threads
-                                                                           : k * per_thread);
+  // [256 thread-bests][collect buffer: k * per_thread keys at most, a power of two for the sort]
+  p.list_cap = emit_all ? 0
+                        : kBm25Threads + next_pow2(k * per_thread < kBm25Threads ? kBm25Threads
+                                                                                 : k * per_thread);
   p.smem_bytes = p.tile_docs * 4 + p.list_cap * 8 + kBm25TermChunk * (8 + 8 + 4);
   return p;
 }
@@ -131,10 +133,10 @@ bm25_score_kernel(Bm25View ix, const int32_t* __restrict__ q_terms,
         const int64_t pos = lo + (lane + 1) * step - 1;
         const bool below = pos < hi && __ldg(ix.post_doc + pos) < d0;
         const int cnt = __popc(__ballot_sync(kFullMask, below));
-        const int64_t nlo = lo + cnt * step;
+        // probes 0..cnt-1 are below the target; probe cnt (if it exists and is in range) is not
         const int64_t nhi = lo + (cnt + 1) * step - 1;
-        lo = nlo;
-        hi = nhi < hi ? nhi : hi;
+        if (cnt < 32 && nhi < hi) hi = nhi;
+        lo += cnt * step;
       }
       if (lane == 0) { s_lo[j] = lo; s_hi[j] = term_end; s_idf[j] = idf; }
     }

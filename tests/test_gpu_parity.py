@@ -382,3 +382,24 @@ def test_sharded_fuse_equals_unsharded_hybrid(small):
                                WRRF_K, 2 * k)
     assert np.array_equal(counts, res["counts"])
     assert np.array_equal(ids, res["ids"]) and np.array_equal(scores, res["scores"])
+
+
+def test_bm25_long_posting_lists_many_tiles():
+    """Posting lists of 10^4..10^5 entries cut by many document tiles: exercises every level of
+    the 32-ary slice search, including terms whose postings all lie before / after a tile."""
+    n, vocab = 300_000, 300
+    doc_ptr, tokens = synth.zipf_corpus(n, vocab, 1.1, seed=41, len_lo=8, len_hi=20)
+    tokens[doc_ptr[200_000]:] = np.minimum(tokens[doc_ptr[200_000]:], 40)   # rare terms end early
+    ix = csr.from_token_ids(doc_ptr, tokens, vocab, 1.7, 0.83, 0.05)
+    index = engine.Bm25Index(ix.term_ptr, ix.post_doc, ix.post_tf, ix.doc_len, ix.idf, ix.k1,
+                             ix.b, ix.avgdl)
+    tq = synth.zipf_queries(6, 8, vocab, 1.1, seed=42)
+    tq[0, :] = [299, 250, 200, 150, 100, 60, 45, 41]       # lists that stop at document 200 000
+    for k in (10, 100):
+        scores, docs, counts = index.search([list(map(int, t)) for t in tq], k)
+        for q in range(6):
+            all_scores = csr.scores(ix, [int(t) for t in tq[q]])
+            want = retrieval.bm25_topk(all_scores, k)
+            check_ids_only(docs[q, :counts[q]], want, all_scores, f"bm25 long q{q} k{k}")
+            np.testing.assert_allclose(scores[q, :counts[q]], all_scores[docs[q, :counts[q]]],
+                                       rtol=1e-5, atol=1e-6)
