@@ -273,8 +273,8 @@ size_t dense_ws_bytes(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
   const int gmax = std::max(dense_group(ctx, ix, k), 1);
   const int nqp = pad_queries(nq, gmax);
   if (dense_use_tc(ctx, ix, nq, k))
-    return padded(dense_tc_cand_keys(ctx->dp, ix->n, k) * 8) + padded(static_cast<size_t>(nq) * 4) +
-           padded(static_cast<size_t>(dense_scan_max_grid(ctx->dp)) * k * 8) + 1024;
+    return padded(dense_tc_cand_keys(ctx->dp, ix->n, k) * 8) + 2 * padded(static_cast<size_t>(nq) * 4) +
+           padded(static_cast<size_t>(nq) * dense_scan_max_grid(ctx->dp) * k * 8) + 2048;
   if (k <= kMaxFusedK)
     return padded(static_cast<size_t>(nqp) * dense_scan_max_grid(ctx->dp) * k * 8) + 256;
   const int64_t n_pow2 = next_pow2(static_cast<int>(std::max<int64_t>(ix->n, 2)));
@@ -322,27 +322,19 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
         q0 += per;
       }
     }
-    // queries whose candidate lists could not prove exactness go through the exact scan
-    std::vector<int32_t> host_flags(static_cast<size_t>(nq));
-    ANR_CUDA(cudaMemcpyAsync(host_flags.data(), flags, static_cast<size_t>(nq) * 4,
-                             cudaMemcpyDeviceToHost, stream));
-    ANR_CUDA(cudaStreamSynchronize(stream));
-    const int64_t stride = static_cast<int64_t>(dense_scan_max_grid(ctx->dp)) * k;
-    uint64_t* cand = nullptr;
-    for (int q = 0; q < nq; ++q) {
-      if (!host_flags[q]) continue;
-      if (!cand) cand = arena.take<uint64_t>(static_cast<size_t>(stride));
-      int grid = 0;
-      ANR_CUDA(launch_dense_scan_topk(ctx->dp, ix->emb, ix->n, ix->ld,
-                                      q_dev + static_cast<size_t>(q) * ix->ld, 1, k, mask_dev, cand,
-                                      stride, &grid, stream));
-      TopkOut o = out;
-      if (o.keys) o.keys += q * out.stride_q;
-      if (o.scores) o.scores += q * out.stride_q;
-      if (o.ids) o.ids += q * out.stride_q;
-      if (o.counts) o.counts += q * out.count_stride;
-      ANR_CUDA(launch_topk_final(cand, stride, grid * k, grid * k, 0, 1, k, o, stream));
-    }
+    // Queries whose candidate lists could not prove exactness go through the exact scan.  The
+    // list is compacted and consumed on the device (both launches return at once when it is
+    // empty), so the call stays asynchronous and capturable in a CUDA graph.
+    const int fb_grid = dense_scan_flagged_grid(ctx->dp, ix->n, ix->ld, k);
+    const int64_t fb_stride = static_cast<int64_t>(fb_grid) * k;
+    int32_t* n_flagged = arena.take<int32_t>(1);
+    int32_t* flagged = arena.take<int32_t>(static_cast<size_t>(nq));
+    uint64_t* fb_cand = arena.take<uint64_t>(static_cast<size_t>(nq) * fb_stride);
+    ANR_CUDA(launch_compact_flags(flags, nq, n_flagged, flagged, stream));
+    ANR_CUDA(launch_dense_scan_flagged(ctx->dp, ix->emb, ix->n, ix->ld, q_dev, n_flagged, flagged, k,
+                                       mask_dev, fb_cand, fb_stride, stream));
+    ANR_CUDA(launch_topk_final_flagged(fb_cand, fb_stride, static_cast<int>(fb_stride), nq, k, out,
+                                       n_flagged, flagged, stream));
     return ANR_OK;
   }
   const int nqp = pad_queries(nq, gmax);

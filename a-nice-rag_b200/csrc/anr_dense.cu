@@ -34,12 +34,14 @@ struct ScanLayout {
   int n_cwarps;  // consumer warps that own stages (n_stages is a multiple of it)
 };
 
+// One full pass over the corpus by this CTA (see the file header).  Every thread of the CTA
+// calls it; shared memory is (re)initialised on entry, so it can be called repeatedly.
 template <int NQ, int RW, bool EMIT_ALL>
-__global__ void __launch_bounds__(kScanThreads, 1)
-dense_scan_kernel(const float* __restrict__ emb, int64_t n, int ld, const float* __restrict__ q,
-                  int k, const uint32_t* __restrict__ mask, uint64_t* __restrict__ out,
-                  int64_t out_stride_q, ScanLayout L) {
-  extern __shared__ __align__(128) unsigned char smem[];
+__device__ __forceinline__ void dense_scan_body(const float* __restrict__ emb, int64_t n, int ld,
+                                                const float* __restrict__ q, int k,
+                                                const uint32_t* __restrict__ mask,
+                                                uint64_t* __restrict__ out, int64_t out_stride_q,
+                                                const ScanLayout& L, unsigned char* smem) {
   float* qs = reinterpret_cast<float*>(smem + L.q_off);
   float* ring = reinterpret_cast<float*>(smem + L.ring_off);
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + L.list_off);  // [NQ][list_cap]
@@ -174,6 +176,42 @@ dense_scan_kernel(const float* __restrict__ emb, int64_t n, int ld, const float*
   }
 }
 
+template <int NQ, int RW, bool EMIT_ALL>
+__global__ void __launch_bounds__(kScanThreads, 1)
+dense_scan_kernel(const float* __restrict__ emb, int64_t n, int ld, const float* __restrict__ q,
+                  int k, const uint32_t* __restrict__ mask, uint64_t* __restrict__ out,
+                  int64_t out_stride_q, ScanLayout L) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  dense_scan_body<NQ, RW, EMIT_ALL>(emb, n, ld, q, k, mask, out, out_stride_q, L, smem);
+}
+
+// Exact rescan of the queries the tensor-core path could not certify (anr_dense_tc.cu): the
+// list of flagged queries lives on the device, so no host round trip is needed -- one launch,
+// which returns at once when the list is empty (the common case) and otherwise runs one full
+// single-query pass per flagged query.  cand: [flagged slot][cta * k + i].
+template <int RW>
+__global__ void __launch_bounds__(kScanThreads, 1)
+dense_scan_flagged_kernel(const float* __restrict__ emb, int64_t n, int ld,
+                          const float* __restrict__ q_all, const int32_t* __restrict__ n_flagged,
+                          const int32_t* __restrict__ flagged, int k,
+                          const uint32_t* __restrict__ mask, uint64_t* __restrict__ cand,
+                          int64_t cand_stride, ScanLayout L) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int nf = *n_flagged;
+  for (int f = 0; f < nf; ++f) {
+    dense_scan_body<1, RW, false>(emb, n, ld, q_all + static_cast<size_t>(flagged[f]) * ld, k, mask,
+                                  cand + f * cand_stride, cand_stride, L, smem);
+    __syncthreads();
+    if (threadIdx.x == 0) {   // the next pass initialises the barriers again
+      uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+      for (int s = 0; s < 2 * kScanMaxStages; ++s)
+        if (s < L.n_stages || (s >= kScanMaxStages && s < kScanMaxStages + L.n_stages))
+          asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[s])) : "memory");
+    }
+    __syncthreads();
+  }
+}
+
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
 static bool make_scan_layout(const DeviceProps& dp, int ld, int nq, int rw, int k, bool emit_all,
@@ -284,6 +322,46 @@ cudaError_t launch_dense_scan_topk(const DeviceProps& dp, const float* emb, int6
   if (k < 1 || k > kMaxFusedK) return cudaErrorInvalidValue;
   return dispatch_scan<false>(dp, emb, n, ld, q_dev, nq, k, mask, cand, cand_stride_q, grid_out,
                               stream);
+}
+
+template <int RW>
+static cudaError_t launch_flagged_t(const DeviceProps& dp, const float* emb, int64_t n, int ld,
+                                    const float* q_all, const int32_t* n_flagged,
+                                    const int32_t* flagged, int k, const uint32_t* mask,
+                                    uint64_t* cand, int64_t cand_stride, cudaStream_t stream) {
+  ScanLayout L;
+  if (!make_scan_layout(dp, ld, 1, RW, k, false, &L)) return cudaErrorInvalidConfiguration;
+  auto kern = dense_scan_flagged_kernel<RW>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       L.total_bytes);
+  if (e != cudaSuccess) return e;
+  const int64_t n_tiles = (n + RW - 1) / RW;
+  int grid = static_cast<int>(n_tiles < dp.sm_count ? n_tiles : dp.sm_count);
+  if (grid < 1) grid = 1;
+  kern<<<grid, kScanThreads, L.total_bytes, stream>>>(emb, n, ld, q_all, n_flagged, flagged, k, mask,
+                                                      cand, cand_stride, L);
+  return cudaGetLastError();
+}
+
+// grid the flagged rescan uses = candidates per flagged query / k
+int dense_scan_flagged_grid(const DeviceProps& dp, int64_t n, int ld, int k) {
+  const int rw = choose_rw(dp, ld, 1, k, false);
+  if (rw < 1) return 0;
+  const int64_t n_tiles = (n + rw - 1) / rw;
+  return static_cast<int>(n_tiles < dp.sm_count ? (n_tiles < 1 ? 1 : n_tiles) : dp.sm_count);
+}
+
+cudaError_t launch_dense_scan_flagged(const DeviceProps& dp, const float* emb, int64_t n, int ld,
+                                      const float* q_all, const int32_t* n_flagged,
+                                      const int32_t* flagged, int k, const uint32_t* mask,
+                                      uint64_t* cand, int64_t cand_stride, cudaStream_t stream) {
+  if (k < 1 || k > kMaxFusedK) return cudaErrorInvalidValue;
+  switch (choose_rw(dp, ld, 1, k, false)) {
+    case 4: return launch_flagged_t<4>(dp, emb, n, ld, q_all, n_flagged, flagged, k, mask, cand, cand_stride, stream);
+    case 2: return launch_flagged_t<2>(dp, emb, n, ld, q_all, n_flagged, flagged, k, mask, cand, cand_stride, stream);
+    case 1: return launch_flagged_t<1>(dp, emb, n, ld, q_all, n_flagged, flagged, k, mask, cand, cand_stride, stream);
+    default: return cudaErrorInvalidConfiguration;
+  }
 }
 
 cudaError_t launch_dense_scan_all(const DeviceProps& dp, const float* emb, int64_t n, int ld,

@@ -40,6 +40,18 @@ int dense_scan_max_grid(const DeviceProps& dp);
 // Largest number of queries (8, 4, 2, 1; 0 = rows too long) one pass can stage in shared
 // memory next to a >= 3-stage row ring.
 int dense_scan_max_queries(const DeviceProps& dp, int ld, int k, bool emit_all);
+// Device-driven exact rescan of flagged queries (see anr_dense.cu): one single-query pass per
+// entry of flagged[0 .. *n_flagged), candidates to cand[slot * cand_stride + cta * k + i].
+int dense_scan_flagged_grid(const DeviceProps& dp, int64_t n, int ld, int k);
+cudaError_t launch_dense_scan_flagged(const DeviceProps& dp, const float* emb, int64_t n, int ld,
+                                      const float* q_all, const int32_t* n_flagged,
+                                      const int32_t* flagged, int k, const uint32_t* mask,
+                                      uint64_t* cand, int64_t cand_stride, cudaStream_t stream);
+cudaError_t launch_compact_flags(const int32_t* flags, int nq, int32_t* n_flagged, int32_t* flagged,
+                                 cudaStream_t stream);
+cudaError_t launch_topk_final_flagged(const uint64_t* cand, int64_t cand_stride, int m, int nq,
+                                      int k, const TopkOut& out, const int32_t* n_flagged,
+                                      const int32_t* flagged, cudaStream_t stream);
 // Full materialisation: keys[q * keys_stride_q + row] for every row (0 for masked rows).
 cudaError_t launch_dense_scan_all(const DeviceProps& dp, const float* emb, int64_t n, int ld,
                                   const float* q_dev, int nq, const uint32_t* mask,

@@ -65,14 +65,18 @@ topk_final_kernel(const uint64_t* __restrict__ cand, int64_t stride_q, int m, in
 constexpr int kSmallThreads = 256;
 constexpr int kSmallCap = 2048;
 
+// n_active / row_map (nullable): only the first *n_active blocks work, block b writes result
+// row row_map[b] (the device-side list of queries the tensor-core path flagged).
 __global__ void __launch_bounds__(kSmallThreads)
 topk_final_small_kernel(const uint64_t* __restrict__ cand, int64_t stride_q, int m, int seg_len,
-                        int64_t seg_stride, int k, TopkOut o) {
+                        int64_t seg_stride, int k, TopkOut o,
+                        const int32_t* __restrict__ n_active, const int32_t* __restrict__ row_map) {
   __shared__ uint64_t best[kSmallThreads];
   __shared__ uint64_t sel[kSmallCap];
   __shared__ int n_sel;
-  const int q = blockIdx.x;
-  const uint64_t* c = cand + q * stride_q;
+  if (n_active && static_cast<int>(blockIdx.x) >= *n_active) return;
+  const uint64_t* c = cand + blockIdx.x * stride_q;
+  const int q = row_map ? row_map[blockIdx.x] : blockIdx.x;
   uint64_t b = 0ull;
   for (int i = threadIdx.x; i < m; i += kSmallThreads) {
     const uint64_t v = c[(i / seg_len) * seg_stride + (i % seg_len)];
@@ -111,11 +115,58 @@ cudaError_t launch_topk_final(const uint64_t* cand, int64_t cand_stride_q, int m
   if (nq < 1) return cudaSuccess;
   if (static_cast<int64_t>(k) * ((m + kSmallThreads - 1) / kSmallThreads) <= kSmallCap) {
     topk_final_small_kernel<<<nq, kSmallThreads, 0, stream>>>(cand, cand_stride_q, m, seg_len,
-                                                              seg_stride, k, out);
+                                                              seg_stride, k, out, nullptr, nullptr);
     return cudaGetLastError();
   }
   topk_final_kernel<<<nq, kFinalThreads, 0, stream>>>(cand, cand_stride_q, m, seg_len, seg_stride,
                                                       k, out);
+  return cudaGetLastError();
+}
+
+// flags[0..nq) -> n_flagged, flagged[] (ascending query indices); one small block
+__global__ void __launch_bounds__(256)
+compact_flags_kernel(const int32_t* __restrict__ flags, int nq, int32_t* __restrict__ n_flagged,
+                     int32_t* __restrict__ flagged) {
+  __shared__ int count;
+  if (threadIdx.x == 0) count = 0;
+  __syncthreads();
+  for (int base = 0; base < nq; base += 256) {   // ordered: one chunk of 256 queries at a time
+    const int q = base + threadIdx.x;
+    const bool f = q < nq && flags[q] != 0;
+    const unsigned ballot = __ballot_sync(kFullMask, f);
+    __shared__ int warp_off[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) warp_off[warp] = __popc(ballot);
+    __syncthreads();
+    int off = count;
+    for (int w = 0; w < warp; ++w) off += warp_off[w];
+    if (f) flagged[off + __popc(ballot & ((1u << lane) - 1))] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int total = 0;
+      for (int w = 0; w < 8; ++w) total += warp_off[w];
+      count += total;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_flagged = count;
+}
+
+cudaError_t launch_compact_flags(const int32_t* flags, int nq, int32_t* n_flagged, int32_t* flagged,
+                                 cudaStream_t stream) {
+  compact_flags_kernel<<<1, 256, 0, stream>>>(flags, nq, n_flagged, flagged);
+  return cudaGetLastError();
+}
+
+// Merge of the flagged rescan: block b < *n_flagged ranks cand[b] into result row flagged[b].
+cudaError_t launch_topk_final_flagged(const uint64_t* cand, int64_t cand_stride, int m, int nq,
+                                      int k, const TopkOut& out, const int32_t* n_flagged,
+                                      const int32_t* flagged, cudaStream_t stream) {
+  if (k < 1 || k > kMaxFusedK || m < 1) return cudaErrorInvalidValue;
+  if (static_cast<int64_t>(k) * ((m + kSmallThreads - 1) / kSmallThreads) > kSmallCap)
+    return cudaErrorInvalidConfiguration;
+  topk_final_small_kernel<<<nq, kSmallThreads, 0, stream>>>(cand, cand_stride, m, m, 0, k, out,
+                                                            n_flagged, flagged);
   return cudaGetLastError();
 }
 
