@@ -26,10 +26,12 @@ __device__ __forceinline__ void emit_entry(uint64_t key, int64_t slot, const Top
 // the sharded search uses seg_len = k, seg_stride = n_queries * k.
 __global__ void __launch_bounds__(kFinalThreads)
 topk_final_kernel(const uint64_t* __restrict__ cand, int64_t stride_q, int m, int seg_len,
-                  int64_t seg_stride, int k, TopkOut o) {
+                  int64_t seg_stride, int k, TopkOut o, const int32_t* __restrict__ n_active,
+                  const int32_t* __restrict__ row_map) {
   __shared__ uint64_t keys[kFinalSortCap];
-  const int q = blockIdx.x;
-  const uint64_t* c = cand + q * stride_q;
+  if (n_active && static_cast<int>(blockIdx.x) >= *n_active) return;
+  const uint64_t* c = cand + blockIdx.x * stride_q;
+  const int q = row_map ? row_map[blockIdx.x] : blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int p2;
   if (m <= kFinalSortCap) {
@@ -119,7 +121,7 @@ cudaError_t launch_topk_final(const uint64_t* cand, int64_t cand_stride_q, int m
     return cudaGetLastError();
   }
   topk_final_kernel<<<nq, kFinalThreads, 0, stream>>>(cand, cand_stride_q, m, seg_len, seg_stride,
-                                                      k, out);
+                                                      k, out, nullptr, nullptr);
   return cudaGetLastError();
 }
 
@@ -164,9 +166,11 @@ cudaError_t launch_topk_final_flagged(const uint64_t* cand, int64_t cand_stride,
                                       const int32_t* flagged, cudaStream_t stream) {
   if (k < 1 || k > kMaxFusedK || m < 1) return cudaErrorInvalidValue;
   if (static_cast<int64_t>(k) * ((m + kSmallThreads - 1) / kSmallThreads) > kSmallCap)
-    return cudaErrorInvalidConfiguration;
-  topk_final_small_kernel<<<nq, kSmallThreads, 0, stream>>>(cand, cand_stride, m, m, 0, k, out,
-                                                            n_flagged, flagged);
+    topk_final_kernel<<<nq, kFinalThreads, 0, stream>>>(cand, cand_stride, m, m, 0, k, out,
+                                                        n_flagged, flagged);
+  else
+    topk_final_small_kernel<<<nq, kSmallThreads, 0, stream>>>(cand, cand_stride, m, m, 0, k, out,
+                                                              n_flagged, flagged);
   return cudaGetLastError();
 }
 
