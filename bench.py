@@ -413,7 +413,11 @@ def run_ours(args):
         "e2e": {"value": B * args.steps / (ms_e2e * 1e-3), "unit": "queries/s",
                 "h2d_bytes_per_step": int(q_pin.numel() * 4 + t_pin.numel() * 4 + off_pin.numel() * 4),
                 "d2h_bytes_per_step": int(h_ids.numel() * 4 + h_scores.numel() * 8 + h_counts.numel() * 4)},
-        "gpu_launches": int((scan_n.value + bm_n.value) + 4 * args.steps),
+        # kernels of this repo launched per step: dense (CUDA-core scan + final | tcgen05:
+        # pre-pass(es) + threshold + scan + rescore + flag compaction + flagged rescan + its merge),
+        # BM25 score + final, weights, WRRF; sharded: + the two merges of anr_sharded_fuse
+        "gpu_launches": int(args.steps * (
+            ((8 if B > 32 else 7) if B > 8 else 2) + 2 + 2 + (2 if world > 1 else 0))),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                      "kernel": ("dense_tc_pair_kernel" if B > 32 else "dense_tc_kernel") if B > 8
