@@ -20,6 +20,8 @@
 //
 // Algorithmic HBM bytes per query: 8 B per posting of every query-term occurrence
 // (4 B doc id + 4 B precomputed weight) + k*8 B of candidates per tile.
+#include <cstdlib>
+
 #include "anr_internal.h"
 #include "anr_topk.cuh"
 
@@ -63,8 +65,13 @@ Bm25Plan bm25_make_plan(const DeviceProps& dp, int n_docs, int nq, int k, bool e
   int64_t tiles_wanted = (2LL * dp.sm_count + nq - 1) / nq;
   if (tiles_wanted < 1) tiles_wanted = 1;
   int64_t tile = (static_cast<int64_t>(n_docs) + tiles_wanted - 1) / tiles_wanted;
+  int64_t tile_max = 12288;
+  if (const char* e = getenv("ANR_BM25_TILE")) {   // tuning knob for profiling runs
+    const int64_t v = atoll(e);
+    if (v >= 1024 && v <= 49152) tile_max = v;
+  }
   if (tile < 1024) tile = 1024;
-  if (tile > 12288) tile = 12288;
+  if (tile > tile_max) tile = tile_max;
   // the collect buffer holds k * ceil(tile / 256) keys at most: keep it <= 2048 entries
   if (!emit_all && k > 0) {
     const int64_t per_thread = 2048 / k > 1 ? 2048 / k : 1;

@@ -85,19 +85,21 @@ def resolve_frame(df: pd.DataFrame) -> Tuple[DenseEntry, Optional[np.ndarray]]:
     if entry is not None:
         return entry, None
     entry = _dense.get(df.attrs.get(ATTR_KEY, -1))
-    if entry is not None:
+    if entry is not None and "id" in df.columns:
+        # O(1) checks only: this runs on every query (a full pass over a 1M-row id column
+        # costs more than the search itself)
         n = len(df)
         labels = df.index
-        ids = df["id"].to_numpy(dtype=object) if "id" in df.columns else None
-        if ids is not None and n == entry.n and isinstance(labels, pd.RangeIndex) \
-                and labels.start == 0 and labels.step == 1:
-            if n == 0 or (ids[0] == entry.ids[0] and ids[n - 1] == entry.ids[n - 1]):
+        id_col = df["id"]
+        if n == entry.n and isinstance(labels, pd.RangeIndex) and labels.start == 0 \
+                and labels.step == 1:
+            if n == 0 or (id_col.iat[0] == entry.ids[0] and id_col.iat[n - 1] == entry.ids[n - 1]):
                 return entry, None
         rows = np.asarray(labels)
-        if ids is not None and n and rows.dtype.kind in "iu" and rows.min() >= 0 \
-                and rows.max() < entry.n and labels.is_unique:
+        if n and rows.dtype.kind in "iu" and rows.min() >= 0 and rows.max() < entry.n \
+                and labels.is_unique:
             probe = np.unique(np.linspace(0, n - 1, num=min(n, 8)).astype(np.int64))
-            if all(ids[p] == entry.ids[rows[p]] for p in probe):
+            if all(id_col.iat[int(p)] == entry.ids[rows[p]] for p in probe):
                 return entry, rows.astype(np.int64)
     # unknown frame: pack and upload it (np.stack raises for ragged rows, like the reference)
     packed = np.ascontiguousarray(np.stack(df["embedding"].values), dtype=np.float32)
