@@ -838,6 +838,45 @@ int anr_bm25_create(anr_ctx* ctx, const int64_t* term_ptr, const int32_t* post_d
   return ANR_OK;
 }
 
+int anr_bm25_reweight(anr_ctx* ctx, anr_bm25* index, const int32_t* post_tf, const int32_t* doc_len,
+                      const double* idf, double k1, double b, double avgdl) {
+  if (!ctx || !index || !idf || (index->nnz > 0 && !post_tf) || (index->n_docs > 0 && !doc_len))
+    return fail(ANR_ERR_INVALID, "anr_bm25_reweight: NULL argument");
+  if (index->device != ctx->dp.device) return fail(ANR_ERR_INVALID, "index lives on another device");
+  DeviceGuard guard(ctx->dp.device);
+  cudaStream_t stream = ctx->stream;
+  const size_t pn = static_cast<size_t>(std::max<int64_t>(index->nnz, 1));
+  const size_t need = padded(pn * 4) + padded(static_cast<size_t>(std::max(index->n_docs, 1)) * 4) +
+                      padded(static_cast<size_t>(std::max(index->n_terms, 1)) * 8) + 2048;
+  if (int rc = ws_reserve(ctx, need)) return rc;
+  Arena arena{ctx->ws, ctx->ws_bytes};
+  const int32_t* tf_dev = post_tf;
+  const int32_t* dl_dev = doc_len;
+  if (index->nnz > 0 && !is_device_ptr(post_tf)) {
+    int32_t* p = arena.take<int32_t>(pn);
+    ANR_CUDA(cudaMemcpyAsync(p, post_tf, pn * 4, cudaMemcpyHostToDevice, stream));
+    tf_dev = p;
+  }
+  if (index->n_docs > 0 && !is_device_ptr(doc_len)) {
+    int32_t* p = arena.take<int32_t>(static_cast<size_t>(index->n_docs));
+    ANR_CUDA(cudaMemcpyAsync(p, doc_len, static_cast<size_t>(index->n_docs) * 4,
+                             cudaMemcpyHostToDevice, stream));
+    dl_dev = p;
+  }
+  if (index->n_terms > 0) {
+    double* idf64 = arena.take<double>(static_cast<size_t>(index->n_terms));
+    ANR_CUDA(cudaMemcpyAsync(idf64, idf, static_cast<size_t>(index->n_terms) * 8, cudaMemcpyDefault,
+                             stream));
+    f64_to_f32_kernel<<<(index->n_terms + 255) / 256, 256, 0, stream>>>(idf64, index->idf,
+                                                                        index->n_terms);
+    ANR_CUDA(cudaGetLastError());
+  }
+  ANR_CUDA(launch_bm25_weights(index->post_doc, tf_dev, dl_dev, index->nnz, k1, b, avgdl,
+                               index->post_w, stream));
+  ANR_CUDA(cudaStreamSynchronize(stream));   // host sources may be reused by the caller
+  return ANR_OK;
+}
+
 int anr_bm25_destroy(anr_bm25* index) {
   if (!index) return ANR_OK;
   DeviceGuard guard(index->device);

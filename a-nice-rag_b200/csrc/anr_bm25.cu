@@ -65,7 +65,7 @@ Bm25Plan bm25_make_plan(const DeviceProps& dp, int n_docs, int nq, int k, bool e
   int64_t tiles_wanted = (2LL * dp.sm_count + nq - 1) / nq;
   if (tiles_wanted < 1) tiles_wanted = 1;
   int64_t tile = (static_cast<int64_t>(n_docs) + tiles_wanted - 1) / tiles_wanted;
-  int64_t tile_max = 12288;
+  int64_t tile_max = 6144;   // measured: 6144 beats 4096 / 8192 / 12288 / 24576 at batch 64 (profiles/)
   if (const char* e = getenv("ANR_BM25_TILE")) {   // tuning knob for profiling runs
     const int64_t v = atoll(e);
     if (v >= 1024 && v <= 49152) tile_max = v;

@@ -29,6 +29,20 @@ def _no_device(exc: BaseException) -> bool:
     return isinstance(exc, native.AnrError) and exc.code == 3
 
 
+def _alloc_matrix(n: int, d: int):
+    """[n, d] fp32 host buffer; page-locked (faster, asynchronous H2D) when it is big and a GPU
+    is present.  Returns (numpy view, owner object to keep alive)."""
+    if n * d * 4 >= (64 << 20):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                owner = torch.empty((n, d), dtype=torch.float32, pin_memory=True)
+                return owner.numpy(), owner
+        except Exception:  # pragma: no cover - pinning is an optimisation only
+            pass
+    return np.empty((n, d), dtype=np.float32), None
+
+
 class _AttrOnlyBM25Okapi:
     """Stand-in for ``rank_bm25.BM25Okapi`` when that package is absent at unpickle time.
 
@@ -108,40 +122,58 @@ class DatabaseManager:
                 raise FileNotFoundError(f"Database not found: {db_path}")
             conn = sqlite3.connect(db_path)
             cursor = conn.cursor()
-            cursor.execute("SELECT id, content, source, embedding, url FROM chunks")
-            rows = cursor.fetchall()
-            if not rows:
+            n_rows = cursor.execute("SELECT COUNT(*) FROM chunks").fetchone()[0]
+            if not n_rows:
                 self.logger.warning(f"No chunks found in {db_path}")
                 return pd.DataFrame()
+            cursor.execute("SELECT id, content, source, embedding, url FROM chunks")
 
-            # one packed [N, D] buffer; D is fixed by the first decodable row
-            ids, documents, sources, urls, blobs = [], [], [], [], []
-            for cid, content, source, blob, url in rows:
-                try:
-                    if len(memoryview(blob)) % 4 != 0:
-                        raise ValueError("buffer size must be a multiple of element size")
-                except (ValueError, TypeError) as e:
-                    self.logger.warning(f"Skipping invalid row {cid}: {e}")
-                    continue
-                ids.append(cid)
-                documents.append(content)
-                sources.append(source)
-                urls.append(url)
-                blobs.append(blob)
-            widths = {len(memoryview(b)) for b in blobs}
-            if len(widths) == 1:
-                d = widths.pop() // 4
-                packed = np.frombuffer(b"".join(blobs), dtype=np.float32).reshape(len(blobs), d)
+            # Rows are streamed straight into ONE preallocated (pinned when a GPU is present)
+            # [N, D] buffer -- no per-row arrays, no second copy; D is fixed by the first
+            # decodable row.  A table with ragged widths keeps the reference's frame instead.
+            ids, documents, sources, urls = [], [], [], []
+            packed = keep = None
+            ragged = None            # list of per-row arrays once widths disagree
+            n_ok = 0
+            while True:
+                rows = cursor.fetchmany(16384)
+                if not rows:
+                    break
+                for cid, content, source, blob, url in rows:
+                    try:
+                        view = memoryview(blob)
+                        if len(view) % 4 != 0:
+                            raise ValueError("buffer size must be a multiple of element size")
+                    except (ValueError, TypeError) as e:
+                        self.logger.warning(f"Skipping invalid row {cid}: {e}")
+                        continue
+                    row = np.frombuffer(view, dtype=np.float32)
+                    if packed is None and ragged is None:
+                        packed, keep = _alloc_matrix(n_rows, row.shape[0])
+                    if ragged is None and row.shape[0] != packed.shape[1]:
+                        ragged = [np.array(packed[i]) for i in range(n_ok)]
+                        packed = keep = None
+                    if ragged is None:
+                        packed[n_ok] = row
+                    else:
+                        ragged.append(row)
+                    ids.append(cid)
+                    documents.append(content)
+                    sources.append(source)
+                    urls.append(url)
+                    n_ok += 1
+            if ragged is None and packed is not None:
+                packed = packed[:n_ok]
                 embeddings = list(packed)            # N row views, like the per-row frombuffer
-            else:                                    # ragged widths: keep the reference's frame,
-                packed = None                        # searches will fail in np.stack like it does
-                embeddings = [np.frombuffer(b, dtype=np.float32) for b in blobs]
+            else:                                    # searches will fail in np.stack like the
+                embeddings = ragged or []            # reference does on such a table
             df = pd.DataFrame({
                 "id": ids, "document": documents, "source": sources,
                 "embedding": pd.Series(embeddings, dtype=object), "url": urls,
             })
             if packed is not None and len(df):
                 entry = registry.register_frame(df, packed)
+                entry.keepalive = keep               # the pinned allocation behind `packed`
                 try:
                     entry.index()                    # upload now: queries must not pay for it
                 except Exception as e:
@@ -172,7 +204,7 @@ class DatabaseManager:
                 data = pickle.load(f)
             result = (data["bm25"], data["sections"], data["section_ids"])
             try:
-                registry.resolve_bm25(result[0])     # CSR inversion + upload, once
+                registry.resolve_bm25(result[0], cache_for=filepath)   # CSR (cached on disk) + upload
             except Exception as e:
                 if not _no_device(e):
                     raise

@@ -235,6 +235,15 @@ class Bm25Index:
         return cls(term_ptr, post_doc, post_tf, doc_len, idf, bm25.k1, bm25.b, bm25.avgdl,
                    vocab=vocab, device=device)
 
+    def reweight(self, post_tf, doc_len, idf, k1: float, b: float, avgdl: float) -> None:
+        """New k1 / b / avgdl / idf on the same postings (one step of a parameter sweep)."""
+        def prep(x, dtype):
+            return x.contiguous() if hasattr(x, "data_ptr") else np.ascontiguousarray(x, dtype=dtype)
+        post_tf, doc_len, idf = prep(post_tf, np.int32), prep(doc_len, np.int32), prep(idf, np.float64)
+        native.call("anr_bm25_reweight", context(self.ctx_device).handle, self.handle,
+                    native.ptr(post_tf), native.ptr(doc_len), native.ptr(idf), float(k1), float(b),
+                    float(avgdl))
+
     # -- queries --------------------------------------------------------------
     def term_ids(self, tokens: Iterable[str]) -> np.ndarray:
         """Token strings -> term ids in query order, -1 for tokens absent from the vocabulary."""

@@ -135,9 +135,57 @@ def lookup_identity(df: pd.DataFrame) -> Optional[DenseEntry]:
 
 
 # ---------------------------------------------------------------------------------
+CSR_CACHE_SUFFIX = ".anr_csr.npz"
+
+
+def _csr_cache_load(pickle_path: str):
+    """CSR arrays saved next to the BM25 pickle by an earlier load, if still valid (same pickle
+    size and mtime).  The Python inversion of a real index takes minutes at 1M documents; the
+    cache makes it a one-off."""
+    import os
+    path = pickle_path + CSR_CACHE_SUFFIX
+    try:
+        st = os.stat(pickle_path)
+        with np.load(path, allow_pickle=True) as z:
+            if int(z["pickle_size"]) != st.st_size or int(z["pickle_mtime_ns"]) != st.st_mtime_ns:
+                return None
+            return {k: z[k] for k in ("vocab", "term_ptr", "post_doc", "post_tf", "doc_len", "idf",
+                                      "k1", "b", "avgdl")}
+    except (OSError, KeyError, ValueError):
+        return None
+
+
+def _csr_cache_save(pickle_path: str, vocab, term_ptr, post_doc, post_tf, doc_len, idf, k1, b,
+                    avgdl) -> None:
+    import os
+    try:
+        st = os.stat(pickle_path)
+        tmp = pickle_path + CSR_CACHE_SUFFIX + ".tmp.npz"
+        np.savez(tmp, vocab=np.array(list(vocab.keys()), dtype=object), term_ptr=term_ptr,
+                 post_doc=post_doc, post_tf=post_tf, doc_len=doc_len, idf=idf, k1=np.float64(k1),
+                 b=np.float64(b), avgdl=np.float64(avgdl), pickle_size=np.int64(st.st_size),
+                 pickle_mtime_ns=np.int64(st.st_mtime_ns))
+        os.replace(tmp, pickle_path + CSR_CACHE_SUFFIX)
+    except OSError as e:   # read-only directory etc.: the cache is an optimisation only
+        logger.info(f"CSR cache not written for {pickle_path}: {e}")
+
+
 class Bm25Entry:
-    def __init__(self, bm25):
-        self.index = engine.Bm25Index.from_okapi(bm25)
+    def __init__(self, bm25, cache_for: Optional[str] = None):
+        cached = _csr_cache_load(cache_for) if cache_for else None
+        if cached is not None and float(cached["k1"]) == float(bm25.k1) \
+                and float(cached["b"]) == float(bm25.b) and len(cached["doc_len"]) == len(bm25.doc_len):
+            vocab = {tok: i for i, tok in enumerate(cached["vocab"].tolist())}
+            self.index = engine.Bm25Index(cached["term_ptr"], cached["post_doc"], cached["post_tf"],
+                                          cached["doc_len"], cached["idf"], float(cached["k1"]),
+                                          float(cached["b"]), float(cached["avgdl"]), vocab=vocab)
+        else:
+            vocab, term_ptr, post_doc, post_tf, doc_len, idf = engine.invert_okapi(bm25)
+            if cache_for:
+                _csr_cache_save(cache_for, vocab, term_ptr, post_doc, post_tf, doc_len, idf,
+                                bm25.k1, bm25.b, bm25.avgdl)
+            self.index = engine.Bm25Index(term_ptr, post_doc, post_tf, doc_len, idf, bm25.k1,
+                                          bm25.b, bm25.avgdl, vocab=vocab)
         self._masks: Dict[Tuple[int, str], Tuple[object, object, int]] = {}
 
     def filter_mask(self, sections, filename_type_filter: str):
@@ -157,14 +205,14 @@ class Bm25Entry:
 _bm25: Dict[int, Tuple[weakref.ref, Bm25Entry]] = {}
 
 
-def resolve_bm25(bm25) -> Bm25Entry:
+def resolve_bm25(bm25, cache_for: Optional[str] = None) -> Bm25Entry:
     entry = getattr(bm25, "_anr_entry", None)
     if isinstance(entry, Bm25Entry):
         return entry
     hit = _bm25.get(id(bm25))
     if hit is not None and hit[0]() is bm25:
         return hit[1]
-    entry = Bm25Entry(bm25)
+    entry = Bm25Entry(bm25, cache_for=cache_for)
     try:
         bm25._anr_entry = entry
     except AttributeError:  # __slots__ / frozen object

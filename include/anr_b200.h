@@ -97,6 +97,13 @@ int anr_bm25_create(anr_ctx* ctx, const int64_t* term_ptr, const int32_t* post_d
                     const int32_t* post_tf, const int32_t* doc_len, const double* idf,
                     int32_t n_terms, int32_t n_docs, double k1, double b, double avgdl,
                     anr_bm25** out);
+/* Re-parameterise an existing index in place: new k1 / b / avgdl (posting weights recomputed
+ * from post_tf / doc_len, which the caller supplies again -- the index keeps only the weights)
+ * and a new idf table (the epsilon floor is part of it).  The postings themselves are reused:
+ * this is the inner step of a k1 / b / epsilon sweep such as src/processing/bm25_test.py:180-315
+ * (50 trials over the same corpus).  post_tf is [n_postings] in index order. */
+int anr_bm25_reweight(anr_ctx* ctx, anr_bm25* index, const int32_t* post_tf, const int32_t* doc_len,
+                      const double* idf, double k1, double b, double avgdl);
 int anr_bm25_destroy(anr_bm25* index);
 int anr_bm25_shape(const anr_bm25* index, int32_t* n_terms, int32_t* n_docs, int64_t* n_postings);
 

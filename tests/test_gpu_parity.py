@@ -403,3 +403,22 @@ def test_bm25_long_posting_lists_many_tiles():
             check_ids_only(docs[q, :counts[q]], want, all_scores, f"bm25 long q{q} k{k}")
             np.testing.assert_allclose(scores[q, :counts[q]], all_scores[docs[q, :counts[q]]],
                                        rtol=1e-5, atol=1e-6)
+
+
+def test_bm25_reweight_equals_rebuilt_index(small):
+    """k1 / b / epsilon sweep step (src/processing/bm25_test.py): re-weighting the resident
+    postings must equal building a fresh index with the new parameters."""
+    from oracle import bm25_okapi
+    case, ix = small["case"], small["ix"]
+    corpus = synth.doc_token_lists(case["doc_ptr"], case["tokens"])
+    other = bm25_okapi.BM25Okapi(corpus, k1=0.857, b=0.686, epsilon=0.075)   # results/bm25_optimization_results.csv:2
+    idf = np.zeros(int(case["vocab"]), dtype=np.float64)
+    for tok, val in other.idf.items():
+        idf[int(tok[1:])] = val
+    index = engine.Bm25Index(ix.term_ptr, ix.post_doc, ix.post_tf, ix.doc_len, ix.idf, ix.k1, ix.b,
+                             ix.avgdl)
+    index.reweight(ix.post_tf, ix.doc_len, idf, 0.857, 0.686, other.avgdl)
+    for q in range(4):
+        toks = synth.token_strings(case["term_queries"][q])
+        got = index.scores(term_ids_of(case, ix, q))
+        np.testing.assert_allclose(got, other.get_scores(toks), rtol=1e-5, atol=1e-6)

@@ -213,3 +213,45 @@ def test_offline_tokeniser_on_frozen_golden_sample():
     assert len(rows) == 60
     for row in rows:
         assert pp.preprocess_text(row["query"]) == ast.literal_eval(row["tokens_regular"]), row
+
+
+def test_csr_cache_roundtrip_and_invalidation(tmp_path, small_case):
+    _, okapi = csr_from_case(small_case)
+    n = len(okapi.doc_freqs)
+    srcs = list(small_case["sources"])
+    pkl = str(tmp_path / "b.pkl")
+    synth.write_bm25_pickle(pkl, okapi, [""] * n, synth.chunk_ids(n, srcs), srcs)
+    assert registry._csr_cache_load(pkl) is None
+    vocab, term_ptr, post_doc, post_tf, doc_len, idf = engine.invert_okapi(okapi)
+    registry._csr_cache_save(pkl, vocab, term_ptr, post_doc, post_tf, doc_len, idf, okapi.k1,
+                             okapi.b, okapi.avgdl)
+    got = registry._csr_cache_load(pkl)
+    assert got is not None and got["vocab"].tolist() == list(vocab.keys())
+    for name, want in (("term_ptr", term_ptr), ("post_doc", post_doc), ("post_tf", post_tf),
+                       ("doc_len", doc_len), ("idf", idf)):
+        assert np.array_equal(got[name], want), name
+    assert float(got["avgdl"]) == okapi.avgdl
+    os.utime(pkl, ns=(1, 1))                      # the pickle changed: the cache is stale
+    assert registry._csr_cache_load(pkl) is None
+
+
+def test_loader_streams_into_one_matrix_and_handles_ragged_tables(tmp_path):
+    pkg = importlib.import_module("a-nice-rag_b200")
+    n, d = 40_000, 16                              # several fetchmany() batches
+    emb = synth.unit_vectors(n, d, seed=3)
+    srcs = synth.sources(n, seed=4)
+    ids = synth.chunk_ids(n, srcs)
+    db = str(tmp_path / "big.db")
+    synth.write_chunks_db(db, ids, [""] * n, srcs, emb)
+    df = pkg.DatabaseManager().load_embeddings_from_sql(db)
+    entry, subset = registry.resolve_frame(df)
+    assert subset is None and entry.packed.shape == (n, d) and np.array_equal(entry.packed, emb)
+    assert all(e.base is not None for e in df["embedding"].iloc[:5])      # views, not copies
+    # a table whose rows disagree on the width keeps the reference's frame (np.stack fails later)
+    db2 = str(tmp_path / "ragged.db")
+    odd = [("odd", "x", "CG1", np.zeros(d + 4, dtype=np.float32).tobytes(), "u")]
+    synth.write_chunks_db(db2, ids[:10], [""] * 10, srcs[:10], emb[:10], extra_rows=odd)
+    df2 = pkg.DatabaseManager().load_embeddings_from_sql(db2)
+    assert len(df2) == 11 and df2["embedding"].iloc[10].shape == (d + 4,)
+    assert registry.ATTR_KEY not in df2.attrs
+    assert np.array_equal(np.stack(df2["embedding"].iloc[:10].values), emb[:10])
