@@ -70,6 +70,10 @@ struct anr_dense {
   // max row norm, for the tf32 error bound of the tensor-core scan (computed on first need)
   mutable float norm_max = 0.f;
   mutable bool norm_valid = false;
+  // bf16 copy of emb ([n, ld]) for the GEMM path, built on first use when enabled
+  // (anr_dense_set_shadow / ANR_TC_BF16=1)
+  mutable void* shadow = nullptr;
+  mutable bool want_shadow = false;
 };
 
 struct anr_bm25 {
@@ -261,7 +265,25 @@ cudaError_t out_flush(const OutBuf<T>& o, cudaStream_t stream, bool* any_host) {
 inline bool dense_use_tc(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
   return nq > 8 && k <= kMaxFusedK && dense_tc_supported(ctx->dp, ix->n, ix->ld, k);
 }
+// Batches of more than 32 queries: the tiled GEMM (one pass over the corpus for up to 1024 queries).
+inline bool dense_shadow_wanted(const anr_dense* ix) {
+  static const bool env = getenv("ANR_TC_BF16") != nullptr && atoi(getenv("ANR_TC_BF16")) != 0;
+  return (ix->want_shadow || env) && ix->ld % 64 == 0;
+}
+inline int dense_gemm_min_queries() {
+  static const int v = getenv("ANR_GEMM_MIN_QUERIES") ? atoi(getenv("ANR_GEMM_MIN_QUERIES")) : 33;
+  return v;
+}
+inline bool dense_use_gemm(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
+  return nq >= dense_gemm_min_queries() && k <= kMaxFusedK &&
+         dense_gemm_supported(ctx->dp, ix->n, ix->ld, k, dense_shadow_wanted(ix));
+}
+inline int dense_gemm_total_padded(int nq) {
+  const int g = dense_gemm_max_queries();
+  return nq / g * g + (nq % g ? dense_gemm_padded_queries(nq % g) : 0);
+}
 inline int dense_padded_queries(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
+  if (dense_use_gemm(ctx, ix, nq, k)) return dense_gemm_total_padded(nq);
   if (dense_use_tc(ctx, ix, nq, k)) {
     const int p = 2 * dense_tc_queries_per_pass();   // the pair pass reads 64 query rows
     return (nq + p - 1) / p * p;
@@ -272,6 +294,10 @@ inline int dense_padded_queries(const anr_ctx* ctx, const anr_dense* ix, int nq,
 size_t dense_ws_bytes(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
   const int gmax = std::max(dense_group(ctx, ix, k), 1);
   const int nqp = pad_queries(nq, gmax);
+  if (dense_use_gemm(ctx, ix, nq, k))
+    return padded(dense_gemm_scratch_bytes(ctx->dp, ix->n, ix->ld, nq, k)) +
+           2 * padded(static_cast<size_t>(nq) * 4) +
+           padded(static_cast<size_t>(nq) * dense_scan_max_grid(ctx->dp) * k * 8) + 4096;
   if (dense_use_tc(ctx, ix, nq, k))
     return padded(dense_tc_cand_keys(ctx->dp, ix->n, k) * 8) + 2 * padded(static_cast<size_t>(nq) * 4) +
            padded(static_cast<size_t>(nq) * dense_scan_max_grid(ctx->dp) * k * 8) + 2048;
@@ -287,7 +313,8 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
                    cudaStream_t stream) {
   const int gmax = dense_group(ctx, ix, k);
   if (gmax < 1) return fail(ANR_ERR_UNSUPPORTED, "embedding rows too long for the scan kernel");
-  if (dense_use_tc(ctx, ix, nq, k)) {
+  const bool gemm = dense_use_gemm(ctx, ix, nq, k);
+  if (gemm || dense_use_tc(ctx, ix, nq, k)) {
     if (!ix->norm_valid) {  // once per index: the error bound needs max |row|
       float* d_norm = arena.take<float>(1);
       ANR_CUDA(launch_row_norm_max(ix->emb, ix->n, ix->ld, d_norm, stream));
@@ -295,6 +322,42 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
       ANR_CUDA(cudaStreamSynchronize(stream));
       ix->norm_valid = true;
     }
+  }
+  if (gemm) {
+    if (dense_shadow_wanted(ix) && !ix->shadow) {  // once per index: the bf16 operand copy
+      ANR_CUDA(cudaMalloc(&ix->shadow, static_cast<size_t>(ix->n) * ix->ld * 2));
+      ANR_CUDA(launch_f32_to_bf16(ix->emb, ix->shadow, ix->n * ix->ld, stream));
+    }
+    unsigned char* scratch =
+        arena.take<unsigned char>(dense_gemm_scratch_bytes(ctx->dp, ix->n, ix->ld, nq, k));
+    int32_t* flags = arena.take<int32_t>(static_cast<size_t>(nq));
+    const int per = dense_gemm_max_queries();
+    for (int q0 = 0; q0 < nq; q0 += per) {
+      TopkOut o = out;
+      if (o.keys) o.keys += q0 * out.stride_q;
+      if (o.scores) o.scores += q0 * out.stride_q;
+      if (o.ids) o.ids += q0 * out.stride_q;
+      if (o.counts) o.counts += q0 * out.count_stride;
+      ProfileScope prof(ctx, 2, stream);
+      EventPair* ev = profile_take(ctx, 0);
+      ANR_CUDA(launch_dense_gemm(ctx->dp, ix->emb, ix->shadow, ix->n, ix->ld,
+                                 q_dev + static_cast<size_t>(q0) * ix->ld, std::min(per, nq - q0), k,
+                                 mask_dev, ix->norm_max, scratch, o, flags + q0,
+                                 ev ? ev->start : nullptr, ev ? ev->stop : nullptr, stream));
+    }
+    const int fb_grid = dense_scan_flagged_grid(ctx->dp, ix->n, ix->ld, k);
+    const int64_t fb_stride = static_cast<int64_t>(fb_grid) * k;
+    int32_t* n_flagged = arena.take<int32_t>(1);
+    int32_t* flagged = arena.take<int32_t>(static_cast<size_t>(nq));
+    uint64_t* fb_cand = arena.take<uint64_t>(static_cast<size_t>(nq) * fb_stride);
+    ANR_CUDA(launch_compact_flags(flags, nq, n_flagged, flagged, stream));
+    ANR_CUDA(launch_dense_scan_flagged(ctx->dp, ix->emb, ix->n, ix->ld, q_dev, n_flagged, flagged, k,
+                                       mask_dev, fb_cand, fb_stride, stream));
+    ANR_CUDA(launch_topk_final_flagged(fb_cand, fb_stride, static_cast<int>(fb_stride), nq, k, out,
+                                       n_flagged, flagged, stream));
+    return ANR_OK;
+  }
+  if (dense_use_tc(ctx, ix, nq, k)) {
     const int per = dense_tc_queries_per_pass();
     uint64_t* tc_cand = arena.take<uint64_t>(dense_tc_cand_keys(ctx->dp, ix->n, k));
     int32_t* flags = arena.take<int32_t>(static_cast<size_t>(nq));
@@ -455,7 +518,7 @@ int stage_queries(const anr_dense* ix, const float* queries, int nq, int nqp, Ar
   return ANR_OK;
 }
 size_t stage_queries_bytes(const anr_dense* ix, int nq) {
-  return padded(static_cast<size_t>(nq + 64) * ix->ld * 4) + 256;
+  return padded(static_cast<size_t>(nq + 256) * ix->ld * 4) + 256;
 }
 
 // Stage a bit mask ([ceil(n/32)] words) if it lives on the host.
@@ -667,6 +730,11 @@ int anr_dense_upload(anr_ctx* ctx, anr_dense* index, int64_t row0, const float* 
     return fail(ANR_ERR_INVALID, "anr_dense_upload: row range out of bounds");
   DeviceGuard guard(ctx->dp.device);
   index->norm_valid = false;
+  if (index->shadow) {  // rebuilt on the next tensor-core search
+    ANR_CUDA(cudaDeviceSynchronize());
+    cudaFree(index->shadow);
+    index->shadow = nullptr;
+  }
   ANR_CUDA(copy_rows(index->emb + static_cast<size_t>(row0) * index->ld, index->ld, rows, index->d,
                      n_rows, ctx->stream));
   // the source may be a pageable/pinned buffer the caller is about to reuse
@@ -678,7 +746,20 @@ int anr_dense_destroy(anr_dense* index) {
   if (!index) return ANR_OK;
   DeviceGuard guard(index->device);
   if (index->owned && index->emb) cudaFree(index->emb);
+  if (index->shadow) cudaFree(index->shadow);
   delete index;
+  return ANR_OK;
+}
+
+int anr_dense_set_shadow(anr_dense* index, int32_t enable) {
+  if (!index) return fail(ANR_ERR_INVALID, "index is NULL");
+  DeviceGuard guard(index->device);
+  index->want_shadow = enable != 0;
+  if (!enable && index->shadow) {
+    ANR_CUDA(cudaDeviceSynchronize());
+    cudaFree(index->shadow);
+    index->shadow = nullptr;
+  }
   return ANR_OK;
 }
 
@@ -1133,7 +1214,8 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
   // The CUDA-core scan leaves ~90 KB of shared memory per SM free: BM25 CTAs co-reside with it,
   // so for small batches BM25 runs on the side stream underneath the scan.  The tensor-core
   // scan fills the SM, there the two run back to back on one stream.
-  const bool overlap = !dense_use_tc(ctx, dense, nq, k_dense);
+  const bool overlap =
+      !dense_use_tc(ctx, dense, nq, k_dense) && !dense_use_gemm(ctx, dense, nq, k_dense);
   cudaStream_t bm25_stream = overlap ? ctx->side : stream;
   if (overlap) {
     ANR_CUDA(cudaEventRecord(ctx->ev_fork, stream));

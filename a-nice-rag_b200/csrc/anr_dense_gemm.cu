@@ -1,0 +1,519 @@
+// Dense inner-product search for query batches of 64 and more as a TILED GEMM on the
+// 5th-generation tensor cores:  S[rows, queries] = E · Qᵀ  with 128-row x NQ-query output tiles
+// (NQ = 64, 128 or 256), both operands streamed per 128-byte K slab by TMA into one shared-memory
+// ring, accumulators in TMEM (double buffered: 2 x NQ columns), tcgen05.mma issued by one thread.
+//
+// Differences from the 32-query scan in anr_dense_tc.cu (which keeps its query block resident):
+//   * the query slab travels with the corpus slab (it comes out of L2: the whole query block is
+//     a few MB), so the tile can be 256 queries wide and a batch of 1024 queries costs ONE pass
+//     over the corpus in HBM instead of 32;
+//   * the score matrix is still never written.  A strided SAMPLE of row tiles is scored first
+//     (same kernel, SAMPLE = true: the epilogue reduces every 32-row group to its per-query
+//     maximum); the r-th largest group maximum of a query is a lower bound of its r-th best score
+//     over the whole corpus, so the main pass only has to APPEND the few thousand rows per query
+//     that beat it to a per-query candidate buffer (one atomicAdd per survivor);
+//   * operands are either the fp32 corpus read as tf32 (kind::tf32) or a bf16 shadow copy of it
+//     (kind::f16, half the bytes, twice the rate, 3.2x wider error margin).
+// Tensor-core scores only NOMINATE: dense_tc_rescore_kernel recomputes every candidate within a
+// rigorous error margin of the k-th best in exact fp32 and flags the query for the exact scan
+// when the lists cannot prove exactness (anr_dense_tc.cu).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "anr_internal.h"
+#include "anr_tc.cuh"
+#include "anr_topk.cuh"
+
+namespace anr {
+
+constexpr int kGmRows = 128;          // corpus rows per tile = UMMA M
+constexpr int kGmThreads = 192;       // TMA producer warp, MMA warp, 4 epilogue warps
+constexpr int kGmEpiWarps = 4;
+constexpr int kGmMaxStages = 12;
+constexpr int kGmABytes = kGmRows * 128;   // one corpus slab: 128 rows x 128 bytes of K
+constexpr int kGmThrThreads = 512;
+
+struct GemmLayout {
+  int thr_off, stage_off, bar_off, total_bytes;
+  int n_stages, n_slabs, stage_bytes;
+};
+
+template <int NQ, bool BF16>
+struct GemmCfg {
+  static constexpr int kSlabElems = BF16 ? 64 : 32;            // elements per 128-byte K slab
+  static constexpr int kBBytes = NQ * 128;
+  static constexpr int kStageBytes = kGmABytes + kBBytes;
+  static constexpr uint32_t kFmt = BF16 ? 1u : 2u;             // F16F32 format: 1 = bf16, 2 = tf32
+  // D = F32 (bits 4-5 = 1), A/B format (bits 7-9, 10-12), both K-major, N >> 3 at 17, M >> 4 at 24
+  static constexpr uint32_t kIdesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) |
+                                     (static_cast<uint32_t>(NQ >> 3) << 17) |
+                                     (static_cast<uint32_t>(kGmRows >> 4) << 24);
+  static constexpr int kTmemCols = 2 * NQ;                     // 128, 256 or 512: powers of two
+};
+
+// element `lane` of v[] maximised over the 32 lanes (31 shuffles)
+__device__ __forceinline__ float warp_transpose_max32(float (&v)[32], int lane) {
+  int o = 16;
+#pragma unroll
+  for (int c = 32; c > 1; c >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < c / 2; ++j) {
+      const float send = upper ? v[j] : v[j + c / 2];
+      const float keep = upper ? v[j + c / 2] : v[j];
+      v[j] = fmaxf(keep, __shfl_xor_sync(kFullMask, send, o));
+    }
+    o >>= 1;
+  }
+  return v[0];
+}
+
+// Survivors are staged per epilogue warp in shared memory (ballot + prefix count, no atomics) and
+// appended to the per-query global buffers in bulk, many independent atomicAdds in flight at
+// once: a returning global atomicAdd costs ~1 us, and issued one lane at a time from divergent
+// branches they made the epilogue -- not the tensor pipe -- the bottleneck (profiles/).
+constexpr int kGmStage = 384;        // staged survivors per epilogue warp
+constexpr int kGmFlushAt = 256;      // flush at a chunk boundary once this many are staged
+struct GemmStage {
+  uint64_t key[kGmStage];
+  int32_t q[kGmStage];
+};
+
+// whole warp, converged; n = staged entries
+static __device__ __noinline__ void gemm_flush(GemmStage* st, int n, uint64_t* __restrict__ cand,
+                                               int32_t* __restrict__ cnt, int cap, int lane) {
+  __syncwarp();
+#pragma unroll 4
+  for (int i = lane; i < n; i += 32) {
+    const int q = st->q[i];
+    const uint64_t key = st->key[i];
+    const int slot = atomicAdd(cnt + q, 1);
+    if (slot < cap) cand[static_cast<int64_t>(q) * cap + slot] = key;
+  }
+  __syncwarp();
+}
+
+// Row tile t of this launch covers corpus rows [t * tile_stride * 128, +128).
+//   SAMPLE = false: rows whose score beats thr[query] are appended to cand[query][cap] / cnt[query]
+//   SAMPLE = true : gmax[query * gmax_stride + t * 4 + quadrant] = max score of that 32-row group
+template <int NQ, bool BF16, bool SAMPLE>
+__global__ void __launch_bounds__(kGmThreads, 1)
+dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  int64_t n, int64_t n_row_tiles, int64_t tile_stride, int n_qblocks,
+                  const uint32_t* __restrict__ mask, const float* __restrict__ thr,
+                  uint64_t* __restrict__ cand, int32_t* __restrict__ cnt, int cap,
+                  float* __restrict__ gmax, int64_t gmax_stride, GemmLayout L) {
+  using Cfg = GemmCfg<NQ, BF16>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* ring = smem;                                   // n_stages x [A slab | B slab]
+  float* thr_s = reinterpret_cast<float*>(smem + L.thr_off);    // [n_qblocks * NQ]
+  GemmStage* stages = reinterpret_cast<GemmStage*>(smem + L.stage_off);   // [4 epilogue warps]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* empty = full + kGmMaxStages;
+  uint64_t* acc_full = empty + kGmMaxStages;    // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t my_row_tiles =
+      n_row_tiles > blockIdx.x ? (n_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (!SAMPLE)
+    for (int i = threadIdx.x; i < n_qblocks * NQ; i += blockDim.x) thr_s[i] = thr[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < L.n_stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], kGmEpiWarps);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- TMA producer ----
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t it = 0; it < my_row_tiles; ++it) {
+        const int row0 = static_cast<int>((blockIdx.x + it * gridDim.x) * tile_stride * kGmRows);
+        for (int qb = 0; qb < n_qblocks; ++qb) {
+          for (int kb = 0; kb < L.n_slabs; ++kb) {
+            mbar_wait(&empty[s], ph ^ 1u);
+            unsigned char* st = ring + static_cast<size_t>(s) * Cfg::kStageBytes;
+            mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
+            tma_load_2d(st, &map_a, kb * Cfg::kSlabElems, row0, &full[s]);
+            tma_load_2d(st + kGmABytes, &map_b, kb * Cfg::kSlabElems, qb * NQ, &full[s]);
+            if (++s == L.n_stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ----
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const int64_t my_tiles = my_row_tiles * n_qblocks;
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        const int a = static_cast<int>(t & 1);
+        const uint32_t aph = static_cast<uint32_t>(t >> 1) & 1u;
+        mbar_wait(&acc_empty[a], aph ^ 1u);  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(a * NQ);
+        for (int kb = 0; kb < L.n_slabs; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(ring + static_cast<size_t>(s) * Cfg::kStageBytes);
+          const uint64_t da = tc_smem_desc(st);
+          const uint64_t db = tc_smem_desc(st + kGmABytes);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {  // 32 bytes of K per instruction (8 tf32 / 16 bf16)
+            if (BF16)
+              tc_mma_bf16(tmem_d, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2),
+                          Cfg::kIdesc, (kb | kk) != 0 ? 1u : 0u);
+            else
+              tc_mma_tf32(tmem_d, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2),
+                          Cfg::kIdesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
+          if (++s == L.n_stages) { s = 0; ph ^= 1u; }
+        }
+        tc_commit(&acc_full[a]);
+      }
+    }
+  } else {
+    // ---- epilogue: TMEM lane = corpus row, column = query ----
+    const int quad = warp & 3;  // the TMEM lane quadrant this warp may read
+    GemmStage* st = stages + quad;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int wn = 0;   // survivors staged by this warp (warp-uniform)
+    int64_t t = 0;
+    for (int64_t it = 0; it < my_row_tiles; ++it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t row = tile * tile_stride * kGmRows + quad * 32 + lane;
+      bool ok = row < n;
+      if (ok && mask) ok = (__ldg(mask + (row >> 5)) >> (row & 31)) & 1u;
+      for (int qb = 0; qb < n_qblocks; ++qb, ++t) {
+        const int a = static_cast<int>(t & 1);
+        const uint32_t aph = static_cast<uint32_t>(t >> 1) & 1u;
+        mbar_wait(&acc_full[a], aph);
+        tc_fence_after();
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(a * NQ);
+#pragma unroll 1
+        for (int c = 0; c < NQ / 32; ++c) {
+          uint32_t v[32];
+          tc_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+          const int q0 = qb * NQ + c * 32;
+          if (SAMPLE) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = ok ? __uint_as_float(v[j]) : -INFINITY;
+            const float m = warp_transpose_max32(f, lane);
+            gmax[static_cast<int64_t>(q0 + lane) * gmax_stride + tile * 4 + quad] = m;
+          } else {
+            const float4* th = reinterpret_cast<const float4*>(thr_s + q0);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 tq = th[j4];
+              const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const float sc = __uint_as_float(v[j4 * 4 + jj]);
+                const bool hit = ok && sc > tv[jj];
+                const unsigned b = __ballot_sync(kFullMask, hit);
+                if (b) {  // warp-uniform, a few times per chunk
+                  if (wn + 32 > kGmStage) {
+                    gemm_flush(st, wn, cand, cnt, cap, lane);
+                    wn = 0;
+                  }
+                  if (hit) {
+                    const int slot = wn + __popc(b & lt_mask);
+                    st->key[slot] = make_key(sc, static_cast<uint32_t>(row));
+                    st->q[slot] = q0 + j4 * 4 + jj;
+                  }
+                  wn += __popc(b);
+                }
+              }
+            }
+            if (wn >= kGmFlushAt) {
+              gemm_flush(st, wn, cand, cnt, cap, lane);
+              wn = 0;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[a]);
+      }
+    }
+    if (!SAMPLE) gemm_flush(st, wn, cand, cnt, cap, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// Starting thresholds from the sample's group maxima.  The rank-th largest of the 512 per-thread
+// bests is reached by `rank` distinct groups, hence by `rank` distinct rows: a lower bound of the
+// rank-th best score of the corpus.  Queries >= n_real (zero padding) never nominate anything.
+__global__ void __launch_bounds__(kGmThrThreads)
+dense_gemm_thr_kernel(const float* __restrict__ gmax, int64_t gmax_stride, int m, int rank,
+                      int n_real, float* __restrict__ thr, uint64_t* __restrict__ thr_key) {
+  __shared__ uint64_t best[kGmThrThreads];
+  const int q = blockIdx.x;
+  if (q >= n_real) {
+    if (threadIdx.x == 0) {
+      thr[q] = INFINITY;
+      thr_key[q] = 0ull;
+    }
+    return;
+  }
+  const float* g = gmax + static_cast<int64_t>(q) * gmax_stride;
+  float b = -INFINITY;
+  for (int i = threadIdx.x; i < m; i += kGmThrThreads) b = fmaxf(b, g[i]);
+  best[threadIdx.x] = b == -INFINITY ? 0ull : make_key(b, 0u);
+  block_bitonic_sort_desc(best, kGmThrThreads);
+  if (threadIdx.x == 0) {
+    const uint64_t kth = best[rank - 1];
+    thr[q] = kth ? key_score(kth) : -INFINITY;
+    thr_key[q] = kth ? (kth | 0xffffffffull) : 0ull;
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                   int64_t n4) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 p;
+    p.x = *reinterpret_cast<uint32_t*>(&lo);
+    p.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(out)[i] = p;
+  }
+}
+
+cudaError_t launch_f32_to_bf16(const float* in, void* out, int64_t count, cudaStream_t stream) {
+  if (count <= 0) return cudaSuccess;
+  const int64_t n4 = count / 4;  // callers pass multiples of 4 (ld % 4 == 0)
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f32_to_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      in, static_cast<__nv_bfloat16*>(out), n4);
+  return cudaGetLastError();
+}
+
+// ---- host side ---------------------------------------------------------------------------
+constexpr int kGmTargetCand = 4096;   // rows per query the sample threshold should let through
+constexpr int kGmCap = 4 * kGmTargetCand;
+
+static int gemm_thr_rank(int k) { return k <= 10 ? 16 : k + 32; }
+
+// rows of the strided sample: rank * n / sample ~= kGmTargetCand, whole waves of tiles
+static int64_t gemm_sample_tiles(const DeviceProps& dp, int64_t n, int k) {
+  const int64_t want_rows = (static_cast<int64_t>(gemm_thr_rank(k)) * n + kGmTargetCand - 1) / kGmTargetCand;
+  int64_t tiles = (want_rows + kGmRows - 1) / kGmRows;
+  tiles = (tiles + dp.sm_count - 1) / dp.sm_count * dp.sm_count;
+  return tiles;
+}
+
+int dense_gemm_block(int nq) { return nq <= 64 ? 64 : (nq <= 128 ? 128 : 256); }
+int dense_gemm_max_queries() { return 1024; }
+int dense_gemm_padded_queries(int nq) {
+  const int b = dense_gemm_block(nq);
+  return (nq + b - 1) / b * b;
+}
+
+static bool make_gemm_layout(const DeviceProps& dp, int ld, bool bf16, int nq_block, int nq_pad,
+                             GemmLayout* L) {
+  const int slab = bf16 ? 64 : 32;
+  if (ld % slab != 0) return false;
+  L->n_slabs = ld / slab;
+  L->stage_bytes = kGmABytes + nq_block * 128;
+  const int thr_bytes = nq_pad * 4;
+  const int bar_bytes = (2 * kGmMaxStages + 4) * 8 + 16;
+  const int stage_bytes = kGmEpiWarps * static_cast<int>(sizeof(GemmStage));
+  const int avail =
+      dp.max_smem_optin - 1024 /* alignment slack */ - thr_bytes - stage_bytes - bar_bytes - 256;
+  int n_stages = avail / L->stage_bytes;
+  if (n_stages < 3) return false;
+  if (n_stages > kGmMaxStages) n_stages = kGmMaxStages;
+  L->n_stages = n_stages;
+  L->thr_off = n_stages * L->stage_bytes;
+  L->stage_off = (L->thr_off + thr_bytes + 15) / 16 * 16;
+  L->bar_off = L->stage_off + stage_bytes;
+  L->total_bytes = L->bar_off + bar_bytes;
+  return true;
+}
+
+bool dense_gemm_supported(const DeviceProps& dp, int64_t n, int ld, int k, bool bf16) {
+  if (getenv("ANR_DISABLE_GEMM") || getenv("ANR_DISABLE_TC")) return false;
+  if (k < 1 || k > 128 || n >= (1ll << 31)) return false;
+  GemmLayout L;
+  if (!make_gemm_layout(dp, ld, bf16, 256, dense_gemm_max_queries(), &L)) return false;
+  // the sample must be a small part of the corpus, or the pre-pass does not pay off
+  const int64_t n_tiles = (n + kGmRows - 1) / kGmRows;
+  return n_tiles >= 4 * gemm_sample_tiles(dp, n, k);
+}
+
+// scratch (bytes) one launch of up to dense_gemm_max_queries() queries needs
+size_t dense_gemm_scratch_bytes(const DeviceProps& dp, int64_t n, int ld, int nq, int k) {
+  const size_t nq_pad = static_cast<size_t>(dense_gemm_padded_queries(std::min(nq, dense_gemm_max_queries())));
+  const size_t groups = static_cast<size_t>(gemm_sample_tiles(dp, n, k)) * 4;
+  return nq_pad * kGmCap * 8 + nq_pad * groups * 4 + nq_pad * (4 + 4 + 8) +
+         nq_pad * static_cast<size_t>(ld) * 2 + 4096;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn gemm_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) ==
+            cudaSuccess &&
+        st == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// 2-D [rows, ld] row-major matrix of fp32 or bf16, box [box_rows x 128 bytes], 128-byte swizzle
+static bool gemm_encode_map(CUtensorMap* map, const void* base, int64_t rows, int ld, int box_rows,
+                            bool bf16) {
+  EncodeTiledFn fn = gemm_encode_fn();
+  if (!fn) return false;
+  const int esz = bf16 ? 2 : 4;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esz};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+            const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NQ, bool BF16>
+static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& map_a,
+                                    const CUtensorMap& map_b, int64_t n, int n_qblocks,
+                                    const uint32_t* mask, int64_t sample_tiles, int n_real, int k,
+                                    float* gmax, float* thr, uint64_t* thr_key, uint64_t* cand,
+                                    int32_t* cnt, const GemmLayout& L, cudaEvent_t ev_start,
+                                    cudaEvent_t ev_stop, cudaStream_t stream) {
+  const int smem = L.total_bytes + 1024;  // room to align the dynamic base to 1024 bytes
+  cudaError_t e = cudaFuncSetAttribute(dense_gemm_kernel<NQ, BF16, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(dense_gemm_kernel<NQ, BF16, false>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  const int64_t n_tiles = (n + kGmRows - 1) / kGmRows;
+  const int64_t stride = n_tiles / sample_tiles;
+  const int64_t gstride = sample_tiles * 4;
+  const int nq_pad = n_qblocks * NQ;
+  dense_gemm_kernel<NQ, BF16, true><<<dp.sm_count, kGmThreads, smem, stream>>>(
+      map_a, map_b, n, sample_tiles, stride, n_qblocks, mask, nullptr, nullptr, nullptr, 0, gmax,
+      gstride, L);
+  dense_gemm_thr_kernel<<<nq_pad, kGmThrThreads, 0, stream>>>(
+      gmax, gstride, static_cast<int>(gstride), gemm_thr_rank(k), n_real, thr, thr_key);
+  if (ev_start) cudaEventRecord(ev_start, stream);   // brackets the main GEMM kernel only
+  const int grid = static_cast<int>(std::min<int64_t>(dp.sm_count, n_tiles));
+  dense_gemm_kernel<NQ, BF16, false><<<grid, kGmThreads, smem, stream>>>(
+      map_a, map_b, n, n_tiles, 1, n_qblocks, mask, thr, cand, cnt, kGmCap, nullptr, 0, L);
+  if (ev_stop) cudaEventRecord(ev_stop, stream);
+  return cudaGetLastError();
+}
+
+// One launch group: n_real <= dense_gemm_max_queries() queries at q_dev ([padded, ld] fp32, zero
+// rows as padding) against the corpus (emb fp32 [n, ld]; shadow = its bf16 copy or null ->
+// tf32 on the fp32 words).  Exact top-k of the n_real queries through `out`, flags[0..n_real).
+cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const void* shadow, int64_t n,
+                              int ld, const float* q_dev, int n_real, int k, const uint32_t* mask,
+                              float emb_norm_max, unsigned char* scratch, const TopkOut& out,
+                              int32_t* flags, cudaEvent_t ev_start, cudaEvent_t ev_stop,
+                              cudaStream_t stream) {
+  const bool bf16 = shadow != nullptr;
+  const int nqb_size = dense_gemm_block(n_real);
+  const int nq_pad = dense_gemm_padded_queries(n_real);
+  const int n_qblocks = nq_pad / nqb_size;
+  GemmLayout L;
+  if (!make_gemm_layout(dp, ld, bf16, nqb_size, nq_pad, &L)) return cudaErrorInvalidConfiguration;
+  const int64_t sample_tiles = gemm_sample_tiles(dp, n, k);
+
+  // carve the scratch
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    unsigned char* p = scratch + off;
+    off += (bytes + 255) & ~static_cast<size_t>(255);
+    return p;
+  };
+  uint64_t* cand = reinterpret_cast<uint64_t*>(take(static_cast<size_t>(nq_pad) * kGmCap * 8));
+  float* gmax = reinterpret_cast<float*>(take(static_cast<size_t>(nq_pad) * sample_tiles * 4 * 4));
+  float* thr = reinterpret_cast<float*>(take(static_cast<size_t>(nq_pad) * 4));
+  int32_t* cnt = reinterpret_cast<int32_t*>(take(static_cast<size_t>(nq_pad) * 4));
+  uint64_t* thr_key = reinterpret_cast<uint64_t*>(take(static_cast<size_t>(nq_pad) * 8));
+  const void* q_ops = q_dev;
+  if (bf16) {
+    void* q16 = take(static_cast<size_t>(nq_pad) * ld * 2);
+    cudaError_t e = launch_f32_to_bf16(q_dev, q16, static_cast<int64_t>(nq_pad) * ld, stream);
+    if (e != cudaSuccess) return e;
+    q_ops = q16;
+  }
+  cudaError_t e = cudaMemsetAsync(cnt, 0, static_cast<size_t>(nq_pad) * 4, stream);
+  if (e != cudaSuccess) return e;
+
+  CUtensorMap map_a, map_b;
+  if (!gemm_encode_map(&map_a, bf16 ? shadow : static_cast<const void*>(emb), n, ld, kGmRows, bf16) ||
+      !gemm_encode_map(&map_b, q_ops, nq_pad, ld, nqb_size, bf16))
+    return cudaErrorInvalidValue;
+
+#define ANR_GEMM_CASE(NQV, BFV)                                                                   \
+  e = gemm_launch_pair<NQV, BFV>(dp, map_a, map_b, n, n_qblocks, mask, sample_tiles, n_real, k,  \
+                                 gmax, thr, thr_key, cand, cnt, L, ev_start, ev_stop, stream)
+  if (bf16) {
+    if (nqb_size == 64) ANR_GEMM_CASE(64, true);
+    else if (nqb_size == 128) ANR_GEMM_CASE(128, true);
+    else ANR_GEMM_CASE(256, true);
+  } else {
+    if (nqb_size == 64) ANR_GEMM_CASE(64, false);
+    else if (nqb_size == 128) ANR_GEMM_CASE(128, false);
+    else ANR_GEMM_CASE(256, false);
+  }
+#undef ANR_GEMM_CASE
+  if (e != cudaSuccess) return e;
+  // error bound of the product sum relative to |q| * |e| (Cauchy-Schwarz): tf32 truncates each
+  // operand by < 2^-10 relative; bf16 rounds to nearest, <= 2^-8 relative per operand; plus
+  // fp32 accumulation noise
+  const float eps_rel = bf16 ? 8.1e-3f : 2.5e-3f;
+  return launch_dense_tc_rescore_append(cand, cnt, kGmCap, emb, ld, q_dev, n_real, k,
+                                        emb_norm_max * eps_rel, thr_key, out, flags, stream);
+}
+
+}  // namespace anr

@@ -25,6 +25,7 @@
 #include <cstdlib>
 
 #include "anr_internal.h"
+#include "anr_tc.cuh"
 #include "anr_topk.cuh"
 
 namespace anr {
@@ -49,58 +50,6 @@ struct TcLayout {
   int n_stages, n_slabs, kl;
 };
 
-// ---- PTX wrappers ---------------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
-      "{%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-// shared-memory matrix descriptor, K-major, SWIZZLE_128B: start >> 4 | LBO (unused, 1) << 16 |
-// SBO (8 rows x 128 B = 1024 B) >> 4 << 32 | version 1 << 46 | layout SWIZZLE_128B (2) << 61
-__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
-  return static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) |
-         (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(kTcIdesc), "r"(accumulate)
-      : "memory");
-}
-// arrive on an mbarrier once every MMA issued so far by this thread has completed
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
 
 // ---- the scan --------------------------------------------------------------------------
 // EMIT = false: cand is [kTcQueries][grid][kTcEpiWarps][kl] candidate keys with tf32 scores
@@ -192,7 +141,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
           for (int kk = 0; kk < kTcSlab / 8; ++kk)  // K = 8 tf32 = 32 bytes per MMA
             tc_mma_tf32(tmem_d, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2),
-                        (kb | kk) != 0 ? 1u : 0u);
+                        kTcIdesc, (kb | kk) != 0 ? 1u : 0u);
           tc_commit(&empty[s]);  // stage reusable once these MMAs have read it
           if (++s == L.n_stages) { s = 0; ph ^= 1u; }
         }
@@ -270,30 +219,6 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 // HBM ONCE per pair: rank r loads rows [64r, 64r + 64) of the box and the TMA multicasts them
 // into BOTH CTAs' rings, so HBM traffic per query halves.  A stage may be refilled only after
 // both CTAs' MMAs have read it: every commit arrives on the "empty" barrier of both CTAs.
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* map, int c0,
-                                                  int c1, uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      ".multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(smem_dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "h"(cta_mask)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
-      "[%0], %1;" ::"r"(smem_u32(bar)),
-      "h"(cta_mask)
-      : "memory");
-}
 
 // map_a: box [64 rows x 32 floats]; map_b: [64 queries, ld], box [32 x 32].
 // cand: [64 queries][n_clusters][kTcEpiWarps][kl]
@@ -384,7 +309,7 @@ dense_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
           for (int kk = 0; kk < kTcSlab / 8; ++kk)
             tc_mma_tf32(tmem_d, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2),
-                        (kb | kk) != 0 ? 1u : 0u);
+                        kTcIdesc, (kb | kk) != 0 ? 1u : 0u);
           tc_commit_mcast(&empty[s], 0x3);
           if (++s == L.n_stages) { s = 0; ph ^= 1u; }
         }
@@ -485,8 +410,8 @@ dense_tc_thr_kernel(const uint64_t* __restrict__ cand, int m, int kl,
 __global__ void __launch_bounds__(kTcRescoreThreads)
 dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
                         const float* __restrict__ emb, int ld, const float* __restrict__ q_dev,
-                        int k, float emb_norm_max, const uint64_t* __restrict__ thr0, TopkOut o,
-                        int32_t* __restrict__ flags) {
+                        int k, float eps_scale, const uint64_t* __restrict__ thr0, TopkOut o,
+                        int32_t* __restrict__ flags, const int32_t* __restrict__ cnt, int cap) {
   __shared__ uint64_t top[kTcRescoreThreads];    // per-thread best tf32 keys
   __shared__ uint64_t sel[kTcRescoreCap];        // candidates inside the margin, then exact keys
   __shared__ int n_sel, bad;
@@ -494,11 +419,14 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
   const int q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_warps = kTcRescoreThreads / 32;
-  const uint64_t* c = cand + static_cast<int64_t>(q) * n_lists * kl;
-  const int m = n_lists * kl;
+  // cnt == nullptr: n_lists bounded candidate lists of kl keys (0 = empty slot);
+  // cnt != nullptr: one append buffer of cap keys per query holding min(cnt[q], cap) keys
+  const uint64_t* c = cand + static_cast<int64_t>(q) * (cnt ? cap : n_lists * kl);
+  const int m = cnt ? min(cnt[q], cap) : n_lists * kl;
+  if (cnt) n_lists = 0;
   const float* qv = q_dev + static_cast<size_t>(q) * ld;
 
-  if (threadIdx.x == 0) { n_sel = 0; bad = 0; q_norm2 = 0.f; }
+  if (threadIdx.x == 0) { n_sel = 0; bad = (cnt && cnt[q] > cap) ? 1 : 0; q_norm2 = 0.f; }
   __syncthreads();
   // |q|^2
   float part = 0.f;
@@ -520,7 +448,7 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
   const uint64_t kth = top[k - 1];
   // error bound of a tf32 product sum: each operand loses < 2^-10 relative (13 mantissa bits
   // dropped), accumulation noise D * 2^-22 -> |err| <= 2.5e-3 * |q| * |e| (Cauchy-Schwarz)
-  const float eps = 2.5e-3f * sqrtf(q_norm2) * emb_norm_max;
+  const float eps = eps_scale * sqrtf(q_norm2);
   // fewer than k candidates exist at all: everything nominated is rescored
   const float cut = kth ? key_score(kth) - 2.f * eps : -INFINITY;
   __syncthreads();
@@ -581,9 +509,9 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
     if (o.scores) o.scores[slot] = valid ? key_score(key) : 0.f;
     if (o.ids) o.ids[slot] = valid ? static_cast<int32_t>(out_id) : -1;
   }
-  const int cnt = __syncthreads_count(key != 0ull);
+  const int n_out = __syncthreads_count(key != 0ull);
   if (threadIdx.x == 0) {
-    if (o.counts) o.counts[q * o.count_stride] = cnt;
+    if (o.counts) o.counts[q * o.count_stride] = n_out;
     flags[q] = bad;
   }
 }
@@ -754,7 +682,8 @@ cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, 
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dense_tc_rescore_kernel<<<n_real, kTcRescoreThreads, 0, stream>>>(
-      cand, grid * kTcEpiWarps, L.kl, emb, ld, q_dev, k, emb_norm_max, thr0, out, flags);
+      cand, grid * kTcEpiWarps, L.kl, emb, ld, q_dev, k, 2.5e-3f * emb_norm_max, thr0, out, flags,
+      nullptr, 0);
   return cudaGetLastError();
 }
 
@@ -802,7 +731,18 @@ cudaError_t launch_dense_tc_pair(const DeviceProps& dp, const float* emb, int64_
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dense_tc_rescore_kernel<<<n_real, kTcRescoreThreads, 0, stream>>>(
-      cand, n_clusters * kTcEpiWarps, L.kl, emb, ld, q_dev, k, emb_norm_max, thr0, out, flags);
+      cand, n_clusters * kTcEpiWarps, L.kl, emb, ld, q_dev, k, 2.5e-3f * emb_norm_max, thr0, out,
+      flags, nullptr, 0);
+  return cudaGetLastError();
+}
+
+// Rescoring over per-query append buffers (the GEMM path, anr_dense_gemm.cu).
+cudaError_t launch_dense_tc_rescore_append(const uint64_t* cand, const int32_t* cnt, int cap,
+                                           const float* emb, int ld, const float* q_dev, int n_real,
+                                           int k, float eps_scale, const uint64_t* thr_key,
+                                           const TopkOut& out, int32_t* flags, cudaStream_t stream) {
+  dense_tc_rescore_kernel<<<n_real, kTcRescoreThreads, 0, stream>>>(
+      cand, 0, 0, emb, ld, q_dev, k, eps_scale, thr_key, out, flags, cnt, cap);
   return cudaGetLastError();
 }
 

@@ -80,6 +80,25 @@ cudaError_t launch_dense_tc_pair(const DeviceProps& dp, const float* emb, int64_
                                  cudaStream_t stream);
 bool dense_tc_pair_enabled();
 
+// ---- tiled GEMM scan for batches of 64+ queries (anr_dense_gemm.cu) ---------------------------
+// 128-row x 64/128/256-query tcgen05 tiles, both operands streamed by TMA; tf32 on the fp32 corpus
+// or bf16 on a shadow copy; sample pre-pass thresholds + per-query append buffers + exact fp32
+// rescoring (launch_dense_tc_rescore_append).
+bool dense_gemm_supported(const DeviceProps& dp, int64_t n, int ld, int k, bool bf16);
+int dense_gemm_max_queries();              // queries one launch group takes
+int dense_gemm_padded_queries(int nq);     // rows q_dev must hold for a group of nq queries
+size_t dense_gemm_scratch_bytes(const DeviceProps& dp, int64_t n, int ld, int nq, int k);
+cudaError_t launch_f32_to_bf16(const float* in, void* out, int64_t count, cudaStream_t stream);
+cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const void* shadow, int64_t n,
+                              int ld, const float* q_dev, int n_real, int k, const uint32_t* mask,
+                              float emb_norm_max, unsigned char* scratch, const TopkOut& out,
+                              int32_t* flags, cudaEvent_t ev_start, cudaEvent_t ev_stop,
+                              cudaStream_t stream);
+cudaError_t launch_dense_tc_rescore_append(const uint64_t* cand, const int32_t* cnt, int cap,
+                                           const float* emb, int ld, const float* q_dev, int n_real,
+                                           int k, float eps_scale, const uint64_t* thr_key,
+                                           const TopkOut& out, int32_t* flags, cudaStream_t stream);
+
 // ---- top-k ------------------------------------------------------------------
 // Per query: select the best k (<= kMaxFusedK) of m candidate keys, sorted best first.
 // Candidate i of query q is cand[q * cand_stride_q + (i / seg_len) * seg_stride + i % seg_len].

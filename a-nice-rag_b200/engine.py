@@ -143,6 +143,11 @@ class DenseIndex:
         native.call("anr_dense_upload", context(self.ctx_device).handle, self.handle, int(row0),
                     native.ptr(rows), int(rows.shape[0]))
 
+    def set_shadow(self, enable: bool = True) -> None:
+        """Batches of more than 32 queries nominate candidates on a bf16 copy of the matrix
+        (half the HBM bytes per pass); results are unchanged (exact fp32 rescoring)."""
+        native.call("anr_dense_set_shadow", self.handle, 1 if enable else 0)
+
     def search(self, queries, k: int, row_mask: Optional[np.ndarray] = None, id_base: int = 0):
         """-> (scores f32 [b, k], rows i32 [b, k], counts i32 [b]); rows = -1 past counts."""
         q = _as_f32_matrix(queries)

@@ -71,6 +71,12 @@ int anr_dense_upload(anr_ctx* ctx, anr_dense* index, int64_t row0, const float* 
                      int64_t n_rows);
 int anr_dense_destroy(anr_dense* index);
 int anr_dense_shape(const anr_dense* index, int64_t* n, int32_t* d);
+/* enable != 0: batches of more than 32 queries nominate candidates on a bf16 shadow copy of the
+ * matrix ([n, d] bf16, built on the next such search; d % 64 == 0) instead of reading the fp32
+ * words as tf32: half the HBM bytes and twice the tensor-core rate per pass.  Results do not
+ * change: every candidate inside the (wider) error margin is rescored in exact fp32, as in
+ * np.dot of src/search_engine.py:81. */
+int anr_dense_set_shadow(anr_dense* index, int32_t enable);
 
 /* Inner-product top-k of each query against all (mask-eligible) rows, best
  * first.  Replaces np.dot + argpartition + argsort[::-1] of

@@ -108,3 +108,80 @@ def test_tc_large_k_on_200k_rows(k):
         assert counts[q] == k
         want_rows, want_scores = retrieval.dense_topk(queries[q], emb, k)
         check_topk(rows[q], scores[q], want_rows, want_scores, full[q], f"tc k{k} q{q}")
+
+
+# ---- tiled GEMM path (anr_dense_gemm.cu): batches of more than 32 queries on >= ~76k rows ------
+@pytest.fixture(scope="module")
+def big_corpus():
+    import torch
+    n, d = 160_000, 1024
+    g = torch.Generator(device="cuda").manual_seed(4242)
+    emb_dev = torch.randn(n, d, generator=g, device="cuda", dtype=torch.float32)
+    emb_dev /= emb_dev.norm(dim=1, keepdim=True)
+    return emb_dev.cpu().numpy(), emb_dev
+
+
+def _check_batch(emb, queries, scores, rows, counts, k, tag, mask=None, every=1):
+    for q in range(0, queries.shape[0], every):
+        assert counts[q] == k, (tag, q, counts[q])
+        want_rows, want_scores = retrieval.dense_topk(queries[q], emb, k, mask)
+        check_topk(rows[q], scores[q], want_rows, want_scores, queries[q] @ emb.T, f"{tag} q{q}")
+
+
+@pytest.mark.parametrize("shadow", [False, True])
+@pytest.mark.parametrize("nq,k", [(33, 10), (64, 10), (65, 1), (128, 26), (200, 100), (300, 10)])
+def test_gemm_batches_vs_oracle(big_corpus, nq, k, shadow):
+    emb, emb_dev = big_corpus
+    index = engine.DenseIndex(emb_dev, borrow=True)
+    index.set_shadow(shadow)
+    queries = synth.unit_vectors(nq, 1024, seed=900 + nq)
+    scores, rows, counts = index.search(queries, k)
+    _check_batch(emb, queries, scores, rows, counts, k, f"gemm nq{nq} k{k} bf16={shadow}",
+                 every=max(nq // 24, 1))
+
+
+@pytest.mark.parametrize("shadow", [False, True])
+def test_gemm_with_mask_and_unnormalised_rows(shadow):
+    rng = np.random.default_rng(17)
+    n, d, nq = 100_000, 512, 70
+    emb = (synth.unit_vectors(n, d, seed=33) * rng.uniform(0.2, 6.0, size=(n, 1))).astype(np.float32)
+    index = engine.DenseIndex(emb)
+    index.set_shadow(shadow)
+    mask = rng.random(n) < 0.6
+    queries = (synth.unit_vectors(nq, d, seed=34) * 3.0).astype(np.float32)
+    scores, rows, counts = index.search(queries, 10, row_mask=engine.pack_mask(mask))
+    _check_batch(emb, queries, scores, rows, counts, 10, f"gemm mask bf16={shadow}", mask=mask, every=3)
+    assert mask[rows].all()
+
+
+def test_gemm_candidate_overflow_takes_the_exact_fallback(big_corpus):
+    """20 000 identical rows overflow a query's append buffer (16 384 keys): the query is flagged
+    and rerun through the exact scan, whose tie rule (lower row first) decides."""
+    emb, _ = big_corpus
+    emb = emb[:120_000].copy()
+    emb[5000:25000] = emb[5000]
+    index = engine.DenseIndex(emb)
+    queries = synth.unit_vectors(64, 1024, seed=12)
+    queries[5] = emb[5000]
+    queries[61] = emb[7000]
+    scores, rows, counts = index.search(queries, 10)
+    assert rows[5].tolist() == list(range(5000, 5010))
+    assert rows[61].tolist() == list(range(5000, 5010))
+    _check_batch(emb, queries, scores, rows, counts, 10, "gemm overflow", every=7)
+
+
+def test_gemm_and_scan_paths_agree(big_corpus):
+    emb, emb_dev = big_corpus
+    index = engine.DenseIndex(emb_dev, borrow=True)
+    queries = synth.unit_vectors(96, 1024, seed=99)
+    s_g, r_g, _ = index.search(queries, 10)
+    index.set_shadow(True)
+    s_b, r_b, _ = index.search(queries, 10)
+    os.environ["ANR_DISABLE_TC"] = "1"
+    try:
+        s_sc, r_sc, _ = index.search(queries, 10)
+    finally:
+        del os.environ["ANR_DISABLE_TC"]
+    assert (r_g == r_sc).mean() > 0.99 and (r_b == r_sc).mean() > 0.99
+    np.testing.assert_allclose(s_g, s_sc, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(s_b, s_sc, rtol=1e-5, atol=1e-6)
