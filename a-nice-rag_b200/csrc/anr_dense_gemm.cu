@@ -30,8 +30,9 @@
 namespace anr {
 
 constexpr int kGmRows = 128;          // corpus rows per tile = UMMA M
-constexpr int kGmThreads = 192;       // TMA producer warp, MMA warp, 4 epilogue warps
-constexpr int kGmEpiWarps = 4;
+constexpr int kGmThreads = 320;       // TMA producer warp, MMA warp, up to 8 epilogue warps
+constexpr int kGmEpiWarps = 8;        // 4 or 8 launched: one or two per TMEM lane quadrant (two:
+                                      // each takes every other 32-column chunk)
 constexpr int kGmMaxStages = 12;
 constexpr int kGmABytes = kGmRows * 128;   // one corpus slab: 128 rows x 128 bytes of K
 constexpr int kGmThrThreads = 512;
@@ -75,12 +76,21 @@ __device__ __forceinline__ float warp_transpose_max32(float (&v)[32], int lane) 
 // appended to the per-query global buffers in bulk, many independent atomicAdds in flight at
 // once: a returning global atomicAdd costs ~1 us, and issued one lane at a time from divergent
 // branches they made the epilogue -- not the tensor pipe -- the bottleneck (profiles/).
-constexpr int kGmStage = 384;        // staged survivors per epilogue warp
-constexpr int kGmFlushAt = 256;      // flush at a chunk boundary once this many are staged
+constexpr int kGmStage = 192;        // staged survivors per epilogue warp
+constexpr int kGmFlushAt = 96;       // flush at a chunk boundary once this many are staged
 struct GemmStage {
   uint64_t key[kGmStage];
   int32_t q[kGmStage];
 };
+
+// A chunk's survivors (bit j of hm = column q0 + j beats its threshold) -> the warp's staging
+// buffer; out of line: the hot loop only builds the masks (the caller spills v[] to its stack
+// frame for the call, which is cheaper than a 31-select multiplexer per survivor).  Returns the
+// new staged count.
+static __device__ __noinline__ int gemm_stage_hits(GemmStage* st, int wn, uint32_t hm,
+                                                   const uint32_t* v, int q0, uint32_t row,
+                                                   uint64_t* __restrict__ cand,
+                                                   int32_t* __restrict__ cnt, int cap, int lane);
 
 // whole warp, converged; n = staged entries
 static __device__ __noinline__ void gemm_flush(GemmStage* st, int n, uint64_t* __restrict__ cand,
@@ -96,11 +106,49 @@ static __device__ __noinline__ void gemm_flush(GemmStage* st, int n, uint64_t* _
   __syncwarp();
 }
 
+static __device__ __noinline__ int gemm_stage_hits(GemmStage* st, int wn, uint32_t hm,
+                                                   const uint32_t* v, int q0, uint32_t row,
+                                                   uint64_t* __restrict__ cand,
+                                                   int32_t* __restrict__ cnt, int cap, int lane) {
+  const int mine = __popc(hm);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(kFullMask, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(kFullMask, incl, 31);
+  if (total > kGmStage) {  // a burst (e.g. a block of duplicate rows): append directly
+    while (hm) {
+      const int j = __ffs(hm) - 1;
+      hm &= hm - 1;
+      const int q = q0 + j;
+      const int slot = atomicAdd(cnt + q, 1);
+      if (slot < cap)
+        cand[static_cast<int64_t>(q) * cap + slot] = make_key(__uint_as_float(v[j]), row);
+    }
+    return wn;
+  }
+  if (wn + total > kGmStage) {
+    gemm_flush(st, wn, cand, cnt, cap, lane);
+    wn = 0;
+  }
+  int slot = wn + incl - mine;
+  while (hm) {
+    const int j = __ffs(hm) - 1;
+    hm &= hm - 1;
+    st->key[slot] = make_key(__uint_as_float(v[j]), row);
+    st->q[slot] = q0 + j;
+    ++slot;
+  }
+  return wn + total;
+}
+
 // Row tile t of this launch covers corpus rows [t * tile_stride * 128, +128).
 //   SAMPLE = false: rows whose score beats thr[query] are appended to cand[query][cap] / cnt[query]
 //   SAMPLE = true : gmax[query * gmax_stride + t * 4 + quadrant] = max score of that 32-row group
 template <int NQ, bool BF16, bool SAMPLE>
-__global__ void __launch_bounds__(kGmThreads, 1)
+__global__ void __launch_bounds__(kGmThreads, 1)   // launched with 64 + 32 * {4, 8} threads
 dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   int64_t n, int64_t n_row_tiles, int64_t tile_stride, int n_qblocks,
                   const uint32_t* __restrict__ mask, const float* __restrict__ thr,
@@ -118,6 +166,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_epi = static_cast<int>(blockDim.x >> 5) - 2;   // 4 or 8
   const int64_t my_row_tiles =
       n_row_tiles > blockIdx.x ? (n_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -130,7 +179,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], kGmEpiWarps);
+      mbar_init(&acc_empty[a], n_epi);
     }
     mbar_fence_init();
   }
@@ -200,9 +249,9 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   } else {
     // ---- epilogue: TMEM lane = corpus row, column = query ----
-    const int quad = warp & 3;  // the TMEM lane quadrant this warp may read
-    GemmStage* st = stages + quad;
-    const unsigned lt_mask = (1u << lane) - 1u;
+    const int quad = warp & 3;         // the TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;  // the two warps of a quadrant take alternate 32-column chunks
+    GemmStage* st = stages + (warp - 2);
     int wn = 0;   // survivors staged by this warp (warp-uniform)
     int64_t t = 0;
     for (int64_t it = 0; it < my_row_tiles; ++it) {
@@ -218,7 +267,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(a * NQ);
 #pragma unroll 1
-        for (int c = 0; c < NQ / 32; ++c) {
+        for (int c = half; c < NQ / 32; c += (n_epi >> 2)) {
           uint32_t v[32];
           tc_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
           const int q0 = qb * NQ + c * 32;
@@ -230,29 +279,18 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             gmax[static_cast<int64_t>(q0 + lane) * gmax_stride + tile * 4 + quad] = m;
           } else {
             const float4* th = reinterpret_cast<const float4*>(thr_s + q0);
+            uint32_t hm = 0u;
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const float4 tq = th[j4];
-              const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const float sc = __uint_as_float(v[j4 * 4 + jj]);
-                const bool hit = ok && sc > tv[jj];
-                const unsigned b = __ballot_sync(kFullMask, hit);
-                if (b) {  // warp-uniform, a few times per chunk
-                  if (wn + 32 > kGmStage) {
-                    gemm_flush(st, wn, cand, cnt, cap, lane);
-                    wn = 0;
-                  }
-                  if (hit) {
-                    const int slot = wn + __popc(b & lt_mask);
-                    st->key[slot] = make_key(sc, static_cast<uint32_t>(row));
-                    st->q[slot] = q0 + j4 * 4 + jj;
-                  }
-                  wn += __popc(b);
-                }
-              }
+              hm |= (__uint_as_float(v[j4 * 4 + 0]) > tq.x ? 1u : 0u) << (j4 * 4 + 0);
+              hm |= (__uint_as_float(v[j4 * 4 + 1]) > tq.y ? 1u : 0u) << (j4 * 4 + 1);
+              hm |= (__uint_as_float(v[j4 * 4 + 2]) > tq.z ? 1u : 0u) << (j4 * 4 + 2);
+              hm |= (__uint_as_float(v[j4 * 4 + 3]) > tq.w ? 1u : 0u) << (j4 * 4 + 3);
             }
+            if (!ok) hm = 0u;
+            if (__any_sync(kFullMask, hm != 0u))
+              wn = gemm_stage_hits(st, wn, hm, v, q0, static_cast<uint32_t>(row), cand, cnt, cap, lane);
             if (wn >= kGmFlushAt) {
               gemm_flush(st, wn, cand, cnt, cap, lane);
               wn = 0;
@@ -438,14 +476,18 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
   const int64_t stride = n_tiles / sample_tiles;
   const int64_t gstride = sample_tiles * 4;
   const int nq_pad = n_qblocks * NQ;
-  dense_gemm_kernel<NQ, BF16, true><<<dp.sm_count, kGmThreads, smem, stream>>>(
+  // two epilogue warps per quadrant once a tile has enough 32-column chunks to share
+  static const int epi_env = getenv("ANR_GEMM_EPI_WARPS") ? atoi(getenv("ANR_GEMM_EPI_WARPS")) : 0;
+  const int n_epi = epi_env == 4 || epi_env == 8 ? epi_env : (NQ >= 128 ? 8 : 4);
+  const int threads = 64 + 32 * n_epi;
+  dense_gemm_kernel<NQ, BF16, true><<<dp.sm_count, threads, smem, stream>>>(
       map_a, map_b, n, sample_tiles, stride, n_qblocks, mask, nullptr, nullptr, nullptr, 0, gmax,
       gstride, L);
   dense_gemm_thr_kernel<<<nq_pad, kGmThrThreads, 0, stream>>>(
       gmax, gstride, static_cast<int>(gstride), gemm_thr_rank(k), n_real, thr, thr_key);
   if (ev_start) cudaEventRecord(ev_start, stream);   // brackets the main GEMM kernel only
   const int grid = static_cast<int>(std::min<int64_t>(dp.sm_count, n_tiles));
-  dense_gemm_kernel<NQ, BF16, false><<<grid, kGmThreads, smem, stream>>>(
+  dense_gemm_kernel<NQ, BF16, false><<<grid, threads, smem, stream>>>(
       map_a, map_b, n, n_tiles, 1, n_qblocks, mask, thr, cand, cnt, kGmCap, nullptr, 0, L);
   if (ev_stop) cudaEventRecord(ev_stop, stream);
   return cudaGetLastError();
