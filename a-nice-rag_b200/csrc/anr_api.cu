@@ -85,6 +85,15 @@ struct anr_bm25 {
   int32_t n_terms = 0;
   int32_t n_docs = 0;
   int64_t nnz = 0;
+  // dense rows of the head terms for the pruned top-k scan (anr_bm25.cu), built on first use
+  mutable uint8_t* head_slot = nullptr;    // [n_terms]
+  mutable int32_t* head_terms = nullptr;   // [n_head]
+  mutable float* head_w = nullptr;         // [n_head][head_ld]
+  mutable float* head_max = nullptr;       // [n_head]
+  mutable int64_t head_ld = 0;
+  mutable int32_t n_head = 0;
+  mutable bool head_built = false;         // slot map + allocation exist
+  mutable bool head_filled = false;        // rows hold the current posting weights
 };
 
 namespace {
@@ -439,10 +448,66 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
 }
 
 // ---- BM25 top-k pipeline on device buffers ---------------------------------------------
+Bm25View bm25_view(const anr_bm25* ix);
+
+// Head terms of the pruned scan: df >= n_docs / div (ANR_BM25_HEAD_DIV, default 8), the
+// kBm25MaxHead most frequent at most, within a memory budget of a quarter of the postings' size
+// or 1 GB, whichever is larger.
+int bm25_ensure_heads(const anr_bm25* ix, cudaStream_t stream) {
+  if (ix->head_built && ix->head_filled) return ANR_OK;
+  if (!ix->head_built) {
+    std::vector<int64_t> tp(static_cast<size_t>(ix->n_terms) + 1);
+    ANR_CUDA(cudaMemcpyAsync(tp.data(), ix->term_ptr, tp.size() * 8, cudaMemcpyDeviceToHost, stream));
+    ANR_CUDA(cudaStreamSynchronize(stream));
+    static const int div = getenv("ANR_BM25_HEAD_DIV") ? std::max(atoi(getenv("ANR_BM25_HEAD_DIV")), 1) : 8;
+    const int64_t min_df = std::max<int64_t>(ix->n_docs / div, 1);
+    std::vector<std::pair<int64_t, int32_t>> heads;
+    for (int32_t t = 0; t < ix->n_terms; ++t) {
+      const int64_t df = tp[t + 1] - tp[t];
+      if (df >= min_df) heads.emplace_back(-df, t);
+    }
+    std::sort(heads.begin(), heads.end());
+    {  // the pruning bound needs non-negative contributions: an index with a negative idf
+       // (possible only when BM25Okapi's average idf is negative) is scanned unpruned
+      std::vector<float> idf_h(static_cast<size_t>(std::max(ix->n_terms, 1)), 0.f);
+      ANR_CUDA(cudaMemcpyAsync(idf_h.data(), ix->idf, static_cast<size_t>(ix->n_terms) * 4,
+                               cudaMemcpyDeviceToHost, stream));
+      ANR_CUDA(cudaStreamSynchronize(stream));
+      for (int32_t t = 0; t < ix->n_terms; ++t)
+        if (idf_h[t] < 0.f) { heads.clear(); break; }
+    }
+    const int64_t ld = bm25_head_ld(ix->n_docs);
+    const size_t budget = std::max<size_t>(static_cast<size_t>(ix->nnz) * 2, static_cast<size_t>(1) << 30);
+    size_t n_head = std::min<size_t>(heads.size(), kBm25MaxHead);
+    n_head = std::min<size_t>(n_head, budget / (static_cast<size_t>(ld) * 4));
+    std::vector<uint8_t> slot(static_cast<size_t>(std::max(ix->n_terms, 1)), 0xff);
+    std::vector<int32_t> terms(std::max<size_t>(n_head, 1), 0);
+    for (size_t h = 0; h < n_head; ++h) {
+      slot[heads[h].second] = static_cast<uint8_t>(h);
+      terms[h] = heads[h].second;
+    }
+    ANR_CUDA(cudaMalloc(&ix->head_slot, slot.size()));
+    ANR_CUDA(cudaMalloc(&ix->head_terms, terms.size() * 4));
+    ANR_CUDA(cudaMalloc(&ix->head_w, std::max<size_t>(n_head, 1) * ld * 4));
+    ANR_CUDA(cudaMalloc(&ix->head_max, std::max<size_t>(n_head, 1) * 4));
+    ANR_CUDA(cudaMemcpyAsync(ix->head_slot, slot.data(), slot.size(), cudaMemcpyHostToDevice, stream));
+    ANR_CUDA(cudaMemcpyAsync(ix->head_terms, terms.data(), terms.size() * 4, cudaMemcpyHostToDevice,
+                             stream));
+    ANR_CUDA(cudaStreamSynchronize(stream));   // the host vectors go out of scope
+    ix->head_ld = ld;
+    ix->n_head = static_cast<int32_t>(n_head);
+    ix->head_built = true;
+  }
+  ANR_CUDA(launch_bm25_head_fill(bm25_view(ix), ix->head_terms, ix->n_head, ix->head_w,
+                                 ix->head_max, ix->head_ld, stream));
+  ix->head_filled = true;
+  return ANR_OK;
+}
+
 size_t bm25_ws_bytes(const anr_ctx* ctx, const anr_bm25* ix, int nq, int k) {
   if (k <= kMaxFusedK) {
     const Bm25Plan plan = bm25_make_plan(ctx->dp, ix->n_docs, nq, k, false);
-    return padded(static_cast<size_t>(nq) * plan.n_tiles * k * 8) + 256;
+    return padded(static_cast<size_t>(nq) * plan.n_tiles * k * 8) + padded(static_cast<size_t>(nq) * 4) + 512;
   }
   const int64_t n_pow2 = next_pow2(std::max(ix->n_docs, 2));
   return padded(static_cast<size_t>(std::min(nq, 8)) * n_pow2 * 8) + 256;
@@ -470,10 +535,22 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
       return fail(ANR_ERR_UNSUPPORTED, "bm25 tile does not fit in shared memory");
     const int64_t stride = static_cast<int64_t>(plan.n_tiles) * k;
     uint64_t* cand = arena.take<uint64_t>(static_cast<size_t>(nq) * stride);
+    float* theta = arena.take<float>(static_cast<size_t>(nq));
+    // safe dynamic pruning over the dense rows of the head terms (corpora of 8192+ documents)
+    const bool no_prune = getenv("ANR_DISABLE_BM25_PRUNE") != nullptr;
+    Bm25HeadView hd;
+    if (!no_prune && ix->n_docs >= 8192 && nq >= 16) {   // (measured: no gain below ~16 queries)
+      if (int rc = bm25_ensure_heads(ix, stream)) return rc;
+      hd.slot_of = ix->head_slot;
+      hd.head_w = ix->head_w;
+      hd.head_max = ix->head_max;
+      hd.head_ld = ix->head_ld;
+      hd.n_head = ix->n_head;
+    }
     {
       ProfileScope prof(ctx, 1, stream);
-      ANR_CUDA(launch_bm25_score_topk(v, terms_dev, offsets_dev, nq, k, mask_dev, plan, cand,
-                                      stride, stream));
+      ANR_CUDA(launch_bm25_score_topk(v, hd.n_head > 0 ? &hd : nullptr, terms_dev, offsets_dev, nq,
+                                      k, mask_dev, plan, cand, stride, theta, stream));
     }
     const int m = static_cast<int>(stride);
     ANR_CUDA(launch_topk_final(cand, stride, m, m, 0, nq, k, out, stream));
@@ -954,6 +1031,17 @@ int anr_bm25_reweight(anr_ctx* ctx, anr_bm25* index, const int32_t* post_tf, con
   }
   ANR_CUDA(launch_bm25_weights(index->post_doc, tf_dev, dl_dev, index->nnz, k1, b, avgdl,
                                index->post_w, stream));
+  // new weights and idf: the dense head rows (and the negative-idf check) are redone by the next search
+  if (index->head_built) {
+    ANR_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(index->head_slot); index->head_slot = nullptr;
+    cudaFree(index->head_terms); index->head_terms = nullptr;
+    cudaFree(index->head_w); index->head_w = nullptr;
+    cudaFree(index->head_max); index->head_max = nullptr;
+    index->head_built = false;
+    index->n_head = 0;
+  }
+  index->head_filled = false;
   ANR_CUDA(cudaStreamSynchronize(stream));   // host sources may be reused by the caller
   return ANR_OK;
 }
@@ -965,6 +1053,10 @@ int anr_bm25_destroy(anr_bm25* index) {
   if (index->post_doc) cudaFree(index->post_doc);
   if (index->post_w) cudaFree(index->post_w);
   if (index->idf) cudaFree(index->idf);
+  if (index->head_slot) cudaFree(index->head_slot);
+  if (index->head_terms) cudaFree(index->head_terms);
+  if (index->head_w) cudaFree(index->head_w);
+  if (index->head_max) cudaFree(index->head_max);
   delete index;
   return ANR_OK;
 }

@@ -123,6 +123,26 @@ struct Bm25View {
   int32_t n_docs;
   int64_t nnz;
 };
+// ---- BM25 head terms: dense rows for safe dynamic pruning (anr_bm25.cu) ----------------------
+// Terms with df >= n_docs / 8 (at most kBm25MaxHead) are stored a second time as dense rows
+// head_w[slot][doc] (0 where the term is absent) so that their weight for ONE document is one
+// load.  The top-k kernel then streams only the postings of the other (rare, high-idf) terms,
+// bounds what the head terms can still add, and completes the score of the few documents that
+// can still reach the tile's k-th best (MaxScore-style pruning; results are unchanged).
+constexpr int kBm25MaxHead = 128;
+struct Bm25HeadView {
+  const uint8_t* slot_of = nullptr;   // [n_terms] head slot of a term, 0xff = not a head term
+  const float* head_w = nullptr;      // [n_head][head_ld]
+  const float* head_max = nullptr;    // [n_head] largest weight of the row
+  int64_t head_ld = 0;
+  int32_t n_head = 0;
+};
+int64_t bm25_head_ld(int n_docs);
+// head_max must hold n_head floats; both arrays are (re)written
+cudaError_t launch_bm25_head_fill(const Bm25View& ix, const int32_t* head_terms, int n_head,
+                                  float* head_w, float* head_max, int64_t head_ld,
+                                  cudaStream_t stream);
+
 cudaError_t launch_bm25_weights(const int32_t* post_doc, const int32_t* post_tf,
                                 const int32_t* doc_len, int64_t nnz, double k1, double b,
                                 double avgdl, float* post_w, cudaStream_t stream);
@@ -134,10 +154,11 @@ struct Bm25Plan {
 };
 Bm25Plan bm25_make_plan(const DeviceProps& dp, int n_docs, int nq, int k, bool emit_all);
 // cand[q * cand_stride_q + tile * k + i] candidate keys (ids = doc index)
-cudaError_t launch_bm25_score_topk(const Bm25View& ix, const int32_t* q_terms,
+// hd (nullable) + theta (nq floats of scratch, nullable) enable the pruned scan.
+cudaError_t launch_bm25_score_topk(const Bm25View& ix, const Bm25HeadView* hd, const int32_t* q_terms,
                                    const int32_t* q_offsets, int nq, int k,
                                    const uint32_t* doc_mask, const Bm25Plan& plan, uint64_t* cand,
-                                   int64_t cand_stride_q, cudaStream_t stream);
+                                   int64_t cand_stride_q, float* theta, cudaStream_t stream);
 // keys[q * keys_stride_q + doc] for every doc (0 for masked docs)
 cudaError_t launch_bm25_score_all(const Bm25View& ix, const int32_t* q_terms,
                                   const int32_t* q_offsets, int nq, const uint32_t* doc_mask,

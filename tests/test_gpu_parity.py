@@ -422,3 +422,99 @@ def test_bm25_reweight_equals_rebuilt_index(small):
         toks = synth.token_strings(case["term_queries"][q])
         got = index.scores(term_ids_of(case, ix, q))
         np.testing.assert_allclose(got, other.get_scores(toks), rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------
+# BM25 pruned scan (anr_bm25.cu, PRUNE): dense head rows + MaxScore-style bound, 8192+ documents
+@pytest.fixture(scope="module")
+def group_corpus():
+    n, vocab = 70_000, 4000
+    doc_ptr, tokens = synth.zipf_corpus(n, vocab, 1.1, seed=51, len_lo=40, len_hi=120)
+    ix = csr.from_token_ids(doc_ptr, tokens, vocab, 1.7, 0.83, 0.05)
+    index = engine.Bm25Index(ix.term_ptr, ix.post_doc, ix.post_tf, ix.doc_len, ix.idf, ix.k1,
+                             ix.b, ix.avgdl)
+    return ix, index, vocab
+
+
+def _check_bm25_batch(ix, queries, scores, docs, counts, k, what, mask=None):
+    n_terms = len(ix.term_ptr) - 1
+    for q, terms in enumerate(queries):
+        all_scores = csr.scores(ix, [int(t) if 0 <= int(t) < n_terms else -1 for t in terms])
+        if mask is None:
+            want = retrieval.bm25_topk(all_scores, k)
+        else:   # the filtered branch (search_engine.py:224-233): stable descending sort of the kept docs
+            kept = np.flatnonzero(mask)
+            want = kept[np.argsort(-all_scores[kept], kind="stable")][:k]
+        assert counts[q] == len(want), (what, q, counts[q], len(want))
+        check_ids_only(docs[q, :counts[q]], want, all_scores, f"{what} q{q} k{k}")
+        np.testing.assert_allclose(scores[q, :counts[q]], all_scores[docs[q, :counts[q]]],
+                                   rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("nq,k", [(1, 10), (8, 10), (16, 1), (17, 100), (64, 10), (70, 32), (33, 128)])
+def test_bm25_group_batches_vs_oracle(group_corpus, nq, k):
+    ix, index, vocab = group_corpus
+    tq = synth.zipf_queries(nq, 8, vocab, 1.1, seed=60 + nq)
+    queries = [list(map(int, t)) for t in tq]
+    if nq > 3:
+        queries[1] = queries[1] + queries[1][:3]            # duplicate terms count twice
+        queries[2] = [vocab + 5, -1] + queries[2]            # unknown terms contribute nothing
+        queries[3] = []                                      # empty query: every score is 0
+        queries[0] = [0, 1, 2, 3, 0]                         # head terms only: nothing is pruned
+    scores, docs, counts = index.search(queries, k)
+    _check_bm25_batch(ix, queries, scores, docs, counts, k, f"group nq{nq}")
+
+
+def test_bm25_pruned_agrees_with_unpruned_scan(group_corpus):
+    ix, index, vocab = group_corpus
+    tq = synth.zipf_queries(40, 8, vocab, 1.1, seed=77)
+    queries = [list(map(int, t)) for t in tq]
+    s_g, d_g, c_g = index.search(queries, 10)
+    os.environ["ANR_DISABLE_BM25_PRUNE"] = "1"
+    try:
+        s_o, d_o, c_o = index.search(queries, 10)
+    finally:
+        del os.environ["ANR_DISABLE_BM25_PRUNE"]
+    assert np.array_equal(c_g, c_o)
+    np.testing.assert_allclose(s_g, s_o, rtol=1e-5, atol=1e-6)
+    assert (d_g == d_o).mean() > 0.98
+
+
+def test_bm25_group_long_queries_take_the_unpruned_path(group_corpus):
+    """More than 64 terms in a query (one staged chunk): that query is scanned unpruned, next to
+    pruned 3- and 33-term queries in the same launch."""
+    ix, index, vocab = group_corpus
+    long_q = synth.zipf_queries(20, 70, vocab, 1.1, seed=81)
+    queries = [list(map(int, t)) for t in long_q]
+    queries[4] = queries[4][:3]
+    queries[9] = queries[9][:33]
+    scores, docs, counts = index.search(queries, 10)
+    _check_bm25_batch(ix, queries, scores, docs, counts, 10, "group long")
+
+
+def test_bm25_group_with_doc_mask(group_corpus):
+    ix, index, vocab = group_corpus
+    rng = np.random.default_rng(5)
+    mask = rng.random(ix.doc_len.shape[0]) < 0.3
+    tq = synth.zipf_queries(40, 8, vocab, 1.1, seed=91)
+    queries = [list(map(int, t)) for t in tq]
+    scores, docs, counts = index.search(queries, 10, doc_mask=engine.pack_mask(mask))
+    _check_bm25_batch(ix, queries, scores, docs, counts, 10, "group mask", mask=mask)
+    assert mask[docs].all()
+
+
+def test_bm25_group_after_reweight(group_corpus):
+    ix, index, vocab = group_corpus
+    other = csr.from_token_ids(*_group_tokens(), vocab, 0.9, 0.7, 0.075)
+    index2 = engine.Bm25Index(ix.term_ptr, ix.post_doc, ix.post_tf, ix.doc_len, ix.idf, ix.k1,
+                              ix.b, ix.avgdl)
+    tq = synth.zipf_queries(16, 8, vocab, 1.1, seed=95)
+    queries = [list(map(int, t)) for t in tq]
+    index2.search(queries, 10)                      # builds the dense head rows with the OLD weights
+    index2.reweight(other.post_tf, other.doc_len, other.idf, 0.9, 0.7, other.avgdl)
+    scores, docs, counts = index2.search(queries, 10)
+    _check_bm25_batch(other, queries, scores, docs, counts, 10, "group reweight")
+
+
+def _group_tokens():
+    return synth.zipf_corpus(70_000, 4000, 1.1, seed=51, len_lo=40, len_hi=120)
