@@ -100,51 +100,9 @@ Bm25Plan bm25_make_plan(const DeviceProps& dp, int n_docs, int nq, int k, bool e
   return p;
 }
 
-// k-th largest of the 256 per-thread best keys (0 when fewer than k threads hold one): a lower
-// bound of the k-th best key of the tile.  Every thread calls; tbest is 256 keys of scratch.
 __device__ __forceinline__ uint64_t kth_of_thread_bests(uint64_t best, int k, uint64_t* tbest,
                                                         uint64_t* s_out) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (k <= 32) {
-    // every warp sorts its 32 keys in registers (shuffles, no barrier), warp 0 then pops the
-    // largest head k times
-    uint64_t v = best;
-#pragma unroll
-    for (int size = 2; size <= 32; size <<= 1)
-#pragma unroll
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        const uint64_t other = __shfl_xor_sync(kFullMask, v, stride);
-        const bool keep_max = ((lane & stride) == 0) == ((lane & size) == 0);
-        v = keep_max ? (v > other ? v : other) : (v < other ? v : other);
-      }
-    tbest[threadIdx.x] = v;   // warp w's keys, descending, at tbest[32 w ..]
-    __syncthreads();
-    if (warp == 0) {
-      int head = 0;   // lanes 0..7: read position in warp `lane`'s sorted run
-      uint64_t kth = 0ull;
-      for (int it = 0; it < k; ++it) {
-        const uint64_t c = (lane < kBm25Threads / 32 && head < 32) ? tbest[lane * 32 + head] : 0ull;
-        uint64_t m = c;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-          const uint64_t other = __shfl_xor_sync(kFullMask, m, o);
-          m = other > m ? other : m;
-        }
-        m = __shfl_sync(kFullMask, m, 0);   // max over lanes 0..7
-        kth = m;
-        if (m == 0ull) break;               // fewer than k threads hold a document
-        if (c == m) ++head;                 // keys are unique: exactly one lane advances
-      }
-      if (lane == 0) *s_out = kth;
-    }
-    __syncthreads();
-  } else {
-    tbest[threadIdx.x] = best;
-    block_bitonic_sort_desc(tbest, kBm25Threads);
-    if (threadIdx.x == 0) *s_out = k <= kBm25Threads ? tbest[k - 1] : 0ull;
-    __syncthreads();
-  }
-  return *s_out;
+  return block_kth_of_thread_bests<kBm25Threads / 32>(best, k, tbest, s_out);
 }
 
 template <bool EMIT_ALL, bool PRUNE>
@@ -442,7 +400,7 @@ bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_te
   for (int i = threadIdx.x; i < sel_cap; i += kBm25Threads) sel[i] = 0ull;
   uint64_t thr = 0ull;   // 0: everything that holds a key is collected
   // few listed survivors: rank them all directly, no threshold needed
-  const bool small = listed && n_cand <= kBm25Threads;
+  const bool small = listed && n_cand <= 64;
   if (!small) thr = kth_of_thread_bests(best, k, tbest, &s_thr);
   else __syncthreads();
   const int n_sweep = listed ? n_cand : nd;

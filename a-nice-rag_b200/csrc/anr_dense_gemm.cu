@@ -333,10 +333,10 @@ dense_gemm_thr_kernel(const float* __restrict__ gmax, int64_t gmax_stride, int m
   const float* g = gmax + static_cast<int64_t>(q) * gmax_stride;
   float b = -INFINITY;
   for (int i = threadIdx.x; i < m; i += kGmThrThreads) b = fmaxf(b, g[i]);
-  best[threadIdx.x] = b == -INFINITY ? 0ull : make_key(b, 0u);
-  block_bitonic_sort_desc(best, kGmThrThreads);
+  __shared__ uint64_t s_kth;
+  const uint64_t kth = block_kth_of_thread_bests<kGmThrThreads / 32>(
+      b == -INFINITY ? 0ull : make_key(b, 0u), rank, best, &s_kth);
   if (threadIdx.x == 0) {
-    const uint64_t kth = best[rank - 1];
     thr[q] = kth ? key_score(kth) : -INFINITY;
     thr_key[q] = kth ? (kth | 0xffffffffull) : 0ull;
   }

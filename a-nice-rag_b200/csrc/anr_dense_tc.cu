@@ -436,16 +436,16 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
   // T = k-th largest of the 512 per-thread bests: a lower bound of the k-th best tf32 score
   // (k distinct candidates reach it).  A lower T only widens the rescored margin, so exactness
   // is unaffected and no list of candidates has to be maintained here.
+  __shared__ uint64_t s_kth;
+  uint64_t kth;
   {
     uint64_t b = 0ull;
     for (int i = threadIdx.x; i < m; i += kTcRescoreThreads) {
       const uint64_t v = c[i];
       b = v > b ? v : b;
     }
-    top[threadIdx.x] = b;
+    kth = block_kth_of_thread_bests<kTcRescoreThreads / 32>(b, k, top, &s_kth);
   }
-  block_bitonic_sort_desc(top, kTcRescoreThreads);
-  const uint64_t kth = top[k - 1];
   // error bound of a tf32 product sum: each operand loses < 2^-10 relative (13 mantissa bits
   // dropped), accumulation noise D * 2^-22 -> |err| <= 2.5e-3 * |q| * |e| (Cauchy-Schwarz)
   const float eps = eps_scale * sqrtf(q_norm2);
@@ -475,31 +475,60 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
     if (threadIdx.x == 0) bad = 1;
     ns = kTcRescoreCap;
   }
-  // exact fp32 inner products, one warp per candidate
-  for (int i = warp; i < ns; i += n_warps) {
-    const uint32_t row = key_id(sel[i]);
-    const float* e = emb + static_cast<size_t>(row) * ld;
-    float acc = 0.f;
+  // exact fp32 inner products, one warp per candidate, two candidates in flight per warp (the
+  // rows are random 4 KB reads: latency, not bytes).  The summation order per row is fixed.
+  for (int i = warp; i < ns; i += 2 * n_warps) {
+    const int i2 = i + n_warps;
+    const bool two = i2 < ns;
+    const uint32_t row_a = key_id(sel[i]);
+    const uint32_t row_b = two ? key_id(sel[i2]) : row_a;
+    const float* ea = emb + static_cast<size_t>(row_a) * ld;
+    const float* eb = emb + static_cast<size_t>(row_b) * ld;
+    float acc_a = 0.f, acc_b = 0.f;
     for (int col = lane * 4; col < ld; col += 128) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(e + col));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(qv + col));
-      acc = fmaf(a.x, b.x, acc);
-      acc = fmaf(a.y, b.y, acc);
-      acc = fmaf(a.z, b.z, acc);
-      acc = fmaf(a.w, b.w, acc);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ea + col));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(eb + col));
+      const float4 qq = __ldg(reinterpret_cast<const float4*>(qv + col));
+      acc_a = fmaf(a.x, qq.x, acc_a);
+      acc_a = fmaf(a.y, qq.y, acc_a);
+      acc_a = fmaf(a.z, qq.z, acc_a);
+      acc_a = fmaf(a.w, qq.w, acc_a);
+      acc_b = fmaf(b.x, qq.x, acc_b);
+      acc_b = fmaf(b.y, qq.y, acc_b);
+      acc_b = fmaf(b.z, qq.z, acc_b);
+      acc_b = fmaf(b.w, qq.w, acc_b);
     }
-    acc = warp_sum(acc);
+    acc_a = warp_sum(acc_a);
+    acc_b = warp_sum(acc_b);
     __syncwarp();
-    if (lane == 0) sel[i] = make_key(acc, row);
+    if (lane == 0) {
+      sel[i] = make_key(acc_a, row_a);
+      if (two) sel[i2] = make_key(acc_b, row_b);
+    }
   }
   __syncthreads();
-  const int sp2 = next_pow2(ns < 2 ? 2 : ns);
-  for (int i = ns + threadIdx.x; i < sp2; i += blockDim.x) sel[i] = 0ull;
-  block_bitonic_sort_desc(sel, sp2);
   uint64_t key = 0ull;
-  if (threadIdx.x < k) {
-    key = threadIdx.x < ns ? sel[threadIdx.x] : 0ull;
-    const int64_t slot = q * o.stride_q + threadIdx.x;
+  int my_rank = threadIdx.x;
+  if (ns <= kTcRescoreThreads) {
+    // rank by counting (keys carry unique row ids): no sort, no barriers
+    my_rank = k;   // = nothing to emit
+    if (threadIdx.x < ns) {
+      key = sel[threadIdx.x];
+      int rank = 0;
+      for (int j = 0; j < ns; ++j) rank += sel[j] > key;
+      my_rank = rank;
+    }
+    if (my_rank >= k) key = 0ull;
+    // slots past the number of candidates are empty
+    if (threadIdx.x >= ns && threadIdx.x < k) my_rank = threadIdx.x;
+  } else {
+    const int sp2 = next_pow2(ns);
+    for (int i = ns + threadIdx.x; i < sp2; i += blockDim.x) sel[i] = 0ull;
+    block_bitonic_sort_desc(sel, sp2);
+    if (threadIdx.x < k) key = sel[threadIdx.x];
+  }
+  if (my_rank < k) {
+    const int64_t slot = q * o.stride_q + my_rank;
     const bool valid = key != 0ull;
     const uint32_t id = key_id(key);
     const uint32_t out_id =

@@ -111,4 +111,56 @@ __device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* keys, int n_po
   __syncthreads();
 }
 
+// k-th largest of the per-thread best keys of a block of NWARPS warps (0 when fewer than k
+// threads hold a key): with every thread owning a disjoint set of candidates, k distinct
+// candidates reach it, so it bounds the k-th best candidate from below.  Every thread calls;
+// tbest holds NWARPS * 32 keys of scratch, *s_out one key.
+//   k <= 32: every warp sorts its 32 keys in registers (shuffles, no barrier), warp 0 then pops
+//            the largest run head k times; larger k: block-wide bitonic sort.
+template <int NWARPS>
+__device__ __forceinline__ uint64_t block_kth_of_thread_bests(uint64_t best, int k, uint64_t* tbest,
+                                                              uint64_t* s_out) {
+  static_assert(NWARPS <= 32, "one lane of warp 0 per sorted run");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (k <= 32) {
+    uint64_t v = best;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const uint64_t other = __shfl_xor_sync(kFullMask, v, stride);
+        const bool keep_max = ((lane & stride) == 0) == ((lane & size) == 0);
+        v = keep_max ? (v > other ? v : other) : (v < other ? v : other);
+      }
+    tbest[threadIdx.x] = v;   // warp w's keys, descending, at tbest[32 w ..]
+    __syncthreads();
+    if (warp == 0) {
+      int head = 0;   // lanes 0..NWARPS-1: read position in warp `lane`'s sorted run
+      uint64_t kth = 0ull;
+      for (int it = 0; it < k; ++it) {
+        const uint64_t c = (lane < NWARPS && head < 32) ? tbest[lane * 32 + head] : 0ull;
+        uint64_t m = c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const uint64_t other = __shfl_xor_sync(kFullMask, m, o);
+          m = other > m ? other : m;
+        }
+        kth = m;
+        if (m == 0ull) break;               // fewer than k threads hold a key
+        // equal keys in two runs (possible only for keys without unique ids): one lane advances
+        const unsigned who = __ballot_sync(kFullMask, c == m);
+        if (lane == __ffs(who) - 1) ++head;
+      }
+      if (lane == 0) *s_out = kth;
+    }
+    __syncthreads();
+  } else {
+    tbest[threadIdx.x] = best;
+    block_bitonic_sort_desc(tbest, NWARPS * 32);
+    if (threadIdx.x == 0) *s_out = k <= NWARPS * 32 ? tbest[k - 1] : 0ull;
+    __syncthreads();
+  }
+  return *s_out;
+}
+
 }  // namespace anr
