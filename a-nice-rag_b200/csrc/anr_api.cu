@@ -279,12 +279,17 @@ inline bool dense_shadow_wanted(const anr_dense* ix) {
   static const bool env = getenv("ANR_TC_BF16") != nullptr && atoi(getenv("ANR_TC_BF16")) != 0;
   return (ix->want_shadow || env) && ix->ld % 64 == 0;
 }
-inline int dense_gemm_min_queries() {
+// Without a shadow copy the CUDA-core fp32 scan (<= 8 queries) and the 32-query tf32 scan read
+// the same bytes as the GEMM would, with less set-up; WITH a bf16 shadow the GEMM pass reads half
+// the bytes of any fp32 scan, so every batch size takes it (a 64-query tile, zero-padded).
+inline int dense_gemm_min_queries(const anr_dense* ix) {
   static const int v = getenv("ANR_GEMM_MIN_QUERIES") ? atoi(getenv("ANR_GEMM_MIN_QUERIES")) : 33;
-  return v;
+  static const int vs =
+      getenv("ANR_GEMM_MIN_QUERIES_SHADOW") ? atoi(getenv("ANR_GEMM_MIN_QUERIES_SHADOW")) : 1;
+  return dense_shadow_wanted(ix) ? vs : v;
 }
 inline bool dense_use_gemm(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
-  return nq >= dense_gemm_min_queries() && k <= kMaxFusedK &&
+  return nq >= dense_gemm_min_queries(ix) && k <= kMaxFusedK &&
          dense_gemm_supported(ctx->dp, ix->n, ix->ld, k, dense_shadow_wanted(ix));
 }
 inline int dense_gemm_total_padded(int nq) {

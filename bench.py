@@ -358,6 +358,20 @@ def run_ours(args):
         step_device()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
+    # batch-1 again through the fp32 CUDA-core scan (north_star kernel (1)): without the bf16 shadow
+    ms_b1_scan, lat_scan = None, []
+    if args.dense_operands == "bf16":
+        dense.set_shadow(False)
+        for _ in range(5):
+            step_device(1)
+        ms_b1_scan = timed(lambda: step_device(1), max(args.steps, 50)) / max(args.steps, 50)
+        if world == 1:
+            for i in range(args.latency_iters + 20):
+                t0 = time.perf_counter()
+                step_e2e(1)
+                if i >= 20:
+                    lat_scan.append(1e3 * (time.perf_counter() - t0))
+        dense.set_shadow(True)
 
     if rank != 0:
         if world > 1:
@@ -370,11 +384,13 @@ def run_ours(args):
     traffic = None        # dram bytes per launch, from the committed ncu captures
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     rows_local = hi - lo
-    gemm = B > 32 and rows_local >= 80_000          # anr_dense_gemm.cu takes these batches
+    # anr_dense_gemm.cu takes batches > 32, and every batch when a bf16 shadow exists
+    gemm = (B > 32 or args.dense_operands == "bf16") and rows_local >= 80_000
     shadow = gemm and args.dense_operands == "bf16"
-    dense_kernel = ((f"dense_gemm_kernel<64, {'bf16' if shadow else 'tf32'}>" if gemm else
-                     ("dense_tc_pair_kernel" if B > 32 else "dense_tc_kernel<0>")) if B > 8
-                    else "dense_scan_kernel<1, 4, 0>")
+    tile_q = 64 if B <= 64 else (128 if B <= 128 else 256)
+    dense_kernel = (f"dense_gemm_kernel<{tile_q}, {'bf16' if shadow else 'tf32'}>" if gemm else
+                    (("dense_tc_pair_kernel" if B > 32 else "dense_tc_kernel<0>") if B > 8
+                     else "dense_scan_kernel<1, 4, 0>"))
     # algorithmic bytes of one launch: every row once, in the operand type the kernel reads
     scan_bytes = rows_local * D * (2 if shadow else 4)
     scan_avg_ms = scan_ms.value / max(scan_n.value, 1)
@@ -444,21 +460,29 @@ def run_ours(args):
         # kernels of this repo launched per step: dense (CUDA-core scan + final | tcgen05:
         # pre-pass(es) + threshold + scan + rescore + flag compaction + flagged rescan + its merge),
         # BM25 score + final, weights, WRRF; sharded: + the two merges of anr_sharded_fuse
-        # GEMM path (B > 32): [query -> bf16] + sample pass + thresholds + GEMM + rescore + flag
-        # compaction + flagged rescan + its merge
+        # GEMM path: [query -> bf16] + sample pass + thresholds + GEMM + rescore + flag
+        # compaction + flagged rescan + its merge; BM25: [sample launch] + scan + final top-k;
+        # then the weight upload kernel and WRRF
         "gpu_launches": int(args.steps * (
-            ((7 + (1 if shadow else 0) if gemm else (8 if B > 32 else 7)) if B > 8 else 2)
-            + 2 + 2 + (2 if world > 1 else 0))),
+            (7 + (1 if shadow else 0) if gemm else ((8 if B > 32 else 7) if B > 8 else 2))
+            + (3 if B >= 16 else 2) + 2 + (2 if world > 1 else 0))),
         # the kernel with the largest share of the step; the other one follows
         "roofline": dominant,
         "roofline_other": bm_roof if dominant is dense_roof else dense_roof,
-        "dense_operands": ("bf16 shadow copy" if shadow else "fp32 words as tf32") if B > 8 else "fp32",
+        "dense_operands": ("bf16 shadow copy" if shadow else "fp32 words as tf32") if (B > 8 or gemm) else "fp32",
         "dense_tc_pass": {"what": "sample pre-pass + threshold + scan + exact rescoring",
                           "avg_ms": pass_ms.value / max(pass_n.value, 1), "passes": int(pass_n.value),
                           "share_of_step": pass_ms.value / ms_dev if ms_dev else None},
         "batch1": {"device_ms": ms_b1_dev, "device_qps": 1e3 / ms_b1_dev if ms_b1_dev else None,
                    "e2e_p50_ms": statistics.median(lat) if lat else None,
-                   "e2e_p95_ms": (sorted(lat)[int(0.95 * len(lat))] if lat else None)},
+                   "e2e_p95_ms": (sorted(lat)[int(0.95 * len(lat))] if lat else None),
+                   "dense_path": ("bf16 shadow GEMM pass + exact fp32 rescoring" if shadow
+                                  else "fp32 CUDA-core scan")},
+        "batch1_fp32_scan": ({"device_ms": ms_b1_scan,
+                              "e2e_p50_ms": statistics.median(lat_scan) if lat_scan else None,
+                              "hbm_gbs": rows_local * D * 4 / (ms_b1_scan * 1e-3) / 1e9,
+                              "frac_of_peak": rows_local * D * 4 / (ms_b1_scan * 1e-3) / 1e9 / peak}
+                             if ms_b1_scan else None),
         "clocks": clocks, "parity_checked_queries": checked,
     }
     if cpu:

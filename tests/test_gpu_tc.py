@@ -140,6 +140,22 @@ def test_gemm_batches_vs_oracle(big_corpus, nq, k, shadow):
                  every=max(nq // 24, 1))
 
 
+@pytest.mark.parametrize("nq,k", [(1, 10), (3, 25), (9, 10), (32, 100)])
+def test_gemm_small_batches_take_the_shadow_pass(big_corpus, nq, k):
+    """With a bf16 shadow enabled every batch size goes through the GEMM pass (half the bytes of
+    an fp32 scan); results must still be the exact fp32 ranking."""
+    emb, emb_dev = big_corpus
+    index = engine.DenseIndex(emb_dev, borrow=True)
+    index.set_shadow(True)
+    queries = synth.unit_vectors(nq, 1024, seed=700 + nq)
+    scores, rows, counts = index.search(queries, k)
+    _check_batch(emb, queries, scores, rows, counts, k, f"gemm small nq{nq} k{k}")
+    index.set_shadow(False)
+    s2, r2, _ = index.search(queries, k)
+    np.testing.assert_allclose(scores, s2, rtol=1e-5, atol=1e-6)
+    assert (rows == r2).mean() > 0.99
+
+
 @pytest.mark.parametrize("shadow", [False, True])
 def test_gemm_with_mask_and_unnormalised_rows(shadow):
     rng = np.random.default_rng(17)
