@@ -147,7 +147,14 @@ static __device__ __noinline__ int gemm_stage_hits(GemmStage* st, int wn, uint32
 // Row tile t of this launch covers corpus rows [t * tile_stride * 128, +128).
 //   SAMPLE = false: rows whose score beats thr[query] are appended to cand[query][cap] / cnt[query]
 //   SAMPLE = true : gmax[query * gmax_stride + t * 4 + quadrant] = max score of that 32-row group
-template <int NQ, bool BF16, bool SAMPLE>
+//
+// PAIR = true: clusters of two CTAs on neighbouring row tiles share every QUERY slab -- rank r
+// loads half of it and the TMA multicasts that half into both CTAs' rings, so the L2 -> SM
+// traffic per 128 x NQ tile drops from 16 + NQ/8 KB to 16 + NQ/16 KB per slab.  (ncu: at 256
+// queries per tile the single-CTA kernel is bound by the ~12 TB/s the L2 can deliver, not by the
+// tensor pipe.)  A stage may be refilled only when BOTH CTAs' MMAs have read it: every commit
+// arrives on the "empty" barrier of both CTAs.
+template <int NQ, bool BF16, bool SAMPLE, bool PAIR>
 __global__ void __launch_bounds__(kGmThreads, 1)   // launched with 64 + 32 * {4, 8} threads
 dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   int64_t n, int64_t n_row_tiles, int64_t tile_stride, int n_qblocks,
@@ -167,15 +174,23 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_epi = static_cast<int>(blockDim.x >> 5) - 2;   // 4 or 8
-  const int64_t my_row_tiles =
-      n_row_tiles > blockIdx.x ? (n_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // work units: row tiles (PAIR: pairs of neighbouring row tiles, one per CTA of the cluster)
+  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int64_t unit0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int64_t unit_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const int64_t n_units = PAIR ? (n_row_tiles + 1) / 2 : n_row_tiles;
+  const int64_t my_row_tiles = n_units > unit0 ? (n_units - unit0 + unit_step - 1) / unit_step : 0;
+  auto tile_of = [&](int64_t it) -> int64_t {
+    const int64_t u = unit0 + it * unit_step;
+    return PAIR ? 2 * u + rank : u;   // may be == n_row_tiles for the odd tile out: all zero rows
+  };
 
   if (!SAMPLE)
     for (int i = threadIdx.x; i < n_qblocks * NQ; i += blockDim.x) thr_s[i] = thr[i];
   if (threadIdx.x == 0) {
     for (int s = 0; s < L.n_stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], PAIR ? 2 : 1);   // PAIR: one commit from each CTA of the cluster
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
@@ -192,6 +207,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -201,14 +217,18 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       int s = 0;
       uint32_t ph = 0;
       for (int64_t it = 0; it < my_row_tiles; ++it) {
-        const int row0 = static_cast<int>((blockIdx.x + it * gridDim.x) * tile_stride * kGmRows);
+        const int row0 = static_cast<int>(tile_of(it) * tile_stride * kGmRows);
         for (int qb = 0; qb < n_qblocks; ++qb) {
           for (int kb = 0; kb < L.n_slabs; ++kb) {
             mbar_wait(&empty[s], ph ^ 1u);
             unsigned char* st = ring + static_cast<size_t>(s) * Cfg::kStageBytes;
             mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
             tma_load_2d(st, &map_a, kb * Cfg::kSlabElems, row0, &full[s]);
-            tma_load_2d(st + kGmABytes, &map_b, kb * Cfg::kSlabElems, qb * NQ, &full[s]);
+            if (PAIR)   // my half of the query slab, into both CTAs
+              tma_load_2d_mcast(st + kGmABytes + rank * (Cfg::kBBytes / 2), &map_b,
+                                kb * Cfg::kSlabElems, qb * NQ + rank * (NQ / 2), &full[s], 0x3);
+            else
+              tma_load_2d(st + kGmABytes, &map_b, kb * Cfg::kSlabElems, qb * NQ, &full[s]);
             if (++s == L.n_stages) { s = 0; ph ^= 1u; }
           }
         }
@@ -241,7 +261,9 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               tc_mma_tf32(tmem_d, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2),
                           Cfg::kIdesc, (kb | kk) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty[s]);  // the stage may be refilled once these MMAs have read it
+          // the stage may be refilled once these MMAs (PAIR: and the peer's) have read it
+          if (PAIR) tc_commit_mcast(&empty[s], 0x3);
+          else tc_commit(&empty[s]);
           if (++s == L.n_stages) { s = 0; ph ^= 1u; }
         }
         tc_commit(&acc_full[a]);
@@ -255,9 +277,9 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     int wn = 0;   // survivors staged by this warp (warp-uniform)
     int64_t t = 0;
     for (int64_t it = 0; it < my_row_tiles; ++it) {
-      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t tile = tile_of(it);
       const int64_t row = tile * tile_stride * kGmRows + quad * 32 + lane;
-      bool ok = row < n;
+      bool ok = row < n && tile < n_row_tiles;
       if (ok && mask) ok = (__ldg(mask + (row >> 5)) >> (row & 31)) & 1u;
       for (int qb = 0; qb < n_qblocks; ++qb, ++t) {
         const int a = static_cast<int>(t & 1);
@@ -276,7 +298,8 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = ok ? __uint_as_float(v[j]) : -INFINITY;
             const float m = warp_transpose_max32(f, lane);
-            gmax[static_cast<int64_t>(q0 + lane) * gmax_stride + tile * 4 + quad] = m;
+            if (tile < n_row_tiles)
+              gmax[static_cast<int64_t>(q0 + lane) * gmax_stride + tile * 4 + quad] = m;
           } else {
             const float4* th = reinterpret_cast<const float4*>(thr_s + q0);
             uint32_t hm = 0u;
@@ -307,6 +330,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -458,20 +482,43 @@ static bool gemm_encode_map(CUtensorMap* map, const void* base, int64_t rows, in
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+template <int NQ, bool BF16, bool SAMPLE, bool PAIR>
+static cudaError_t gemm_launch_one(int grid, int threads, int smem, cudaStream_t stream,
+                                   const CUtensorMap& map_a, const CUtensorMap& map_b, int64_t n,
+                                   int64_t n_row_tiles, int64_t tile_stride, int n_qblocks,
+                                   const uint32_t* mask, const float* thr, uint64_t* cand,
+                                   int32_t* cnt, int cap, float* gmax, int64_t gstride,
+                                   const GemmLayout& L) {
+  auto kern = dense_gemm_kernel<NQ, BF16, SAMPLE, PAIR>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(static_cast<unsigned>(threads));
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, map_a, map_b, n, n_row_tiles, tile_stride, n_qblocks, mask,
+                            thr, cand, cnt, cap, gmax, gstride, L);
+}
+
+// sample pass + thresholds + main pass.  map_b_half: the query matrix with boxes of NQ / 2 rows
+// (what each CTA of a pair loads and multicasts).
 template <int NQ, bool BF16>
 static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& map_a,
-                                    const CUtensorMap& map_b, int64_t n, int n_qblocks,
-                                    const uint32_t* mask, int64_t sample_tiles, int n_real, int k,
-                                    float* gmax, float* thr, uint64_t* thr_key, uint64_t* cand,
-                                    int32_t* cnt, const GemmLayout& L, cudaEvent_t ev_start,
-                                    cudaEvent_t ev_stop, cudaStream_t stream) {
+                                    const CUtensorMap& map_b, const CUtensorMap& map_b_half,
+                                    int64_t n, int n_qblocks, const uint32_t* mask,
+                                    int64_t sample_tiles, int n_real, int k, float* gmax, float* thr,
+                                    uint64_t* thr_key, uint64_t* cand, int32_t* cnt,
+                                    const GemmLayout& L, cudaEvent_t ev_start, cudaEvent_t ev_stop,
+                                    cudaStream_t stream) {
   const int smem = L.total_bytes + 1024;  // room to align the dynamic base to 1024 bytes
-  cudaError_t e = cudaFuncSetAttribute(dense_gemm_kernel<NQ, BF16, true>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(dense_gemm_kernel<NQ, BF16, false>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return e;
   const int64_t n_tiles = (n + kGmRows - 1) / kGmRows;
   const int64_t stride = n_tiles / sample_tiles;
   const int64_t gstride = sample_tiles * 4;
@@ -480,17 +527,34 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
   static const int epi_env = getenv("ANR_GEMM_EPI_WARPS") ? atoi(getenv("ANR_GEMM_EPI_WARPS")) : 0;
   const int n_epi = epi_env == 4 || epi_env == 8 ? epi_env : (NQ >= 128 ? 8 : 4);
   const int threads = 64 + 32 * n_epi;
-  dense_gemm_kernel<NQ, BF16, true><<<dp.sm_count, threads, smem, stream>>>(
-      map_a, map_b, n, sample_tiles, stride, n_qblocks, mask, nullptr, nullptr, nullptr, 0, gmax,
-      gstride, L);
+  // CTA pairs share the query slabs once those dominate the L2 traffic of a tile
+  static const int pair_env = getenv("ANR_GEMM_PAIR") ? atoi(getenv("ANR_GEMM_PAIR")) : -1;
+  const bool pair = (pair_env >= 0 ? pair_env != 0 : NQ >= 128) && dp.sm_count % 2 == 0 &&
+                    n_tiles >= dp.sm_count;
+  cudaError_t e;
+  if (pair)
+    e = gemm_launch_one<NQ, BF16, true, true>(dp.sm_count, threads, smem, stream, map_a, map_b_half, n,
+                                              sample_tiles, stride, n_qblocks, mask, nullptr, nullptr,
+                                              nullptr, 0, gmax, gstride, L);
+  else
+    e = gemm_launch_one<NQ, BF16, true, false>(dp.sm_count, threads, smem, stream, map_a, map_b, n,
+                                               sample_tiles, stride, n_qblocks, mask, nullptr, nullptr,
+                                               nullptr, 0, gmax, gstride, L);
+  if (e != cudaSuccess) return e;
   dense_gemm_thr_kernel<<<nq_pad, kGmThrThreads, 0, stream>>>(
       gmax, gstride, static_cast<int>(gstride), gemm_thr_rank(k), n_real, thr, thr_key);
   if (ev_start) cudaEventRecord(ev_start, stream);   // brackets the main GEMM kernel only
   const int grid = static_cast<int>(std::min<int64_t>(dp.sm_count, n_tiles));
-  dense_gemm_kernel<NQ, BF16, false><<<grid, threads, smem, stream>>>(
-      map_a, map_b, n, n_tiles, 1, n_qblocks, mask, thr, cand, cnt, kGmCap, nullptr, 0, L);
+  if (pair)
+    e = gemm_launch_one<NQ, BF16, false, true>(dp.sm_count, threads, smem, stream, map_a, map_b_half, n,
+                                               n_tiles, 1, n_qblocks, mask, thr, cand, cnt, kGmCap,
+                                               nullptr, 0, L);
+  else
+    e = gemm_launch_one<NQ, BF16, false, false>(grid, threads, smem, stream, map_a, map_b, n, n_tiles,
+                                                1, n_qblocks, mask, thr, cand, cnt, kGmCap, nullptr,
+                                                0, L);
   if (ev_stop) cudaEventRecord(ev_stop, stream);
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // One launch group: n_real <= dense_gemm_max_queries() queries at q_dev ([padded, ld] fp32, zero
@@ -531,14 +595,16 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
   cudaError_t e = cudaMemsetAsync(cnt, 0, static_cast<size_t>(nq_pad) * 4, stream);
   if (e != cudaSuccess) return e;
 
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_b_half;
   if (!gemm_encode_map(&map_a, bf16 ? shadow : static_cast<const void*>(emb), n, ld, kGmRows, bf16) ||
-      !gemm_encode_map(&map_b, q_ops, nq_pad, ld, nqb_size, bf16))
+      !gemm_encode_map(&map_b, q_ops, nq_pad, ld, nqb_size, bf16) ||
+      !gemm_encode_map(&map_b_half, q_ops, nq_pad, ld, nqb_size / 2, bf16))
     return cudaErrorInvalidValue;
 
 #define ANR_GEMM_CASE(NQV, BFV)                                                                   \
-  e = gemm_launch_pair<NQV, BFV>(dp, map_a, map_b, n, n_qblocks, mask, sample_tiles, n_real, k,  \
-                                 gmax, thr, thr_key, cand, cnt, L, ev_start, ev_stop, stream)
+  e = gemm_launch_pair<NQV, BFV>(dp, map_a, map_b, map_b_half, n, n_qblocks, mask, sample_tiles,  \
+                                 n_real, k, gmax, thr, thr_key, cand, cnt, L, ev_start, ev_stop,   \
+                                 stream)
   if (bf16) {
     if (nqb_size == 64) ANR_GEMM_CASE(64, true);
     else if (nqb_size == 128) ANR_GEMM_CASE(128, true);
