@@ -11,3 +11,4 @@ from . import config, engine, registry  # noqa: F401
 from .config import Config, InfoSource, SourceConfig  # noqa: F401
 from .database_manager import DatabaseManager  # noqa: F401
 from .search_engine import SearchEngine  # noqa: F401
+from .batch_retrieval import retrieve_documents_batch  # noqa: F401

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -74,6 +75,8 @@ struct anr_dense {
   // (anr_dense_set_shadow / ANR_TC_BF16=1)
   mutable void* shadow = nullptr;
   mutable bool want_shadow = false;
+  // indices are shared between contexts / threads: the lazily built members above are guarded
+  mutable std::mutex lazy;
 };
 
 struct anr_bm25 {
@@ -94,6 +97,7 @@ struct anr_bm25 {
   mutable int32_t n_head = 0;
   mutable bool head_built = false;         // slot map + allocation exist
   mutable bool head_filled = false;        // rows hold the current posting weights
+  mutable std::mutex lazy;                 // guards the lazily built members (shared index)
 };
 
 namespace {
@@ -329,6 +333,7 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
   if (gmax < 1) return fail(ANR_ERR_UNSUPPORTED, "embedding rows too long for the scan kernel");
   const bool gemm = dense_use_gemm(ctx, ix, nq, k);
   if (gemm || dense_use_tc(ctx, ix, nq, k)) {
+    std::lock_guard<std::mutex> lock(ix->lazy);
     if (!ix->norm_valid) {  // once per index: the error bound needs max |row|
       float* d_norm = arena.take<float>(1);
       ANR_CUDA(launch_row_norm_max(ix->emb, ix->n, ix->ld, d_norm, stream));
@@ -338,9 +343,20 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
     }
   }
   if (gemm) {
-    if (dense_shadow_wanted(ix) && !ix->shadow) {  // once per index: the bf16 operand copy
-      ANR_CUDA(cudaMalloc(&ix->shadow, static_cast<size_t>(ix->n) * ix->ld * 2));
-      ANR_CUDA(launch_f32_to_bf16(ix->emb, ix->shadow, ix->n * ix->ld, stream));
+    if (dense_shadow_wanted(ix)) {  // once per index: the bf16 operand copy
+      std::lock_guard<std::mutex> lock(ix->lazy);
+      if (!ix->shadow) {
+        void* sh = nullptr;
+        ANR_CUDA(cudaMalloc(&sh, static_cast<size_t>(ix->n) * ix->ld * 2));
+        cudaError_t e = launch_f32_to_bf16(ix->emb, sh, ix->n * ix->ld, stream);
+        // other streams may use the copy as soon as the pointer is published
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) {
+          cudaFree(sh);
+          return fail_cuda("bf16 shadow copy", e);
+        }
+        ix->shadow = sh;
+      }
     }
     unsigned char* scratch =
         arena.take<unsigned char>(dense_gemm_scratch_bytes(ctx->dp, ix->n, ix->ld, nq, k));
@@ -459,6 +475,7 @@ Bm25View bm25_view(const anr_bm25* ix);
 // kBm25MaxHead most frequent at most, within a memory budget of a quarter of the postings' size
 // or 1 GB, whichever is larger.
 int bm25_ensure_heads(const anr_bm25* ix, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(ix->lazy);
   if (ix->head_built && ix->head_filled) return ANR_OK;
   if (!ix->head_built) {
     std::vector<int64_t> tp(static_cast<size_t>(ix->n_terms) + 1);
@@ -505,6 +522,7 @@ int bm25_ensure_heads(const anr_bm25* ix, cudaStream_t stream) {
   }
   ANR_CUDA(launch_bm25_head_fill(bm25_view(ix), ix->head_terms, ix->n_head, ix->head_w,
                                  ix->head_max, ix->head_ld, stream));
+  ANR_CUDA(cudaStreamSynchronize(stream));   // other streams may read the rows once the flag is set
   ix->head_filled = true;
   return ANR_OK;
 }

@@ -97,8 +97,13 @@ def load_reference():
             se = _load("search_engine.py", "_anr_ref_search_engine")
             dm = _load("database_manager.py", "_anr_ref_database_manager")
             cfg = _load("config.py", "_anr_ref_config")
+            # the orchestrator imports the three modules above by their plain names
+            sys.modules["search_engine"], sys.modules["database_manager"] = se, dm
+            sys.modules["config"] = cfg
+            qrr = _load("query_rag_retrieval.py", "_anr_ref_query_rag_retrieval")
         _cache["ns"] = types.SimpleNamespace(
-            search_engine=se, database_manager=dm, config=cfg,
+            search_engine=se, database_manager=dm, config=cfg, query_rag_retrieval=qrr,
             SearchEngine=se.SearchEngine, DatabaseManager=dm.DatabaseManager, Config=cfg.Config,
+            InfoSource=cfg.InfoSource, RetrievalEvaluationSystem=qrr.RetrievalEvaluationSystem,
         )
     return _cache["ns"]

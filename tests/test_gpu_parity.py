@@ -518,3 +518,62 @@ def test_bm25_group_after_reweight(group_corpus):
 
 def _group_tokens():
     return synth.zipf_corpus(70_000, 4000, 1.1, seed=51, len_lo=40, len_hi=120)
+
+
+# ---------------------------------------------------------------------------------------
+# batched orchestrator: retrieve_documents for B queries == the per-query pipeline
+def test_retrieve_documents_batch_equals_per_query_orchestrator(small):
+    """a-nice-rag_b200.batch_retrieval.retrieve_documents_batch vs oracle.orchestrator (the
+    restatement of query_rag_retrieval.py:149-411 that tests/test_oracle.py pins against the
+    unmodified reference method), both over the drop-in SearchEngine: two dense models + BM25,
+    filters, full ranking (similarity_k >= N), return_docs."""
+    import types
+    import pandas as pd
+    from oracle import orchestrator
+    pkg = importlib.import_module("a-nice-rag_b200")
+    batch = importlib.import_module("a-nice-rag_b200.batch_retrieval")
+    case = small["case"]
+    n = case["emb"].shape[0]
+    srcs = list(case["sources"])
+    ids = synth.chunk_ids(n, srcs)
+    rng = np.random.default_rng(3)
+    emb2 = (case["emb"] + 0.3 * rng.standard_normal(case["emb"].shape)).astype(np.float32)
+
+    def frame(e):
+        return pd.DataFrame({"id": ids, "document": [f"doc {i}" for i in range(n)], "source": srcs,
+                             "embedding": list(e), "url": [""] * n})
+    sections = [types.SimpleNamespace(page_content=f"doc {i}", metadata={"id": ids[i], "source": srcs[i]})
+                for i in range(n)]
+    nice = pkg.InfoSource("nice")
+    system = types.SimpleNamespace(
+        config=pkg.Config(), search_engine=pkg.SearchEngine(None, None),
+        embeddings_data={nice: {"voyage-3-large": frame(case["emb"]), "Qwen3": frame(emb2)}},
+        bm25_data={nice: (small["okapi"], sections, ids)})
+    weights = {"voyage-3-large": 5.0, "Qwen3": 2.0, "BM25": 1.0}
+    nq = min(12, case["queries"].shape[0])
+    qe = {"voyage-3-large": np.ascontiguousarray(case["queries"][:nq]),
+          "Qwen3": np.ascontiguousarray(np.roll(case["queries"][:nq], 1, axis=0))}
+    toks = [synth.token_strings(case["term_queries"][q]) for q in range(nq)]
+    toks[nq // 2] = []                                    # no BM25 list for this query
+    cases = [dict(similarity_k=10, common_sections_n=10, use_hybrid_search=True),
+             dict(similarity_k=10, common_sections_n=7, use_hybrid_search=False),
+             dict(similarity_k=25, common_sections_n=15, use_hybrid_search=True,
+                  filename_type_filter="CG, NG"),
+             dict(similarity_k=3000, common_sections_n=40, use_hybrid_search=True),
+             dict(similarity_k=10, common_sections_n=10, use_hybrid_search=True, return_docs=True),
+             dict(similarity_k=10, common_sections_n=10, use_hybrid_search=True,
+                  filename_type_filter="ZZ")]
+    for kw in cases:
+        got = batch.retrieve_documents_batch(system, qe, None, toks, info_source="NICE",
+                                             model_weights=weights, wrrf_k=40, **kw)
+        assert len(got) == nq
+        for q in range(nq):
+            one = {m: e[q] for m, e in qe.items()}
+            want = orchestrator.retrieve_documents(system, nice, one, None, toks[q],
+                                                   model_weights=weights, wrrf_k=40, **kw)
+            if kw.get("return_docs"):
+                assert [d["id"] for d in got[q]] == [d["id"] for d in want], (kw, q)
+                np.testing.assert_allclose([d["similarity"] for d in got[q]],
+                                           [d["similarity"] for d in want], rtol=1e-6)
+            else:
+                assert got[q] == want, (kw, q)

@@ -134,3 +134,56 @@ def test_restatement_matches_reference_import(small_case):
              (["x", "y"], "other")]
     assert se.weighted_reciprocal_rank_fusion(lists, WEIGHTS, 40) == \
         retrieval.weighted_rrf(lists, WEIGHTS, 40)
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="reference sources not mounted")
+def test_orchestrator_restatement_matches_reference_method(small_case, built):
+    """oracle.orchestrator.retrieve_documents == the UNMODIFIED
+    RetrievalEvaluationSystem.retrieve_documents (query_rag_retrieval.py:149-411) driven with the
+    reference's own SearchEngine: several dense models, BM25, filters, full ranking, return_docs."""
+    import types
+    import pandas as pd
+    from oracle import orchestrator
+    ref = reference_loader.load_reference()
+    n = small_case["emb"].shape[0]
+    srcs = list(small_case["sources"])
+    ids = synth.chunk_ids(n, srcs)
+    emb = small_case["emb"]
+    rng = np.random.default_rng(3)
+    emb2 = (emb + 0.3 * rng.standard_normal(emb.shape)).astype(np.float32)   # a second "model"
+
+    def frame(e):
+        return pd.DataFrame({"id": ids, "document": [f"doc {i}" for i in range(n)], "source": srcs,
+                             "embedding": list(e), "url": [""] * n})
+    ix, okapi = built
+    sections = [types.SimpleNamespace(page_content=f"doc {i}", metadata={"id": ids[i], "source": srcs[i]})
+                for i in range(n)]
+    system = object.__new__(ref.RetrievalEvaluationSystem)     # no Voyage client, no databases on disk
+    system.config = ref.Config()
+    system.search_engine = ref.SearchEngine(None, None)
+    nice = ref.InfoSource("nice")
+    system.embeddings_data = {nice: {"voyage-3-large": frame(emb), "Qwen3": frame(emb2)}}
+    system.bm25_data = {nice: (okapi, sections, ids)}
+    weights = {"voyage-3-large": 5.0, "Qwen3": 2.0, "BM25": 1.0}
+    cases = [dict(similarity_k=10, common_sections_n=10, use_hybrid_search=True),
+             dict(similarity_k=10, common_sections_n=7, use_hybrid_search=False),
+             dict(similarity_k=25, common_sections_n=15, use_hybrid_search=True,
+                  filename_type_filter="CG, NG"),
+             dict(similarity_k=3000, common_sections_n=40, use_hybrid_search=True),   # k >= N
+             dict(similarity_k=10, common_sections_n=10, use_hybrid_search=True, return_docs=True),
+             dict(similarity_k=10, common_sections_n=10, use_hybrid_search=True,
+                  filename_type_filter="ZZ")]
+    for kw in cases:
+        for q in range(3):
+            qe = {"voyage-3-large": small_case["queries"][q], "Qwen3": small_case["queries"][q + 3]}
+            toks = synth.token_strings(small_case["term_queries"][q])
+            want = system.retrieve_documents(qe, None, toks, info_source="NICE", model_weights=weights,
+                                             wrrf_k=40, use_reranker=False, **kw)
+            got = orchestrator.retrieve_documents(system, nice, qe, None, toks, model_weights=weights,
+                                                  wrrf_k=40, use_reranker=False, **kw)
+            if kw.get("return_docs"):
+                assert [d["id"] for d in got] == [d["id"] for d in want]
+                assert [d["similarity"] for d in got] == [d["similarity"] for d in want]
+            else:
+                assert got == want, (kw, q)
+            assert len(want) > 0 or kw.get("filename_type_filter") == "ZZ"
