@@ -339,6 +339,198 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
 }
 
+// ---- cta_group::2: one 256-row x NQ-query MMA over a CTA pair ------------------------------------
+// The CTAs of a cluster of two own neighbouring 128-row tiles.  Each keeps ITS rows of the corpus
+// slab and ITS HALF of the query slab (NQ / 2 rows) in shared memory; the leader CTA (rank 0)
+// issues tcgen05.mma.cta_group::2 (M = 256): the tensor cores of both SMs read A from their own
+// CTA and the two halves of B from both, and write each CTA's 128 x NQ accumulator into its own
+// TMEM.  Per CTA and K slab that is 16 + NQ/16 KB of TMA writes and operand reads instead of
+// 16 + NQ/8 KB -- the shared-memory traffic that bounds the single-CTA kernel at NQ = 256.
+//   full[s]      (leader only) armed by the leader's producer with the bytes of BOTH CTAs; the
+//                peer's TMA loads signal it through its shared::cluster address
+//   empty[s]     (both) one multicast commit from the leader's MMA thread
+//   acc_full[a]  (both) one multicast commit;  acc_empty[a] (leader) all epilogue warps of both CTAs
+template <int NQ, bool BF16, bool SAMPLE>
+__global__ void __launch_bounds__(kGmThreads, 1)
+dense_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   int64_t n, int64_t n_row_tiles, int64_t tile_stride, int n_qblocks,
+                   const uint32_t* __restrict__ mask, const float* __restrict__ thr,
+                   uint64_t* __restrict__ cand, int32_t* __restrict__ cnt, int cap,
+                   float* __restrict__ gmax, int64_t gmax_stride, GemmLayout L) {
+  using Cfg = GemmCfg<NQ, BF16>;
+  constexpr int kBHalf = Cfg::kBBytes / 2;
+  constexpr int kStage2 = kGmABytes + kBHalf;
+  // M = 256 (both CTAs), N = NQ
+  constexpr uint32_t kIdesc2 = (1u << 4) | (Cfg::kFmt << 7) | (Cfg::kFmt << 10) |
+                               (static_cast<uint32_t>(NQ >> 3) << 17) | (16u << 24);
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* ring = smem;
+  float* thr_s = reinterpret_cast<float*>(smem + L.thr_off);
+  GemmStage* stages = reinterpret_cast<GemmStage*>(smem + L.stage_off);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* empty = full + kGmMaxStages;
+  uint64_t* acc_full = empty + kGmMaxStages;    // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_epi = static_cast<int>(blockDim.x >> 5) - 2;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int64_t unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
+  const int64_t n_units = (n_row_tiles + 1) / 2;
+  const int64_t my_units = n_units > unit0 ? (n_units - unit0 + unit_step - 1) / unit_step : 0;
+  auto tile_of = [&](int64_t it) -> int64_t { return 2 * (unit0 + it * unit_step) + rank; };
+
+  if (!SAMPLE)
+    for (int i = threadIdx.x; i < n_qblocks * NQ; i += blockDim.x) thr_s[i] = thr[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < L.n_stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 2 * n_epi);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {   // one warp of EACH CTA: the pair allocates the same columns in both TMEMs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- TMA producer (both CTAs): my rows of A, my half of B; bytes counted on the leader ----
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t it = 0; it < my_units; ++it) {
+        const int row0 = static_cast<int>(tile_of(it) * tile_stride * kGmRows);
+        for (int qb = 0; qb < n_qblocks; ++qb) {
+          for (int kb = 0; kb < L.n_slabs; ++kb) {
+            mbar_wait(&empty[s], ph ^ 1u);
+            unsigned char* st = ring + static_cast<size_t>(s) * kStage2;
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kStage2);
+            const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), 0);
+            tma_load_2d_cg2(st, &map_a, kb * Cfg::kSlabElems, row0, lead_full);
+            tma_load_2d_cg2(st + kGmABytes, &map_b, kb * Cfg::kSlabElems, qb * NQ + rank * (NQ / 2),
+                            lead_full);
+            if (++s == L.n_stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: the leader CTA only ----
+    if (lane == 0 && rank == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const int64_t my_tiles = my_units * n_qblocks;
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        const int a = static_cast<int>(t & 1);
+        const uint32_t aph = static_cast<uint32_t>(t >> 1) & 1u;
+        mbar_wait(&acc_empty[a], aph ^ 1u);  // the epilogues of BOTH CTAs have drained it
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(a * NQ);
+        for (int kb = 0; kb < L.n_slabs; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(ring + static_cast<size_t>(s) * kStage2);
+          const uint64_t da = tc_smem_desc(st);
+          const uint64_t db = tc_smem_desc(st + kGmABytes);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            if (BF16)
+              tc2_mma_bf16(tmem_d, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2),
+                           kIdesc2, (kb | kk) != 0 ? 1u : 0u);
+            else
+              tc2_mma_tf32(tmem_d, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2),
+                           kIdesc2, (kb | kk) != 0 ? 1u : 0u);
+          }
+          tc2_commit_mcast(&empty[s], 0x3);
+          if (++s == L.n_stages) { s = 0; ph ^= 1u; }
+        }
+        tc2_commit_mcast(&acc_full[a], 0x3);
+      }
+    }
+  } else {
+    // ---- epilogue (both CTAs): as in dense_gemm_kernel ----
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    GemmStage* st = stages + (warp - 2);
+    int wn = 0;
+    int64_t t = 0;
+    for (int64_t it = 0; it < my_units; ++it) {
+      const int64_t tile = tile_of(it);
+      const int64_t row = tile * tile_stride * kGmRows + quad * 32 + lane;
+      bool ok = row < n && tile < n_row_tiles;
+      if (ok && mask) ok = (__ldg(mask + (row >> 5)) >> (row & 31)) & 1u;
+      for (int qb = 0; qb < n_qblocks; ++qb, ++t) {
+        const int a = static_cast<int>(t & 1);
+        const uint32_t aph = static_cast<uint32_t>(t >> 1) & 1u;
+        mbar_wait(&acc_full[a], aph);
+        tc_fence_after();
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(a * NQ);
+#pragma unroll 1
+        for (int c = half; c < NQ / 32; c += (n_epi >> 2)) {
+          uint32_t v[32];
+          tc_ld_32x32(taddr + static_cast<uint32_t>(c * 32), v);
+          const int q0 = qb * NQ + c * 32;
+          if (SAMPLE) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = ok ? __uint_as_float(v[j]) : -INFINITY;
+            const float m = warp_transpose_max32(f, lane);
+            if (tile < n_row_tiles)
+              gmax[static_cast<int64_t>(q0 + lane) * gmax_stride + tile * 4 + quad] = m;
+          } else {
+            const float4* th = reinterpret_cast<const float4*>(thr_s + q0);
+            uint32_t hm = 0u;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 tq = th[j4];
+              hm |= (__uint_as_float(v[j4 * 4 + 0]) > tq.x ? 1u : 0u) << (j4 * 4 + 0);
+              hm |= (__uint_as_float(v[j4 * 4 + 1]) > tq.y ? 1u : 0u) << (j4 * 4 + 1);
+              hm |= (__uint_as_float(v[j4 * 4 + 2]) > tq.z ? 1u : 0u) << (j4 * 4 + 2);
+              hm |= (__uint_as_float(v[j4 * 4 + 3]) > tq.w ? 1u : 0u) << (j4 * 4 + 3);
+            }
+            if (!ok) hm = 0u;
+            if (__any_sync(kFullMask, hm != 0u))
+              wn = gemm_stage_hits(st, wn, hm, v, q0, static_cast<uint32_t>(row), cand, cnt, cap, lane);
+            if (wn >= kGmFlushAt) {
+              gemm_flush(st, wn, cand, cnt, cap, lane);
+              wn = 0;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[a]), 0));
+      }
+    }
+    if (!SAMPLE) gemm_flush(st, wn, cand, cnt, cap, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs are done with each other's shared memory, barriers and TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
 // Starting thresholds from the sample's group maxima.  The rank-th largest of the 512 per-thread
 // bests is reached by `rank` distinct groups, hence by `rank` distinct rows: a lower bound of the
 // rank-th best score of the corpus.  Queries >= n_real (zero padding) never nominate anything.
@@ -410,12 +602,13 @@ int dense_gemm_padded_queries(int nq) {
   return (nq + b - 1) / b * b;
 }
 
-static bool make_gemm_layout(const DeviceProps& dp, int ld, bool bf16, int nq_block, int nq_pad,
+// b_rows: query rows each CTA holds per slab (nq_block, or nq_block / 2 under cta_group::2)
+static bool make_gemm_layout(const DeviceProps& dp, int ld, bool bf16, int b_rows, int nq_pad,
                              GemmLayout* L) {
   const int slab = bf16 ? 64 : 32;
   if (ld % slab != 0) return false;
   L->n_slabs = ld / slab;
-  L->stage_bytes = kGmABytes + nq_block * 128;
+  L->stage_bytes = kGmABytes + b_rows * 128;
   const int thr_bytes = nq_pad * 4;
   const int bar_bytes = (2 * kGmMaxStages + 4) * 8 + 16;
   const int stage_bytes = kGmEpiWarps * static_cast<int>(sizeof(GemmStage));
@@ -508,6 +701,40 @@ static cudaError_t gemm_launch_one(int grid, int threads, int smem, cudaStream_t
                             thr, cand, cnt, cap, gmax, gstride, L);
 }
 
+template <int NQ, bool BF16, bool SAMPLE>
+static cudaError_t gemm2_launch_one(int grid, int threads, int smem, cudaStream_t stream,
+                                    const CUtensorMap& map_a, const CUtensorMap& map_b_half, int64_t n,
+                                    int64_t n_row_tiles, int64_t tile_stride, int n_qblocks,
+                                    const uint32_t* mask, const float* thr, uint64_t* cand,
+                                    int32_t* cnt, int cap, float* gmax, int64_t gstride,
+                                    const GemmLayout& L) {
+  auto kern = dense_gemm2_kernel<NQ, BF16, SAMPLE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(static_cast<unsigned>(threads));
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, map_a, map_b_half, n, n_row_tiles, tile_stride, n_qblocks,
+                            mask, thr, cand, cnt, cap, gmax, gstride, L);
+}
+
+// 0 = one CTA per tile, 1 = CTA pairs multicast the query slabs, 2 = cta_group::2 MMAs over a pair
+static int gemm_mode(const DeviceProps& dp, int nq_block, int64_t n_tiles) {
+  static const int env = getenv("ANR_GEMM_MODE") ? atoi(getenv("ANR_GEMM_MODE")) : -1;
+  if (dp.sm_count % 2 != 0 || n_tiles < dp.sm_count) return 0;
+  if (env >= 0 && env <= 2) return env;
+  return nq_block >= 128 ? 2 : 0;
+}
+
 // sample pass + thresholds + main pass.  map_b_half: the query matrix with boxes of NQ / 2 rows
 // (what each CTA of a pair loads and multicasts).
 template <int NQ, bool BF16>
@@ -527,11 +754,23 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
   static const int epi_env = getenv("ANR_GEMM_EPI_WARPS") ? atoi(getenv("ANR_GEMM_EPI_WARPS")) : 0;
   const int n_epi = epi_env == 4 || epi_env == 8 ? epi_env : (NQ >= 128 ? 8 : 4);
   const int threads = 64 + 32 * n_epi;
-  // CTA pairs share the query slabs once those dominate the L2 traffic of a tile
-  static const int pair_env = getenv("ANR_GEMM_PAIR") ? atoi(getenv("ANR_GEMM_PAIR")) : -1;
-  const bool pair = (pair_env >= 0 ? pair_env != 0 : NQ >= 128) && dp.sm_count % 2 == 0 &&
-                    n_tiles >= dp.sm_count;
+  const int mode = gemm_mode(dp, NQ, n_tiles);
+  const bool pair = mode == 1;
   cudaError_t e;
+  if (mode == 2) {
+    e = gemm2_launch_one<NQ, BF16, true>(dp.sm_count, threads, smem, stream, map_a, map_b_half, n,
+                                         sample_tiles, stride, n_qblocks, mask, nullptr, nullptr,
+                                         nullptr, 0, gmax, gstride, L);
+    if (e != cudaSuccess) return e;
+    dense_gemm_thr_kernel<<<nq_pad, kGmThrThreads, 0, stream>>>(
+        gmax, gstride, static_cast<int>(gstride), gemm_thr_rank(k), n_real, thr, thr_key);
+    if (ev_start) cudaEventRecord(ev_start, stream);
+    e = gemm2_launch_one<NQ, BF16, false>(dp.sm_count, threads, smem, stream, map_a, map_b_half, n,
+                                          n_tiles, 1, n_qblocks, mask, thr, cand, cnt, kGmCap, nullptr,
+                                          0, L);
+    if (ev_stop) cudaEventRecord(ev_stop, stream);
+    return e != cudaSuccess ? e : cudaGetLastError();
+  }
   if (pair)
     e = gemm_launch_one<NQ, BF16, true, true>(dp.sm_count, threads, smem, stream, map_a, map_b_half, n,
                                               sample_tiles, stride, n_qblocks, mask, nullptr, nullptr,
@@ -570,7 +809,9 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
   const int nq_pad = dense_gemm_padded_queries(n_real);
   const int n_qblocks = nq_pad / nqb_size;
   GemmLayout L;
-  if (!make_gemm_layout(dp, ld, bf16, nqb_size, nq_pad, &L)) return cudaErrorInvalidConfiguration;
+  const int mode = gemm_mode(dp, nqb_size, (n + kGmRows - 1) / kGmRows);
+  if (!make_gemm_layout(dp, ld, bf16, mode == 2 ? nqb_size / 2 : nqb_size, nq_pad, &L))
+    return cudaErrorInvalidConfiguration;
   const int64_t sample_tiles = gemm_sample_tiles(dp, n, k);
 
   // carve the scratch
