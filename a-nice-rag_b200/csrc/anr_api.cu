@@ -1326,11 +1326,13 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
   ob.scores = list_scores + stride;
   ob.counts = lens + 1;
   ob.id_map = doc_to_id;
-  // The CUDA-core scan leaves ~90 KB of shared memory per SM free: BM25 CTAs co-reside with it,
-  // so for small batches BM25 runs on the side stream underneath the scan.  The tensor-core
-  // scan fills the SM, there the two run back to back on one stream.
-  const bool overlap =
-      !dense_use_tc(ctx, dense, nq, k_dense) && !dense_use_gemm(ctx, dense, nq, k_dense);
+  // BM25 always runs on the side stream next to the dense pass.  The CUDA-core scan leaves ~90 KB
+  // of shared memory per SM free, so BM25 CTAs co-reside with it; the tensor-core passes fill the
+  // SM, there the gain is that the latency-bound ends of one pipeline (BM25's sample launch, the
+  // dense pass' threshold / rescoring / fallback kernels) run under the other's main kernel
+  // (measured at batch 64: 0.749 -> 0.656 ms per step).  ANR_HYBRID_OVERLAP=0 serialises them.
+  static const int overlap_env = getenv("ANR_HYBRID_OVERLAP") ? atoi(getenv("ANR_HYBRID_OVERLAP")) : -1;
+  const bool overlap = overlap_env != 0;
   cudaStream_t bm25_stream = overlap ? ctx->side : stream;
   if (overlap) {
     ANR_CUDA(cudaEventRecord(ctx->ev_fork, stream));

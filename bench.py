@@ -331,13 +331,20 @@ def run_ours(args):
         step_e2e()
     native.call("anr_ctx_profile_enable", ctx.handle, 1)
     import ctypes as C
+    # sharded: BM25 runs through the shard's side context (its own scratch and event pool)
+    bm_ctx = shard._side_ctx if world > 1 else ctx
+    if bm_ctx is not ctx:
+        native.call("anr_ctx_profile_enable", bm_ctx.handle, 1)
     for kind in (0, 1, 2):
         native.call("anr_ctx_profile_read", ctx.handle, kind, None, None)   # reset counters
+    native.call("anr_ctx_profile_read", bm_ctx.handle, 1, None, None)
     ms_dev = timed(step_device, args.steps)
     scan_ms, scan_n, bm_ms, bm_n = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
     pass_ms, pass_n = C.c_double(), C.c_int64()
     native.call("anr_ctx_profile_read", ctx.handle, 0, C.byref(scan_ms), C.byref(scan_n))
-    native.call("anr_ctx_profile_read", ctx.handle, 1, C.byref(bm_ms), C.byref(bm_n))
+    native.call("anr_ctx_profile_read", bm_ctx.handle, 1, C.byref(bm_ms), C.byref(bm_n))
+    if bm_ctx is not ctx:
+        native.call("anr_ctx_profile_enable", bm_ctx.handle, 0)
     native.call("anr_ctx_profile_read", ctx.handle, 2, C.byref(pass_ms), C.byref(pass_n))
     native.call("anr_ctx_profile_enable", ctx.handle, 0)
     ms_e2e = timed(step_e2e, args.steps)
@@ -417,7 +424,42 @@ def run_ours(args):
                "kernel": "bm25_score_kernel", "bytes_per_launch": bm_bytes,
                "avg_launch_ms": bm_avg_ms, "launches": int(bm_n.value),
                "share_of_step": bm_ms.value / ms_dev if ms_dev else None}
-    dominant = dense_roof if scan_ms.value >= bm_ms.value else bm_roof
+    # BM25 runs on the library's side stream UNDER the dense pass: its in-step event time includes
+    # waiting for SMs the dense kernel holds, so it is also timed alone (same batch, same kernels)
+    bm_alone_ms = None
+    if world == 1:
+        k_sc = torch.empty((B, TOPK), dtype=torch.float32, device=device)
+        k_id = torch.empty((B, TOPK), dtype=torch.int32, device=device)
+        k_ct = torch.empty((B,), dtype=torch.int32, device=device)
+
+        def bm25_only():
+            native.call("anr_bm25_search", ctx.handle, bm25.handle, t_dev.data_ptr(),
+                        off_dev.data_ptr(), B, TOPK, None, None, 0, k_sc.data_ptr(), k_id.data_ptr(),
+                        k_ct.data_ptr(), engine.torch_stream_ptr())
+        native.call("anr_ctx_profile_enable", ctx.handle, 1)
+        for _ in range(3):
+            bm25_only()
+        native.call("anr_ctx_profile_read", ctx.handle, 1, None, None)
+        for _ in range(10):
+            bm25_only()
+        torch.cuda.synchronize()
+        a_ms, a_n = C.c_double(), C.c_int64()
+        native.call("anr_ctx_profile_read", ctx.handle, 1, C.byref(a_ms), C.byref(a_n))
+        native.call("anr_ctx_profile_enable", ctx.handle, 0)
+        bm_alone_ms = a_ms.value / max(a_n.value, 1)
+        # the roofline figures of the BM25 launch come from this pass; its in-step event time
+        # (which includes waiting for SMs the dense kernel holds) is kept beside them
+        bm_roof["overlapped"] = ("runs on a side stream under the dense pass: avg_launch_ms / achieved "
+                                 "/ frac are the same launch timed right after the timed region "
+                                 "without the dense pass; in_step_ms is its event time inside the step")
+        bm_roof["in_step_ms"] = bm_avg_ms
+        if bm_alone_ms:
+            bm_roof["avg_launch_ms"] = bm_alone_ms
+            bm_roof["achieved"] = bm_bytes / (bm_alone_ms * 1e-3) / 1e9
+            bm_roof["frac"] = bm_roof["achieved"] / peak
+    # dominant kernel = larger exclusive time (BM25 judged by its time alone when overlapped)
+    bm_cmp = bm_alone_ms * max(bm_n.value, 1) if bm_alone_ms else bm_ms.value
+    dominant = dense_roof if scan_ms.value >= bm_cmp else bm_roof
 
     # ---- CPU baseline + parity of this very batch (N = 1) --------------------------------------
     cpu = None
