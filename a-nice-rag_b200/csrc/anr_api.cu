@@ -707,7 +707,13 @@ int anr_ctx_create(int device, anr_ctx** out) {
   ctx->dp.max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
   DeviceGuard guard(device);
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {
+    // BM25 of a hybrid query runs here under the dense pass: lowest priority, so that pending CTAs
+    // of the (bandwidth-bound, persistent) dense kernels are placed first
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    e = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, lo);
+  }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   if (e != cudaSuccess) {
@@ -1331,6 +1337,9 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
   // SM, there the gain is that the latency-bound ends of one pipeline (BM25's sample launch, the
   // dense pass' threshold / rescoring / fallback kernels) run under the other's main kernel
   // (measured at batch 64: 0.749 -> 0.656 ms per step).  ANR_HYBRID_OVERLAP=0 serialises them.
+  // (Tried and dropped: capping the 64-query GEMM ring at 4-6 stages so that two BM25 CTAs fit
+  // beside it, dense first, low-priority side stream -- the block scheduler keeps refilling the
+  // SMs with BM25 CTAs and the persistent dense CTAs still start only when that queue drains.)
   static const int overlap_env = getenv("ANR_HYBRID_OVERLAP") ? atoi(getenv("ANR_HYBRID_OVERLAP")) : -1;
   const bool overlap = overlap_env != 0;
   cudaStream_t bm25_stream = overlap ? ctx->side : stream;

@@ -444,6 +444,10 @@ static cudaError_t launch_score_t(const Bm25View& ix, const Bm25HeadView& hd, co
   auto kern = bm25_score_kernel<EMIT_ALL, PRUNE>;
   cudaError_t e =
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
+  // same L1 / shared-memory split as the dense kernels, so that CTAs of both can share an SM
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   // grid.y is limited to 65535 queries per launch
   for (int q0 = 0; q0 < nq; q0 += 65535) {
