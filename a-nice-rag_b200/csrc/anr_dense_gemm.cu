@@ -586,6 +586,20 @@ constexpr int kGmTargetCand = 4096;   // rows per query the sample threshold sho
 constexpr int kGmCap = 4 * kGmTargetCand;
 
 static int gemm_thr_rank(int k) { return k <= 10 ? 16 : k + 32; }
+// Rank actually used for a corpus of n rows sampled by sample_tiles tiles.  When the sample is a
+// large part of a small corpus (one wave of tiles is the minimum), rank 16 of the sample sits only
+// ~100 rows deep in the corpus: inside the bf16 error margin of the k-th best, so most queries
+// were flagged for the exact rescan (125k-row shards: 0.73 ms per 64 queries instead of 0.2).
+// The threshold is therefore kept at least kGmMinCand corpus rows deep.
+constexpr int kGmMinCand = 1024;
+static int gemm_thr_rank_for(int64_t n, int64_t sample_tiles, int k) {
+  const int64_t sample_rows = sample_tiles * kGmRows;
+  const int64_t deep = (kGmMinCand * sample_rows + n - 1) / n;
+  int64_t rank = std::max<int64_t>(gemm_thr_rank(k), deep);
+  rank = std::min<int64_t>(rank, 448);                       // <= per-thread bests of the kernel
+  rank = std::min<int64_t>(rank, sample_tiles * 4);          // <= number of group maxima
+  return static_cast<int>(std::max<int64_t>(rank, 1));
+}
 
 // rows of the strided sample: rank * n / sample ~= kGmTargetCand, whole waves of tiles
 static int64_t gemm_sample_tiles(const DeviceProps& dp, int64_t n, int k) {
@@ -763,7 +777,8 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
                                          nullptr, 0, gmax, gstride, L);
     if (e != cudaSuccess) return e;
     dense_gemm_thr_kernel<<<nq_pad, kGmThrThreads, 0, stream>>>(
-        gmax, gstride, static_cast<int>(gstride), gemm_thr_rank(k), n_real, thr, thr_key);
+        gmax, gstride, static_cast<int>(gstride), gemm_thr_rank_for(n, sample_tiles, k), n_real, thr,
+        thr_key);
     if (ev_start) cudaEventRecord(ev_start, stream);
     e = gemm2_launch_one<NQ, BF16, false>(dp.sm_count, threads, smem, stream, map_a, map_b_half, n,
                                           n_tiles, 1, n_qblocks, mask, thr, cand, cnt, kGmCap, nullptr,
@@ -781,7 +796,8 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
                                                nullptr, 0, gmax, gstride, L);
   if (e != cudaSuccess) return e;
   dense_gemm_thr_kernel<<<nq_pad, kGmThrThreads, 0, stream>>>(
-      gmax, gstride, static_cast<int>(gstride), gemm_thr_rank(k), n_real, thr, thr_key);
+      gmax, gstride, static_cast<int>(gstride), gemm_thr_rank_for(n, sample_tiles, k), n_real, thr,
+      thr_key);
   if (ev_start) cudaEventRecord(ev_start, stream);   // brackets the main GEMM kernel only
   const int grid = static_cast<int>(std::min<int64_t>(dp.sm_count, n_tiles));
   if (pair)

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import itertools
 import logging
+import os
 import threading
 import weakref
 from typing import Dict, Optional, Tuple
@@ -46,6 +47,11 @@ class DenseEntry:
         with self._build_lock:
             if self._index is None:
                 self._index = engine.DenseIndex(self.packed)
+                # bf16 shadow copy for the tensor-core nomination pass (half the HBM bytes per
+                # search, +50 % device memory, identical results); ANR_DENSE_SHADOW=0 turns it off.
+                # Only indices large enough for that pass (>= ~76k rows, d % 64 == 0) ever build it.
+                if os.environ.get("ANR_DENSE_SHADOW", "1") != "0" and self.d % 64 == 0:
+                    self._index.set_shadow(True)
             return self._index
 
     def filter_mask(self, filename_type_filter: str):
