@@ -60,6 +60,16 @@ def torch_stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream or 1
 
 
+def _sync_producer_stream(*tensors) -> None:
+    """Device tensors handed to the library may still be being written on torch's current stream;
+    the library reads them on its own (non-blocking) stream, so wait for the producer once."""
+    for x in tensors:
+        if hasattr(x, "is_cuda") and x.is_cuda:
+            import torch
+            torch.cuda.current_stream(x.device).synchronize()
+            return
+
+
 def context(device: Optional[int] = None) -> Context:
     device = current_device() if device is None else device
     cache = getattr(_tls, "contexts", None)
@@ -131,6 +141,7 @@ class DenseIndex:
         elif n is None or d is None:
             raise ValueError("give embeddings or (n, d)")
         handle = C.c_void_p()
+        _sync_producer_stream(embeddings)
         native.call("anr_dense_create", ctx.handle, native.ptr(embeddings), int(n), int(d),
                     1 if borrow else 0, C.byref(handle))
         self.handle = handle
@@ -140,6 +151,7 @@ class DenseIndex:
 
     def upload(self, row0: int, rows) -> None:
         rows = rows if hasattr(rows, "data_ptr") else _as_f32_matrix(rows)
+        _sync_producer_stream(rows)
         native.call("anr_dense_upload", context(self.ctx_device).handle, self.handle, int(row0),
                     native.ptr(rows), int(rows.shape[0]))
 
@@ -223,6 +235,7 @@ class Bm25Index:
         self.n_terms = int(term_ptr.shape[0]) - 1 if n_terms is None else int(n_terms)
         self.n_docs = int(doc_len.shape[0]) if n_docs is None else int(n_docs)
         handle = C.c_void_p()
+        _sync_producer_stream(term_ptr, post_doc, post_tf, doc_len, idf)
         native.call("anr_bm25_create", ctx.handle, native.ptr(term_ptr), native.ptr(post_doc),
                     native.ptr(post_tf), native.ptr(doc_len), native.ptr(idf), self.n_terms,
                     self.n_docs, float(k1), float(b), float(avgdl), C.byref(handle))
