@@ -507,7 +507,8 @@ def run_ours(args):
         # then the weight upload kernel and WRRF
         "gpu_launches": int(args.steps * (
             (7 + (1 if shadow else 0) if gemm else ((8 if B > 32 else 7) if B > 8 else 2))
-            + (3 if B >= 16 else 2) + 2 + (2 if world > 1 else 0))),
+            + (3 if B >= 16 and (rows_local + 6143) // 6144 >= 32 else 2) + 2
+            + (2 if world > 1 else 0))),
         # the kernel with the largest share of the step; the other one follows
         "roofline": dominant,
         "roofline_other": bm_roof if dominant is dense_roof else dense_roof,

@@ -255,3 +255,36 @@ def test_loader_streams_into_one_matrix_and_handles_ragged_tables(tmp_path):
     assert len(df2) == 11 and df2["embedding"].iloc[10].shape == (d + 4,)
     assert registry.ATTR_KEY not in df2.attrs
     assert np.array_equal(np.stack(df2["embedding"].iloc[:10].values), emb[:10])
+
+
+# ---------------------------------------------------------------------------------------
+# batched orchestrator: input validation and id space (no GPU needed)
+def test_retrieve_documents_batch_validates_like_the_reference(pkg):
+    import types
+    batch = importlib.import_module("a-nice-rag_b200.batch_retrieval")
+    system = types.SimpleNamespace(config=pkg.Config(), embeddings_data={}, bm25_data={},
+                                   search_engine=None)
+    q = np.zeros((2, 8), dtype=np.float32)
+    with pytest.raises(ValueError, match="cannot be empty"):
+        batch.retrieve_documents_batch(system, {})
+    with pytest.raises(ValueError, match="must be a numpy array"):
+        batch.retrieve_documents_batch(system, {"voyage-3-large": [[0.0]]})
+    with pytest.raises(ValueError, match="cannot be empty"):
+        batch.retrieve_documents_batch(system, {"voyage-3-large": np.zeros((0, 8), np.float32)})
+    with pytest.raises(ValueError, match="positive integers"):
+        batch.retrieve_documents_batch(system, {"voyage-3-large": q}, similarity_k=0)
+    with pytest.raises(ValueError, match="Invalid info_source"):
+        batch.retrieve_documents_batch(system, {"voyage-3-large": q}, info_source="nowhere")
+    with pytest.raises(ValueError, match="one embedding per query"):
+        batch.retrieve_documents_batch(system, {"voyage-3-large": q, "Qwen3": np.zeros((3, 8), np.float32)})
+    # no data for the source: one empty result per query (query_rag_retrieval.py:183-185)
+    assert batch.retrieve_documents_batch(system, {"voyage-3-large": q}) == [[], []]
+
+
+def test_batch_id_space_is_first_seen_first_and_shared():
+    batch = importlib.import_module("a-nice-rag_b200.batch_retrieval")
+    space = batch._IdSpace()
+    a = space.codes(["x", "y", "x", "z"])
+    b = space.codes(["z", "w", "y"])
+    assert a.tolist() == [0, 1, 0, 2] and b.tolist() == [2, 3, 1]
+    assert space.names == ["x", "y", "z", "w"]
