@@ -1,4 +1,4 @@
-// Dense inner-product search for query batches of 64 and more as a TILED GEMM on the
+// Dense inner-product search for query batches of more than 32 queries as a TILED GEMM on the
 // 5th-generation tensor cores:  S[rows, queries] = E · Qᵀ  with 128-row x NQ-query output tiles
 // (NQ = 64, 128 or 256), both operands streamed per 128-byte K slab by TMA into one shared-memory
 // ring, accumulators in TMEM (double buffered: 2 x NQ columns), tcgen05.mma issued by one thread.
@@ -11,7 +11,7 @@
 //     (same kernel, SAMPLE = true: the epilogue reduces every 32-row group to its per-query
 //     maximum); the r-th largest group maximum of a query is a lower bound of its r-th best score
 //     over the whole corpus, so the main pass only has to APPEND the few thousand rows per query
-//     that beat it to a per-query candidate buffer (one atomicAdd per survivor);
+//     that beat it to a per-query candidate buffer (staged per warp, flushed in bulk);
 //   * operands are either the fp32 corpus read as tf32 (kind::tf32) or a bf16 shadow copy of it
 //     (kind::f16, half the bytes, twice the rate, 3.2x wider error margin).
 // Tensor-core scores only NOMINATE: dense_tc_rescore_kernel recomputes every candidate within a

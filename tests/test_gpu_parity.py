@@ -427,7 +427,7 @@ def test_bm25_reweight_equals_rebuilt_index(small):
 # ---------------------------------------------------------------------------------------
 # BM25 pruned scan (anr_bm25.cu, PRUNE): dense head rows + MaxScore-style bound, 8192+ documents
 @pytest.fixture(scope="module")
-def group_corpus():
+def prune_corpus():
     n, vocab = 70_000, 4000
     doc_ptr, tokens = synth.zipf_corpus(n, vocab, 1.1, seed=51, len_lo=40, len_hi=120)
     ix = csr.from_token_ids(doc_ptr, tokens, vocab, 1.7, 0.83, 0.05)
@@ -452,8 +452,8 @@ def _check_bm25_batch(ix, queries, scores, docs, counts, k, what, mask=None):
 
 
 @pytest.mark.parametrize("nq,k", [(1, 10), (8, 10), (16, 1), (17, 100), (64, 10), (70, 32), (33, 128)])
-def test_bm25_group_batches_vs_oracle(group_corpus, nq, k):
-    ix, index, vocab = group_corpus
+def test_bm25_pruned_batches_vs_oracle(prune_corpus, nq, k):
+    ix, index, vocab = prune_corpus
     tq = synth.zipf_queries(nq, 8, vocab, 1.1, seed=60 + nq)
     queries = [list(map(int, t)) for t in tq]
     if nq > 3:
@@ -462,11 +462,11 @@ def test_bm25_group_batches_vs_oracle(group_corpus, nq, k):
         queries[3] = []                                      # empty query: every score is 0
         queries[0] = [0, 1, 2, 3, 0]                         # head terms only: nothing is pruned
     scores, docs, counts = index.search(queries, k)
-    _check_bm25_batch(ix, queries, scores, docs, counts, k, f"group nq{nq}")
+    _check_bm25_batch(ix, queries, scores, docs, counts, k, f"pruned nq{nq}")
 
 
-def test_bm25_pruned_agrees_with_unpruned_scan(group_corpus):
-    ix, index, vocab = group_corpus
+def test_bm25_pruned_agrees_with_unpruned_scan(prune_corpus):
+    ix, index, vocab = prune_corpus
     tq = synth.zipf_queries(40, 8, vocab, 1.1, seed=77)
     queries = [list(map(int, t)) for t in tq]
     s_g, d_g, c_g = index.search(queries, 10)
@@ -480,32 +480,32 @@ def test_bm25_pruned_agrees_with_unpruned_scan(group_corpus):
     assert (d_g == d_o).mean() > 0.98
 
 
-def test_bm25_group_long_queries_take_the_unpruned_path(group_corpus):
+def test_bm25_pruned_long_queries_take_the_unpruned_path(prune_corpus):
     """More than 64 terms in a query (one staged chunk): that query is scanned unpruned, next to
     pruned 3- and 33-term queries in the same launch."""
-    ix, index, vocab = group_corpus
+    ix, index, vocab = prune_corpus
     long_q = synth.zipf_queries(20, 70, vocab, 1.1, seed=81)
     queries = [list(map(int, t)) for t in long_q]
     queries[4] = queries[4][:3]
     queries[9] = queries[9][:33]
     scores, docs, counts = index.search(queries, 10)
-    _check_bm25_batch(ix, queries, scores, docs, counts, 10, "group long")
+    _check_bm25_batch(ix, queries, scores, docs, counts, 10, "pruned long")
 
 
-def test_bm25_group_with_doc_mask(group_corpus):
-    ix, index, vocab = group_corpus
+def test_bm25_pruned_with_doc_mask(prune_corpus):
+    ix, index, vocab = prune_corpus
     rng = np.random.default_rng(5)
     mask = rng.random(ix.doc_len.shape[0]) < 0.3
     tq = synth.zipf_queries(40, 8, vocab, 1.1, seed=91)
     queries = [list(map(int, t)) for t in tq]
     scores, docs, counts = index.search(queries, 10, doc_mask=engine.pack_mask(mask))
-    _check_bm25_batch(ix, queries, scores, docs, counts, 10, "group mask", mask=mask)
+    _check_bm25_batch(ix, queries, scores, docs, counts, 10, "pruned mask", mask=mask)
     assert mask[docs].all()
 
 
-def test_bm25_group_after_reweight(group_corpus):
-    ix, index, vocab = group_corpus
-    other = csr.from_token_ids(*_group_tokens(), vocab, 0.9, 0.7, 0.075)
+def test_bm25_pruned_after_reweight(prune_corpus):
+    ix, index, vocab = prune_corpus
+    other = csr.from_token_ids(*_prune_tokens(), vocab, 0.9, 0.7, 0.075)
     index2 = engine.Bm25Index(ix.term_ptr, ix.post_doc, ix.post_tf, ix.doc_len, ix.idf, ix.k1,
                               ix.b, ix.avgdl)
     tq = synth.zipf_queries(16, 8, vocab, 1.1, seed=95)
@@ -513,10 +513,10 @@ def test_bm25_group_after_reweight(group_corpus):
     index2.search(queries, 10)                      # builds the dense head rows with the OLD weights
     index2.reweight(other.post_tf, other.doc_len, other.idf, 0.9, 0.7, other.avgdl)
     scores, docs, counts = index2.search(queries, 10)
-    _check_bm25_batch(other, queries, scores, docs, counts, 10, "group reweight")
+    _check_bm25_batch(other, queries, scores, docs, counts, 10, "pruned reweight")
 
 
-def _group_tokens():
+def _prune_tokens():
     return synth.zipf_corpus(70_000, 4000, 1.1, seed=51, len_lo=40, len_hi=120)
 
 
