@@ -453,7 +453,9 @@ def run_ours(args):
                                  "/ frac are the same launch timed right after the timed region "
                                  "without the dense pass; in_step_ms is its event time inside the step")
         bm_roof["in_step_ms"] = bm_avg_ms
+        bm_roof["in_step_share"] = bm_roof["share_of_step"]
         if bm_alone_ms:
+            bm_roof["share_of_step"] = bm_alone_ms * max(bm_n.value, 1) / ms_dev if ms_dev else None
             bm_roof["avg_launch_ms"] = bm_alone_ms
             bm_roof["achieved"] = bm_bytes / (bm_alone_ms * 1e-3) / 1e9
             bm_roof["frac"] = bm_roof["achieved"] / peak
