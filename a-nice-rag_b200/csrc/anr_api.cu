@@ -55,6 +55,9 @@ struct anr_ctx {
   size_t ws_bytes = 0;
   // profiling (anr_ctx_profile_*): event pairs recorded around the dominant kernels
   bool profiling = false;
+  // anr_ctx_set_beside_dense: this context's BM25 searches run next to a dense pass issued
+  // through another context / stream (the sharded search does that)
+  bool beside_dense = false;
   // kind 0 = dense scan kernel, 1 = BM25 score kernel, 2 = a whole tensor-core pass
   // (sample pre-pass + threshold + scan + rescoring)
   std::vector<EventPair> pool[3];  // created lazily, reused after every read
@@ -550,10 +553,12 @@ Bm25View bm25_view(const anr_bm25* ix) {
 
 int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
                   const int32_t* offsets_dev, int nq, int k, const uint32_t* mask_dev,
-                  Arena& arena, const TopkOut& out, cudaStream_t stream) {
+                  Arena& arena, const TopkOut& out, cudaStream_t stream,
+                  bool beside_dense = false) {
   const Bm25View v = bm25_view(ix);
   if (k <= kMaxFusedK) {
-    const Bm25Plan plan = bm25_make_plan(ctx->dp, ix->n_docs, nq, k, false);
+    Bm25Plan plan = bm25_make_plan(ctx->dp, ix->n_docs, nq, k, false);
+    plan.beside_dense = beside_dense || ctx->beside_dense;
     if (plan.smem_bytes > ctx->dp.max_smem_optin)
       return fail(ANR_ERR_UNSUPPORTED, "bm25 tile does not fit in shared memory");
     const int64_t stride = static_cast<int64_t>(plan.n_tiles) * k;
@@ -762,6 +767,12 @@ int anr_ctx_destroy(anr_ctx* ctx) {
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+  return ANR_OK;
+}
+
+int anr_ctx_set_beside_dense(anr_ctx* ctx, int32_t enable) {
+  if (!ctx) return fail(ANR_ERR_INVALID, "ctx is NULL");
+  ctx->beside_dense = enable != 0;
   return ANR_OK;
 }
 
@@ -1348,7 +1359,7 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
     ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
   }
   if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k_bm25, doc_mask_dev, arena, ob,
-                             bm25_stream))
+                             bm25_stream, overlap))
     return rc;
   if (overlap) ANR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k_dense, row_mask_dev, arena, od, stream))

@@ -127,11 +127,31 @@ bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_te
   __shared__ int n_h;
   __shared__ float h_ub;
 
-  // sample launch (n_sampled == 0): every tile_stride-th tile; main launch: every tile that the
-  // sample launch has not already finished
-  const int tile = n_sampled == 0 ? blockIdx.x * tile_stride : blockIdx.x;
-  const int q = blockIdx.y;
-  if (n_sampled > 0 && tile % tile_stride == 0 && tile / tile_stride < n_sampled) return;
+  // n_sampled > 0: grid = (queries, tiles), queries fastest, and the tiles are visited in an order
+  // that starts with every tile_stride-th one: the first wave of CTAs plays the role of a sample
+  // pass (it publishes a k-th best score per query) and everything dispatched later prunes
+  // against it.  n_sampled <= 0: grid = (tiles, queries), natural order.
+  int tile, q;
+  if (n_sampled == -2) {          // separate sample launch: every tile_stride-th tile
+    tile = blockIdx.x * tile_stride;
+    q = blockIdx.y;
+  } else if (n_sampled < -2) {    // main launch after a separate sample launch: skip its tiles
+    tile = blockIdx.x;
+    q = blockIdx.y;
+    if (tile % tile_stride == 0) return;
+  } else if (n_sampled > 0) {
+    q = blockIdx.x;
+    const int y = blockIdx.y;
+    if (y < n_sampled) {
+      tile = y * tile_stride;
+    } else {
+      const int j = y - n_sampled;
+      tile = j + j / (tile_stride - 1) + 1;   // the j-th tile that is not a multiple of tile_stride
+    }
+  } else {
+    tile = blockIdx.x;
+    q = blockIdx.y;
+  }
   const int d0 = tile * tile_docs;
   const int d1 = min(ix.n_docs, d0 + tile_docs);
   const int nd = d1 - d0;
@@ -453,20 +473,34 @@ static cudaError_t launch_score_t(const Bm25View& ix, const Bm25HeadView& hd, co
   for (int q0 = 0; q0 < nq; q0 += 65535) {
     const int nb = nq - q0 < 65535 ? nq - q0 : 65535;
     dim3 grid(plan.n_tiles, nb);
-    int n_sampled = -1, stride = 1;   // -1: one launch over every tile
-    if (PRUNE && theta && plan.n_tiles >= 32) {
-      // sample launch: every 16th tile first, so that every query has a published k-th best
-      // score (theta) before the bulk of its tiles starts
-      stride = 16;
-      n_sampled = (plan.n_tiles + stride - 1) / stride;
-      dim3 grid_s(n_sampled, nb);
+    static const int fold_env = getenv("ANR_BM25_FOLD") ? atoi(getenv("ANR_BM25_FOLD")) : -1;
+    const bool fold = fold_env >= 0 ? fold_env != 0 : !plan.beside_dense;
+    if (PRUNE && theta && plan.n_tiles >= 32 && !fold) {
+      // two launches: sample tiles, then the rest.  Beside the dense pass of a hybrid query this
+      // is the better shape: the short first launch leaves the SMs to the dense pass' own short
+      // kernels and its main kernel starts early (0.658 vs 0.674 ms per hybrid step); alone, the
+      // folded single launch below is ~8 % faster.
+      const int stride = 16;
+      dim3 grid_s((plan.n_tiles + stride - 1) / stride, nb);
       kern<<<grid_s, kBm25Threads, plan.smem_bytes, stream>>>(
           ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
-          out + q0 * out_stride_q, out_stride_q, theta + q0, stride, 0);
+          out + q0 * out_stride_q, out_stride_q, theta + q0, stride, -2);
+      kern<<<grid, kBm25Threads, plan.smem_bytes, stream>>>(
+          ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
+          out + q0 * out_stride_q, out_stride_q, theta + q0, stride, -3);
+    } else if (PRUNE && theta && plan.n_tiles >= 32 && plan.n_tiles <= 65535) {
+      // one launch, sample tiles first (see the kernel): no second launch, no idle tail between
+      const int stride = 16;
+      const int n_sampled = (plan.n_tiles + stride - 1) / stride;
+      dim3 grid_f(nb, plan.n_tiles);
+      kern<<<grid_f, kBm25Threads, plan.smem_bytes, stream>>>(
+          ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
+          out + q0 * out_stride_q, out_stride_q, theta + q0, stride, n_sampled);
+    } else {
+      kern<<<grid, kBm25Threads, plan.smem_bytes, stream>>>(
+          ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
+          out + q0 * out_stride_q, out_stride_q, theta ? theta + q0 : nullptr, 1, -1);
     }
-    kern<<<grid, kBm25Threads, plan.smem_bytes, stream>>>(
-        ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
-        out + q0 * out_stride_q, out_stride_q, theta ? theta + q0 : nullptr, stride, n_sampled);
   }
   return cudaGetLastError();
 }

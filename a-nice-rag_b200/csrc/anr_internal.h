@@ -151,6 +151,7 @@ struct Bm25Plan {
   int n_tiles;
   int list_cap;
   int smem_bytes;
+  bool beside_dense = false;   // the scan runs on a side stream next to the dense pass (hybrid)
 };
 Bm25Plan bm25_make_plan(const DeviceProps& dp, int n_docs, int nq, int k, bool emit_all);
 // cand[q * cand_stride_q + tile * k + i] candidate keys (ids = doc index)

@@ -58,6 +58,7 @@ class ShardedHybrid:
         # pass, as anr_hybrid_search does on one GPU
         self._side = torch.cuda.Stream(device=self.device)
         self._side_ctx = engine.Context(self.device.index)
+        native.call("anr_ctx_set_beside_dense", self._side_ctx.handle, 1)
         self._fork = torch.cuda.Event()
         self._join = torch.cuda.Event()
 

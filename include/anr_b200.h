@@ -46,6 +46,10 @@ const char* anr_last_error(void);
 /* ---- context ------------------------------------------------------------ */
 int anr_ctx_create(int device, anr_ctx** out);
 int anr_ctx_destroy(anr_ctx* ctx);
+/* Hint: BM25 searches issued through this context run on a stream of their own NEXT TO a dense
+ * pass issued through another context (the sharded search, a-nice-rag_b200/sharded.py).  Only the
+ * launch shape changes (a separate short sample launch instead of one folded launch). */
+int anr_ctx_set_beside_dense(anr_ctx* ctx, int32_t enable);
 int anr_ctx_sync(anr_ctx* ctx);
 /* sm count, total/free HBM bytes of the context's device (any pointer may be NULL) */
 int anr_ctx_info(anr_ctx* ctx, int32_t* sm_count, int64_t* hbm_total, int64_t* hbm_free);
