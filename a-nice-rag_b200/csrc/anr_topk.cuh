@@ -116,7 +116,9 @@ __device__ __forceinline__ void block_bitonic_sort_desc(uint64_t* keys, int n_po
 // candidates reach it, so it bounds the k-th best candidate from below.  Every thread calls;
 // tbest holds NWARPS * 32 keys of scratch, *s_out one key.
 //   k <= 32: every warp sorts its 32 keys in registers (shuffles, no barrier), warp 0 then pops
-//            the largest run head k times; larger k: block-wide bitonic sort.
+//            the largest run head k times; larger k: block-wide bitonic sort (measured: a pop is
+//            a ~175-cycle dependent chain, so beyond a few dozen pops the 45 stages of a 512-key
+//            bitonic sort win: rank 155 cost +26 us per dense pass with pops).
 template <int NWARPS>
 __device__ __forceinline__ uint64_t block_kth_of_thread_bests(uint64_t best, int k, uint64_t* tbest,
                                                               uint64_t* s_out) {
