@@ -205,6 +205,27 @@ def test_wrrf_bit_exact_random_lists():
         assert scores.tolist() == [s for _, s in want], trial
 
 
+def test_wrrf_small_unions_warp_path_bit_exact():
+    """Unions of <= 64 entries (the hybrid query's 2 lists x k) take the warp-per-query kernel:
+    overlapping lists, duplicates inside a list, empty lists, exact ties, top_n cuts."""
+    rng = np.random.default_rng(13)
+    for trial in range(60):
+        n_lists = int(rng.integers(1, 5))
+        stride = int(rng.integers(1, 64 // n_lists + 1))
+        lists = [rng.integers(0, 40, size=rng.integers(0, stride + 1)).tolist() for _ in range(n_lists)]
+        lists[0] = (lists[0] + [7] * stride)[:stride]           # longest list fixes the stride
+        weights = [float(w) for w in rng.choice([0.5, 1.0, 1.0, 5.0], size=n_lists)]
+        rrf_k = float(rng.choice([40, 60]))
+        want = retrieval.weighted_rrf([(l, str(i)) for i, l in enumerate(lists)],
+                                      {str(i): w for i, w in enumerate(weights)}, rrf_k)
+        ids, scores = engine.wrrf_fuse(lists, weights, rrf_k)
+        assert ids.tolist() == [i for i, _ in want], (trial, lists)
+        assert scores.tolist() == [s for _, s in want], trial
+        top_n = int(rng.integers(1, 12))
+        ids, scores = engine.wrrf_fuse(lists, weights, rrf_k, top_n=top_n)
+        assert ids.tolist() == [i for i, _ in want][:top_n], trial
+
+
 def test_wrrf_equal_weight_ties_keep_insertion_order():
     a, b = [10, 11, 12, 13], [20, 21, 22, 23]
     ids, scores = engine.wrrf_fuse([a, b], [1.0, 1.0], 40.0)
