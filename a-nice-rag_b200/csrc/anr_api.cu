@@ -846,6 +846,7 @@ int anr_dense_upload(anr_ctx* ctx, anr_dense* index, int64_t row0, const float* 
   if (row0 < 0 || n_rows < 0 || row0 + n_rows > index->n)
     return fail(ANR_ERR_INVALID, "anr_dense_upload: row range out of bounds");
   DeviceGuard guard(ctx->dp.device);
+  std::lock_guard<std::mutex> lock(index->lazy);
   index->norm_valid = false;
   if (index->shadow) {  // rebuilt on the next tensor-core search
     ANR_CUDA(cudaDeviceSynchronize());
@@ -871,6 +872,7 @@ int anr_dense_destroy(anr_dense* index) {
 int anr_dense_set_shadow(anr_dense* index, int32_t enable) {
   if (!index) return fail(ANR_ERR_INVALID, "index is NULL");
   DeviceGuard guard(index->device);
+  std::lock_guard<std::mutex> lock(index->lazy);
   index->want_shadow = enable != 0;
   if (!enable && index->shadow) {
     ANR_CUDA(cudaDeviceSynchronize());

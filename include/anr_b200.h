@@ -79,7 +79,8 @@ int anr_dense_shape(const anr_dense* index, int64_t* n, int32_t* d);
  * matrix ([n, d] bf16, built on the next such search; d % 64 == 0) instead of reading the fp32
  * words as tf32: half the HBM bytes and twice the tensor-core rate per pass.  Results do not
  * change: every candidate inside the (wider) error margin is rescored in exact fp32, as in
- * np.dot of src/search_engine.py:81. */
+ * np.dot of src/search_engine.py:81.  Like anr_dense_upload and anr_bm25_reweight this MUTATES the
+ * index: do not call it while another thread is searching the same index. */
 int anr_dense_set_shadow(anr_dense* index, int32_t enable);
 
 /* Inner-product top-k of each query against all (mask-eligible) rows, best
