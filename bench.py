@@ -349,6 +349,24 @@ def run_ours(args):
     native.call("anr_ctx_profile_enable", ctx.handle, 0)
     ms_e2e = timed(step_e2e, args.steps)
 
+    # ---- filtered variant: a "CG,NG"-style source filter keeping ~2/3 of the rows,
+    #      passed as row / document bit masks (search_engine.py:36-55, :221-231) ----------------
+    ms_filtered = None
+    if world == 1:
+        rng = np.random.default_rng(99)
+        keep = rng.random(hi - lo) < (2.0 / 3.0)
+        words = torch.from_numpy(engine.pack_mask(keep).view(np.int32)).to(device)
+
+        def step_filtered():
+            native.call("anr_hybrid_search", ctx.handle, dense.handle, bm25.handle,
+                        q_dev.data_ptr(), t_dev.data_ptr(), off_dev.data_ptr(), B, TOPK, TOPK,
+                        words.data_ptr(), words.data_ptr(), None, 0, W_DENSE, W_BM25, WRRF_K, TOPK,
+                        out_ids.data_ptr(), out_scores.data_ptr(), out_counts.data_ptr(), None, None,
+                        None, None, engine.torch_stream_ptr())
+        for _ in range(3):
+            step_filtered()
+        ms_filtered = timed(step_filtered, args.steps)
+
     # ---- batch-1 latency through the C-ABI with host buffers (p50 of wall-clock per call) -----
     lat = []
     if world == 1:
@@ -528,6 +546,10 @@ def run_ours(args):
                               "hbm_gbs": rows_local * D * 4 / (ms_b1_scan * 1e-3) / 1e9,
                               "frac_of_peak": rows_local * D * 4 / (ms_b1_scan * 1e-3) / 1e9 / peak}
                              if ms_b1_scan else None),
+        "filtered": ({"what": "same step with row / document masks keeping 2/3 of the corpus "
+                              "(the reference's source-prefix filter)",
+                      "value": B * args.steps / (ms_filtered * 1e-3), "unit": "queries/s",
+                      "ms_per_step": ms_filtered / args.steps} if ms_filtered else None),
         "clocks": clocks, "parity_checked_queries": checked,
     }
     if cpu:
