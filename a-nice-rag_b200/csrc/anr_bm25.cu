@@ -159,7 +159,10 @@ bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_te
 
   {  // tile_docs is a multiple of 32: whole float4s
     float4* a4 = reinterpret_cast<float4*>(acc);
-    for (int i = threadIdx.x; i < (nd + 3) / 4; i += blockDim.x) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int n4 = (nd + 3) >> 2;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n4; i += kBm25Threads) a4[i] = z;
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -169,26 +172,74 @@ bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_te
   for (int c0 = t_begin; c0 < t_end; c0 += kBm25TermChunk) {
     const int nc = min(kBm25TermChunk, t_end - c0);
     __syncthreads();  // previous chunk's bounds are no longer read; acc zeroing is visible
+    if (prune) {
+      // ---- which head terms are left to the dense rows (non-essential)?  Warp 0, one lane per
+      // term (two for 33..64 terms).  With a published bound theta for this query, only as many
+      // head terms -- cheapest upper bound first -- as keep the sum of their bounds BELOW theta:
+      // then the pruning test always has room (cut = theta - ub > 0) and no tile falls back to
+      // completing every document (queries with 6-7 head terms did: 19 % of all instructions).
+      // The other head terms are streamed from their postings like any tail term.  Without a
+      // bound (sample tiles) every head term with a positive idf is non-essential, as before.
+      if (warp == 0) {
+        const float theta0 = theta_g ? __ldcg(theta_g + q) : 0.f;
+        int slot_e[2] = {-1, -1};
+        float ub_e[2] = {0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = lane + 32 * e;
+          if (j < nc) {
+            const int term = q_terms[c0 + j];
+            if (term >= 0 && term < ix.n_terms) {
+              const float idf = ix.idf[term];
+              const int sl = hd.slot_of[term];
+              if (idf > 0.f && sl != 0xff) {
+                slot_e[e] = sl;
+                ub_e[e] = idf * hd.head_max[sl];
+              }
+            }
+          }
+        }
+        if (theta0 > 0.f) {
+          // cum[e] = sum of the bounds of all head occurrences ordered at or before mine by (ub, j)
+          float cum[2] = {0.f, 0.f};
+          for (int jj = 0; jj < nc; ++jj) {
+            const int owner = jj & 31, sl2 = jj >> 5;
+            const int s_jj = __shfl_sync(kFullMask, sl2 ? slot_e[1] : slot_e[0], owner);
+            const float u_jj = __shfl_sync(kFullMask, sl2 ? ub_e[1] : ub_e[0], owner);
+            if (s_jj < 0) continue;   // warp-uniform
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int j = lane + 32 * e;
+              if (slot_e[e] >= 0 && (u_jj < ub_e[e] || (u_jj == ub_e[e] && jj <= j))) cum[e] += u_jj;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (slot_e[e] >= 0 && !(cum[e] * (1.f + 1e-4f) < theta0)) slot_e[e] = -1;   // essential
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (lane + 32 * e < nc) s_slot[lane + 32 * e] = slot_e[e];
+      }
+      __syncthreads();
+    }
     // ---- first posting of every term inside the tile: one WARP per term, 32-ary search
     //      (5 dependent loads for 2^23 postings instead of 23 for a binary search) ----
     for (int j = warp; j < nc; j += kBm25Threads / 32) {
       const int term = q_terms[c0 + j];
       int64_t lo = 0, hi = 0;
       float idf = 0.f;
-      int slot = -1;
+      const int slot = prune ? s_slot[j] : -1;
       if (term >= 0 && term < ix.n_terms) {
         idf = ix.idf[term];
-        if (idf != 0.f) {  // `idf.get(q) or 0`: a zero idf contributes nothing
-          // a head term with a positive idf is NOT streamed by the pruned scan
-          if (prune && idf > 0.f && hd.slot_of[term] != 0xff) {
-            slot = hd.slot_of[term];
-          } else {
-            lo = ix.term_ptr[term];
-            hi = ix.term_ptr[term + 1];
-          }
+        // `idf.get(q) or 0`: a zero idf contributes nothing; a non-essential head term is NOT
+        // streamed by the pruned scan
+        if (idf != 0.f && slot < 0) {
+          lo = ix.term_ptr[term];
+          hi = ix.term_ptr[term + 1];
         }
       }
-      if (PRUNE && lane == 0) s_slot[j] = slot;
+      if (PRUNE && !prune && lane == 0) s_slot[j] = -1;
       const int64_t term_end = hi;
       while (hi > lo) {   // invariant: the answer (first index with doc >= d0) lies in [lo, hi]
         const int64_t len = hi - lo;
