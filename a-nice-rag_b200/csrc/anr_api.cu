@@ -50,7 +50,7 @@ struct anr_ctx {
   cudaStream_t stream = nullptr;
   // BM25 of a hybrid query runs on `side` under the dense scan (fork/join through the events)
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;
   unsigned char* ws = nullptr;  // device scratch, grown on demand
   size_t ws_bytes = 0;
   // profiling (anr_ctx_profile_*): event pairs recorded around the dominant kernels
@@ -329,9 +329,10 @@ size_t dense_ws_bytes(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
   return padded(static_cast<size_t>(group) * n_pow2 * 8) + 256;
 }
 
+// ev_pre_main (nullable) is recorded when the pass' first long kernel is next in line on `stream`.
 int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq, int k,
                    const uint32_t* mask_dev, Arena& arena, const TopkOut& out,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, cudaEvent_t ev_pre_main = nullptr) {
   const int gmax = dense_group(ctx, ix, k);
   if (gmax < 1) return fail(ANR_ERR_UNSUPPORTED, "embedding rows too long for the scan kernel");
   const bool gemm = dense_use_gemm(ctx, ix, nq, k);
@@ -376,7 +377,8 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
       ANR_CUDA(launch_dense_gemm(ctx->dp, ix->emb, ix->shadow, ix->n, ix->ld,
                                  q_dev + static_cast<size_t>(q0) * ix->ld, std::min(per, nq - q0), k,
                                  mask_dev, ix->norm_max, scratch, o, flags + q0,
-                                 ev ? ev->start : nullptr, ev ? ev->stop : nullptr, stream));
+                                 ev ? ev->start : nullptr, ev ? ev->stop : nullptr, stream,
+                                 q0 == 0 ? ev_pre_main : nullptr));
     }
     const int fb_grid = dense_scan_flagged_grid(ctx->dp, ix->n, ix->ld, k);
     const int64_t fb_stride = static_cast<int64_t>(fb_grid) * k;
@@ -390,6 +392,7 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
                                        n_flagged, flagged, stream));
     return ANR_OK;
   }
+  if (ev_pre_main) ANR_CUDA(cudaEventRecord(ev_pre_main, stream));   // (paths without a pre-pass)
   if (dense_use_tc(ctx, ix, nq, k)) {
     const int per = dense_tc_queries_per_pass();
     uint64_t* tc_cand = arena.take<uint64_t>(dense_tc_cand_keys(ctx->dp, ix->n, k));
@@ -551,29 +554,58 @@ Bm25View bm25_view(const anr_bm25* ix) {
   return v;
 }
 
+// State of a BM25 top-k scan issued in two phases around the dense pass of a hybrid query.
+struct Bm25Run {
+  bool active = false;
+  Bm25Plan plan;
+  Bm25HeadView hd;
+  uint64_t* cand = nullptr;
+  float* theta = nullptr;
+  int64_t stride = 0;
+};
+
+// phase 0: the whole search.  Hybrid queries split it: phase 1 = set-up + the short sample launch
+// of the pruned scan (state kept in *run), phase 2 = the main launch + final top-k, enqueued once
+// the dense pass' main kernel is next in line on its own stream (see anr_hybrid_search).
 int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
                   const int32_t* offsets_dev, int nq, int k, const uint32_t* mask_dev,
                   Arena& arena, const TopkOut& out, cudaStream_t stream,
-                  bool beside_dense = false) {
+                  bool beside_dense = false, int phase = 0, Bm25Run* run = nullptr) {
   const Bm25View v = bm25_view(ix);
   if (k <= kMaxFusedK) {
-    Bm25Plan plan = bm25_make_plan(ctx->dp, ix->n_docs, nq, k, false);
-    plan.beside_dense = beside_dense || ctx->beside_dense;
-    if (plan.smem_bytes > ctx->dp.max_smem_optin)
-      return fail(ANR_ERR_UNSUPPORTED, "bm25 tile does not fit in shared memory");
-    const int64_t stride = static_cast<int64_t>(plan.n_tiles) * k;
-    uint64_t* cand = arena.take<uint64_t>(static_cast<size_t>(nq) * stride);
-    float* theta = arena.take<float>(static_cast<size_t>(nq));
-    // safe dynamic pruning over the dense rows of the head terms (corpora of 8192+ documents)
-    const bool no_prune = getenv("ANR_DISABLE_BM25_PRUNE") != nullptr;
-    Bm25HeadView hd;
-    if (!no_prune && ix->n_docs >= 8192 && nq >= 16) {   // (measured: no gain below ~16 queries)
-      if (int rc = bm25_ensure_heads(ix, stream)) return rc;
-      hd.slot_of = ix->head_slot;
-      hd.head_w = ix->head_w;
-      hd.head_max = ix->head_max;
-      hd.head_ld = ix->head_ld;
-      hd.n_head = ix->n_head;
+    Bm25Run local;
+    Bm25Run& r = run ? *run : local;
+    if (!(phase == 2 && r.active)) {
+      r.plan = bm25_make_plan(ctx->dp, ix->n_docs, nq, k, false);
+      r.plan.beside_dense = beside_dense || ctx->beside_dense;
+      if (r.plan.smem_bytes > ctx->dp.max_smem_optin)
+        return fail(ANR_ERR_UNSUPPORTED, "bm25 tile does not fit in shared memory");
+      r.stride = static_cast<int64_t>(r.plan.n_tiles) * k;
+      r.cand = arena.take<uint64_t>(static_cast<size_t>(nq) * r.stride);
+      r.theta = arena.take<float>(static_cast<size_t>(nq));
+      // safe dynamic pruning over the dense rows of the head terms (corpora of 8192+ documents)
+      const bool no_prune = getenv("ANR_DISABLE_BM25_PRUNE") != nullptr;
+      r.hd = Bm25HeadView();
+      if (!no_prune && ix->n_docs >= 8192 && nq >= 16) {   // (measured: no gain below ~16 queries)
+        if (int rc = bm25_ensure_heads(ix, stream)) return rc;
+        r.hd.slot_of = ix->head_slot;
+        r.hd.head_w = ix->head_w;
+        r.hd.head_max = ix->head_max;
+        r.hd.head_ld = ix->head_ld;
+        r.hd.n_head = ix->n_head;
+      }
+      r.active = true;
+    }
+    Bm25Plan plan = r.plan;
+    plan.phase = phase;
+    const Bm25HeadView& hd = r.hd;
+    uint64_t* cand = r.cand;
+    float* theta = r.theta;
+    const int64_t stride = r.stride;
+    if (phase == 1) {
+      ANR_CUDA(launch_bm25_score_topk(v, hd.n_head > 0 ? &hd : nullptr, terms_dev, offsets_dev, nq,
+                                      k, mask_dev, plan, cand, stride, theta, stream));
+      return ANR_OK;
     }
     {
       ProfileScope prof(ctx, 1, stream);
@@ -584,6 +616,7 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
     ANR_CUDA(launch_topk_final(cand, stride, m, m, 0, nq, k, out, stream));
     return ANR_OK;
   }
+  if (phase == 1) return ANR_OK;   // the full-ranking path has no sample launch
   if (ix->n_docs > (1 << 30)) return fail(ANR_ERR_UNSUPPORTED, "k > 128 needs n_docs <= 2^30");
   const int64_t n_pow2 = next_pow2(std::max(ix->n_docs, 2));
   const int group = std::min(nq, 8);
@@ -721,6 +754,7 @@ int anr_ctx_create(int device, anr_ctx** out) {
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_mid, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     anr_ctx_destroy(ctx);
     return fail_cuda("stream/event creation", e);
@@ -764,6 +798,7 @@ int anr_ctx_destroy(anr_ctx* ctx) {
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1360,12 +1395,30 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
     ANR_CUDA(cudaEventRecord(ctx->ev_fork, stream));
     ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
   }
-  if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k_bm25, doc_mask_dev, arena, ob,
-                             bm25_stream, overlap))
-    return rc;
-  if (overlap) ANR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
-  if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k_dense, row_mask_dev, arena, od, stream))
-    return rc;
+  if (overlap) {
+    // side: BM25 sample launch | main: dense pre-pass kernels, then the dense main kernel | side:
+    // the BM25 main launch, held back until the dense main kernel is next in line, so that the
+    // persistent, bandwidth-bound dense kernel takes its SMs first (a BM25 main launch that got
+    // there first stretched the dense kernel from 0.31 to 0.52 ms) | join
+    Bm25Run run;
+    if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k_bm25, doc_mask_dev, arena, ob,
+                               bm25_stream, true, 1, &run))
+      return rc;
+    if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k_dense, row_mask_dev, arena, od, stream,
+                                ctx->ev_mid))
+      return rc;
+    ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_mid, 0));
+    if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k_bm25, doc_mask_dev, arena, ob,
+                               bm25_stream, true, 2, &run))
+      return rc;
+    ANR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+  } else {
+    if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k_bm25, doc_mask_dev, arena, ob,
+                               bm25_stream, false))
+      return rc;
+    if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k_dense, row_mask_dev, arena, od, stream))
+      return rc;
+  }
   if (overlap) ANR_CUDA(cudaStreamWaitEvent(stream, ctx->ev_join, 0));
   ANR_CUDA(launch_wrrf_fuse(lists, lens, w_dev, 2, stride, nq, rrf_k, top_n, nullptr, o_ids.dev,
                             o_scores.dev, o_counts.dev, stream));

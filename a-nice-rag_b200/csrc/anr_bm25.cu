@@ -184,6 +184,7 @@ bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_te
         const float theta0 = theta_g ? __ldcg(theta_g + q) : 0.f;
         int slot_e[2] = {-1, -1};
         float ub_e[2] = {0.f, 0.f};
+        float tail_idf = 0.f;   // largest idf among my terms that are not head terms
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = lane + 32 * e;
@@ -195,11 +196,19 @@ bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_te
               if (idf > 0.f && sl != 0xff) {
                 slot_e[e] = sl;
                 ub_e[e] = idf * hd.head_max[sl];
+              } else {
+                tail_idf = fmaxf(tail_idf, idf);
               }
             }
           }
         }
-        if (theta0 > 0.f) {
+        // No bound published yet (sample tiles): GUESS one for the classification only -- the idf
+        // of the rarest other term (a document that holds it typically scores at least that).  A
+        // wrong guess costs time, never correctness: the pruning test uses the real bounds.
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tail_idf = fmaxf(tail_idf, __shfl_xor_sync(kFullMask, tail_idf, o));
+        const float theta_cls = theta0 > 0.f ? theta0 : tail_idf;
+        if (theta_cls > 0.f) {
           // cum[e] = sum of the bounds of all head occurrences ordered at or before mine by (ub, j)
           float cum[2] = {0.f, 0.f};
           for (int jj = 0; jj < nc; ++jj) {
@@ -215,7 +224,7 @@ bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_te
           }
 #pragma unroll
           for (int e = 0; e < 2; ++e)
-            if (slot_e[e] >= 0 && !(cum[e] * (1.f + 1e-4f) < theta0)) slot_e[e] = -1;   // essential
+            if (slot_e[e] >= 0 && !(cum[e] * (1.f + 1e-4f) < theta_cls)) slot_e[e] = -1;   // essential
         }
 #pragma unroll
         for (int e = 0; e < 2; ++e)
@@ -533,12 +542,16 @@ static cudaError_t launch_score_t(const Bm25View& ix, const Bm25HeadView& hd, co
       // folded single launch below is ~8 % faster.
       const int stride = 16;
       dim3 grid_s((plan.n_tiles + stride - 1) / stride, nb);
-      kern<<<grid_s, kBm25Threads, plan.smem_bytes, stream>>>(
-          ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
-          out + q0 * out_stride_q, out_stride_q, theta + q0, stride, -2);
-      kern<<<grid, kBm25Threads, plan.smem_bytes, stream>>>(
-          ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
-          out + q0 * out_stride_q, out_stride_q, theta + q0, stride, -3);
+      if (plan.phase != 2)
+        kern<<<grid_s, kBm25Threads, plan.smem_bytes, stream>>>(
+            ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
+            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, -2);
+      if (plan.phase != 1)
+        kern<<<grid, kBm25Threads, plan.smem_bytes, stream>>>(
+            ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
+            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, -3);
+    } else if (plan.phase == 1) {
+      // no separate sample launch in this plan: everything happens in phase 2
     } else if (PRUNE && theta && plan.n_tiles >= 32 && plan.n_tiles <= 65535) {
       // one launch, sample tiles first (see the kernel): no second launch, no idle tail between
       const int stride = 16;
@@ -562,7 +575,7 @@ cudaError_t launch_bm25_score_topk(const Bm25View& ix, const Bm25HeadView* hd, c
                                    int64_t cand_stride_q, float* theta, cudaStream_t stream) {
   if (k < 1 || k > kMaxFusedK) return cudaErrorInvalidValue;
   if (hd && hd->n_head > 0) {
-    if (theta) {
+    if (theta && plan.phase != 2) {
       cudaError_t e = cudaMemsetAsync(theta, 0, static_cast<size_t>(nq) * 4, stream);
       if (e != cudaSuccess) return e;
     }

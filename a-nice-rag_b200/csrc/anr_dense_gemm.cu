@@ -758,7 +758,7 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
                                     int64_t sample_tiles, int n_real, int k, float* gmax, float* thr,
                                     uint64_t* thr_key, uint64_t* cand, int32_t* cnt,
                                     const GemmLayout& L, cudaEvent_t ev_start, cudaEvent_t ev_stop,
-                                    cudaStream_t stream) {
+                                    cudaStream_t stream, cudaEvent_t ev_pre_main) {
   const int smem = L.total_bytes + 1024;  // room to align the dynamic base to 1024 bytes
   const int64_t n_tiles = (n + kGmRows - 1) / kGmRows;
   const int64_t stride = n_tiles / sample_tiles;
@@ -779,6 +779,7 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
     dense_gemm_thr_kernel<<<nq_pad, kGmThrThreads, 0, stream>>>(
         gmax, gstride, static_cast<int>(gstride), gemm_thr_rank_for(n, sample_tiles, k), n_real, thr,
         thr_key);
+    if (ev_pre_main) cudaEventRecord(ev_pre_main, stream);   // the main kernel is next in line
     if (ev_start) cudaEventRecord(ev_start, stream);
     e = gemm2_launch_one<NQ, BF16, false>(dp.sm_count, threads, smem, stream, map_a, map_b_half, n,
                                           n_tiles, 1, n_qblocks, mask, thr, cand, cnt, kGmCap, nullptr,
@@ -798,6 +799,7 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
   dense_gemm_thr_kernel<<<nq_pad, kGmThrThreads, 0, stream>>>(
       gmax, gstride, static_cast<int>(gstride), gemm_thr_rank_for(n, sample_tiles, k), n_real, thr,
       thr_key);
+  if (ev_pre_main) cudaEventRecord(ev_pre_main, stream);   // the main kernel is next in line
   if (ev_start) cudaEventRecord(ev_start, stream);   // brackets the main GEMM kernel only
   const int grid = static_cast<int>(std::min<int64_t>(dp.sm_count, n_tiles));
   if (pair)
@@ -819,7 +821,7 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
                               int ld, const float* q_dev, int n_real, int k, const uint32_t* mask,
                               float emb_norm_max, unsigned char* scratch, const TopkOut& out,
                               int32_t* flags, cudaEvent_t ev_start, cudaEvent_t ev_stop,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, cudaEvent_t ev_pre_main) {
   const bool bf16 = shadow != nullptr;
   const int nqb_size = dense_gemm_block(n_real);
   const int nq_pad = dense_gemm_padded_queries(n_real);
@@ -861,7 +863,7 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
 #define ANR_GEMM_CASE(NQV, BFV)                                                                   \
   e = gemm_launch_pair<NQV, BFV>(dp, map_a, map_b, map_b_half, n, n_qblocks, mask, sample_tiles,  \
                                  n_real, k, gmax, thr, thr_key, cand, cnt, L, ev_start, ev_stop,   \
-                                 stream)
+                                 stream, ev_pre_main)
   if (bf16) {
     if (nqb_size == 64) ANR_GEMM_CASE(64, true);
     else if (nqb_size == 128) ANR_GEMM_CASE(128, true);

@@ -93,7 +93,7 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
                               int ld, const float* q_dev, int n_real, int k, const uint32_t* mask,
                               float emb_norm_max, unsigned char* scratch, const TopkOut& out,
                               int32_t* flags, cudaEvent_t ev_start, cudaEvent_t ev_stop,
-                              cudaStream_t stream);
+                              cudaStream_t stream, cudaEvent_t ev_pre_main = nullptr);
 cudaError_t launch_dense_tc_rescore_append(const uint64_t* cand, const int32_t* cnt, int cap,
                                            const float* emb, int ld, const float* q_dev, int n_real,
                                            int k, float eps_scale, const uint64_t* thr_key,
@@ -152,6 +152,8 @@ struct Bm25Plan {
   int list_cap;
   int smem_bytes;
   bool beside_dense = false;   // the scan runs on a side stream next to the dense pass (hybrid)
+  int phase = 0;               // 0 = whole scan; 1 = only the separate sample launch (if the plan
+                               // has one); 2 = everything after it
 };
 Bm25Plan bm25_make_plan(const DeviceProps& dp, int n_docs, int nq, int k, bool emit_all);
 // cand[q * cand_stride_q + tile * k + i] candidate keys (ids = doc index)
