@@ -1445,6 +1445,65 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
   return ANR_OK;
 }
 
+// Both local searches of ONE shard in one call, as sortable keys with global ids (what the
+// sharded merge consumes): out_keys is [2, n_queries, k], plane 0 = dense, plane 1 = BM25.  Same
+// two-stream schedule as anr_hybrid_search (BM25 sample launch | dense pre-pass | dense main kernel
+// | BM25 main launch | join); device pointers only.
+int anr_hybrid_search_keys(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25,
+                           const float* queries, const int32_t* q_terms, const int32_t* q_offsets,
+                           int32_t nq, int32_t k, const uint32_t* row_mask, const uint32_t* doc_mask,
+                           int64_t row_base, int64_t doc_base, uint64_t* out_keys, void* stream_v) {
+  if (!ctx || !dense || !bm25 || !queries || !q_offsets || !out_keys)
+    return fail(ANR_ERR_INVALID, "anr_hybrid_search_keys: NULL argument");
+  if (nq < 1 || k < 1) return fail(ANR_ERR_INVALID, "anr_hybrid_search_keys: bad shape");
+  if (dense->device != ctx->dp.device || bm25->device != ctx->dp.device)
+    return fail(ANR_ERR_INVALID, "index lives on another device");
+  if (dense->n == 0 || bm25->n_docs == 0)
+    return fail(ANR_ERR_INVALID, "anr_hybrid_search_keys: empty index");
+  if (!is_device_ptr(out_keys) || !is_device_ptr(queries) || !is_device_ptr(q_offsets))
+    return fail(ANR_ERR_INVALID, "anr_hybrid_search_keys takes device pointers");
+  DeviceGuard guard(ctx->dp.device);
+  cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  const size_t need = stage_queries_bytes(dense, nq) + stage_mask_bytes(row_mask, dense->n) +
+                      stage_terms_bytes(q_terms, q_offsets, nq) +
+                      stage_mask_bytes(doc_mask, bm25->n_docs) +
+                      dense_ws_bytes(ctx, dense, nq, k) + bm25_ws_bytes(ctx, bm25, nq, k) + 4096;
+  if (int rc = ws_reserve(ctx, need)) return rc;
+  Arena arena{ctx->ws, ctx->ws_bytes};
+  const float* q_dev = nullptr;
+  const uint32_t* row_mask_dev = nullptr;
+  const uint32_t* doc_mask_dev = nullptr;
+  QueryTerms qt;
+  if (int rc = stage_queries(dense, queries, nq, dense_padded_queries(ctx, dense, nq, k), arena,
+                              stream, &q_dev)) return rc;
+  if (int rc = stage_mask(row_mask, dense->n, arena, stream, &row_mask_dev)) return rc;
+  if (int rc = stage_terms(q_terms, q_offsets, nq, arena, stream, &qt)) return rc;
+  if (int rc = stage_mask(doc_mask, bm25->n_docs, arena, stream, &doc_mask_dev)) return rc;
+  TopkOut od;
+  od.keys = out_keys;
+  od.stride_q = k;
+  od.id_base = row_base;
+  TopkOut ob;
+  ob.keys = out_keys + static_cast<size_t>(nq) * k;
+  ob.stride_q = k;
+  ob.id_base = doc_base;
+  ANR_CUDA(cudaEventRecord(ctx->ev_fork, stream));
+  ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  Bm25Run run;
+  if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k, doc_mask_dev, arena, ob,
+                             ctx->side, true, 1, &run))
+    return rc;
+  if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k, row_mask_dev, arena, od, stream, ctx->ev_mid))
+    return rc;
+  ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_mid, 0));
+  if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k, doc_mask_dev, arena, ob,
+                             ctx->side, true, 2, &run))
+    return rc;
+  ANR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+  ANR_CUDA(cudaStreamWaitEvent(stream, ctx->ev_join, 0));
+  return ANR_OK;
+}
+
 // ---- sharded merge ----------------------------------------------------------------------
 int anr_topk_merge(anr_ctx* ctx, const uint64_t* keys, int32_t n_parts, int32_t n_queries,
                    int32_t k, float* out_scores, int32_t* out_ids, int32_t* out_counts,

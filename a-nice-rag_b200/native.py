@@ -54,6 +54,7 @@ SIGNATURES = {
                           _F64, _I32, _P, _P, _P, _P, _P, _P, _P, _P],
     "anr_dense_search_keys": [_P, _P, _P, _I32, _I32, _P, _I64, _P, _P],
     "anr_bm25_search_keys": [_P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _P, _P],
+    "anr_hybrid_search_keys": [_P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _I64, _P, _P],
     "anr_topk_merge": [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P],
     "anr_sharded_fuse": [_P, _P, _I32, _I32, _I32, _F64, _F64, _F64, _I32, _P, _P, _P, _P],
 }

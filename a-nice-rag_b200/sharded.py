@@ -54,13 +54,6 @@ class ShardedHybrid:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = torch.device("cuda", engine.current_device())
         self._buf = {}
-        # BM25 runs on a side stream with its own library context (own scratch) next to the dense
-        # pass, as anr_hybrid_search does on one GPU
-        self._side = torch.cuda.Stream(device=self.device)
-        self._side_ctx = engine.Context(self.device.index)
-        native.call("anr_ctx_set_beside_dense", self._side_ctx.handle, 1)
-        self._fork = torch.cuda.Event()
-        self._join = torch.cuda.Event()
 
     def _buffers(self, b: int, k: int, top_n: int):
         key = (b, k, top_n)
@@ -79,23 +72,17 @@ class ShardedHybrid:
                w_bm25: float, rrf_k: float, top_n: int):
         """queries [b, d] fp32, CSR term ids int32: device tensors.  Returns device tensors
         (ids [b, top_n] int32 GLOBAL ids, scores f64, counts).  Enqueued on torch's current
-        stream (BM25 on a side stream that forks from / joins it): 2 local searches, 1 all-gather,
-        1 merge+fuse call."""
+        stream: 1 call for both local searches, 1 all-gather, 1 merge+fuse call."""
         t = self.torch
         ctx = engine.context(self.device.index)
         stream = engine.torch_stream_ptr()
         buf = self._buffers(b, k, top_n)
         local, gathered = buf["local"], buf["gathered"]
-        main = t.cuda.current_stream()
-        self._fork.record(main)
-        self._side.wait_event(self._fork)
-        native.call("anr_bm25_search_keys", self._side_ctx.handle, self.bm25.handle,
-                    terms_dev.data_ptr(), offsets_dev.data_ptr(), b, k, None, None, self.doc_base,
-                    local[1].data_ptr(), self._side.cuda_stream)
-        self._join.record(self._side)
-        native.call("anr_dense_search_keys", ctx.handle, self.dense.handle, queries_dev.data_ptr(),
-                    b, k, None, self.row_base, local[0].data_ptr(), stream)
-        main.wait_event(self._join)
+        # both local searches in one library call: BM25 on the context's side stream around the
+        # dense pass (sample launch | dense pre-pass | dense main kernel | BM25 main launch | join)
+        native.call("anr_hybrid_search_keys", ctx.handle, self.dense.handle, self.bm25.handle,
+                    queries_dev.data_ptr(), terms_dev.data_ptr(), offsets_dev.data_ptr(), b, k, None,
+                    None, self.row_base, self.doc_base, local.data_ptr(), stream)
         if self.world > 1:
             self.dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=self.group)
         else:

@@ -332,7 +332,7 @@ def run_ours(args):
     native.call("anr_ctx_profile_enable", ctx.handle, 1)
     import ctypes as C
     # sharded: BM25 runs through the shard's side context (its own scratch and event pool)
-    bm_ctx = shard._side_ctx if world > 1 else ctx
+    bm_ctx = ctx
     if bm_ctx is not ctx:
         native.call("anr_ctx_profile_enable", bm_ctx.handle, 1)
     for kind in (0, 1, 2):

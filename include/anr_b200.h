@@ -178,6 +178,16 @@ int anr_bm25_search_keys(anr_ctx* ctx, const anr_bm25* index, const int32_t* q_t
                          const int32_t* q_offsets, int32_t n_queries, int32_t k,
                          const uint32_t* doc_mask, const int32_t* doc_to_id, int64_t id_base,
                          uint64_t* out_keys, void* stream);
+/* Both local searches of one SHARD in one call (a-nice-rag_b200/sharded.py): out_keys is
+ * [2, n_queries, k] sortable keys with global ids (plane 0 = dense rows + row_base, plane 1 = BM25
+ * documents + doc_base), the input of anr_sharded_fuse after the all-gather.  Device pointers
+ * only; BM25 runs on the context's side stream around the dense pass as in anr_hybrid_search. */
+int anr_hybrid_search_keys(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25,
+                           const float* queries, const int32_t* q_terms, const int32_t* q_offsets,
+                           int32_t n_queries, int32_t k, const uint32_t* row_mask,
+                           const uint32_t* doc_mask, int64_t row_base, int64_t doc_base,
+                           uint64_t* out_keys, void* stream);
+
 /* keys: [n_parts, n_queries, k] (the all-gather output) -> merged top-k. */
 int anr_topk_merge(anr_ctx* ctx, const uint64_t* keys, int32_t n_parts, int32_t n_queries,
                    int32_t k, float* out_scores, int32_t* out_ids, int32_t* out_counts,

@@ -405,6 +405,33 @@ def test_sharded_fuse_equals_unsharded_hybrid(small):
     assert np.array_equal(ids, res["ids"]) and np.array_equal(scores, res["scores"])
 
 
+def test_hybrid_search_keys_equals_the_two_key_searches(small):
+    """anr_hybrid_search_keys (what a shard calls: both searches in one call, BM25 on the side
+    stream around the dense pass) returns exactly the keys of the two separate calls."""
+    import torch
+    case, ix = small["case"], small["ix"]
+    queries = case["queries"]
+    nq, k = queries.shape[0], 10
+    term_queries = [term_ids_of(case, ix, q) for q in range(nq)]
+    terms, offsets = engine.Bm25Index.pack_queries(term_queries)
+    ctx = engine.context()
+    dev = torch.device("cuda", 0)
+    q_dev = torch.from_numpy(np.ascontiguousarray(queries)).to(dev)
+    t_dev, o_dev = torch.from_numpy(terms).to(dev), torch.from_numpy(offsets).to(dev)
+    both = torch.zeros((2, nq, k), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    native.call("anr_hybrid_search_keys", ctx.handle, small["dense"].handle, small["bm25"].handle,
+                q_dev.data_ptr(), t_dev.data_ptr(), o_dev.data_ptr(), nq, k, None, None, 1000, 5000,
+                both.data_ptr(), None)
+    native.call("anr_ctx_sync", ctx.handle)
+    want = np.zeros((2, nq, k), dtype=np.uint64)
+    native.call("anr_dense_search_keys", ctx.handle, small["dense"].handle, native.ptr(queries), nq, k,
+                None, 1000, native.ptr(want[0]), None)
+    native.call("anr_bm25_search_keys", ctx.handle, small["bm25"].handle, native.ptr(terms),
+                native.ptr(offsets), nq, k, None, None, 5000, native.ptr(want[1]), None)
+    assert np.array_equal(both.cpu().numpy().view(np.uint64), want)
+
+
 def test_bm25_long_posting_lists_many_tiles():
     """Posting lists of 10^4..10^5 entries cut by many document tiles: exercises every level of
     the 32-ary slice search, including terms whose postings all lie before / after a tile."""
