@@ -191,6 +191,11 @@ def check_against_cpu(results, got, queries_n: int):
     return queries_n
 
 
+def workload_name(args) -> str:
+    return (f"{args.chunks} chunks x {D}-d fp32 + BM25 {args.chunks} docs V={VOCAB} Zipf {ZIPF_S}, "
+            f"{N_TERMS}-term queries, top-{TOPK} WRRF (w 5:1, k=40)")
+
+
 # ---------------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the CPU port on this box's host cores; rank 0 only."""
@@ -222,9 +227,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.chunks} chunks x {D}-d fp32 + BM25 {args.chunks} docs "
-                               f"V={VOCAB} Zipf {ZIPF_S}, {N_TERMS}-term queries, top-{TOPK} WRRF",
-                   "batch": per_step},
+        # the same workload as the CUDA arm's line; a step here is a bounded sample of its batch
+        "config": {"workload": workload_name(args), "batch": args.batch,
+                   "sample_queries_per_step": per_step},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": f"{per_step} queries per step over the full corpus; numpy "
                                    "BLAS dot + CSR BM25 + Python RRF on a pre-stacked matrix"},
@@ -481,6 +486,33 @@ def run_ours(args):
     bm_cmp = bm_alone_ms * max(bm_n.value, 1) if bm_alone_ms else bm_ms.value
     dominant = dense_roof if scan_ms.value >= bm_cmp else bm_roof
 
+    # ---- the same step replayed from a CUDA graph (graph.HybridGraph) -----------------
+    # Reported beside the eager numbers, which stay the headline: one launch instead of ~20 plus
+    # the fork/join event traffic.  Results must equal the eager call's bit for bit.
+    graph_rec = None
+    if world == 1:
+        try:
+            graph_mod = importlib.import_module("a-nice-rag_b200.graph")
+            graph_rec = {}
+            n_it = max(args.steps, 50)
+            for b_g in sorted({1, B}):
+                hg = graph_mod.HybridGraph(dense, bm25, b_g, N_TERMS * b_g, TOPK, TOPK, W_DENSE,
+                                           W_BM25, WRRF_K, TOPK)
+                hg.load(q_dev[:b_g], t_dev[:N_TERMS * b_g], off_dev[:b_g + 1])
+                for _ in range(5):
+                    hg.replay()
+                step_device(b_g)
+                torch.cuda.synchronize()
+                same = bool(torch.equal(hg.ids, out_ids[:b_g]) and
+                            torch.equal(hg.scores, out_scores[:b_g]) and
+                            torch.equal(hg.counts, out_counts[:b_g]))
+                ms_g = timed(hg.replay, n_it) / n_it
+                graph_rec[f"batch{b_g}"] = {"replay_ms": ms_g, "queries_per_s": 1e3 * b_g / ms_g,
+                                            "identical_to_eager": same}
+                del hg
+        except Exception as exc:   # never lose the headline line to the optional replay leg
+            graph_rec = {"error": repr(exc)[:300]}
+
     # ---- CPU baseline + parity of this very batch (N = 1) --------------------------------------
     cpu = None
     checked = 0
@@ -511,9 +543,7 @@ def run_ours(args):
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak" if args.chunks_per_gpu else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.chunks} chunks x {D}-d fp32 + BM25 {args.chunks} docs "
-                               f"V={VOCAB} Zipf {ZIPF_S}, {N_TERMS}-term queries, top-{TOPK} WRRF "
-                               f"(w 5:1, k=40)", "batch": B, "sharding": f"chunks/{world}",
+        "config": {"workload": workload_name(args), "batch": B, "sharding": f"chunks/{world}",
                    "l2": "inputs larger than L2 (corpus shard >= 0.5 GB per GPU)",
                    "bm25_postings_local": n_postings},
         "e2e": {"value": B * args.steps / (ms_e2e * 1e-3), "unit": "queries/s",
@@ -550,6 +580,7 @@ def run_ours(args):
                               "(the reference's source-prefix filter)",
                       "value": B * args.steps / (ms_filtered * 1e-3), "unit": "queries/s",
                       "ms_per_step": ms_filtered / args.steps} if ms_filtered else None),
+        "cuda_graph": graph_rec,
         "clocks": clocks, "parity_checked_queries": checked,
     }
     if cpu:
