@@ -631,6 +631,9 @@ static bool make_gemm_layout(const DeviceProps& dp, int ld, bool bf16, int b_row
   int n_stages = avail / L->stage_bytes;
   if (n_stages < 3) return false;
   if (n_stages > kGmMaxStages) n_stages = kGmMaxStages;
+  // tuning knob for co-residency experiments: a shorter ring leaves shared memory to BM25 CTAs
+  static const int cap_env = getenv("ANR_GEMM_MAX_STAGES") ? atoi(getenv("ANR_GEMM_MAX_STAGES")) : 0;
+  if (cap_env >= 3 && n_stages > cap_env) n_stages = cap_env;
   L->n_stages = n_stages;
   L->thr_off = n_stages * L->stage_bytes;
   L->stage_off = (L->thr_off + thr_bytes + 15) / 16 * 16;

@@ -8,6 +8,7 @@ CUDA library; nothing in this module computes a score on the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import re
 import threading
 import weakref
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
@@ -89,13 +90,24 @@ def parse_prefixes(filename_type_filter: str) -> Tuple[str, ...]:
     return tuple(p.strip().upper() for p in filename_type_filter.split(","))
 
 
-def prefix_mask(sources: Sequence[Optional[str]], filename_type_filter: str) -> np.ndarray:
-    """bool[n]: upper-cased source starts with any prefix (None / non-string -> False)."""
+def prefix_mask(sources: Sequence[Optional[str]], filename_type_filter: str,
+                frame_semantics: bool = False) -> np.ndarray:
+    """bool[n]: upper-cased source starts with any prefix (None / non-string -> False).
+
+    ``frame_semantics``: the DataFrame filter (search_engine.py:41-46) joins SEVERAL prefixes
+    into the un-escaped regex ``^(?:A|B)``, so a prefix holding a regex metacharacter acts as a
+    pattern there (and a malformed one raises, which the search methods turn into an empty
+    result); a single prefix, and the BM25 filter (:224-231) always, compare literally.
+    """
     prefixes = parse_prefixes(filename_type_filter)
+    test = None
+    if frame_semantics and len(prefixes) > 1 and any(re.escape(p) != p for p in prefixes):
+        test = re.compile("^(?:" + "|".join(prefixes) + ")").search
     out = np.zeros(len(sources), dtype=bool)
     for i, src in enumerate(sources):
         if isinstance(src, str):
-            out[i] = src.upper().startswith(prefixes)
+            up = src.upper()
+            out[i] = up.startswith(prefixes) if test is None else test(up) is not None
     return out
 
 

@@ -58,7 +58,7 @@ class DenseEntry:
         """(bool[n], device words or None, eligible count), cached per filter string."""
         hit = self._masks.get(filename_type_filter)
         if hit is None:
-            mask = engine.prefix_mask(self.sources, filename_type_filter)
+            mask = engine.prefix_mask(self.sources, filename_type_filter, frame_semantics=True)
             hit = (mask, device_words(engine.pack_mask(mask)), int(mask.sum()))
             self._masks[filename_type_filter] = hit
         return hit

@@ -75,7 +75,8 @@ class SearchEngine:
         Kept for callers that use it directly; the searches below do not materialise the
         filtered frame, they pass the same predicate to the kernels as a row bit mask.
         """
-        mask = engine.prefix_mask(df["source"].to_numpy(dtype=object), filename_type_filter)
+        mask = engine.prefix_mask(df["source"].to_numpy(dtype=object), filename_type_filter,
+                                  frame_semantics=True)
         filtered_df = df[mask].copy()
         prefix_str = ", ".join(engine.parse_prefixes(filename_type_filter))
         self.logger.info(

@@ -11,6 +11,12 @@
  *     host pointer the call returns after the results have landed; when all
  *     outputs are device pointers the call is asynchronous on `stream`;
  *   - `stream` is a cudaStream_t passed as void* (NULL = the context's stream);
+ *   - an all-device-pointer search call may be captured into a CUDA graph
+ *     (cudaStreamBeginCapture on `stream`) once the same call has run eagerly on
+ *     that context: the first call sizes the context's workspace and builds the
+ *     lazily created index members, which synchronise.  A captured graph bakes in
+ *     workspace addresses, so give it a context nothing else uses
+ *     (a-nice-rag_b200/graph.py, tests/test_gpu_graph.py);
  *   - a context (workspace + streams) must not be used by two threads at once;
  *     index objects are immutable after creation and may be shared;
  *   - there is NO CPU implementation behind any of these: without a B200 (sm_100)

@@ -19,15 +19,25 @@ def parse_prefixes(filename_type_filter: str) -> Tuple[str, ...]:
     return tuple(part.strip().upper() for part in filename_type_filter.split(","))
 
 
-def filter_mask(sources: Sequence[Optional[str]], filename_type_filter: str) -> np.ndarray:
+def filter_mask(sources: Sequence[Optional[str]], filename_type_filter: str,
+                frame: bool = False) -> np.ndarray:
     """Row mask: upper-cased source starts with any prefix (search_engine.py:40-46).
 
-    ``None``/NaN sources are False (``na=False``).  The multi-prefix branch of
-    the reference builds an un-escaped regex ``^(?:A|B)``; for the alphanumeric
-    prefixes the callers use (``"CG,NG"``) this equals ``startswith``.
+    ``None``/NaN sources are False (``na=False``).  ``frame=True`` restates the DataFrame
+    filter literally: one prefix -> ``startswith`` (:42), several -> the un-escaped regex
+    ``^(?:A|B)`` searched in the upper-cased source (:44-46); ``frame=False`` is the BM25
+    filter's ``any(startswith)`` (:224-231).  For the alphanumeric prefixes the callers use
+    (``"CG,NG"``) the two agree.
     """
     prefixes = parse_prefixes(filename_type_filter)
     out = np.zeros(len(sources), dtype=bool)
+    if frame and len(prefixes) > 1:
+        import re
+        pattern = re.compile("^(?:" + "|".join(prefixes) + ")")
+        for i, src in enumerate(sources):
+            if isinstance(src, str):
+                out[i] = pattern.search(src.upper()) is not None
+        return out
     for i, src in enumerate(sources):
         if isinstance(src, str):
             out[i] = src.upper().startswith(prefixes)

@@ -111,6 +111,71 @@ def test_filter_mask_semantics():
                                                          False, False]
 
 
+FILTER_SOURCES = ["CG12", "cg7", "NG1", "PH2", None, "", "XCG1", " ng3", "C.1", "CX9", "N(G", 7, "ng"]
+# (filter string, frame mask, BM25-style mask): several prefixes are an UN-ESCAPED regex in the
+# DataFrame filter (search_engine.py:44-46) and literal prefixes in the BM25 filter (:224-231)
+FILTER_CASES = [
+    ("CG,NG", [1, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1], None),
+    ("c., ng", [1, 1, 1, 0, 0, 0, 0, 0, 1, 1, 0, 0, 1], [0, 0, 1, 0, 0, 0, 0, 0, 1, 0, 0, 0, 1]),
+    ("C.", [0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0], None),         # single prefix: literal
+    ("CG,", [1, 1, 1, 1, 0, 1, 1, 1, 1, 1, 1, 0, 1], None),         # empty prefix matches every string
+    ("N[A-G],PH", [0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1], [0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0]),
+]
+
+
+@pytest.mark.parametrize("flt,frame_want,bm25_want", FILTER_CASES)
+def test_filter_mask_frame_vs_bm25_semantics(pkg, flt, frame_want, bm25_want):
+    bm25_want = frame_want if bm25_want is None else bm25_want
+    assert retrieval.filter_mask(FILTER_SOURCES, flt, frame=True).astype(int).tolist() == frame_want
+    assert retrieval.filter_mask(FILTER_SOURCES, flt).astype(int).tolist() == bm25_want
+    # the product's host-side mask builder follows the same two rules
+    assert pkg.engine.prefix_mask(FILTER_SOURCES, flt, frame_semantics=True).astype(int).tolist() == frame_want
+    assert pkg.engine.prefix_mask(FILTER_SOURCES, flt).astype(int).tolist() == bm25_want
+
+
+def test_filter_mask_malformed_regex_raises(pkg):
+    import re
+    with pytest.raises(re.error):
+        retrieval.filter_mask(FILTER_SOURCES, "N(G,CG", frame=True)
+    with pytest.raises(re.error):
+        pkg.engine.prefix_mask(FILTER_SOURCES, "N(G,CG", frame_semantics=True)
+    assert pkg.engine.prefix_mask(FILTER_SOURCES, "N(G,CG").astype(int).tolist() == \
+        [1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0]
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="reference sources not mounted")
+@pytest.mark.parametrize("flt", [c[0] for c in FILTER_CASES] + ["N(G,CG"])
+def test_filter_masks_match_reference_filters(pkg, flt):
+    """Both filters of the UNMODIFIED reference: the DataFrame one (rows kept by
+    _filter_by_filename_type) and the BM25 one (sections that can be returned)."""
+    import re
+    import pandas as pd
+    ref = reference_loader.load_reference()
+    se = ref.SearchEngine(None, None)
+    df = pd.DataFrame({"source": FILTER_SOURCES})
+    try:
+        kept = se._filter_by_filename_type(df, flt).index.tolist()
+    except re.error:
+        with pytest.raises(re.error):
+            pkg.engine.prefix_mask(FILTER_SOURCES, flt, frame_semantics=True)
+    else:
+        assert np.flatnonzero(pkg.engine.prefix_mask(FILTER_SOURCES, flt, frame_semantics=True)).tolist() == kept
+        assert np.flatnonzero(retrieval.filter_mask(FILTER_SOURCES, flt, frame=True)).tolist() == kept
+
+    class Sec:
+        def __init__(self, source):
+            self.metadata = {"source": source}
+
+    class Scores:                                  # bm25.get_scores: every section scores 1.0
+        def get_scores(self, _tokens):
+            return np.ones(len(strs))
+
+    strs = [s for s in FILTER_SOURCES if isinstance(s, str)]
+    ids = [str(i) for i in range(len(strs))]
+    got = se._core_bm25_search(["x"], Scores(), [Sec(s) for s in strs], ids, len(strs), flt)
+    assert [ids[i] for i in np.flatnonzero(pkg.engine.prefix_mask(strs, flt))] == got
+
+
 @pytest.mark.skipif(not reference_loader.available(), reason="reference sources not mounted")
 def test_restatement_matches_reference_import(small_case):
     """Direct check against the reference's SearchEngine (no golden file in between)."""
