@@ -8,6 +8,11 @@ in the reference are the construction call
 ``BM25Okapi(corpus, k1=1.7, b=0.83, epsilon=0.05)``
 (``src/processing/bm25_search.py:77``, params ``:136-139``) and the scoring call
 ``bm25.get_scores(query_tokens)`` (``src/search_engine.py:219``).
+The only published vector for this arithmetic -- the usage example in the package's README,
+``get_scores("windy London")`` over three sentences = ``[0., 0.93729472, 0.]`` with the default
+parameters -- is reproduced to its 8 printed digits (``tests/test_oracle.py::
+test_bm25_okapi_published_known_answer``; on the device in ``tests/test_gpu_parity.py``).  One
+vector on a three-document corpus is an anchor, not a pin: the header stays "unpinned".
 
 Attribute names (``corpus_size, avgdl, doc_freqs, idf, doc_len, k1, b, epsilon,
 average_idf``) match the package because real pickles written by

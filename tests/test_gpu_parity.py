@@ -625,3 +625,17 @@ def test_retrieve_documents_batch_equals_per_query_orchestrator(small):
                                            [d["similarity"] for d in want], rtol=1e-6)
             else:
                 assert got[q] == want, (kw, q)
+
+
+def test_bm25_published_known_answer_on_the_device():
+    """rank_bm25's README example (tests/test_oracle.py::test_bm25_okapi_published_known_answer)
+    through the product path: pickle-shaped object -> CSR inversion -> anr_bm25_scores / search."""
+    from oracle import bm25_okapi
+    corpus = ["Hello there good man!", "It is quite windy in London", "How is the weather today?"]
+    okapi = bm25_okapi.BM25Okapi([doc.split(" ") for doc in corpus])
+    index = engine.Bm25Index.from_okapi(okapi)
+    terms = index.term_ids(["windy", "London"])
+    np.testing.assert_allclose(index.scores(terms), [0.0, 0.93729472, 0.0], rtol=1e-6, atol=0)
+    scores, docs, counts = index.search([terms], 1)
+    assert counts[0] == 1 and docs[0, 0] == 1
+    np.testing.assert_allclose(scores[0, 0], 0.93729472, rtol=1e-6)

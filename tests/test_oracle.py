@@ -6,7 +6,7 @@ import pytest
 
 from helpers import (B, EPS, K1, WEIGHTS, WRRF_K, check_ids_only, check_topk, csr_from_case,
                      filter_mask, okapi_from_case, synth, tag)
-from oracle import csr, pipeline, reference_loader, retrieval
+from oracle import bm25_okapi, csr, pipeline, reference_loader, retrieval
 
 FILTERS = (None, "CG,NG", "cg", "ZZ")
 KS = (10, 100, 3000)
@@ -101,6 +101,25 @@ def test_pipeline_matches_golden_fusion(small_case, built):
         # fused list is exact GIVEN the lists; lists themselves are checked above
         pipeline.check_fused([i for i, _ in res["fused"]], [s for _, s in res["fused"]],
                              res["dense_ids"], res["bm25_ids"], (5.0, 1.0), WRRF_K, 2 * k)
+
+
+def test_bm25_okapi_published_known_answer():
+    """The one known-answer vector published for the third-party arithmetic: the usage example in
+    the README of rank_bm25 (dorianbrown/rank_bm25, 0.2.x) -- default k1=1.5, b=0.75,
+    epsilon=0.25 -- prints ``array([0., 0.93729472, 0.])`` for the query "windy London" and
+    returns the London sentence from ``get_top_n``.  (The package itself is not available
+    offline; the vector is quoted from its documentation, 8 significant digits.)  "is" occurs in
+    two of the three documents, so the same corpus also exercises the negative-idf floor."""
+    corpus = ["Hello there good man!", "It is quite windy in London", "How is the weather today?"]
+    tokenized = [doc.split(" ") for doc in corpus]
+    bm25 = bm25_okapi.BM25Okapi(tokenized)
+    scores = bm25.get_scores("windy London".split(" "))
+    np.testing.assert_allclose(scores, [0.0, 0.93729472, 0.0], rtol=0, atol=5e-9)
+    assert int(np.argmax(scores)) == 1
+    raw_is = np.log(3 - 2 + 0.5) - np.log(2 + 0.5)
+    assert raw_is < 0 and bm25.idf["is"] == 0.25 * bm25.average_idf
+    np.testing.assert_allclose(csr.scores_for_tokens(csr.from_okapi(bm25), ["windy", "London"]),
+                               [0.0, 0.93729472, 0.0], rtol=0, atol=5e-9)
 
 
 def test_filter_mask_semantics():
