@@ -22,6 +22,7 @@ top-k keys are exchanged with one NCCL all-gather and merged + fused on every ra
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import importlib
 import json
 import os
@@ -335,21 +336,13 @@ def run_ours(args):
         step_device()
         step_e2e()
     native.call("anr_ctx_profile_enable", ctx.handle, 1)
-    import ctypes as C
-    # sharded: BM25 runs through the shard's side context (its own scratch and event pool)
-    bm_ctx = ctx
-    if bm_ctx is not ctx:
-        native.call("anr_ctx_profile_enable", bm_ctx.handle, 1)
     for kind in (0, 1, 2):
         native.call("anr_ctx_profile_read", ctx.handle, kind, None, None)   # reset counters
-    native.call("anr_ctx_profile_read", bm_ctx.handle, 1, None, None)
     ms_dev = timed(step_device, args.steps)
     scan_ms, scan_n, bm_ms, bm_n = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
     pass_ms, pass_n = C.c_double(), C.c_int64()
     native.call("anr_ctx_profile_read", ctx.handle, 0, C.byref(scan_ms), C.byref(scan_n))
-    native.call("anr_ctx_profile_read", bm_ctx.handle, 1, C.byref(bm_ms), C.byref(bm_n))
-    if bm_ctx is not ctx:
-        native.call("anr_ctx_profile_enable", bm_ctx.handle, 0)
+    native.call("anr_ctx_profile_read", ctx.handle, 1, C.byref(bm_ms), C.byref(bm_n))
     native.call("anr_ctx_profile_read", ctx.handle, 2, C.byref(pass_ms), C.byref(pass_n))
     native.call("anr_ctx_profile_enable", ctx.handle, 0)
     ms_e2e = timed(step_e2e, args.steps)
