@@ -192,6 +192,20 @@ def check_against_cpu(results, got, queries_n: int):
     return queries_n
 
 
+def cpu_threads() -> int:
+    """Threads the CPU port really uses: the BLAS pool behind np.dot (the CSR BM25 statement and the
+    Python RRF loop are single-threaded, as in the reference)."""
+    try:
+        from threadpoolctl import threadpool_info
+        n = max((int(p.get("num_threads", 0)) for p in threadpool_info()
+                 if p.get("user_api") == "blas"), default=0)
+        if n > 0:
+            return n
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
 def workload_name(args) -> str:
     return (f"{args.chunks} chunks x {D}-d fp32 + BM25 {args.chunks} docs V={VOCAB} Zipf {ZIPF_S}, "
             f"{N_TERMS}-term queries, top-{TOPK} WRRF (w 5:1, k=40)")
@@ -222,7 +236,7 @@ def run_reference(args):
         dt, _ = cpu_port_run(emb_h, index, queries, terms, per_step)
         total += dt
     qps = per_step * args.steps / total
-    cores = os.cpu_count()
+    cores = cpu_threads()
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -516,7 +530,7 @@ def run_ours(args):
         nq_cpu = min(args.cpu_queries, B)
         cpu_port_run(emb_h, index, q_host, t_host, 1)                       # warm caches / BLAS
         dt, results = cpu_port_run(emb_h, index, q_host, t_host, nq_cpu)
-        cpu = {"value": nq_cpu / dt, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+        cpu = {"value": nq_cpu / dt, "unit": "queries/s", "cores": cpu_threads(), "kind": "port",
                "sample": f"{nq_cpu} of the batch's {B} queries over the full {args.chunks}-chunk "
                          "corpus; numpy BLAS dot + CSR BM25 + Python RRF on a pre-stacked matrix "
                          "(the reference's per-query np.stack and pandas work NOT included)"}

@@ -271,3 +271,46 @@ def test_orchestrator_restatement_matches_reference_method(small_case, built):
             else:
                 assert got == want, (kw, q)
             assert len(want) > 0 or kw.get("filename_type_filter") == "ZZ"
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="reference sources not mounted")
+def test_wrrf_and_topk_restatements_fuzzed_against_the_reference():
+    """Random ranked lists (overlaps, empty lists, duplicate ids inside a list, unknown model
+    names, zero / negative weights, the three wrrf_k values the callers use) and random score
+    vectors with planted ties: bit-identical fusion output and identical filtered BM25 order."""
+    ref = reference_loader.load_reference()
+    se = ref.SearchEngine(None, None)
+    rng = np.random.default_rng(20261018)
+    names = ["voyage-3-large", "BM25", "Qwen3", "unlisted"]
+    weights = {"voyage-3-large": 5.0, "BM25": 1.0, "Qwen3": 0.0}
+    for trial in range(200):
+        lists = []
+        for _ in range(int(rng.integers(1, 6))):
+            n = int(rng.integers(0, 40))
+            ids = [f"id{int(i)}" for i in rng.integers(0, 60, size=n)]
+            lists.append((ids, names[int(rng.integers(0, len(names)))]))
+        w = dict(weights)
+        if trial % 7 == 0:
+            w["BM25"] = -0.5
+        k = (40, 50, 60)[trial % 3]
+        assert se.weighted_reciprocal_rank_fusion(lists, w, k) == retrieval.weighted_rrf(lists, w, k)
+
+    class Sec:
+        def __init__(self, source):
+            self.metadata = {"source": source}
+
+    for trial in range(50):
+        n = int(rng.integers(1, 200))
+        scores = np.round(rng.random(n) * 4, 1)                  # many exact ties
+        srcs = [("CG", "NG", "PH", "cg")[int(i)] + str(trial) for i in rng.integers(0, 4, size=n)]
+        ids = [str(i) for i in range(n)]
+
+        class Okapi:
+            def get_scores(self, _tokens, s=scores):
+                return s
+
+        for flt in ("CG", "cg, ng", "ZZ"):
+            k = int(rng.integers(1, n + 5))
+            got = se._core_bm25_search(["t"], Okapi(), [Sec(s) for s in srcs], ids, k, flt)
+            want = retrieval.bm25_topk(scores, k, srcs, flt)
+            assert got == [ids[i] for i in want]
