@@ -314,3 +314,23 @@ def test_wrrf_and_topk_restatements_fuzzed_against_the_reference():
             got = se._core_bm25_search(["t"], Okapi(), [Sec(s) for s in srcs], ids, k, flt)
             want = retrieval.bm25_topk(scores, k, srcs, flt)
             assert got == [ids[i] for i in want]
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="reference sources not mounted")
+def test_committed_golden_is_what_the_reference_produces_today(small_case, tmp_path):
+    """Re-runs oracle/make_golden.py's small case through the UNMODIFIED reference (SQLite chunks
+    table + BM25 pickle on disk -> DatabaseManager -> SearchEngine) and requires every array of
+    tests/golden/small_case.npz to come out again bit for bit."""
+    from oracle import make_golden
+    inputs = make_golden.small_case_inputs()
+    out = make_golden.run_reference(inputs, ks=(10, 100, 3000), filters=(None, "CG,NG", "cg", "ZZ"),
+                                    tmpdir=str(tmp_path))
+    fresh = {**inputs, **out}
+    assert set(fresh) == set(small_case)
+    for name, want in small_case.items():
+        got = np.asarray(fresh[name])
+        assert got.shape == want.shape, name
+        if want.dtype == object:
+            assert got.tolist() == want.tolist(), name
+        else:
+            np.testing.assert_array_equal(got, want, err_msg=name)
