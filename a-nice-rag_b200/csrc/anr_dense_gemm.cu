@@ -702,6 +702,11 @@ static cudaError_t gemm_launch_one(int grid, int threads, int smem, cudaStream_t
   auto kern = dense_gemm_kernel<NQ, BF16, SAMPLE, PAIR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
+  // a capped ring (co-residency experiments) must keep the max-shared L1 split the BM25 kernels
+  // ask for, or CTAs of the two kernels cannot share an SM
+  if (getenv("ANR_GEMM_MAX_STAGES"))
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(static_cast<unsigned>(threads));
@@ -728,6 +733,9 @@ static cudaError_t gemm2_launch_one(int grid, int threads, int smem, cudaStream_
   auto kern = dense_gemm2_kernel<NQ, BF16, SAMPLE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
+  if (getenv("ANR_GEMM_MAX_STAGES"))
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(static_cast<unsigned>(threads));
