@@ -618,7 +618,7 @@ int dense_gemm_padded_queries(int nq) {
 
 // b_rows: query rows each CTA holds per slab (nq_block, or nq_block / 2 under cta_group::2)
 static bool make_gemm_layout(const DeviceProps& dp, int ld, bool bf16, int b_rows, int nq_pad,
-                             GemmLayout* L) {
+                             GemmLayout* L, int ring_cap = 0) {
   const int slab = bf16 ? 64 : 32;
   if (ld % slab != 0) return false;
   L->n_slabs = ld / slab;
@@ -631,9 +631,8 @@ static bool make_gemm_layout(const DeviceProps& dp, int ld, bool bf16, int b_row
   int n_stages = avail / L->stage_bytes;
   if (n_stages < 3) return false;
   if (n_stages > kGmMaxStages) n_stages = kGmMaxStages;
-  // tuning knob for co-residency experiments: a shorter ring leaves shared memory to BM25 CTAs
-  static const int cap_env = getenv("ANR_GEMM_MAX_STAGES") ? atoi(getenv("ANR_GEMM_MAX_STAGES")) : 0;
-  if (cap_env >= 3 && n_stages > cap_env) n_stages = cap_env;
+  // a shorter ring leaves shared memory to the BM25 CTAs of a hybrid step (gemm_ring_cap)
+  if (ring_cap >= 3 && n_stages > ring_cap) n_stages = ring_cap;
   L->n_stages = n_stages;
   L->thr_off = n_stages * L->stage_bytes;
   L->stage_off = (L->thr_off + thr_bytes + 15) / 16 * 16;
@@ -659,6 +658,10 @@ size_t dense_gemm_scratch_bytes(const DeviceProps& dp, int64_t n, int ld, int nq
   return nq_pad * kGmCap * 8 + nq_pad * groups * 4 + nq_pad * (4 + 4 + 8) +
          nq_pad * static_cast<size_t>(ld) * 2 + 4096;
 }
+
+// host-side only (GemmLayout is a kernel parameter and stays as it is): the launch group being
+// issued by this thread runs with a capped ring
+static thread_local bool t_ring_capped = false;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -702,9 +705,9 @@ static cudaError_t gemm_launch_one(int grid, int threads, int smem, cudaStream_t
   auto kern = dense_gemm_kernel<NQ, BF16, SAMPLE, PAIR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  // a capped ring (co-residency experiments) must keep the max-shared L1 split the BM25 kernels
-  // ask for, or CTAs of the two kernels cannot share an SM
-  if (getenv("ANR_GEMM_MAX_STAGES"))
+  // a capped ring must keep the max-shared L1 split the BM25 kernels ask for, or CTAs of the two
+  // kernels cannot share an SM (without this preference a 4-stage ring gained nothing: 0.651 ms)
+  if (t_ring_capped)
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
   cudaLaunchConfig_t cfg = {};
@@ -733,7 +736,7 @@ static cudaError_t gemm2_launch_one(int grid, int threads, int smem, cudaStream_
   auto kern = dense_gemm2_kernel<NQ, BF16, SAMPLE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
-  if (getenv("ANR_GEMM_MAX_STAGES"))
+  if (t_ring_capped)
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
   cudaLaunchConfig_t cfg = {};
@@ -825,6 +828,23 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+// Ring depth cap of one launch group.  ANR_GEMM_MAX_STAGES=n caps every GEMM launch (profiling);
+// ANR_GEMM_BESIDE_STAGES=n caps only the launches of a hybrid step whose BM25 scan runs beside the
+// main kernel (64-query bf16 tiles, 16+ queries): with a 4-stage ring (96 KB) three 34 KB BM25
+// CTAs fit next to the dense CTA on every SM, and the two main kernels -- one HBM-bound, one
+// issue-bound -- overlap instead of following each other.  Measured on 1M x 1024 + 1M docs, batch
+// 64 (profiles/r1_bench_1gpu_coresident_ring{4,3}.json): 0.630 -> 0.576 / 0.567 ms per step, the
+// dense kernel stretching from 0.313 to 0.40 ms; batch-1 loses 3 %, hence the 16-query floor.
+// Default 0 (off) until the whole GPU suite has run with it.
+static int gemm_ring_cap(bool beside_bm25, bool bf16, int nqb_size, int n_real) {
+  static const int all_env = getenv("ANR_GEMM_MAX_STAGES") ? atoi(getenv("ANR_GEMM_MAX_STAGES")) : 0;
+  static const int beside_env =
+      getenv("ANR_GEMM_BESIDE_STAGES") ? atoi(getenv("ANR_GEMM_BESIDE_STAGES")) : 0;
+  if (all_env >= 3) return all_env;
+  if (beside_env >= 3 && beside_bm25 && bf16 && nqb_size == 64 && n_real >= 16) return beside_env;
+  return 0;
+}
+
 // One launch group: n_real <= dense_gemm_max_queries() queries at q_dev ([padded, ld] fp32, zero
 // rows as padding) against the corpus (emb fp32 [n, ld]; shadow = its bf16 copy or null ->
 // tf32 on the fp32 words).  Exact top-k of the n_real queries through `out`, flags[0..n_real).
@@ -839,7 +859,9 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
   const int n_qblocks = nq_pad / nqb_size;
   GemmLayout L;
   const int mode = gemm_mode(dp, nqb_size, (n + kGmRows - 1) / kGmRows);
-  if (!make_gemm_layout(dp, ld, bf16, mode == 2 ? nqb_size / 2 : nqb_size, nq_pad, &L))
+  const int ring_cap = gemm_ring_cap(ev_pre_main != nullptr, bf16, nqb_size, n_real);
+  t_ring_capped = ring_cap >= 3;
+  if (!make_gemm_layout(dp, ld, bf16, mode == 2 ? nqb_size / 2 : nqb_size, nq_pad, &L, ring_cap))
     return cudaErrorInvalidConfiguration;
   const int64_t sample_tiles = gemm_sample_tiles(dp, n, k);
 
