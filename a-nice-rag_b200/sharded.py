@@ -10,7 +10,7 @@ ranks, so it follows the merge.  BM25 shards score with GLOBAL 
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 

@@ -8,7 +8,7 @@ it restates).  Also the timed CPU baseline of ``bench.py`` (kind "port").
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 

@@ -279,7 +279,6 @@ def test_hybrid_vs_golden(small, flt):
 
 def test_sharded_keys_merge_equals_unsharded(small):
     """3 row shards searched separately, keys concatenated as an all-gather would, merged."""
-    import ctypes as C
     case = small["case"]
     emb, queries = case["emb"], case["queries"]
     nq, k = queries.shape[0], 10

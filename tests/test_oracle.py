@@ -4,8 +4,8 @@ against the reference imported verbatim."""
 import numpy as np
 import pytest
 
-from helpers import (B, EPS, K1, WEIGHTS, WRRF_K, check_ids_only, check_topk, csr_from_case,
-                     filter_mask, okapi_from_case, synth, tag)
+from helpers import (WEIGHTS, WRRF_K, check_ids_only, check_topk, csr_from_case, filter_mask,
+                     synth, tag)
 from oracle import bm25_okapi, csr, pipeline, reference_loader, retrieval
 
 FILTERS = (None, "CG,NG", "cg", "ZZ")
