@@ -15,6 +15,8 @@ One JSON line on stdout (rank 0).  A step = one batch of B hybrid queries.
   cpu_baseline : the CPU oracle port (numpy: BLAS dot + CSR BM25 + Python RRF, pre-stacked
               matrix, i.e. WITHOUT the reference's per-query np.stack / pandas overhead) on a
               bounded sample of the same batch, same corpus, on this box's host cores
+  cuda_graph : the same batch-1 / batch-B steps replayed from a captured CUDA graph
+              (a-nice-rag_b200/graph.py), compared bit for bit with the eager call's output
 N > 1: the SAME 1M-chunk corpus is sharded by chunk over the ranks (strong scaling); local
 top-k keys are exchanged with one NCCL all-gather and merged + fused on every rank.
 --impl reference: only the CPU port is timed (rank 0), none of the CUDA library is loaded.
