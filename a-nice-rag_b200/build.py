@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libanr_b200.so")
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--threads", "0",
     "-Xcompiler", "-fPIC", "--shared",
-    "-Xptxas", "-v", "-Xlinker", "--no-undefined",
+    "-Xptxas", "-v", "-Xlinker", "--no-undefined", "-ldl",
 ]
 
 

@@ -33,6 +33,9 @@ static int fail_cuda(const char* what, cudaError_t e) {
   return fail(e == cudaErrorMemoryAllocation ? ANR_ERR_OOM : ANR_ERR_CUDA, what,
               cudaGetErrorString(e));
 }
+namespace anr {
+int set_error(int code, const char* what, const char* detail) { return fail(code, what, detail); }
+}  // namespace anr
 #define ANR_CUDA(expr)                                       \
   do {                                                       \
     cudaError_t _e = (expr);                                 \

@@ -5,6 +5,10 @@
 
 namespace anr {
 
+// Records the calling thread's anr_last_error() message and returns `code` (anr_api.cu); for the
+// translation units that implement ABI entry points of their own.
+int set_error(int code, const char* what, const char* detail = nullptr);
+
 struct DeviceProps {
   int device = 0;
   int sm_count = 0;

@@ -10,6 +10,7 @@ attaches the CSR inverted index built from the unpickled ``BM25Okapi`` attribute
 """
 from __future__ import annotations
 
+import ctypes as C
 import logging
 import os
 import pickle
@@ -126,42 +127,19 @@ class DatabaseManager:
             if not n_rows:
                 self.logger.warning(f"No chunks found in {db_path}")
                 return pd.DataFrame()
-            cursor.execute("SELECT id, content, source, embedding, url FROM chunks")
-
-            # Rows are streamed straight into ONE preallocated (pinned when a GPU is present)
-            # [N, D] buffer -- no per-row arrays, no second copy; D is fixed by the first
-            # decodable row.  A table with ragged widths keeps the reference's frame instead.
-            ids, documents, sources, urls = [], [], [], []
-            packed = keep = None
+            # Fast path: the BLOBs are stepped through the SQLite C API by the library and copied
+            # straight into ONE preallocated (pinned when a GPU is present) [N, D] buffer, while
+            # this thread fetches the text columns (the library call runs without the GIL).
+            # Tables it does not cover (NULL / ragged / non-BLOB embeddings, libsqlite3 absent)
+            # are streamed row by row below, with the reference's skip-and-warn behaviour.
             ragged = None            # list of per-row arrays once widths disagree
-            n_ok = 0
-            while True:
-                rows = cursor.fetchmany(16384)
-                if not rows:
-                    break
-                for cid, content, source, blob, url in rows:
-                    try:
-                        view = memoryview(blob)
-                        if len(view) % 4 != 0:
-                            raise ValueError("buffer size must be a multiple of element size")
-                    except (ValueError, TypeError) as e:
-                        self.logger.warning(f"Skipping invalid row {cid}: {e}")
-                        continue
-                    row = np.frombuffer(view, dtype=np.float32)
-                    if packed is None and ragged is None:
-                        packed, keep = _alloc_matrix(n_rows, row.shape[0])
-                    if ragged is None and row.shape[0] != packed.shape[1]:
-                        ragged = [np.array(packed[i]) for i in range(n_ok)]
-                        packed = keep = None
-                    if ragged is None:
-                        packed[n_ok] = row
-                    else:
-                        ragged.append(row)
-                    ids.append(cid)
-                    documents.append(content)
-                    sources.append(source)
-                    urls.append(url)
-                    n_ok += 1
+            fast = self._load_uniform_table(conn, db_path, n_rows)
+            if fast is not None:
+                packed, keep, ids, documents, sources, urls = fast
+                n_ok = len(ids)
+            else:
+                packed, keep, ragged, ids, documents, sources, urls, n_ok = \
+                    self._load_row_by_row(cursor, n_rows)
             if ragged is None and packed is not None:
                 packed = packed[:n_ok]
                 embeddings = list(packed)            # N row views, like the per-row frombuffer
@@ -190,6 +168,90 @@ class DatabaseManager:
         finally:
             if "conn" in locals():
                 conn.close()
+
+    def _load_uniform_table(self, conn, db_path: str, n_rows: int):
+        """(packed, keep, ids, documents, sources, urls) when every row of ``chunks`` holds an
+        embedding BLOB of one width (multiple of 4 bytes); None otherwise (the caller then takes
+        the row-by-row path, which reproduces the reference's handling of odd rows)."""
+        first = conn.execute("SELECT embedding FROM chunks LIMIT 1").fetchone()
+        blob = first[0] if first else None
+        if not isinstance(blob, bytes) or len(blob) == 0 or len(blob) % 4 != 0:
+            return None
+        d = len(blob) // 4
+        packed, keep = _alloc_matrix(n_rows, d)
+        rowids = np.empty(n_rows, dtype=np.int64)
+        outcome = {}
+
+        def read_blobs():
+            got, uniform = C.c_int64(), C.c_int32()
+            try:
+                native.call("anr_sqlite_read_blobs", os.fsencode(db_path),
+                            b"SELECT rowid, embedding FROM chunks", packed.ctypes.data, d * 4,
+                            n_rows, rowids.ctypes.data, C.byref(got), C.byref(uniform))
+                outcome["rows"], outcome["uniform"] = got.value, uniform.value
+            except Exception as e:   # library without SQLite, unreadable file, ...
+                outcome["error"] = e
+
+        reader = threading.Thread(target=read_blobs, name="anr-sqlite-blobs")
+        reader.start()
+        try:
+            rows = conn.execute("SELECT rowid, id, content, source, url FROM chunks").fetchall()
+        except sqlite3.Error:
+            rows = None     # e.g. a table without rowid / url: the row-by-row path reports it
+        finally:
+            reader.join()
+        if rows is None:
+            return None
+        if "error" in outcome:
+            self.logger.info(f"Bulk BLOB loader unavailable ({outcome['error']}); reading row by row")
+            return None
+        if not outcome.get("uniform") or outcome.get("rows") != len(rows) or len(rows) != n_rows:
+            return None
+        if not rows:
+            return None
+        rid, ids, documents, sources, urls = (list(c) for c in zip(*rows))
+        # both statements scan the table in rowid order; make sure they saw the same rows
+        if not np.array_equal(rowids, np.asarray(rid, dtype=np.int64)):
+            return None
+        return packed, keep, ids, documents, sources, urls
+
+    def _load_row_by_row(self, cursor, n_rows: int):
+        """The reference's loop (database_manager.py:46-61) streaming into one matrix: rows whose
+        BLOB cannot be read as fp32 are skipped with a warning; D is fixed by the first decodable
+        row; a table with ragged widths keeps per-row arrays like the reference's frame."""
+        cursor.execute("SELECT id, content, source, embedding, url FROM chunks")
+        ids, documents, sources, urls = [], [], [], []
+        packed = keep = None
+        ragged = None
+        n_ok = 0
+        while True:
+            rows = cursor.fetchmany(16384)
+            if not rows:
+                break
+            for cid, content, source, blob, url in rows:
+                try:
+                    view = memoryview(blob)
+                    if len(view) % 4 != 0:
+                        raise ValueError("buffer size must be a multiple of element size")
+                except (ValueError, TypeError) as e:
+                    self.logger.warning(f"Skipping invalid row {cid}: {e}")
+                    continue
+                row = np.frombuffer(view, dtype=np.float32)
+                if packed is None and ragged is None:
+                    packed, keep = _alloc_matrix(n_rows, row.shape[0])
+                if ragged is None and row.shape[0] != packed.shape[1]:
+                    ragged = [np.array(packed[i]) for i in range(n_ok)]
+                    packed = keep = None
+                if ragged is None:
+                    packed[n_ok] = row
+                else:
+                    ragged.append(row)
+                ids.append(cid)
+                documents.append(content)
+                sources.append(source)
+                urls.append(url)
+                n_ok += 1
+        return packed, keep, ragged, ids, documents, sources, urls, n_ok
 
     def load_bm25_from_pickle(self, filepath: str) -> Tuple:
         """Unpickle ``{bm25, sections, section_ids}`` and build the device CSR index."""

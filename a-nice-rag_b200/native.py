@@ -57,6 +57,8 @@ SIGNATURES = {
     "anr_hybrid_search_keys": [_P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _I64, _P, _P],
     "anr_topk_merge": [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P],
     "anr_sharded_fuse": [_P, _P, _I32, _I32, _I32, _F64, _F64, _F64, _I32, _P, _P, _P, _P],
+    "anr_sqlite_read_blobs": [C.c_char_p, C.c_char_p, _P, _I64, _I64, _P, C.POINTER(_I64),
+                              C.POINTER(_I32)],
 }
 EXPORTS = sorted(list(SIGNATURES) + ["anr_abi_version", "anr_last_error"])
 

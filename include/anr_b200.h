@@ -208,6 +208,19 @@ int anr_sharded_fuse(anr_ctx* ctx, const uint64_t* gathered, int32_t n_parts, in
                      int32_t k, double w_dense, double w_bm25, double rrf_k, int32_t top_n,
                      int32_t* out_ids, double* out_scores, int32_t* out_counts, void* stream);
 
+/* ---- bulk loader (host only, no device involved) ------------------------------------------
+ * Replaces the per-row Python loop of DatabaseManager.load_embeddings_from_sql
+ * (src/database_manager.py:35-63: fetchall + np.frombuffer per row): `sql` must yield
+ * (rowid, blob) per row, e.g. "SELECT rowid, embedding FROM chunks"; every BLOB of exactly
+ * row_bytes is copied to dst + i * row_bytes (dst: host memory, pinned or pageable, room for
+ * max_rows rows) and its rowid to rowids[i] (may be NULL).  The scan stops at the first row that
+ * is not a BLOB of that size (NULL, ragged width -- the reference skips or keeps such rows one by
+ * one) or at row max_rows: *uniform = 0 then, and the caller falls back to its row-by-row path;
+ * *uniform = 1 means the whole table was copied, *n_rows rows.  libsqlite3.so.0 is resolved at
+ * run time (ANR_ERR_UNSUPPORTED when it is absent). */
+int anr_sqlite_read_blobs(const char* db_path, const char* sql, void* dst, int64_t row_bytes,
+                          int64_t max_rows, int64_t* rowids, int64_t* n_rows, int32_t* uniform);
+
 #ifdef __cplusplus
 }
 #endif

@@ -257,6 +257,68 @@ def test_loader_streams_into_one_matrix_and_handles_ragged_tables(tmp_path):
     assert np.array_equal(np.stack(df2["embedding"].iloc[:10].values), emb[:10])
 
 
+def test_bulk_blob_loader_abi_and_paths(tmp_path, monkeypatch):
+    """anr_sqlite_read_blobs (host-only entry point) and the two loader paths:
+    a uniform table goes through it, odd tables fall back to the row-by-row loop, and both give
+    the frame the UNMODIFIED reference loader gives where it is mounted."""
+    import ctypes as C
+    pkg = importlib.import_module("a-nice-rag_b200")
+    native = pkg.native
+    n, d = 3000, 20
+    emb = synth.unit_vectors(n, d, seed=5)
+    srcs = synth.sources(n, seed=6)
+    ids = synth.chunk_ids(n, srcs)
+    db = str(tmp_path / "u.db")
+    synth.write_chunks_db(db, ids, [f"doc {i}" for i in range(n)], srcs, emb)
+
+    def read(sql, row_bytes, max_rows):
+        dst = np.zeros((max(max_rows, 1), row_bytes // 4), dtype=np.float32)
+        rowids = np.zeros(max(max_rows, 1), dtype=np.int64)
+        got, uniform = C.c_int64(), C.c_int32()
+        native.call("anr_sqlite_read_blobs", db.encode(), sql, dst.ctypes.data, row_bytes, max_rows,
+                    rowids.ctypes.data, C.byref(got), C.byref(uniform))
+        return dst, rowids, got.value, uniform.value
+
+    dst, rowids, got, uniform = read(b"SELECT rowid, embedding FROM chunks", d * 4, n)
+    assert (got, uniform) == (n, 1) and np.array_equal(dst, emb)
+    assert rowids.tolist() == list(range(1, n + 1))
+    assert read(b"SELECT rowid, embedding FROM chunks", d * 4, n - 1)[2:] == (n - 1, 0)   # table too long
+    assert read(b"SELECT rowid, embedding FROM chunks", d * 4 + 4, n)[2:] == (0, 0)        # other width
+    assert read(b"SELECT rowid, id FROM chunks", d * 4, n)[2:] == (0, 0)                   # not a BLOB
+    with pytest.raises(native.AnrError, match="sqlite3_prepare_v2"):
+        read(b"SELECT rowid, nothing FROM chunks", d * 4, n)
+    with pytest.raises(native.AnrError, match="rowid, blob"):
+        read(b"SELECT embedding FROM chunks", d * 4, n)
+
+    # the loader takes the bulk path for this table ...
+    calls = []
+    real = pkg.DatabaseManager._load_row_by_row
+    monkeypatch.setattr(pkg.DatabaseManager, "_load_row_by_row",
+                        lambda self, *a: calls.append(1) or real(self, *a))
+    df = pkg.DatabaseManager().load_embeddings_from_sql(db, "m")
+    assert not calls and list(df["id"]) == ids and np.array_equal(np.stack(df["embedding"].values), emb)
+    assert list(df["document"]) == [f"doc {i}" for i in range(n)] and list(df["source"]) == srcs
+    # ... and the row-by-row path when a row is odd (NULL embedding in the middle of the table)
+    db2 = str(tmp_path / "odd.db")
+    synth.write_chunks_db(db2, ids, [""] * n, srcs, emb, extra_rows=[("nul", "x", "CG1", None, "u")])
+    df2 = pkg.DatabaseManager().load_embeddings_from_sql(db2, "m")
+    assert calls and list(df2["id"]) == ids
+    if reference_available():
+        from oracle import reference_loader
+        ref = reference_loader.load_reference()
+        for path, ours in ((db, df), (db2, df2)):
+            rdf = ref.DatabaseManager().load_embeddings_from_sql(path, "m")
+            assert list(rdf.columns) == list(ours.columns) and len(rdf) == len(ours)
+            for col in ("id", "document", "source", "url"):
+                assert rdf[col].tolist() == ours[col].tolist()
+            assert all(np.array_equal(a, b) for a, b in zip(rdf["embedding"], ours["embedding"]))
+
+
+def reference_available() -> bool:
+    from oracle import reference_loader
+    return reference_loader.available()
+
+
 # ---------------------------------------------------------------------------------------
 # batched orchestrator: input validation and id space (no GPU needed)
 def test_retrieve_documents_batch_validates_like_the_reference(pkg):
