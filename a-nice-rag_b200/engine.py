@@ -10,6 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import re
 import threading
+from itertools import chain
 import weakref
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -200,31 +201,35 @@ def invert_okapi(bm25) -> Tuple[Dict[str, int], np.ndarray, np.ndarray, np.ndarr
     """
     vocab = {tok: i for i, tok in enumerate(bm25.idf.keys())}
     n_terms = len(vocab)
-    counts = np.zeros(n_terms, dtype=np.int64)
-    term_chunks: List[np.ndarray] = []
-    tf_chunks: List[np.ndarray] = []
-    doc_sizes = np.zeros(len(bm25.doc_freqs), dtype=np.int64)
-    get = vocab.__getitem__
-    for d, freqs in enumerate(bm25.doc_freqs):
-        m = len(freqs)
-        doc_sizes[d] = m
-        if m:
-            term_chunks.append(np.fromiter(map(get, freqs.keys()), dtype=np.int64, count=m))
-            tf_chunks.append(np.fromiter(freqs.values(), dtype=np.int64, count=m))
-    if term_chunks:
-        terms = np.concatenate(term_chunks)
-        tfs = np.concatenate(tf_chunks)
-    else:
-        terms = np.zeros(0, dtype=np.int64)
-        tfs = np.zeros(0, dtype=np.int64)
-    docs = np.repeat(np.arange(len(bm25.doc_freqs), dtype=np.int64), doc_sizes)
-    order = np.argsort(terms, kind="stable")      # stable: documents stay ascending per term
-    counts = np.bincount(terms, minlength=n_terms)
-    term_ptr = np.zeros(n_terms + 1, dtype=np.int64)
-    np.cumsum(counts, out=term_ptr[1:])
+    doc_freqs = bm25.doc_freqs
+    n_docs = len(doc_freqs)
+    doc_sizes = np.fromiter(map(len, doc_freqs), dtype=np.int64, count=n_docs)
+    total = int(doc_sizes.sum())
+    # one pass over all (document, term) pairs in document order: no per-document arrays
+    terms = np.fromiter(map(vocab.__getitem__, chain.from_iterable(doc_freqs)), dtype=np.int32,
+                        count=total)
+    tfs = np.fromiter(chain.from_iterable(map(dict.values, doc_freqs)), dtype=np.int32, count=total)
+    doc_ptr = np.zeros(n_docs + 1, dtype=np.int64)
+    np.cumsum(doc_sizes, out=doc_ptr[1:])
     idf = np.fromiter((bm25.idf[t] for t in vocab), dtype=np.float64, count=n_terms)
-    return (vocab, term_ptr, docs[order].astype(np.int32), tfs[order].astype(np.int32),
-            np.asarray(bm25.doc_len, dtype=np.int32), idf)
+    doc_len = np.asarray(bm25.doc_len, dtype=np.int32)
+    try:   # documents x terms (CSR) -> terms x documents: a linear-time, order-preserving transpose
+        from scipy import sparse
+        # (csr -> csc is a counting sort by column that keeps the row order inside a column and
+        # neither sorts nor merges entries; a dict cannot repeat a term anyway)
+        by_term = sparse.csr_matrix((tfs, terms, doc_ptr), shape=(n_docs, max(n_terms, 1))).tocsc()
+        term_ptr = by_term.indptr.astype(np.int64)[:n_terms + 1]
+        if n_terms == 0:
+            term_ptr = np.zeros(1, dtype=np.int64)
+        return (vocab, term_ptr, by_term.indices.astype(np.int32), by_term.data.astype(np.int32),
+                doc_len, idf)
+    except ImportError:
+        pass
+    docs = np.repeat(np.arange(n_docs, dtype=np.int32), doc_sizes)
+    order = np.argsort(terms, kind="stable")      # stable: documents stay ascending per term
+    term_ptr = np.zeros(n_terms + 1, dtype=np.int64)
+    np.cumsum(np.bincount(terms, minlength=n_terms), out=term_ptr[1:])
+    return vocab, term_ptr, docs[order], tfs[order], doc_len, idf
 
 
 class Bm25Index:
