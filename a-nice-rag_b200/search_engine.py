@@ -115,7 +115,7 @@ class SearchEngine:
         c = int(counts[0])
         rows, scores = rows[0, :c].astype(np.int64), scores[0, :c]
         pos = rows if positions_of is None else positions_of.get_indexer(rows)
-        result_df = df.iloc[pos].copy()
+        result_df = df.take(pos)      # = df.iloc[pos].copy() (:89, :137) without the second copy
         result_df["similarity"] = scores.astype(np.result_type(query_embedding.dtype, np.float32))
         return result_df
 
