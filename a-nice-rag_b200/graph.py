@@ -115,3 +115,82 @@ class HybridGraph:
     def search(self, queries, terms, offsets):
         self.load(queries, terms, offsets)
         return self.replay()
+
+
+class HybridPipeline:
+    """Host buffers in, host buffers out, ``depth`` batches in flight.
+
+    A synchronous call (``anr_hybrid_search`` with host pointers) returns when the results have
+    landed, so the GPU idles while the host stages the next batch: at batch 64 over 1M chunks
+    that is 0.69 ms per step against 0.63 ms of device time.  Here every slot owns a captured
+    step (``HybridGraph``), a stream and pinned host buffers; ``submit`` enqueues H2D copy ->
+    replay -> D2H copy on the slot's stream and returns at once, ``collect`` waits for the oldest
+    slot only.  Results are those of the eager call, bit for bit, in submission order.
+
+    EXPERIMENTAL: written at the end of round 1 after the GPU budget was spent; exercised only by
+    ``tests/test_gpu_zz_pipeline.py`` (opt-in) until it has run on a B200.
+    """
+
+    def __init__(self, dense: engine.DenseIndex, bm25: engine.Bm25Index, batch: int, max_terms: int,
+                 k_dense: int, k_bm25: int, w_dense: float, w_bm25: float, rrf_k: float,
+                 top_n: int, depth: int = 2, **graph_kwargs):
+        import torch
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.torch = torch
+        self.batch, self.max_terms = int(batch), int(max_terms)
+        dev = torch.device("cuda", dense.ctx_device)
+        self.slots = []
+        for _ in range(depth):
+            g = HybridGraph(dense, bm25, batch, max_terms, k_dense, k_bm25, w_dense, w_bm25, rrf_k,
+                            top_n, **graph_kwargs)
+            pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()  # noqa: E731
+            self.slots.append(dict(
+                graph=g, stream=torch.cuda.Stream(dev), done=torch.cuda.Event(),
+                q=pin(batch, dense.d, dtype=torch.float32), terms=pin(self.max_terms, dtype=torch.int32),
+                offsets=pin(batch + 1, dtype=torch.int32), n_terms=0,
+                ids=pin(batch, top_n, dtype=torch.int32), scores=pin(batch, top_n, dtype=torch.float64),
+                counts=pin(batch, dtype=torch.int32), busy=False))
+        self._next = 0          # slot the next submit uses
+        self._oldest = 0        # slot the next collect waits for
+        self._in_flight = 0
+
+    def submit(self, queries: np.ndarray, terms: np.ndarray, offsets: np.ndarray) -> None:
+        """Stages one batch (numpy arrays: [batch, d] fp32, CSR term ids int32, [batch + 1] offsets)
+        and enqueues it.  Call ``collect`` first when ``depth`` batches are already in flight."""
+        t = self.torch
+        if self._in_flight == len(self.slots):
+            raise RuntimeError("pipeline full: collect() the oldest batch first")
+        s = self.slots[self._next]
+        terms = np.ascontiguousarray(terms, dtype=np.int32).reshape(-1)
+        if terms.shape[0] > self.max_terms:
+            raise ValueError(f"{terms.shape[0]} query terms exceed the captured capacity {self.max_terms}")
+        # host-side staging into the slot's pinned buffers (plain memcpy)
+        s["q"].numpy()[...] = queries
+        s["terms"].numpy()[:terms.shape[0]] = terms
+        s["offsets"].numpy()[...] = offsets
+        s["n_terms"] = int(terms.shape[0])
+        g = s["graph"]
+        with t.cuda.stream(s["stream"]):
+            g.load(s["q"], s["terms"][:s["n_terms"]], s["offsets"])
+            g.replay()
+            s["ids"].copy_(g.ids, non_blocking=True)
+            s["scores"].copy_(g.scores, non_blocking=True)
+            s["counts"].copy_(g.counts, non_blocking=True)
+            s["done"].record(s["stream"])
+        s["busy"] = True
+        self._next = (self._next + 1) % len(self.slots)
+        self._in_flight += 1
+
+    def collect(self):
+        """Waits for the OLDEST batch in flight -> (ids [batch, top_n] int32, scores float64,
+        counts int32) as numpy views of the slot's pinned buffers, valid until that slot is
+        submitted to again (``depth`` submits later)."""
+        if self._in_flight == 0:
+            raise RuntimeError("nothing in flight")
+        s = self.slots[self._oldest]
+        s["done"].synchronize()
+        s["busy"] = False
+        self._oldest = (self._oldest + 1) % len(self.slots)
+        self._in_flight -= 1
+        return s["ids"].numpy(), s["scores"].numpy(), s["counts"].numpy()

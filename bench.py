@@ -555,6 +555,41 @@ def run_ours(args):
         except Exception as exc:   # never lose the headline line to the optional replay leg
             graph_rec = {"error": repr(exc)[:300]}
 
+    # ---- OPT-IN (ANR_BENCH_PIPELINE=1): host buffers in / out with two batches in flight
+    #      (graph.HybridPipeline, experimental until it has run on a B200) --------------------------
+    pipe_rec = None
+    if world == 1 and os.environ.get("ANR_BENCH_PIPELINE") == "1":
+        try:
+            graph_mod = importlib.import_module("a-nice-rag_b200.graph")
+            pipe = graph_mod.HybridPipeline(dense, bm25, B, N_TERMS * B, TOPK, TOPK, W_DENSE, W_BM25,
+                                            WRRF_K, TOPK, depth=2)
+            t_flat = t_host.reshape(-1)
+
+            def run_pipe(n_steps):
+                for i in range(n_steps):
+                    if i >= 2:
+                        pipe.collect()
+                    pipe.submit(q_host, t_flat, off_host)
+                last = None
+                for _ in range(min(2, n_steps)):
+                    last = pipe.collect()
+                return last
+            run_pipe(6)
+            step_device()
+            torch.cuda.synchronize()
+            last = run_pipe(3)
+            same = bool(np.array_equal(last[0], out_ids.cpu().numpy()) and
+                        np.array_equal(last[1], out_scores.cpu().numpy()))
+            n_it = max(args.steps, 50)
+            t0 = time.perf_counter()
+            run_pipe(n_it)
+            dt = time.perf_counter() - t0
+            pipe_rec = {"value": B * n_it / dt, "unit": "queries/s", "ms_per_step": 1e3 * dt / n_it,
+                        "depth": 2, "identical_to_eager": same,
+                        "timing": "host wall clock over the whole loop (every result read on the host)"}
+        except Exception as exc:
+            pipe_rec = {"error": repr(exc)[:300]}
+
     # ---- CPU baseline + parity of this very batch (N = 1) --------------------------------------
     cpu = None
     checked = 0
@@ -623,6 +658,7 @@ def run_ours(args):
                       "value": B * args.steps / (ms_filtered * 1e-3), "unit": "queries/s",
                       "ms_per_step": ms_filtered / args.steps} if ms_filtered else None),
         "cuda_graph": graph_rec,
+        "e2e_pipelined": pipe_rec,
         "clocks": clocks, "parity_checked_queries": checked,
     }
     if cpu:
