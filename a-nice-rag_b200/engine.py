@@ -11,6 +11,7 @@ import ctypes as C
 import re
 import threading
 from itertools import chain
+from operator import methodcaller
 import weakref
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -223,7 +224,8 @@ def invert_okapi(bm25) -> Tuple[Dict[str, int], np.ndarray, np.ndarray, np.ndarr
     # one pass over all (document, term) pairs in document order: no per-document arrays
     terms = np.fromiter(map(vocab.__getitem__, chain.from_iterable(doc_freqs)), dtype=np.int32,
                         count=total)
-    tfs = np.fromiter(chain.from_iterable(map(dict.values, doc_freqs)), dtype=np.int32, count=total)
+    tfs = np.fromiter(chain.from_iterable(map(methodcaller("values"), doc_freqs)), dtype=np.int32,
+                      count=total)
     doc_ptr = np.zeros(n_docs + 1, dtype=np.int64)
     np.cumsum(doc_sizes, out=doc_ptr[1:])
     idf = np.fromiter((bm25.idf[t] for t in vocab), dtype=np.float64, count=n_terms)
