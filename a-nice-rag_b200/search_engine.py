@@ -9,6 +9,8 @@ fallback: without the library the import fails, without a B200 the calls raise.
 """
 from __future__ import annotations
 
+import functools
+import inspect
 import logging
 from typing import Dict, Hashable, List, Optional, Sequence, Tuple
 
@@ -30,6 +32,35 @@ def _fatal(exc: BaseException) -> bool:
     a missing device / library is a deployment fault, not a bad query."""
     return isinstance(exc, ImportError) or (
         isinstance(exc, native.AnrError) and exc.code == 3)
+
+
+def _never_raises(empty, what: str):
+    """The reference's convention for its search methods (search_engine.py:94-98, :144-146,
+    :267-269, :291-293): log the error, hand back an empty result.  ``what`` may name the
+    ``model_name`` argument of the call.  Deployment faults (``_fatal``) pass through."""
+    def wrap(method):
+        params = inspect.signature(method)
+
+        @functools.wraps(method)
+        def guarded(self, *args, **kwargs):
+            try:
+                return method(self, *args, **kwargs)
+            except Exception as e:
+                if _fatal(e):
+                    raise
+                try:
+                    bound = params.bind(self, *args, **kwargs)
+                    bound.apply_defaults()
+                    label = what.format(**bound.arguments)
+                except Exception:
+                    label = what
+                self.logger.error(f"Error in {label}: {e}")
+                return empty()
+        return guarded
+    return wrap
+
+
+_NOTHING_LEFT = "No documents found after filtering by filename type: {}"
 
 
 class SearchEngine:
@@ -119,118 +150,77 @@ class SearchEngine:
         result_df["similarity"] = scores.astype(np.result_type(query_embedding.dtype, np.float32))
         return result_df
 
-    def similarity_search_with_embedding(
-        self,
-        query_embedding: np.ndarray,
-        df: pd.DataFrame,
-        model_name: str = "voyage-3-large",
-        similarity_k: int = 25,
-        filename_type_filter: Optional[str] = None,
-    ) -> pd.DataFrame:
-        """Similarity search with a pre-calculated dense embedding (:57-98)."""
-        try:
-            if df.empty:
-                self.logger.warning(
-                    f"No documents found after filtering by filename type: {filename_type_filter}"
-                )
-                return df
-            query_embedding = np.asarray(query_embedding)
-            query_embedding = (
-                query_embedding.reshape(1, -1) if query_embedding.ndim == 1 else query_embedding
-            )
-            result_df = self._dense_topk(query_embedding, df, similarity_k, filename_type_filter)
-            if result_df is None:
-                self.logger.warning(
-                    f"No documents found after filtering by filename type: {filename_type_filter}"
-                )
-                return df.iloc[0:0].copy()
-            return result_df
-        except Exception as e:
-            if _fatal(e):
-                raise
-            self.logger.error(
-                f"Error in {model_name} similarity search with precalculated embedding: {e}"
-            )
-            return pd.DataFrame()
+    @_never_raises(pd.DataFrame, "{model_name} similarity search with precalculated embedding")
+    def similarity_search_with_embedding(self, query_embedding: np.ndarray, df: pd.DataFrame,
+                                         model_name: str = "voyage-3-large", similarity_k: int = 25,
+                                         filename_type_filter: Optional[str] = None) -> pd.DataFrame:
+        """Top-``similarity_k`` rows of ``df`` by inner product with a ready-made query vector, best
+        first, plus a ``similarity`` column (search_engine.py:57-98)."""
+        if df.empty:
+            self.logger.warning(_NOTHING_LEFT.format(filename_type_filter))
+            return df
+        vector = np.asarray(query_embedding)
+        if vector.ndim == 1:
+            vector = vector.reshape(1, -1)
+        hits = self._dense_topk(vector, df, similarity_k, filename_type_filter)
+        if hits is None:
+            self.logger.warning(_NOTHING_LEFT.format(filename_type_filter))
+            return df.iloc[0:0].copy()
+        return hits
 
-    def similarity_search(
-        self,
-        query_text: str,
-        df: pd.DataFrame,
-        model_name: str = "voyage-3-large",
-        similarity_k: int = 25,
-        filename_type_filter: Optional[str] = None,
-        query_embedding: Optional[np.ndarray] = None,
-    ) -> pd.DataFrame:
-        """Similarity search; embeds the query unless an embedding is supplied (:100-146).
+    @_never_raises(pd.DataFrame, "{model_name} similarity search")
+    def similarity_search(self, query_text: str, df: pd.DataFrame, model_name: str = "voyage-3-large",
+                          similarity_k: int = 25, filename_type_filter: Optional[str] = None,
+                          query_embedding: Optional[np.ndarray] = None) -> pd.DataFrame:
+        """Same search from the query TEXT: the vector is the caller's, if given, else it is
+        requested from the embedding service (search_engine.py:100-146).
 
-        A Voyage-generated embedding is float64 in the reference (:157); it is cast to fp32
+        A vector that comes back from Voyage is float64 in the reference (:157); it is cast to fp32
         here (documented deviation, <= 1e-7 absolute on unit vectors).
         """
-        try:
-            if df.empty:
-                self.logger.warning(
-                    f"No documents found after filtering by filename type: {filename_type_filter}"
-                )
-                return df
-            if query_embedding is not None:
-                query_embedding = np.asarray(query_embedding).reshape(1, -1)
-                self.logger.info(f"Using provided pre-calculated {model_name} query embedding")
-            else:
-                query_embedding = self._generate_query_embedding(query_text, model_name)
-                self.logger.info(f"Generated new {model_name} query embedding")
-            result_df = self._dense_topk(query_embedding, df, similarity_k, filename_type_filter)
-            if result_df is None:
-                self.logger.warning(
-                    f"No documents found after filtering by filename type: {filename_type_filter}"
-                )
-                return df.iloc[0:0].copy()
-            self.logger.info(f"{model_name} similarity search found {len(result_df)} results")
-            return result_df
-        except Exception as e:
-            if _fatal(e):
-                raise
-            self.logger.error(f"Error in {model_name} similarity search: {e}")
-            return pd.DataFrame()
+        if df.empty:
+            self.logger.warning(_NOTHING_LEFT.format(filename_type_filter))
+            return df
+        if query_embedding is None:
+            vector = self._generate_query_embedding(query_text, model_name)
+            self.logger.info(f"Generated new {model_name} query embedding")
+        else:
+            vector = np.asarray(query_embedding).reshape(1, -1)
+            self.logger.info(f"Using provided pre-calculated {model_name} query embedding")
+        hits = self._dense_topk(vector, df, similarity_k, filename_type_filter)
+        if hits is None:
+            self.logger.warning(_NOTHING_LEFT.format(filename_type_filter))
+            return df.iloc[0:0].copy()
+        self.logger.info(f"{model_name} similarity search found {len(hits)} results")
+        return hits
 
     def _generate_query_embedding(self, query_text: str, model_name: str) -> np.ndarray:
-        """Network pass-through (Voyage HTTPS), unchanged in meaning from :148-159."""
-        if model_name == "voyage-3-large":
-            if not self.vo:
-                raise ValueError("Voyage client not available")
-            response = self.vo.embed(
-                query_text, input_type="query", model="voyage-3-large", output_dimension=2048
-            ).embeddings
-            return np.array(response).reshape(1, -1)
-        raise ValueError(f"Unsupported model: {model_name}")
+        """Embedding service call (Voyage HTTPS), outside the hot path and unchanged in meaning from
+        search_engine.py:148-159: one (1, 2048) row for ``voyage-3-large``, ValueError otherwise."""
+        if model_name != "voyage-3-large":
+            raise ValueError(f"Unsupported model: {model_name}")
+        if not self.vo:
+            raise ValueError("Voyage client not available")
+        reply = self.vo.embed(query_text, model=model_name, input_type="query", output_dimension=2048)
+        return np.array(reply.embeddings).reshape(1, -1)
 
-    def rerank_documents(
-        self,
-        query_text: str,
-        documents: List,
-        reranker_model: str = "rerank-2",
-        reranker_top_k: Optional[int] = None,
-    ) -> List:
-        """Network pass-through (Voyage rerank), same contract as :161-203."""
+    def rerank_documents(self, query_text: str, documents: List, reranker_model: str = "rerank-2",
+                         reranker_top_k: Optional[int] = None) -> List:
+        """Reranker service call (Voyage), outside the hot path; contract of search_engine.py
+        :161-203: the documents reordered with a ``rerank_score`` each, or the input unchanged when
+        the service fails."""
+        if not documents:
+            return documents
         try:
-            if not documents:
-                return documents
-            texts = [doc.get("document", "") for doc in documents]
+            passages = [d.get("document", "") for d in documents]
             self.logger.info(
-                f"Starting reranking with model '{reranker_model}' for {len(texts)} documents"
-            )
-            outcome = self.vo.rerank(
-                query=query_text, documents=texts, model=reranker_model,
-                top_k=reranker_top_k or len(texts), truncation=True,
-            )
-            reranked = [
-                {**documents[r.index], "rerank_score": r.relevance_score}
-                for r in outcome.results if r.index < len(documents)
-            ]
-            self.logger.info(
-                f"Reranking completed: {len(reranked)} documents reordered by relevance"
-            )
-            return reranked
+                f"Starting reranking with model '{reranker_model}' for {len(passages)} documents")
+            reply = self.vo.rerank(query=query_text, documents=passages, model=reranker_model,
+                                   top_k=reranker_top_k or len(passages), truncation=True)
+            ranked = [dict(documents[hit.index], rerank_score=hit.relevance_score)
+                      for hit in reply.results if hit.index < len(documents)]
+            self.logger.info(f"Reranking completed: {len(ranked)} documents reordered by relevance")
+            return ranked
         except Exception as e:
             self.logger.warning(f"Reranking failed, returning original order: {e}")
             return documents
@@ -261,49 +251,23 @@ class SearchEngine:
         _, docs, counts = index.search([terms], k, doc_mask=mask_words)
         return [bm25_section_ids[int(i)] for i in docs[0, :int(counts[0])]]
 
-    def bm25_search(
-        self,
-        query_text: str,
-        bm25,
-        bm25_sections,
-        bm25_section_ids,
-        similarity_k: int = 25,
-        filename_type_filter: Optional[str] = None,
-        use_lemmatized: bool = True,
-    ) -> List[str]:
-        """BM25 search with preprocessing of the query text (:245-269)."""
-        try:
-            query_tokens = preprocess_text(query_text, use_lemmatization=use_lemmatized)
-            return self._core_bm25_search(
-                query_tokens, bm25, bm25_sections, bm25_section_ids, similarity_k,
-                filename_type_filter,
-            )
-        except Exception as e:
-            if _fatal(e):
-                raise
-            self.logger.error(f"Error in BM25 search: {e}")
-            return []
+    @_never_raises(list, "BM25 search")
+    def bm25_search(self, query_text: str, bm25, bm25_sections, bm25_section_ids,
+                    similarity_k: int = 25, filename_type_filter: Optional[str] = None,
+                    use_lemmatized: bool = True) -> List[str]:
+        """BM25 top-k section ids for a query TEXT (tokenised like the index was;
+        search_engine.py:245-269)."""
+        tokens = preprocess_text(query_text, use_lemmatization=use_lemmatized)
+        return self._core_bm25_search(tokens, bm25, bm25_sections, bm25_section_ids, similarity_k,
+                                      filename_type_filter)
 
-    def bm25_search_preprocessed(
-        self,
-        query_tokens: List[str],
-        bm25,
-        bm25_sections,
-        bm25_section_ids,
-        similarity_k: int = 25,
-        filename_type_filter: Optional[str] = None,
-    ) -> List[str]:
-        """BM25 search over already tokenised queries (:271-293)."""
-        try:
-            return self._core_bm25_search(
-                query_tokens, bm25, bm25_sections, bm25_section_ids, similarity_k,
-                filename_type_filter,
-            )
-        except Exception as e:
-            if _fatal(e):
-                raise
-            self.logger.error(f"Error in preprocessed BM25 search: {e}")
-            return []
+    @_never_raises(list, "preprocessed BM25 search")
+    def bm25_search_preprocessed(self, query_tokens: List[str], bm25, bm25_sections, bm25_section_ids,
+                                 similarity_k: int = 25,
+                                 filename_type_filter: Optional[str] = None) -> List[str]:
+        """BM25 top-k section ids for an already tokenised query (search_engine.py:271-293)."""
+        return self._core_bm25_search(query_tokens, bm25, bm25_sections, bm25_section_ids,
+                                      similarity_k, filename_type_filter)
 
     # ------------------------------------------------------------------ batched extension
     def hybrid_search_batch(

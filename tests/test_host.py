@@ -314,6 +314,35 @@ def test_bulk_blob_loader_abi_and_paths(tmp_path, monkeypatch):
             assert all(np.array_equal(a, b) for a, b in zip(rdf["embedding"], ours["embedding"]))
 
 
+def test_config_values_equal_the_reference_module(pkg):
+    """Every public value of the reference's src/config.py (weights, every SourceConfig field,
+    enum members, the ValueError text) against the product's config."""
+    if not reference_available():
+        pytest.skip("reference sources not mounted")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_config", "/root/reference/src/config.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    ours = pkg.config
+    assert ours.Config.DEFAULT_MODEL_WEIGHTS == ref.Config.DEFAULT_MODEL_WEIGHTS
+    assert list(ours.Config.DEFAULT_MODEL_WEIGHTS) == list(ref.Config.DEFAULT_MODEL_WEIGHTS)
+    assert [(m.name, m.value) for m in ours.InfoSource] == [(m.name, m.value) for m in ref.InfoSource]
+    fields = ("db_path", "bm25_path", "context_description", "not_found_message", "voyage_db_path",
+              "voyage_3_5_db_path", "openai_db_path", "qwen_db_path")
+    for member in ref.InfoSource:
+        theirs = ref.Config.get_source_config(member.value.upper())
+        mine = ours.Config.get_source_config(member.value.upper())
+        assert [getattr(mine, f) for f in fields] == [getattr(theirs, f) for f in fields]
+    assert ours.SourceConfig("a.db", "b.pkl", "c", "d").voyage_db_path == \
+        ref.SourceConfig("a.db", "b.pkl", "c", "d").voyage_db_path == "a.db"
+    for bad in ("nope", "NICE "):
+        with pytest.raises(ValueError) as e_ref:
+            ref.Config.get_source_config(bad)
+        with pytest.raises(ValueError) as e_ours:
+            ours.Config.get_source_config(bad)
+        assert str(e_ours.value) == str(e_ref.value)
+
+
 def reference_available() -> bool:
     from oracle import reference_loader
     return reference_loader.available()
