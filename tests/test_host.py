@@ -379,3 +379,27 @@ def test_batch_id_space_is_first_seen_first_and_shared():
     b = space.codes(["z", "w", "y"])
     assert a.tolist() == [0, 1, 0, 2] and b.tolist() == [2, 3, 1]
     assert space.names == ["x", "y", "z", "w"]
+
+
+def test_reference_arm_contract_under_torchrun(tmp_path):
+    """`bench.py --impl reference` launched like the driver launches it for N > 1: rank 0 alone
+    runs the CPU port and prints ONE JSON line carrying the reference-arm keys; the other rank
+    exits 0 without work.  (Tiny corpus: this checks the contract, not the number.)"""
+    import json
+    import subprocess
+    port = 29600 + (os.getpid() % 300)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+           "--impl", "reference", "--gpus", "2", "--chunks", "4000", "--steps", "2", "--warmup", "1"]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "reference" and rec["n_gpus"] == 2 and rec["steps"] == 2
+    assert rec["metric"].startswith("hybrid queries/sec") and rec["unit"] == "queries/s"
+    assert rec["higher_is_better"] is True and rec["value"] > 0
+    assert rec["cpu_baseline"]["kind"] == "port" and rec["cpu_baseline"]["cores"] >= 1
+    assert rec["e2e"] == {"value": rec["value"], "unit": "queries/s", "h2d_bytes_per_step": 0,
+                          "d2h_bytes_per_step": 0}
+    assert rec["config"]["batch"] == 64 and "4000 chunks" in rec["config"]["workload"]
