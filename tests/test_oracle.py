@@ -334,3 +334,24 @@ def test_committed_golden_is_what_the_reference_produces_today(small_case, tmp_p
             assert got.tolist() == want.tolist(), name
         else:
             np.testing.assert_array_equal(got, want, err_msg=name)
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="reference sources not mounted")
+def test_committed_config0_golden_is_what_the_reference_produces_today(config0_golden, tmp_path):
+    """BASELINE configs[0] (20k chunks x 1024-d, 100 queries, filters None and "CG, NG") through the
+    UNMODIFIED reference again: every stored array of tests/golden/config0_outputs.npz comes out
+    bit for bit (the GPU suite checks the drop-in classes against exactly these arrays)."""
+    from oracle import make_golden
+    case = make_golden.config0_inputs()
+    np.testing.assert_allclose(make_golden.checksum(case), config0_golden["input_checksum"], rtol=1e-12)
+    out = make_golden.run_reference(case, ks=(10,), filters=(None, "CG, NG"), tmpdir=str(tmp_path))
+    out.pop("bm25_all_scores")
+    assert set(out) | {"input_checksum"} == set(config0_golden)
+    for name, got in out.items():
+        want = config0_golden[name]
+        got = np.asarray(got)
+        assert got.shape == want.shape, name
+        if want.dtype == object:
+            assert got.tolist() == want.tolist(), name
+        else:
+            np.testing.assert_array_equal(got, want, err_msg=name)
