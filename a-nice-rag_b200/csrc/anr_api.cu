@@ -585,7 +585,7 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
         return fail(ANR_ERR_UNSUPPORTED, "bm25 tile does not fit in shared memory");
       r.stride = static_cast<int64_t>(r.plan.n_tiles) * k;
       r.cand = arena.take<uint64_t>(static_cast<size_t>(nq) * r.stride);
-      r.theta = arena.take<float>(static_cast<size_t>(nq));
+      r.theta = arena.take<float>(static_cast<size_t>(nq) + kBm25CounterSlots);   // + work counters
       // safe dynamic pruning over the dense rows of the head terms (corpora of 8192+ documents)
       const bool no_prune = getenv("ANR_DISABLE_BM25_PRUNE") != nullptr;
       r.hd = Bm25HeadView();

@@ -105,13 +105,15 @@ __device__ __forceinline__ uint64_t kth_of_thread_bests(uint64_t best, int k, ui
   return block_kth_of_thread_bests<kBm25Threads / 32>(best, k, tbest, s_out);
 }
 
+// One (tile, query) work item.  bx / by are the block coordinates of the item in the grid the
+// classic kernel would have been launched with (bx fastest): the classic kernel passes blockIdx,
+// the persistent one the coordinates of the item it pulled from the work counter.
 template <bool EMIT_ALL, bool PRUNE>
-__global__ void __launch_bounds__(kBm25Threads)
-bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_terms,
-                  const int32_t* __restrict__ q_offsets, int k,
-                  const uint32_t* __restrict__ doc_mask, int tile_docs, int list_cap,
-                  uint64_t* __restrict__ out, int64_t out_stride_q, float* __restrict__ theta_g,
-                  int tile_stride, int n_sampled) {
+__device__ __forceinline__ void
+bm25_tile_item(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* __restrict__ q_terms,
+               const int32_t* __restrict__ q_offsets, int k, const uint32_t* __restrict__ doc_mask,
+               int tile_docs, int list_cap, uint64_t* __restrict__ out, int64_t out_stride_q,
+               float* __restrict__ theta_g, int tile_stride, int n_sampled, int bx, int by) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* acc = reinterpret_cast<float*>(smem);
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(tile_docs) * 4);
@@ -133,15 +135,15 @@ bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_te
   // against it.  n_sampled <= 0: grid = (tiles, queries), natural order.
   int tile, q;
   if (n_sampled == -2) {          // separate sample launch: every tile_stride-th tile
-    tile = blockIdx.x * tile_stride;
-    q = blockIdx.y;
+    tile = bx * tile_stride;
+    q = by;
   } else if (n_sampled < -2) {    // main launch after a separate sample launch: skip its tiles
-    tile = blockIdx.x;
-    q = blockIdx.y;
+    tile = bx;
+    q = by;
     if (tile % tile_stride == 0) return;
   } else if (n_sampled > 0) {
-    q = blockIdx.x;
-    const int y = blockIdx.y;
+    q = bx;
+    const int y = by;
     if (y < n_sampled) {
       tile = y * tile_stride;
     } else {
@@ -149,8 +151,8 @@ bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_te
       tile = j + j / (tile_stride - 1) + 1;   // the j-th tile that is not a multiple of tile_stride
     }
   } else {
-    tile = blockIdx.x;
-    q = blockIdx.y;
+    tile = bx;
+    q = by;
   }
   const int d0 = tile * tile_docs;
   const int d1 = min(ix.n_docs, d0 + tile_docs);
@@ -516,11 +518,88 @@ bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_te
 }
 
 template <bool EMIT_ALL, bool PRUNE>
+__global__ void __launch_bounds__(kBm25Threads)
+bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_terms,
+                  const int32_t* __restrict__ q_offsets, int k,
+                  const uint32_t* __restrict__ doc_mask, int tile_docs, int list_cap,
+                  uint64_t* __restrict__ out, int64_t out_stride_q, float* __restrict__ theta_g,
+                  int tile_stride, int n_sampled) {
+  bm25_tile_item<EMIT_ALL, PRUNE>(ix, hd, q_terms, q_offsets, k, doc_mask, tile_docs, list_cap, out,
+                                  out_stride_q, theta_g, tile_stride, n_sampled, blockIdx.x,
+                                  blockIdx.y);
+}
+
+// EXPERIMENTAL (ANR_BM25_PERSISTENT=<CTAs per SM>, not yet run on a GPU): the same items pulled
+// from a work counter by a grid that is resident from its first cycle.  Nothing is launched
+// behind another kernel's back, so the scan can share SMs with the dense main kernel whatever the
+// launch order, and two batches can be in flight.  Items are
+// taken in the order the hardware would have dispatched the classic grid (bx fastest).
+template <bool PRUNE>
+__global__ void __launch_bounds__(kBm25Threads)
+bm25_score_persistent_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_terms,
+                             const int32_t* __restrict__ q_offsets, int k,
+                             const uint32_t* __restrict__ doc_mask, int tile_docs, int list_cap,
+                             uint64_t* __restrict__ out, int64_t out_stride_q,
+                             float* __restrict__ theta_g, int tile_stride, int n_sampled, int gx,
+                             int gy, int* __restrict__ work_counter) {
+  __shared__ int s_item;
+  const int n_items = gx * gy;
+  for (;;) {
+    __syncthreads();   // the previous item's shared memory is no longer read
+    if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= n_items) return;
+    bm25_tile_item<false, PRUNE>(ix, hd, q_terms, q_offsets, k, doc_mask, tile_docs, list_cap, out,
+                                 out_stride_q, theta_g, tile_stride, n_sampled, item % gx, item / gx);
+  }
+}
+
+// CTAs per SM of the experimental persistent grid (0 = classic launches)
+static int bm25_persistent_ctas() {
+  static const int v = getenv("ANR_BM25_PERSISTENT") ? atoi(getenv("ANR_BM25_PERSISTENT")) : 0;
+  return v > 0 && v <= 16 ? v : 0;
+}
+static int bm25_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
+      n = 148;
+  }
+  return n;
+}
+
+// One classic grid (gx, gy) of items through the persistent kernel.
+template <bool PRUNE>
+static void launch_persistent(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* q_terms,
+                              const int32_t* q_offsets, int k, const uint32_t* doc_mask,
+                              const Bm25Plan& plan, uint64_t* out, int64_t out_stride_q, float* theta,
+                              int tile_stride, int n_sampled, int gx, int gy, int* counter,
+                              cudaStream_t stream) {
+  auto kern = bm25_score_persistent_kernel<PRUNE>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       cudaSharedmemCarveoutMaxShared);
+  const long long items = static_cast<long long>(gx) * gy;
+  const long long resident = static_cast<long long>(bm25_sm_count()) * bm25_persistent_ctas();
+  const unsigned grid = static_cast<unsigned>(items < resident ? items : resident);
+  kern<<<grid, kBm25Threads, plan.smem_bytes, stream>>>(ix, hd, q_terms, q_offsets, k, doc_mask,
+                                                        plan.tile_docs, plan.list_cap, out,
+                                                        out_stride_q, theta, tile_stride, n_sampled,
+                                                        gx, gy, counter);
+}
+
+// counters: two zeroed ints behind the theta array (sample launch, main launch), or null.
+template <bool EMIT_ALL, bool PRUNE>
 static cudaError_t launch_score_t(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* q_terms,
                                   const int32_t* q_offsets, int nq, int k,
                                   const uint32_t* doc_mask, const Bm25Plan& plan, uint64_t* out,
-                                  int64_t out_stride_q, float* theta, cudaStream_t stream) {
+                                  int64_t out_stride_q, float* theta, cudaStream_t stream,
+                                  int* counters = nullptr) {
   if (plan.n_tiles < 1 || nq < 1) return cudaSuccess;
+  const bool persistent = !EMIT_ALL && PRUNE && counters && bm25_persistent_ctas() > 0 && nq <= 65535;
   auto kern = bm25_score_kernel<EMIT_ALL, PRUNE>;
   cudaError_t e =
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
@@ -542,6 +621,17 @@ static cudaError_t launch_score_t(const Bm25View& ix, const Bm25HeadView& hd, co
       // folded single launch below is ~8 % faster.
       const int stride = 16;
       dim3 grid_s((plan.n_tiles + stride - 1) / stride, nb);
+      if constexpr (!EMIT_ALL && PRUNE) {
+        if (persistent) {
+          if (plan.phase != 2)
+            launch_persistent<true>(ix, hd, q_terms, q_offsets, k, doc_mask, plan, out, out_stride_q,
+                                    theta, stride, -2, grid_s.x, nb, counters, stream);
+          if (plan.phase != 1)
+            launch_persistent<true>(ix, hd, q_terms, q_offsets, k, doc_mask, plan, out, out_stride_q,
+                                    theta, stride, -3, grid.x, nb, counters + 1, stream);
+          continue;
+        }
+      }
       if (plan.phase != 2)
         kern<<<grid_s, kBm25Threads, plan.smem_bytes, stream>>>(
             ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
@@ -557,6 +647,13 @@ static cudaError_t launch_score_t(const Bm25View& ix, const Bm25HeadView& hd, co
       const int stride = 16;
       const int n_sampled = (plan.n_tiles + stride - 1) / stride;
       dim3 grid_f(nb, plan.n_tiles);
+      if constexpr (!EMIT_ALL && PRUNE) {
+        if (persistent) {
+          launch_persistent<true>(ix, hd, q_terms, q_offsets, k, doc_mask, plan, out, out_stride_q,
+                                  theta, stride, n_sampled, nb, plan.n_tiles, counters, stream);
+          continue;
+        }
+      }
       kern<<<grid_f, kBm25Threads, plan.smem_bytes, stream>>>(
           ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
           out + q0 * out_stride_q, out_stride_q, theta + q0, stride, n_sampled);
@@ -575,12 +672,14 @@ cudaError_t launch_bm25_score_topk(const Bm25View& ix, const Bm25HeadView* hd, c
                                    int64_t cand_stride_q, float* theta, cudaStream_t stream) {
   if (k < 1 || k > kMaxFusedK) return cudaErrorInvalidValue;
   if (hd && hd->n_head > 0) {
+    // theta is [nq] floats followed by kBm25CounterSlots ints of work counters (anr_api.cu)
     if (theta && plan.phase != 2) {
-      cudaError_t e = cudaMemsetAsync(theta, 0, static_cast<size_t>(nq) * 4, stream);
+      cudaError_t e = cudaMemsetAsync(theta, 0, static_cast<size_t>(nq + kBm25CounterSlots) * 4, stream);
       if (e != cudaSuccess) return e;
     }
     return launch_score_t<false, true>(ix, *hd, q_terms, q_offsets, nq, k, doc_mask, plan, cand,
-                                       cand_stride_q, theta, stream);
+                                       cand_stride_q, theta, stream,
+                                       theta ? reinterpret_cast<int*>(theta + nq) : nullptr);
   }
   return launch_score_t<false, false>(ix, Bm25HeadView(), q_terms, q_offsets, nq, k, doc_mask, plan,
                                       cand, cand_stride_q, nullptr, stream);

@@ -134,6 +134,7 @@ struct Bm25View {
 // bounds what the head terms can still add, and completes the score of the few documents that
 // can still reach the tile's k-th best (MaxScore-style pruning; results are unchanged).
 constexpr int kBm25MaxHead = 128;
+constexpr int kBm25CounterSlots = 8;   // ints of work counters kept behind a search's theta array
 struct Bm25HeadView {
   const uint8_t* slot_of = nullptr;   // [n_terms] head slot of a term, 0xff = not a head term
   const float* head_w = nullptr;      // [n_head][head_ld]

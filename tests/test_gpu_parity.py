@@ -341,6 +341,30 @@ def test_dropin_config0_vs_reference_golden(config0_golden, tmp_path):
             want = retrieval.weighted_rrf(
                 [(res["id"].tolist(), "voyage-3-large"), (hits, "BM25")], WEIGHTS, WRRF_K)
             assert fused == want
+            if q % 9 == 0:
+                # the two text-taking wrappers (search_engine.py:100-146 with the caller's vector,
+                # the reshape(1, -1) branch :121-123 from a 1-D and from a (1, D) array; :245-269
+                # through the tokeniser, with and without lemmatisation: "t123"-style tokens are
+                # fixed points of both) against the same goldens
+                for vec in (case["queries"][q], case["queries"][q].reshape(1, -1)):
+                    res2 = se.similarity_search("ignored text", df, "voyage-3-large", 10, flt,
+                                                query_embedding=vec)
+                    assert res2["id"].tolist() == res["id"].tolist()
+                    assert np.array_equal(res2["similarity"].to_numpy(), res["similarity"].to_numpy())
+                    assert list(res2.columns) == list(res.columns)
+                text = " ".join(toks).upper() + " ?"
+                for lemmatised in (False, True):
+                    hits2 = se.bm25_search(text, bm25, sections, section_ids, 10, flt,
+                                           use_lemmatized=lemmatised)
+                    check_ids_only([row_of[c] for c in hits2],
+                                   config0_golden[f"bm25_ids_{t}_k10"][q], all_scores,
+                                   f"dropin bm25_search(text) q{q} {flt}")
+                    assert hits2 == hits
+    # without a vector and without a Voyage client the text search logs and returns an empty frame
+    # (search_engine.py:125 -> :148-159 raises, :144-146 returns pd.DataFrame())
+    assert se.similarity_search("some text", df, "voyage-3-large", 10).empty
+    assert se.bm25_search("", bm25, sections, section_ids, 10) == []
+    assert se.bm25_search("the of and 12", bm25, sections, section_ids, 10) == []   # stop-words only
     # batched extension == per-query calls
     qs = list(range(0, 16))
     batch = se.hybrid_search_batch(case["queries"][qs],
