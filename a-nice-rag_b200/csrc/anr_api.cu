@@ -227,6 +227,21 @@ __global__ void set_i32_pair_kernel(int32_t* out, int32_t a, int32_t b) {
   out[0] = a;
   out[1] = b;
 }
+// A query WITHOUT terms has no BM25 result at all: the reference returns [] for an empty token list
+// (src/search_engine.py:216-217) before any scoring, whereas scoring nothing would rank the first k
+// documents with score 0.  (A non-empty list of unknown tokens does get that zero-score ranking.)
+__global__ void bm25_clear_empty_queries_kernel(const int32_t* __restrict__ q_offsets, int nq, int k,
+                                                TopkOut out) {
+  const int q = blockIdx.x;
+  if (q >= nq || q_offsets[q + 1] != q_offsets[q]) return;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const int64_t at = q * out.stride_q + i;
+    if (out.keys) out.keys[at] = 0ull;
+    if (out.scores) out.scores[at] = 0.f;
+    if (out.ids) out.ids[at] = -1;
+  }
+  if (threadIdx.x == 0 && out.counts) out.counts[q * out.count_stride] = 0;
+}
 // BM25 results carry document ids in their own space: translate them to row ids of the
 // dense index' space before fusion (done by TopkOut::id_map), nothing else needed here.
 
@@ -539,7 +554,9 @@ int bm25_ensure_heads(const anr_bm25* ix, cudaStream_t stream) {
 size_t bm25_ws_bytes(const anr_ctx* ctx, const anr_bm25* ix, int nq, int k) {
   if (k <= kMaxFusedK) {
     const Bm25Plan plan = bm25_make_plan(ctx->dp, ix->n_docs, nq, k, false);
-    return padded(static_cast<size_t>(nq) * plan.n_tiles * k * 8) + padded(static_cast<size_t>(nq) * 4) + 512;
+    const size_t slots = static_cast<size_t>(std::max(plan.n_tiles, plan.n_runs + plan.n_sampled));
+    return padded(static_cast<size_t>(nq) * slots * k * 8) +
+           padded((static_cast<size_t>(nq) + kBm25CounterSlots) * 4) + 512;
   }
   const int64_t n_pow2 = next_pow2(std::max(ix->n_docs, 2));
   return padded(static_cast<size_t>(std::min(nq, 8)) * n_pow2 * 8) + 256;
@@ -555,6 +572,12 @@ Bm25View bm25_view(const anr_bm25* ix) {
   v.n_docs = ix->n_docs;
   v.nnz = ix->nnz;
   return v;
+}
+
+cudaError_t bm25_clear_empty_queries(const int32_t* offsets_dev, int nq, int k, const TopkOut& out,
+                                     cudaStream_t stream) {
+  bm25_clear_empty_queries_kernel<<<nq, 32, 0, stream>>>(offsets_dev, nq, k, out);
+  return cudaGetLastError();
 }
 
 // State of a BM25 top-k scan issued in two phases around the dense pass of a hybrid query.
@@ -583,9 +606,6 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
       r.plan.beside_dense = beside_dense || ctx->beside_dense;
       if (r.plan.smem_bytes > ctx->dp.max_smem_optin)
         return fail(ANR_ERR_UNSUPPORTED, "bm25 tile does not fit in shared memory");
-      r.stride = static_cast<int64_t>(r.plan.n_tiles) * k;
-      r.cand = arena.take<uint64_t>(static_cast<size_t>(nq) * r.stride);
-      r.theta = arena.take<float>(static_cast<size_t>(nq) + kBm25CounterSlots);   // + work counters
       // safe dynamic pruning over the dense rows of the head terms (corpora of 8192+ documents)
       const bool no_prune = getenv("ANR_DISABLE_BM25_PRUNE") != nullptr;
       r.hd = Bm25HeadView();
@@ -597,6 +617,13 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
         r.hd.head_ld = ix->head_ld;
         r.hd.n_head = ix->n_head;
       }
+      // pruned scans go run by run (one candidate slot per run and per sample tile)
+      r.plan.use_runs = r.hd.n_head > 0 && bm25_runs_enabled() &&
+                        r.plan.run_smem_bytes <= ctx->dp.max_smem_optin;
+      r.stride = static_cast<int64_t>(r.plan.use_runs ? r.plan.n_runs + r.plan.n_sampled
+                                                      : r.plan.n_tiles) * k;
+      r.cand = arena.take<uint64_t>(static_cast<size_t>(nq) * r.stride);
+      r.theta = arena.take<float>(static_cast<size_t>(nq) + kBm25CounterSlots);   // + work counters
       r.active = true;
     }
     Bm25Plan plan = r.plan;
@@ -617,6 +644,7 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
     }
     const int m = static_cast<int>(stride);
     ANR_CUDA(launch_topk_final(cand, stride, m, m, 0, nq, k, out, stream));
+    ANR_CUDA(bm25_clear_empty_queries(offsets_dev, nq, k, out, stream));
     return ANR_OK;
   }
   if (phase == 1) return ANR_OK;   // the full-ranking path has no sample launch
@@ -638,6 +666,7 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
     if (o.counts) o.counts += q0 * out.count_stride;
     ANR_CUDA(launch_emit_sorted(keys, n_pow2, n_pow2, real, k, o, stream));
   }
+  ANR_CUDA(bm25_clear_empty_queries(offsets_dev, nq, k, out, stream));
   return ANR_OK;
 }
 
@@ -913,6 +942,19 @@ int anr_dense_set_shadow(anr_dense* index, int32_t enable) {
   std::lock_guard<std::mutex> lock(index->lazy);
   index->want_shadow = enable != 0;
   if (!enable && index->shadow) {
+    ANR_CUDA(cudaDeviceSynchronize());
+    cudaFree(index->shadow);
+    index->shadow = nullptr;
+  }
+  return ANR_OK;
+}
+
+int anr_dense_invalidate(anr_dense* index) {
+  if (!index) return fail(ANR_ERR_INVALID, "index is NULL");
+  DeviceGuard guard(index->device);
+  std::lock_guard<std::mutex> lock(index->lazy);
+  index->norm_valid = false;
+  if (index->shadow) {   // rebuilt from the current rows by the next tensor-core search
     ANR_CUDA(cudaDeviceSynchronize());
     cudaFree(index->shadow);
     index->shadow = nullptr;
@@ -1384,13 +1426,12 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
   ob.counts = lens + 1;
   ob.id_map = doc_to_id;
   // BM25 always runs on the side stream next to the dense pass.  The CUDA-core scan leaves ~90 KB
-  // of shared memory per SM free, so BM25 CTAs co-reside with it; the tensor-core passes fill the
-  // SM, there the gain is that the latency-bound ends of one pipeline (BM25's sample launch, the
-  // dense pass' threshold / rescoring / fallback kernels) run under the other's main kernel
-  // (measured at batch 64: 0.749 -> 0.656 ms per step).  ANR_HYBRID_OVERLAP=0 serialises them.
-  // (Tried and dropped: capping the 64-query GEMM ring at 4-6 stages so that two BM25 CTAs fit
-  // beside it, dense first, low-priority side stream -- the block scheduler keeps refilling the
-  // SMs with BM25 CTAs and the persistent dense CTAs still start only when that queue drains.)
+  // of shared memory per SM free, so BM25 CTAs co-reside with it; the 64-query GEMM pass of a
+  // hybrid step runs with a 4-stage ring for the same reason (gemm_ring_cap, anr_dense_gemm.cu):
+  // three BM25 CTAs share every SM with the dense CTA.  The wider tensor-core passes fill the SM;
+  // there the gain is that the latency-bound ends of one pipeline (BM25's sample launch, the dense
+  // pass' threshold / rescoring / fallback kernels) run under the other's main kernel.
+  // ANR_HYBRID_OVERLAP=0 serialises the two pipelines.
   static const int overlap_env = getenv("ANR_HYBRID_OVERLAP") ? atoi(getenv("ANR_HYBRID_OVERLAP")) : -1;
   const bool overlap = overlap_env != 0;
   cudaStream_t bm25_stream = overlap ? ctx->side : stream;

@@ -617,15 +617,21 @@ int dense_gemm_padded_queries(int nq) {
 }
 
 // b_rows: query rows each CTA holds per slab (nq_block, or nq_block / 2 under cta_group::2)
+// epilogue warps a launch group of nq_block-query tiles runs with (one or two per TMEM quadrant)
+static int gemm_epi_warps(int nq_block) {
+  static const int epi_env = getenv("ANR_GEMM_EPI_WARPS") ? atoi(getenv("ANR_GEMM_EPI_WARPS")) : 0;
+  return epi_env == 4 || epi_env == 8 ? epi_env : (nq_block >= 128 ? 8 : 4);
+}
+
 static bool make_gemm_layout(const DeviceProps& dp, int ld, bool bf16, int b_rows, int nq_pad,
-                             GemmLayout* L, int ring_cap = 0) {
+                             GemmLayout* L, int ring_cap = 0, int n_epi = kGmEpiWarps) {
   const int slab = bf16 ? 64 : 32;
   if (ld % slab != 0) return false;
   L->n_slabs = ld / slab;
   L->stage_bytes = kGmABytes + b_rows * 128;
   const int thr_bytes = nq_pad * 4;
   const int bar_bytes = (2 * kGmMaxStages + 4) * 8 + 16;
-  const int stage_bytes = kGmEpiWarps * static_cast<int>(sizeof(GemmStage));
+  const int stage_bytes = n_epi * static_cast<int>(sizeof(GemmStage));   // one staging buffer per warp
   const int avail =
       dp.max_smem_optin - 1024 /* alignment slack */ - thr_bytes - stage_bytes - bar_bytes - 256;
   int n_stages = avail / L->stage_bytes;
@@ -779,8 +785,7 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
   const int64_t gstride = sample_tiles * 4;
   const int nq_pad = n_qblocks * NQ;
   // two epilogue warps per quadrant once a tile has enough 32-column chunks to share
-  static const int epi_env = getenv("ANR_GEMM_EPI_WARPS") ? atoi(getenv("ANR_GEMM_EPI_WARPS")) : 0;
-  const int n_epi = epi_env == 4 || epi_env == 8 ? epi_env : (NQ >= 128 ? 8 : 4);
+  const int n_epi = gemm_epi_warps(NQ);
   const int threads = 64 + 32 * n_epi;
   const int mode = gemm_mode(dp, NQ, n_tiles);
   const bool pair = mode == 1;
@@ -828,18 +833,18 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
-// Ring depth cap of one launch group.  ANR_GEMM_MAX_STAGES=n caps every GEMM launch (profiling);
-// ANR_GEMM_BESIDE_STAGES=n caps only the launches of a hybrid step whose BM25 scan runs beside the
-// main kernel (64-query bf16 tiles, 16+ queries): with a 4-stage ring (96 KB) three 34 KB BM25
-// CTAs fit next to the dense CTA on every SM, and the two main kernels -- one HBM-bound, one
-// issue-bound -- overlap instead of following each other.  Measured on 1M x 1024 + 1M docs, batch
-// 64 (profiles/r1_bench_1gpu_coresident_ring{4,3}.json): 0.630 -> 0.576 / 0.567 ms per step, the
-// dense kernel stretching from 0.313 to 0.40 ms; batch-1 loses 3 %, hence the 16-query floor.
-// Default 0 (off) until the whole GPU suite has run with it.
+// Ring depth cap of one launch group.  ANR_GEMM_MAX_STAGES=n caps every GEMM launch (profiling).
+// ANR_GEMM_BESIDE_STAGES=n (default 4, 0 = off) caps the launches of a hybrid step whose BM25 scan
+// runs beside the main kernel (64-query bf16 tiles, 16+ queries): with a 4-stage ring (96 KB)
+// three BM25 CTAs fit next to the dense CTA on every SM, and the two main kernels -- one HBM-bound,
+// one issue-bound -- overlap instead of following each other.  Measured on 1M x 1024 + 1M docs,
+// batch 64: 0.629 -> 0.563 ms per step (round 2, profiles/r2_call1_*; the whole GPU suite passes
+// with it), the dense kernel stretching from 0.32 to 0.39 ms; batch-1 loses 3 %, hence the
+// 16-query floor.
 static int gemm_ring_cap(bool beside_bm25, bool bf16, int nqb_size, int n_real) {
   static const int all_env = getenv("ANR_GEMM_MAX_STAGES") ? atoi(getenv("ANR_GEMM_MAX_STAGES")) : 0;
   static const int beside_env =
-      getenv("ANR_GEMM_BESIDE_STAGES") ? atoi(getenv("ANR_GEMM_BESIDE_STAGES")) : 0;
+      getenv("ANR_GEMM_BESIDE_STAGES") ? atoi(getenv("ANR_GEMM_BESIDE_STAGES")) : 4;
   if (all_env >= 3) return all_env;
   if (beside_env >= 3 && beside_bm25 && bf16 && nqb_size == 64 && n_real >= 16) return beside_env;
   return 0;
@@ -861,7 +866,8 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
   const int mode = gemm_mode(dp, nqb_size, (n + kGmRows - 1) / kGmRows);
   const int ring_cap = gemm_ring_cap(ev_pre_main != nullptr, bf16, nqb_size, n_real);
   t_ring_capped = ring_cap >= 3;
-  if (!make_gemm_layout(dp, ld, bf16, mode == 2 ? nqb_size / 2 : nqb_size, nq_pad, &L, ring_cap))
+  if (!make_gemm_layout(dp, ld, bf16, mode == 2 ? nqb_size / 2 : nqb_size, nq_pad, &L, ring_cap,
+                        gemm_epi_warps(nqb_size)))
     return cudaErrorInvalidConfiguration;
   const int64_t sample_tiles = gemm_sample_tiles(dp, n, k);
 

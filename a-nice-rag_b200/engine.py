@@ -189,6 +189,11 @@ class DenseIndex:
         (half the HBM bytes per pass); results are unchanged (exact fp32 rescoring)."""
         native.call("anr_dense_set_shadow", self.handle, 1 if enable else 0)
 
+    def invalidate(self) -> None:
+        """The rows were rewritten in place by their owner (a borrowed tensor): drop the cached
+        row-norm bound and the bf16 shadow copy; the next search rebuilds them."""
+        native.call("anr_dense_invalidate", self.handle)
+
     def search(self, queries, k: int, row_mask: Optional[np.ndarray] = None, id_base: int = 0):
         """-> (scores f32 [b, k], rows i32 [b, k], counts i32 [b]); rows = -1 past counts."""
         q = _as_f32_matrix(queries)

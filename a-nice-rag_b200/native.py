@@ -42,6 +42,7 @@ SIGNATURES = {
     "anr_dense_destroy": [_P],
     "anr_dense_shape": [_P, C.POINTER(_I64), C.POINTER(_I32)],
     "anr_dense_set_shadow": [_P, _I32],
+    "anr_dense_invalidate": [_P],
     "anr_dense_search": [_P, _P, _P, _I32, _I32, _P, _I64, _P, _P, _P, _P],
     "anr_bm25_create": [_P, _P, _P, _P, _P, _P, _I32, _I32, _F64, _F64, _F64, C.POINTER(_P)],
     "anr_bm25_reweight": [_P, _P, _P, _P, _P, _F64, _F64, _F64],

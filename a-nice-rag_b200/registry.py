@@ -39,6 +39,12 @@ class DenseEntry:
         self.ids = ids                  # object array of chunk ids, for subset validation
         self.sources = sources          # object array of `source` strings, for filters
         self.n, self.d = packed.shape
+        # (row, data pointer) of a few `embedding` cells of the frame this entry was built from:
+        # a frame that carries the same ids but OTHER vectors (df.copy() followed by a new or
+        # renormalised embedding column; the column replaced on the loaded frame itself) must not
+        # resolve to this device matrix -- the reference re-stacks df["embedding"] on every call
+        # (search_engine.py:80).  None = rows are views into `packed` (the loader's frames).
+        self.probe_ptrs: Optional[Dict[int, int]] = None
         self._index: Optional[engine.DenseIndex] = None
         self._masks: Dict[str, Tuple[np.ndarray, object, int]] = {}
         self._build_lock = threading.Lock()
@@ -84,28 +90,62 @@ def register_frame(df: pd.DataFrame, packed: np.ndarray) -> DenseEntry:
     return entry
 
 
+def _cell_ptr(cell) -> int:
+    """Address of the first element of one `embedding` cell (-1 when it is not an ndarray)."""
+    return cell.__array_interface__["data"][0] if isinstance(cell, np.ndarray) else -1
+
+
+def _probe_positions(n: int) -> np.ndarray:
+    return np.unique(np.linspace(0, n - 1, num=min(n, 8)).astype(np.int64))
+
+
+def _same_vectors(entry: DenseEntry, emb_col, positions, rows) -> bool:
+    """Do the probed `embedding` cells of a frame still hold the memory the entry was packed
+    from?  O(1): a handful of pointer compares per query.  (Writing INTO the loader's arrays in
+    place is not detectable this way; DenseIndex.invalidate / a fresh load is the way to do that.)"""
+    row_bytes = entry.packed.strides[0]
+    base = entry.packed.ctypes.data
+    for p, r in zip(positions, rows):
+        cell = emb_col.iat[int(p)]
+        want = base + int(r) * row_bytes if entry.probe_ptrs is None else entry.probe_ptrs.get(int(r))
+        if want is None:
+            continue                      # this row was not probed at registration
+        if _cell_ptr(cell) != want or cell.shape != (entry.d,) or cell.dtype != np.float32:
+            return False
+    return True
+
+
 def resolve_frame(df: pd.DataFrame) -> Tuple[DenseEntry, Optional[np.ndarray]]:
     """-> (entry, None) when ``df`` is a registered frame, (entry, row positions) when it is
     a row subset derived from one; an unknown frame is packed, uploaded and remembered."""
     entry = lookup_identity(df)
     if entry is not None:
-        return entry, None
+        n = len(df)
+        if n == entry.n and "embedding" in df.columns and \
+                (n == 0 or _same_vectors(entry, df["embedding"], sorted(entry.probe_ptrs or {}),
+                                         sorted(entry.probe_ptrs or {}))):
+            return entry, None
+        _forget_identity(id(df), entry.key)     # same object, new vectors: pack it again
     entry = _dense.get(df.attrs.get(ATTR_KEY, -1))
-    if entry is not None and "id" in df.columns:
+    if entry is not None and "id" in df.columns and "embedding" in df.columns:
         # O(1) checks only: this runs on every query (a full pass over a 1M-row id column
         # costs more than the search itself)
         n = len(df)
         labels = df.index
         id_col = df["id"]
+        emb_col = df["embedding"]
         if n == entry.n and isinstance(labels, pd.RangeIndex) and labels.start == 0 \
                 and labels.step == 1:
-            if n == 0 or (id_col.iat[0] == entry.ids[0] and id_col.iat[n - 1] == entry.ids[n - 1]):
+            probe = _probe_positions(n) if n else np.zeros(0, dtype=np.int64)
+            if n == 0 or (id_col.iat[0] == entry.ids[0] and id_col.iat[n - 1] == entry.ids[n - 1]
+                          and _same_vectors(entry, emb_col, probe, probe)):
                 return entry, None
         rows = np.asarray(labels)
         if n and rows.dtype.kind in "iu" and rows.min() >= 0 and rows.max() < entry.n \
                 and labels.is_unique:
-            probe = np.unique(np.linspace(0, n - 1, num=min(n, 8)).astype(np.int64))
-            if all(id_col.iat[int(p)] == entry.ids[rows[p]] for p in probe):
+            probe = _probe_positions(n)
+            if all(id_col.iat[int(p)] == entry.ids[rows[p]] for p in probe) and \
+                    _same_vectors(entry, emb_col, probe, rows[probe]):
                 return entry, rows.astype(np.int64)
     # unknown frame: pack and upload it (np.stack raises for ragged rows, like the reference)
     packed = np.ascontiguousarray(np.stack(df["embedding"].values), dtype=np.float32)
@@ -117,6 +157,9 @@ def resolve_frame(df: pd.DataFrame) -> Tuple[DenseEntry, Optional[np.ndarray]]:
         df["id"].to_numpy(dtype=object) if "id" in df.columns else np.arange(n).astype(object),
         df["source"].to_numpy(dtype=object) if "source" in df.columns
         else np.full(n, None, dtype=object))
+    # packed is a copy (np.stack): remember where the probed cells lived instead
+    emb_col = df["embedding"]
+    entry.probe_ptrs = {int(p): _cell_ptr(emb_col.iat[int(p)]) for p in _probe_positions(n)} if n else {}
     with _lock:
         _dense[entry.key] = entry
     # an unknown frame may carry arbitrary index labels: remember it by identity only
@@ -192,11 +235,15 @@ class Bm25Entry:
                                 bm25.k1, bm25.b, bm25.avgdl)
             self.index = engine.Bm25Index(term_ptr, post_doc, post_tf, doc_len, idf, bm25.k1,
                                           bm25.b, bm25.avgdl, vocab=vocab)
-        self._masks: Dict[Tuple[int, str], Tuple[object, object, int]] = {}
+        self._masks: Dict[tuple, Tuple[object, object, int]] = {}
+        self.fingerprint = bm25_fingerprint(bm25)
 
     def filter_mask(self, sections, filename_type_filter: str):
         """Mask over BM25 doc indices from each section's metadata["source"] (search_engine.py:224-231)."""
-        key = (id(sections), filename_type_filter)
+        # keyed by content, not by id(sections): an id can be reused by another list after GC
+        n = len(sections)
+        probe = tuple(sections[i].metadata.get("source", "") for i in sorted({0, n // 2, n - 1})) if n else ()
+        key = (n, probe, filename_type_filter)
         hit = self._masks.get(key)
         if hit is None:
             sources = [s.metadata.get("source", "") for s in sections]
@@ -211,12 +258,22 @@ class Bm25Entry:
 _bm25: Dict[int, Tuple[weakref.ref, Bm25Entry]] = {}
 
 
+def bm25_fingerprint(bm25) -> tuple:
+    """What a cached device index was built from, as far as O(1) checks can tell: a BM25Okapi whose
+    k1 / b / avgdl were changed, whose corpus grew, or whose idf table was replaced (the
+    parameter sweep of src/processing/bm25_test.py does all of that on fresh objects) must not
+    be searched through the old index.  In-place edits of single idf entries are not detectable."""
+    idf = getattr(bm25, "idf", None)
+    return (float(bm25.k1), float(bm25.b), float(bm25.avgdl), len(bm25.doc_len), id(idf),
+            len(idf) if idf is not None else 0)
+
+
 def resolve_bm25(bm25, cache_for: Optional[str] = None) -> Bm25Entry:
     entry = getattr(bm25, "_anr_entry", None)
-    if isinstance(entry, Bm25Entry):
+    if isinstance(entry, Bm25Entry) and entry.fingerprint == bm25_fingerprint(bm25):
         return entry
     hit = _bm25.get(id(bm25))
-    if hit is not None and hit[0]() is bm25:
+    if hit is not None and hit[0]() is bm25 and hit[1].fingerprint == bm25_fingerprint(bm25):
         return hit[1]
     entry = Bm25Entry(bm25, cache_for=cache_for)
     try:

@@ -68,6 +68,32 @@ class ShardedHybrid:
             )
         return self._buf[key]
 
+    def phases(self, queries_dev, terms_dev, offsets_dev, b: int, k: int, w_dense: float,
+               w_bm25: float, rrf_k: float, top_n: int):
+        """The three parts of ``search`` as separate callables (local searches, all-gather,
+        merge + fusion), for timing them one by one; each enqueues on torch's current stream."""
+        ctx = engine.context(self.device.index)
+        buf = self._buffers(b, k, top_n)
+        local, gathered = buf["local"], buf["gathered"]
+
+        def local_searches():
+            native.call("anr_hybrid_search_keys", ctx.handle, self.dense.handle, self.bm25.handle,
+                        queries_dev.data_ptr(), terms_dev.data_ptr(), offsets_dev.data_ptr(), b, k,
+                        None, None, self.row_base, self.doc_base, local.data_ptr(),
+                        engine.torch_stream_ptr())
+
+        def exchange():
+            if self.world > 1:
+                self.dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=self.group)
+
+        def merge_fuse():
+            src = gathered if self.world > 1 else local
+            native.call("anr_sharded_fuse", ctx.handle, src.data_ptr(), self.world, b, k,
+                        float(w_dense), float(w_bm25), float(rrf_k), top_n, buf["ids"].data_ptr(),
+                        buf["scores"].data_ptr(), buf["counts"].data_ptr(),
+                        engine.torch_stream_ptr())
+        return dict(local=local_searches, exchange=exchange, merge_fuse=merge_fuse)
+
     def search(self, queries_dev, terms_dev, offsets_dev, b: int, k: int, w_dense: float,
                w_bm25: float, rrf_k: float, top_n: int):
         """queries [b, d] fp32, CSR term ids int32: device tensors.  Returns device tensors

@@ -1,31 +1,41 @@
 #!/usr/bin/env python
-"""Headline benchmark: hybrid queries/s (dense top-10 + BM25 top-10 + weighted RRF -> top-10)
-over the BASELINE.json configs[1] corpus -- 1M chunks x 1024-d fp32 + a Zipf(1.1) BM25 corpus of
-1M documents (V=50k, 8-term queries) -- in batches of 64 queries, plus batch-1 latency.
+"""Benchmark of the retrieval hot path: hybrid queries/s (dense top-10 + BM25 top-10 + weighted
+RRF -> top-10) on BASELINE.json configs[1] -- 1M chunks x 1024-d fp32 + a Zipf(1.1) BM25 corpus of
+1M documents (V=50k, 8-term queries) -- in batches of 64 queries, plus batch-1 latency, plus one
+bounded leg per other BASELINE config.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--legs a,b,..]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 One JSON line on stdout (rank 0).  A step = one batch of B hybrid queries.
-  value     : queries/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e       : the same through the C-ABI with pinned HOST buffers (H2D of the queries and D2H
-              of the fused results inside the timed region)
-  roofline  : dense scan kernel, algorithmic bytes (rows x D x 4 per pass) / mean launch time,
-              against MEASURED_PEAKS.json
-  cpu_baseline : the CPU oracle port (numpy: BLAS dot + CSR BM25 + Python RRF, pre-stacked
-              matrix, i.e. WITHOUT the reference's per-query np.stack / pandas overhead) on a
-              bounded sample of the same batch, same corpus, on this box's host cores
-  cuda_graph : the same batch-1 / batch-B steps replayed from a captured CUDA graph
-              (a-nice-rag_b200/graph.py), compared bit for bit with the eager call's output
-N > 1: the SAME 1M-chunk corpus is sharded by chunk over the ranks (strong scaling); local
-top-k keys are exchanged with one NCCL all-gather and merged + fused on every rank.
---impl reference: only the CPU port is timed (rank 0), none of the CUDA library is loaded.
+  value      queries/s, inputs resident in HBM, CUDA events on the launching stream, max over
+             ranks: the MEDIAN of `--blocks` back-to-back blocks of exactly K steps (`blocks` holds
+             min / max / every block)
+  e2e        the same through the C ABI with pinned HOST buffers (H2D of the queries and D2H of
+             the fused results inside the timed region)
+  roofline   the kernel with the largest share of the step: algorithmic bytes per launch / mean
+             launch time (events on the launching stream, live in this run) against
+             MEASURED_PEAKS.json; `traffic` = ncu dram bytes per launch (profiles/traffic.json),
+             `frac_traffic` = traffic / time / peak
+  cpu_baseline  the CPU oracle port (numpy BLAS dot + CSR BM25 + Python RRF on a pre-stacked
+             matrix) on the batch's queries over the full corpus, on this box's host cores; the
+             SAME results are the parity check of every benchmark query (`parity_checked_queries`)
+  legs       config3 (10M x 1024, batch 1024, top-100 dense), config4 (BM25-only, 10M docs,
+             V=500k, batch 256), batch1_10M (batch-1 hybrid at 10M: the >= 70 % HBM target), weak
+             (12.5M chunks per GPU -> 100M on 8 GPUs), each with its own parity count and clocks
+N > 1: the SAME 1M-chunk corpus is sharded by chunk over the ranks (strong scaling, the headline
+line); local top-k keys are exchanged with one NCCL all-gather and merged + fused on every rank;
+`multi_gpu` times the three parts.  Rank 0 re-creates every shard for the CPU port, so the
+all-gathered result of every benchmark query is checked at every N.
+--impl reference: the CPU port alone (rank 0), timed on the host cores; this arm does not import
+the product package, so none of the CUDA library is loaded.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
 import importlib
+import importlib.util
 import json
 import os
 import statistics
@@ -41,12 +51,14 @@ sys.path.insert(0, ROOT)
 
 METRIC = "hybrid queries/sec (1M x 1024-d + BM25, top-10)"
 D = 1024
-VOCAB = 50_000
 ZIPF_S = 1.1
 K1, B_PARAM, EPS = 1.7, 0.83, 0.05
 W_DENSE, W_BM25, WRRF_K = 5.0, 1.0, 40.0
+WEIGHTS = {"voyage-3-large": W_DENSE, "BM25": W_BM25}
 TOPK = 10
 N_TERMS = 8
+Q_SEED, T_SEED = 4321, 2025
+EMB_SEED, POST_SEED = 1234, 2024
 
 
 def parse_args():
@@ -57,16 +69,25 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunks", type=int, default=1_000_000, help="total corpus rows / BM25 docs")
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--vocab", type=int, default=VOCAB)
+    ap.add_argument("--vocab", type=int, default=50_000)
     ap.add_argument("--chunks-per-gpu", type=int, default=0,
-                    help="weak scaling: total corpus = this x world size (overrides --chunks)")
-    ap.add_argument("--cpu-queries", type=int, default=16, help="queries in the CPU sample")
+                    help="headline corpus = this x world size (overrides --chunks)")
+    ap.add_argument("--blocks", type=int, default=11, help="timed blocks of --steps steps each")
+    ap.add_argument("--cpu-queries", type=int, default=64,
+                    help="queries of the batch run through the CPU port (timed + parity)")
     ap.add_argument("--latency-iters", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense-operands", default="bf16", choices=["bf16", "tf32"],
-                    help="operands of the tensor-core nomination pass for batches > 32: a bf16 "
-                         "shadow copy of the matrix (half the HBM bytes) or the fp32 words read as "
-                         "tf32; results are identical (exact fp32 rescoring)")
+                    help="operands of the tensor-core nomination pass: a bf16 shadow copy of the "
+                         "matrix (half the HBM bytes) or the fp32 words read as tf32; results are "
+                         "identical (exact fp32 rescoring)")
+    ap.add_argument("--legs", default="headline,big,weak",
+                    help="comma list of: headline (always), big (10M legs, 1 GPU), weak "
+                         "(12.5M chunks per GPU)")
+    ap.add_argument("--big-chunks", type=int, default=10_000_000)
+    ap.add_argument("--big-vocab", type=int, default=500_000)
+    ap.add_argument("--weak-chunks-per-gpu", type=int, default=12_500_000)
+    ap.add_argument("--leg-steps", type=int, default=10, help="timed steps of each extra leg")
     return ap.parse_args()
 
 
@@ -75,16 +96,30 @@ def dist_env():
             int(os.environ.get("WORLD_SIZE", 1)))
 
 
+def load_synth():
+    """synth.py by PATH: importing it as a-nice-rag_b200.synth would import the package, whose
+    __init__ loads the CUDA library -- the reference arm must not do that."""
+    spec = importlib.util.spec_from_file_location(
+        "anr_bench_synth", os.path.join(ROOT, "a-nice-rag_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as fh:
-            return float(json.load(fh)["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+            p = json.load(fh)
+        return dict(hbm=float(p["hbm_gbs"]), bf16=float(p["bf16_tflops"]),
+                    bf16_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    source="measured")
+    # B200_PROFILING.md fallback figures
+    return dict(hbm=6650.0, bf16=1700.0, bf16_sustained=1400.0, source="fallback")
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while a timed region runs."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -106,17 +141,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self) -> int:
+        return len(self.lines)
+
+    def summary(self, since: int = 0):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for line in self.lines[since:]:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 6:
                 continue
@@ -132,85 +165,143 @@ class ClockSampler:
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
                 "samples": len(sm)}
 
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+
 
 # ---------------------------------------------------------------------------------------
 # synthetic workload (device generation; identical bytes are copied to the host for the CPU arm)
 # ---------------------------------------------------------------------------------------
-def make_queries(batch: int):
-    synth = importlib.import_module("a-nice-rag_b200.synth")
-    q = synth.unit_vectors(batch, D, seed=4321)
-    terms = synth.zipf_queries(batch, N_TERMS, VOCAB, ZIPF_S, seed=2025)   # VOCAB = --vocab
+def make_queries(synth, batch: int, vocab: int):
+    q = synth.unit_vectors(batch, D, seed=Q_SEED)
+    terms = synth.zipf_queries(batch, N_TERMS, vocab, ZIPF_S, seed=T_SEED)
     offsets = np.arange(0, (batch + 1) * N_TERMS, N_TERMS, dtype=np.int32)
     return q, terms, offsets
 
 
-def make_shard(torch, device, lo: int, hi: int, shard_id: int):
-    synth = importlib.import_module("a-nice-rag_b200.synth")
-    emb = synth.unit_vectors_torch(hi - lo, D, 1234 + shard_id, device)
-    post = synth.zipf_postings_torch(hi - lo, VOCAB, ZIPF_S, 2024 + shard_id, device)
+def make_shard(synth, device, lo: int, hi: int, shard_id: int, vocab: int, want_emb=True,
+               want_post=True):
+    emb = synth.unit_vectors_torch(hi - lo, D, EMB_SEED + shard_id, device) if want_emb else None
+    post = (synth.zipf_postings_torch(hi - lo, vocab, ZIPF_S, POST_SEED + shard_id, device)
+            if want_post else None)
     return emb, post
+
+
+def workload_name(chunks: int, vocab: int) -> str:
+    return (f"{chunks} chunks x {D}-d fp32 + BM25 {chunks} docs V={vocab} Zipf {ZIPF_S}, "
+            f"{N_TERMS}-term queries, top-{TOPK} WRRF (w 5:1, k=40)")
+
+
+def headline_config(args) -> dict:
+    """The `config` object: identical in both arms (everything in it follows from the arguments)."""
+    return {"workload": workload_name(args.chunks, args.vocab), "batch": args.batch,
+            "sharding": f"chunks sharded over {args.gpus} GPU(s), queries replicated",
+            "l2": "inputs larger than L2 (corpus >= 0.5 GB per GPU, re-read every step)"}
 
 
 # ---------------------------------------------------------------------------------------
 # CPU arm: the oracle port, timed (and used as the checker of the GPU results)
 # ---------------------------------------------------------------------------------------
-def cpu_port_setup(emb_host, post_host, idf, avgdl):
-    from oracle import csr
-    return emb_host, csr.CsrIndex(
-        term_ptr=post_host["term_ptr"], post_doc=post_host["post_doc"],
-        post_tf=post_host["post_tf"], doc_len=post_host["doc_len"].astype(np.int64), idf=idf,
-        avgdl=avgdl, k1=K1, b=B_PARAM)
-
-
-def cpu_port_run(emb, index, queries, terms, n_queries: int):
-    """Runs n_queries hybrid queries on the CPU; returns (seconds, results)."""
-    from oracle import pipeline
-    weights = {"voyage-3-large": W_DENSE, "BM25": W_BM25}
-    results = []
-    t0 = time.perf_counter()
-    for q in range(n_queries):
-        results.append(pipeline.hybrid_query(queries[q], emb, index, [int(t) for t in terms[q]],
-                                             TOPK, TOPK, weights, WRRF_K, TOPK))
-    return time.perf_counter() - t0, results
-
-
-def check_against_cpu(results, got, queries_n: int):
-    """GPU fused output vs the oracle on the sampled queries (tie-aware on the two lists, exact
-    on the fusion given the lists).  Returns the number of queries checked."""
-    from oracle import pipeline, retrieval
-    for q in range(queries_n):
-        ref = results[q]
-        retrieval.assert_ranking_matches(
-            got["dense_rows"][q, :TOPK], got["dense_scores"][q, :TOPK], ref["dense_ids"],
-            ref["dense_scores"], all_scores=ref.get("dense_all"), rtol=1e-5, atol=1e-6,
-            what=f"bench dense q{q}")
-        b_all = ref["bm25_all"]
-        g_b = got["bm25_ids"][q, :TOPK]
-        s_g, s_w = b_all[g_b], b_all[ref["bm25_docs"]]
-        assert np.all(np.abs(s_g - s_w) <= 1e-5 * np.abs(s_w) + 1e-6), f"bench bm25 q{q}"
-        c = int(got["counts"][q])
-        pipeline.check_fused(got["ids"][q, :c], got["scores"][q, :c], got["dense_rows"][q, :TOPK],
-                             g_b, (W_DENSE, W_BM25), WRRF_K, TOPK)
-    return queries_n
-
-
-def cpu_threads() -> int:
-    """Threads the CPU port really uses: the BLAS pool behind np.dot (the CSR BM25 statement and the
-    Python RRF loop are single-threaded, as in the reference)."""
+def set_cpu_threads() -> int:
+    """All host cores for the BLAS pool, whatever OMP_NUM_THREADS the launcher exported (torchrun
+    sets it to 1).  Returns the BLAS thread count actually in force."""
+    want = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=want)
         n = max((int(p.get("num_threads", 0)) for p in threadpool_info()
                  if p.get("user_api") == "blas"), default=0)
         if n > 0:
             return n
     except Exception:
         pass
-    return os.cpu_count() or 1
+    return want
 
 
-def workload_name(args) -> str:
-    return (f"{args.chunks} chunks x {D}-d fp32 + BM25 {args.chunks} docs V={VOCAB} Zipf {ZIPF_S}, "
-            f"{N_TERMS}-term queries, top-{TOPK} WRRF (w 5:1, k=40)")
+def cpu_index(post_host, idf, avgdl):
+    from oracle import csr
+    return csr.CsrIndex(term_ptr=post_host["term_ptr"], post_doc=post_host["post_doc"],
+                        post_tf=post_host["post_tf"],
+                        doc_len=post_host["doc_len"].astype(np.int64), idf=idf, avgdl=avgdl,
+                        k1=K1, b=B_PARAM)
+
+
+def cpu_port_run(shards, queries, terms, which):
+    """Runs the hybrid queries `which` on the CPU; returns (seconds, {q: result}).  shards =
+    [(first row, emb, CsrIndex)] in row order (one entry = the unsharded corpus)."""
+    from oracle import pipeline
+    results = {}
+    t0 = time.perf_counter()
+    for q in which:
+        tq = [int(t) for t in terms[q]]
+        if len(shards) == 1:
+            results[q] = pipeline.hybrid_query(queries[q], shards[0][1], shards[0][2], tq, TOPK, TOPK,
+                                               WEIGHTS, WRRF_K, TOPK)
+        else:
+            results[q] = pipeline.hybrid_query_sharded(queries[q], shards, tq, TOPK, TOPK, WEIGHTS,
+                                                       WRRF_K, TOPK)
+    return time.perf_counter() - t0, results
+
+
+def check_against_cpu(results, got, shards, queries):
+    """GPU output vs the oracle for every query in `results`: the two ranked lists tie-aware (ids
+    AND the scores the GPU reported, 1e-5 relative; the absolute 1e-6 only guards scores near 0),
+    the fusion exactly given the lists.  Returns the number of queries checked."""
+    from oracle import pipeline, retrieval
+    for q, ref in results.items():
+        d_all = ref.get("dense_all")
+        if d_all is None and not np.array_equal(got["dense_rows"][q, :TOPK], ref["dense_ids"]):
+            d_all = np.concatenate([retrieval.dense_scores(queries[q], emb) for _, emb, _ in shards])
+        retrieval.assert_ranking_matches(
+            got["dense_rows"][q, :TOPK], got["dense_scores"][q, :TOPK], ref["dense_ids"],
+            ref["dense_scores"], all_scores=d_all, rtol=1e-5, atol=1e-6, what=f"bench dense q{q}")
+        retrieval.assert_ranking_matches(
+            got["bm25_ids"][q, :TOPK], got["bm25_scores"][q, :TOPK], ref["bm25_docs"],
+            ref["bm25_all"][ref["bm25_docs"]], all_scores=ref["bm25_all"], rtol=1e-5, atol=1e-6,
+            what=f"bench bm25 q{q}")
+        c = int(got["counts"][q])
+        pipeline.check_fused(got["ids"][q, :c], got["scores"][q, :c], got["dense_rows"][q, :TOPK],
+                             got["bm25_ids"][q, :TOPK], (W_DENSE, W_BM25), WRRF_K, TOPK)
+    return len(results)
+
+
+def stock_path_config0(n_queries: int = 8):
+    """Context figure for `cpu_baseline`: the reference's STOCK per-query path on BASELINE
+    configs[0] (20k chunks x 1024-d, V=50k) restated literally -- np.stack of the object column on
+    every call (src/search_engine.py:80), the rank_bm25 get_scores loop (:219), the Python RRF --
+    next to the pre-stacked / CSR port the baseline line times.  (The unmodified reference itself,
+    timed where it is mounted: profiles/r1_config0_reference_cpu.json, 7.5 queries/s.)"""
+    from oracle import bm25_okapi, retrieval
+    synth = load_synth()
+    n, vocab = 20_000, 50_000
+    emb = synth.unit_vectors(n, D, seed=EMB_SEED)
+    column = np.empty(n, dtype=object)
+    for i in range(n):
+        column[i] = emb[i]
+    doc_ptr, tokens = synth.zipf_corpus(n, vocab, ZIPF_S, seed=POST_SEED)
+    okapi = bm25_okapi.BM25Okapi(synth.doc_token_lists(doc_ptr, tokens), k1=K1, b=B_PARAM,
+                                 epsilon=EPS)
+    queries = synth.unit_vectors(n_queries, D, seed=Q_SEED)
+    tq = synth.zipf_queries(n_queries, N_TERMS, vocab, ZIPF_S, seed=T_SEED)
+    t0 = time.perf_counter()
+    for q in range(n_queries):
+        stacked = np.stack(column)
+        scores = np.dot(queries[q].reshape(1, -1), stacked.T).flatten()
+        d_ids = retrieval.topk_desc(scores, TOPK)
+        b_scores = okapi.get_scores(synth.token_strings(tq[q]))
+        b_ids = retrieval.topk_desc(np.array(b_scores), TOPK)
+        retrieval.weighted_rrf([([int(i) for i in d_ids], "voyage-3-large"),
+                                ([int(i) for i in b_ids], "BM25")], WEIGHTS, WRRF_K)[:TOPK]
+    dt = time.perf_counter() - t0
+    return {"value": n_queries / dt, "unit": "queries/s",
+            "what": f"stock per-query path on configs[0] ({n} chunks, V={vocab}): np.stack per "
+                    f"call + literal BM25Okapi.get_scores + Python RRF, {n_queries} queries"}
 
 
 # ---------------------------------------------------------------------------------------
@@ -220,168 +311,258 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    synth = importlib.import_module("a-nice-rag_b200.synth")
+    synth = load_synth()
+    cores = set_cpu_threads()
     device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
-    emb, post = make_shard(torch, device, 0, args.chunks, 0)   # torch only generates the data
+    emb, post = make_shard(synth, device, 0, args.chunks, 0, args.vocab)   # torch only generates
     emb_host = emb.cpu().numpy()
     post_host = {k: v.cpu().numpy() for k, v in post.items()}
     del emb, post
     idf = synth.idf_from_counts(args.chunks, post_host["nd"], EPS)
     avgdl = float(post_host["doc_len"].astype(np.int64).sum() / args.chunks)
-    queries, terms, _ = make_queries(args.batch)
-    emb_h, index = cpu_port_setup(emb_host, post_host, idf, avgdl)
-    per_step = max(1, min(args.cpu_queries, args.batch) // 2)
-    for _ in range(args.warmup):
-        cpu_port_run(emb_h, index, queries, terms, 1)
-    total = 0.0
-    for _ in range(args.steps):
-        dt, _ = cpu_port_run(emb_h, index, queries, terms, per_step)
+    queries, terms, _ = make_queries(synth, args.batch, args.vocab)
+    shards = [(0, emb_host, cpu_index(post_host, idf, avgdl))]
+    per_step = max(1, min(8, args.batch))
+    for _ in range(min(args.warmup, 3)):
+        cpu_port_run(shards, queries, terms, [0])
+    total, done = 0.0, 0
+    for s in range(args.steps):
+        which = [(s * per_step + i) % args.batch for i in range(per_step)]
+        dt, _ = cpu_port_run(shards, queries, terms, which)
         total += dt
-    qps = per_step * args.steps / total
-    cores = cpu_threads()
+        done += per_step
+    qps = done / total
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        # the same workload as the CUDA arm's line; a step here is a bounded sample of its batch
-        "config": {"workload": workload_name(args), "batch": args.batch,
-                   "sample_queries_per_step": per_step},
+        "config": headline_config(args),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                         "sample": f"{per_step} queries per step over the full corpus; numpy "
-                                   "BLAS dot + CSR BM25 + Python RRF on a pre-stacked matrix"},
+                         "sample": f"{per_step} of the batch's {args.batch} queries per step over "
+                                   "the full corpus; numpy BLAS dot + CSR BM25 + Python RRF on a "
+                                   "pre-stacked matrix"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    rank, local_rank, world = dist_env()
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    pkg = importlib.import_module("a-nice-rag_b200")
-    engine, native, synth = pkg.engine, pkg.native, importlib.import_module("a-nice-rag_b200.synth")
-    sharded = importlib.import_module("a-nice-rag_b200.sharded")
-    ctx = engine.context(local_rank)
+# ---------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------
+class Env:
+    pass
 
-    # ---- corpus shard ------------------------------------------------------------------
-    lo, hi = sharded.shard_range(args.chunks, rank, world)
-    emb, post = make_shard(torch, device, lo, hi, rank)
-    nd, n_docs_total, avgdl = sharded.global_bm25_stats(
-        post["nd"], int(post["doc_len"].to(torch.int64).sum()), hi - lo)
-    idf = synth.idf_from_counts(n_docs_total, nd.cpu().numpy(), EPS)
-    dense = engine.DenseIndex(emb, borrow=True)
-    dense.set_shadow(args.dense_operands == "bf16")
-    bm25 = engine.Bm25Index(post["term_ptr"], post["post_doc"], post["post_tf"], post["doc_len"],
-                            idf, K1, B_PARAM, avgdl, n_terms=VOCAB, n_docs=hi - lo)
-    n_postings = bm25.n_postings
 
-    # ---- queries -------------------------------------------------------------------------
-    B = args.batch
-    q_host, t_host, off_host = make_queries(B)
-    q_pin = torch.from_numpy(q_host).pin_memory()
-    t_pin = torch.from_numpy(t_host.reshape(-1).copy()).pin_memory()
-    off_pin = torch.from_numpy(off_host).pin_memory()
-    q_dev, t_dev, off_dev = q_pin.to(device), t_pin.to(device), off_pin.to(device)
-    out_ids = torch.empty((B, TOPK), dtype=torch.int32, device=device)
-    out_scores = torch.empty((B, TOPK), dtype=torch.float64, device=device)
-    out_counts = torch.empty((B,), dtype=torch.int32, device=device)
-    h_ids = torch.empty((B, TOPK), dtype=torch.int32).pin_memory()
-    h_scores = torch.empty((B, TOPK), dtype=torch.float64).pin_memory()
-    h_counts = torch.empty((B,), dtype=torch.int32).pin_memory()
-    shard = sharded.ShardedHybrid(dense, bm25, row_base=lo) if world > 1 else None
+class Workload:
+    """One rank's shard of a corpus: device tensors + the two indices."""
 
-    def step_device(b=B):
-        stream = engine.torch_stream_ptr()
-        if world > 1:
-            return shard.search(q_dev[:b], t_dev, off_dev, b, TOPK, W_DENSE, W_BM25, WRRF_K, TOPK)
-        native.call("anr_hybrid_search", ctx.handle, dense.handle, bm25.handle, q_dev.data_ptr(),
-                    t_dev.data_ptr(), off_dev.data_ptr(), b, TOPK, TOPK, None, None, None, 0,
-                    W_DENSE, W_BM25, WRRF_K, TOPK, out_ids.data_ptr(), out_scores.data_ptr(),
-                    out_counts.data_ptr(), None, None, None, None, stream)
-        return out_ids, out_scores, out_counts
+    def __init__(self, env, n_total: int, vocab: int, shadow: bool):
+        torch = env.torch
+        self.n_total, self.vocab = n_total, vocab
+        self.lo, self.hi = env.sharded.shard_range(n_total, env.rank, env.world)
+        self.emb, self.post = make_shard(env.synth, env.device, self.lo, self.hi, env.rank, vocab)
+        nd, n_docs_total, self.avgdl = env.sharded.global_bm25_stats(
+            self.post["nd"], int(self.post["doc_len"].to(torch.int64).sum()), self.hi - self.lo)
+        self.nd_global = nd.cpu().numpy()
+        self.idf = env.synth.idf_from_counts(n_docs_total, self.nd_global, EPS)
+        self.dense = env.engine.DenseIndex(self.emb, borrow=True)
+        self.dense.set_shadow(shadow)
+        self.bm25 = env.engine.Bm25Index(
+            self.post["term_ptr"], self.post["post_doc"], self.post["post_tf"], self.post["doc_len"],
+            self.idf, K1, B_PARAM, self.avgdl, n_terms=vocab, n_docs=self.hi - self.lo)
+        self.shard = (env.sharded.ShardedHybrid(self.dense, self.bm25, row_base=self.lo)
+                      if env.world > 1 else None)
 
-    def step_e2e(b=B):
+    @property
+    def rows(self) -> int:
+        return self.hi - self.lo
+
+
+class QueryBatch:
+    def __init__(self, env, batch: int, vocab: int):
+        torch = env.torch
+        self.B = batch
+        self.q_host, self.t_host, self.off_host = make_queries(env.synth, batch, vocab)
+        self.q_pin = torch.from_numpy(self.q_host).pin_memory()
+        self.t_pin = torch.from_numpy(self.t_host.reshape(-1).copy()).pin_memory()
+        self.off_pin = torch.from_numpy(self.off_host).pin_memory()
+        dev = env.device
+        self.q_dev, self.t_dev, self.off_dev = (self.q_pin.to(dev), self.t_pin.to(dev),
+                                                self.off_pin.to(dev))
+        self.out_ids = torch.empty((batch, TOPK), dtype=torch.int32, device=dev)
+        self.out_scores = torch.empty((batch, TOPK), dtype=torch.float64, device=dev)
+        self.out_counts = torch.empty((batch,), dtype=torch.int32, device=dev)
+        self.h_ids = torch.empty((batch, TOPK), dtype=torch.int32).pin_memory()
+        self.h_scores = torch.empty((batch, TOPK), dtype=torch.float64).pin_memory()
+        self.h_counts = torch.empty((batch,), dtype=torch.int32).pin_memory()
+
+
+def barrier(env):
+    env.torch.cuda.synchronize()
+    if env.world > 1:
+        env.dist.barrier()
+    env.torch.cuda.synchronize()
+
+
+def timed(env, fn, steps: int) -> float:
+    """ms for `steps` calls: CUDA events on the launching stream, barrier + synchronize on both
+    sides, max over ranks."""
+    torch = env.torch
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(env)
+    start.record()
+    for _ in range(steps):
+        fn()
+    stop.record()
+    barrier(env)
+    ms = torch.tensor([start.elapsed_time(stop)], device=env.device, dtype=torch.float64)
+    if env.world > 1:
+        env.dist.all_reduce(ms, op=env.dist.ReduceOp.MAX)
+    return float(ms)
+
+
+def step_fns(env, w: Workload, qb: QueryBatch):
+    """(device-resident step, host-buffer step) for batches of b <= qb.B queries."""
+    native, engine, ctx, torch = env.native, env.engine, env.ctx, env.torch
+
+    def step_device(b=qb.B):
+        if w.shard is not None:
+            return w.shard.search(qb.q_dev[:b], qb.t_dev, qb.off_dev, b, TOPK, W_DENSE, W_BM25,
+                                  WRRF_K, TOPK)
+        native.call("anr_hybrid_search", ctx.handle, w.dense.handle, w.bm25.handle,
+                    qb.q_dev.data_ptr(), qb.t_dev.data_ptr(), qb.off_dev.data_ptr(), b, TOPK, TOPK,
+                    None, None, None, 0, W_DENSE, W_BM25, WRRF_K, TOPK, qb.out_ids.data_ptr(),
+                    qb.out_scores.data_ptr(), qb.out_counts.data_ptr(), None, None, None, None,
+                    engine.torch_stream_ptr())
+        return qb.out_ids, qb.out_scores, qb.out_counts
+
+    def step_e2e(b=qb.B):
         """Host buffers in, host buffers out (the call synchronises before returning)."""
-        stream = engine.torch_stream_ptr()
-        if world > 1:
-            qd = q_pin[:b].to(device, non_blocking=True)
-            td = t_pin.to(device, non_blocking=True)
-            od = off_pin.to(device, non_blocking=True)
-            ids, scores, counts = shard.search(qd, td, od, b, TOPK, W_DENSE, W_BM25, WRRF_K, TOPK)
-            h_ids[:b].copy_(ids, non_blocking=True)
-            h_scores[:b].copy_(scores, non_blocking=True)
-            h_counts[:b].copy_(counts, non_blocking=True)
+        if w.shard is not None:
+            qd = qb.q_pin[:b].to(env.device, non_blocking=True)
+            td = qb.t_pin.to(env.device, non_blocking=True)
+            od = qb.off_pin.to(env.device, non_blocking=True)
+            ids, scores, counts = w.shard.search(qd, td, od, b, TOPK, W_DENSE, W_BM25, WRRF_K, TOPK)
+            qb.h_ids[:b].copy_(ids, non_blocking=True)
+            qb.h_scores[:b].copy_(scores, non_blocking=True)
+            qb.h_counts[:b].copy_(counts, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return
-        native.call("anr_hybrid_search", ctx.handle, dense.handle, bm25.handle, q_pin.data_ptr(),
-                    t_pin.data_ptr(), off_pin.data_ptr(), b, TOPK, TOPK, None, None, None, 0,
-                    W_DENSE, W_BM25, WRRF_K, TOPK, h_ids.data_ptr(), h_scores.data_ptr(),
-                    h_counts.data_ptr(), None, None, None, None, stream)
+        native.call("anr_hybrid_search", ctx.handle, w.dense.handle, w.bm25.handle,
+                    qb.q_pin.data_ptr(), qb.t_pin.data_ptr(), qb.off_pin.data_ptr(), b, TOPK, TOPK,
+                    None, None, None, 0, W_DENSE, W_BM25, WRRF_K, TOPK, qb.h_ids.data_ptr(),
+                    qb.h_scores.data_ptr(), qb.h_counts.data_ptr(), None, None, None, None,
+                    engine.torch_stream_ptr())
+    return step_device, step_e2e
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        """ms for `steps` calls: CUDA events on the launching stream, max over ranks."""
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        start.record()
-        for _ in range(steps):
-            fn()
-        stop.record()
-        barrier()
-        ms = torch.tensor([start.elapsed_time(stop)], device=device, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
+def profile_reset(env):
+    for kind in (0, 1, 2):
+        env.native.call("anr_ctx_profile_read", env.ctx.handle, kind, None, None)
 
-    # ---- warm-up, then the timed regions --------------------------------------------------
-    # clocks are sampled from the warm-up to the end of the latency loop (the timed regions
-    # alone can be shorter than one nvidia-smi sampling period)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+def profile_read(env, kind: int):
+    ms, n = C.c_double(), C.c_int64()
+    env.native.call("anr_ctx_profile_read", env.ctx.handle, kind, C.byref(ms), C.byref(n))
+    return ms.value, n.value
+
+
+def full_lists_single_gpu(env, w: Workload, qb: QueryBatch):
+    """The whole batch through the same kernels as the timed steps, with the per-retriever lists."""
+    return env.engine.hybrid_search(w.dense, w.bm25, qb.q_host,
+                                    [list(map(int, t)) for t in qb.t_host], TOPK, TOPK, W_DENSE,
+                                    W_BM25, WRRF_K, TOPK, want_lists=True)
+
+
+def full_lists_sharded(env, w: Workload, qb: QueryBatch):
+    """N > 1: the all-gathered keys of the real NCCL path, decoded on the host: the merged dense
+    and BM25 lists (global ids, the scores the GPUs reported) + the fused output."""
+    torch = env.torch
+    ids, scores, counts = w.shard.search(qb.q_dev, qb.t_dev, qb.off_dev, qb.B, TOPK, W_DENSE, W_BM25,
+                                         WRRF_K, TOPK)
+    torch.cuda.synchronize()
+    gathered = w.shard._buffers(qb.B, TOPK, TOPK)["gathered"].cpu().numpy().view(np.uint64)
+    out = dict(ids=ids.cpu().numpy(), scores=scores.cpu().numpy(), counts=counts.cpu().numpy())
+    for plane, name in ((0, "dense"), (1, "bm25")):
+        keys = gathered[:, plane].transpose(1, 0, 2).reshape(qb.B, -1)       # [B, world * k]
+        keys = np.sort(keys, axis=1)[:, ::-1][:, :TOPK]                      # a larger key is a better hit
+        sc, idv = decode_keys(keys)
+        out["dense_rows" if name == "dense" else "bm25_ids"] = idv
+        out[name + "_scores"] = sc
+    return out
+
+
+def decode_keys(keys: np.ndarray):
+    """Sortable 64-bit keys (anr_common.cuh: orderable(score) << 32 | ~id) -> (fp32 scores, ids)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    ordered = (keys >> np.uint64(32)).astype(np.uint32)
+    bits = np.where(ordered & np.uint32(0x80000000), ordered & np.uint32(0x7fffffff), ~ordered)
+    scores = np.ascontiguousarray(bits, dtype=np.uint32).view(np.float32)
+    ids = (np.uint64(0xffffffff) - (keys & np.uint64(0xffffffff))).astype(np.int64)
+    return scores, ids
+
+
+def run_headline(env, args, peaks, sampler):
+    torch, native, engine = env.torch, env.native, env.engine
+    rank, world = env.rank, env.world
+    shadow = args.dense_operands == "bf16"
+    w = Workload(env, args.chunks, args.vocab, shadow)
+    qb = QueryBatch(env, args.batch, args.vocab)
+    B = qb.B
+    step_device, step_e2e = step_fns(env, w, qb)
+
+    mark = sampler.mark() if sampler else 0
     for _ in range(max(args.warmup, 3)):
         step_device()
         step_e2e()
-    native.call("anr_ctx_profile_enable", ctx.handle, 1)
-    for kind in (0, 1, 2):
-        native.call("anr_ctx_profile_read", ctx.handle, kind, None, None)   # reset counters
-    ms_dev = timed(step_device, args.steps)
-    scan_ms, scan_n, bm_ms, bm_n = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
-    pass_ms, pass_n = C.c_double(), C.c_int64()
-    native.call("anr_ctx_profile_read", ctx.handle, 0, C.byref(scan_ms), C.byref(scan_n))
-    native.call("anr_ctx_profile_read", ctx.handle, 1, C.byref(bm_ms), C.byref(bm_n))
-    native.call("anr_ctx_profile_read", ctx.handle, 2, C.byref(pass_ms), C.byref(pass_n))
-    native.call("anr_ctx_profile_enable", ctx.handle, 0)
-    ms_e2e = timed(step_e2e, args.steps)
+    native.call("anr_ctx_profile_enable", env.ctx.handle, 1)
+    profile_reset(env)
+    block_ms = [timed(env, step_device, args.steps) for _ in range(max(args.blocks, 1))]
+    scan_ms, scan_n = profile_read(env, 0)
+    bm_ms, bm_n = profile_read(env, 1)
+    pass_ms, pass_n = profile_read(env, 2)
+    native.call("anr_ctx_profile_enable", env.ctx.handle, 0)
+    ms_dev = statistics.median(block_ms)          # one block of exactly `steps` steps
+    total_ms = sum(block_ms)
+    e2e_ms = [timed(env, step_e2e, args.steps) for _ in range(3)]
+    ms_e2e = statistics.median(e2e_ms)
+
+    # ---- N > 1: the three parts of a sharded step, each timed alone ---------------------------
+    multi = None
+    if world > 1:
+        ph = w.shard.phases(qb.q_dev, qb.t_dev, qb.off_dev, B, TOPK, W_DENSE, W_BM25, WRRF_K, TOPK)
+        for fn in ph.values():
+            for _ in range(3):
+                fn()
+        multi = {"local_ms": timed(env, ph["local"], args.steps) / args.steps,
+                 "allgather_ms": timed(env, ph["exchange"], args.steps) / args.steps,
+                 "merge_fuse_ms": timed(env, ph["merge_fuse"], args.steps) / args.steps,
+                 "allgather_bytes_per_rank": 2 * B * TOPK * 8,
+                 "what": "the three parts of one sharded step, each enqueued back to back "
+                         "`steps` times and timed alone (max over ranks); in a step they follow "
+                         "each other on one stream"}
 
     # ---- filtered variant (SURVEY 8d): a "CG,NG"-style source filter keeping ~2/3 of the rows,
     #      passed as row / document bit masks (search_engine.py:36-55, :221-231) ----------------
     ms_filtered = None
     if world == 1:
         rng = np.random.default_rng(99)
-        keep = rng.random(hi - lo) < (2.0 / 3.0)
-        words = torch.from_numpy(engine.pack_mask(keep).view(np.int32)).to(device)
+        keep = rng.random(w.rows) < (2.0 / 3.0)
+        words = torch.from_numpy(engine.pack_mask(keep).view(np.int32)).to(env.device)
 
         def step_filtered():
-            native.call("anr_hybrid_search", ctx.handle, dense.handle, bm25.handle,
-                        q_dev.data_ptr(), t_dev.data_ptr(), off_dev.data_ptr(), B, TOPK, TOPK,
+            native.call("anr_hybrid_search", env.ctx.handle, w.dense.handle, w.bm25.handle,
+                        qb.q_dev.data_ptr(), qb.t_dev.data_ptr(), qb.off_dev.data_ptr(), B, TOPK, TOPK,
                         words.data_ptr(), words.data_ptr(), None, 0, W_DENSE, W_BM25, WRRF_K, TOPK,
-                        out_ids.data_ptr(), out_scores.data_ptr(), out_counts.data_ptr(), None, None,
-                        None, None, engine.torch_stream_ptr())
+                        qb.out_ids.data_ptr(), qb.out_scores.data_ptr(), qb.out_counts.data_ptr(),
+                        None, None, None, None, engine.torch_stream_ptr())
         for _ in range(3):
             step_filtered()
-        ms_filtered = timed(step_filtered, args.steps)
+        ms_filtered = timed(env, step_filtered, args.steps)
 
-    # ---- batch-1 latency through the C-ABI with host buffers (p50 of wall-clock per call) -----
+    # ---- batch-1 latency through the C ABI with host buffers (p50 of wall-clock per call) -----
     lat = []
     if world == 1:
         for i in range(args.latency_iters + 20):
@@ -389,290 +570,642 @@ def run_ours(args):
             step_e2e(1)
             if i >= 20:
                 lat.append(1e3 * (time.perf_counter() - t0))
-    ms_b1_dev = timed(lambda: step_device(1), max(args.steps, 50)) / max(args.steps, 50)
-    # keep the GPU under the same load until at least a few clock samples exist
-    # (a fixed count derived from the max-reduced step time: every rank runs the same number
-    # of collectives)
-    for _ in range(int(min(2000, max(10, 1000.0 / max(ms_dev / args.steps, 1e-3))))):
+    n_b1 = max(args.steps, 50)
+    ms_b1_dev = timed(env, lambda: step_device(1), n_b1) / n_b1
+    # keep the GPU under the same load until a few clock samples exist (a fixed count derived from
+    # the max-reduced step time: every rank runs the same number of collectives)
+    for _ in range(int(min(2000, max(10, 500.0 / max(ms_dev / args.steps, 1e-3))))):
         step_device()
     torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
-    # batch-1 again through the fp32 CUDA-core scan (north_star kernel (1)): without the bf16 shadow
+    clocks = sampler.summary(mark) if sampler else None
     ms_b1_scan, lat_scan = None, []
-    if args.dense_operands == "bf16":
-        dense.set_shadow(False)
+    if shadow:   # batch-1 again through the fp32 CUDA-core scan (north_star kernel (1))
+        w.dense.set_shadow(False)
         for _ in range(5):
             step_device(1)
-        ms_b1_scan = timed(lambda: step_device(1), max(args.steps, 50)) / max(args.steps, 50)
+        ms_b1_scan = timed(env, lambda: step_device(1), n_b1) / n_b1
         if world == 1:
             for i in range(args.latency_iters + 20):
                 t0 = time.perf_counter()
                 step_e2e(1)
                 if i >= 20:
                     lat_scan.append(1e3 * (time.perf_counter() - t0))
-        dense.set_shadow(True)
+        w.dense.set_shadow(True)
+        step_device()
 
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+    # ---- the whole batch with its per-retriever lists (what the parity check reads) -----------
+    got = full_lists_sharded(env, w, qb) if world > 1 else (
+        full_lists_single_gpu(env, w, qb) if rank == 0 else None)
 
-    # ---- roofline of the dominant kernel -----------------------------------------------------
-    peak, peak_kind = load_peaks()
-    traffic = None        # dram bytes per launch, from the committed ncu captures
+    # ---- rank 0 alone from here: rooflines, graph replay, CPU port + parity ---------------------
+    res = None
+    if rank == 0:
+        res = headline_report(env, args, peaks, w, qb, got, dict(
+            block_ms=block_ms, ms_dev=ms_dev, total_ms=total_ms, ms_e2e=ms_e2e, e2e_ms=e2e_ms,
+            scan=(scan_ms, scan_n), bm=(bm_ms, bm_n), tc_pass=(pass_ms, pass_n), multi=multi,
+            ms_filtered=ms_filtered, lat=lat, ms_b1_dev=ms_b1_dev, ms_b1_scan=ms_b1_scan,
+            lat_scan=lat_scan, clocks=clocks, shadow=shadow))
+    del w, qb
+    torch.cuda.empty_cache()
+    return res
+
+
+def headline_report(env, args, peaks, w, qb, got, t):
+    torch, native, engine = env.torch, env.native, env.engine
+    world, B = env.world, qb.B
+    peak = peaks["hbm"]
+    shadow = t["shadow"]
+    rows_local = w.rows
+    scan_ms, scan_n = t["scan"]
+    bm_ms, bm_n = t["bm"]
+    pass_ms, pass_n = t["tc_pass"]
+    total_ms, ms_dev = t["total_ms"], t["ms_dev"]
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    rows_local = hi - lo
+    traffic_tbl = {}
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic_tbl = json.load(fh).get("bytes_per_launch", {})
     # anr_dense_gemm.cu takes batches > 32, and every batch when a bf16 shadow exists
-    gemm = (B > 32 or args.dense_operands == "bf16") and rows_local >= 80_000
-    shadow = gemm and args.dense_operands == "bf16"
+    gemm = (B > 32 or shadow) and rows_local >= 80_000
     tile_q = 64 if B <= 64 else (128 if B <= 128 else 256)
     dense_kernel = (f"dense_gemm_kernel<{tile_q}, {'bf16' if shadow else 'tf32'}>" if gemm else
                     (("dense_tc_pair_kernel" if B > 32 else "dense_tc_kernel<0>") if B > 8
                      else "dense_scan_kernel<1, 4, 0>"))
-    # algorithmic bytes of one launch: every row once, in the operand type the kernel reads
-    scan_bytes = rows_local * D * (2 if shadow else 4)
-    scan_avg_ms = scan_ms.value / max(scan_n.value, 1)
+    at_default = args.chunks == 1_000_000 and world == 1 and B == 64
+    scan_bytes = rows_local * D * (2 if (shadow and gemm) else 4)
+    scan_avg_ms = scan_ms / max(scan_n, 1)
     achieved = scan_bytes / (scan_avg_ms * 1e-3) / 1e9 if scan_avg_ms > 0 else 0.0
-    bm_avg_ms = bm_ms.value / max(bm_n.value, 1)
-    # BM25: 8 B (doc id + weight) per posting of every query-term occurrence of the batch
-    nd_local = post["nd"].cpu().numpy()
-    bm_bytes = 8 * int(nd_local[t_host.reshape(-1)].astype(np.int64).sum())
-    bm_achieved = bm_bytes / (bm_avg_ms * 1e-3) / 1e9 if bm_avg_ms > 0 else 0.0
-    if os.path.exists(tpath) and args.chunks == 1_000_000 and world == 1:
-        with open(tpath) as fh:
-            tj = json.load(fh)["bytes_per_launch"]
-        traffic = tj.get(dense_kernel)
-        bm_traffic = tj.get("bm25_score_kernel<0> batch 64") if B == 64 else None
-    else:
-        bm_traffic = None
+    bm_avg_ms = bm_ms / max(bm_n, 1)
+    nd_local = w.post["nd"].cpu().numpy()
+    bm_bytes = 8 * int(nd_local[qb.t_host.reshape(-1)].astype(np.int64).sum())
+    traffic = traffic_tbl.get(dense_kernel + " co-resident") if at_default else None
+    bm_traffic = traffic_tbl.get("bm25_run_kernel batch 64") if at_default else None
     dense_roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                  "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
+                  "frac": achieved / peak, "traffic": traffic, "peak_source": peaks["source"],
                   "kernel": dense_kernel, "bytes_per_launch": scan_bytes,
-                  "avg_launch_ms": scan_avg_ms, "launches": int(scan_n.value),
-                  "share_of_step": scan_ms.value / ms_dev if ms_dev else None}
-    bm_roof = {"bound": "hbm", "achieved": bm_achieved, "peak": peak, "unit": "GB/s",
-               "frac": bm_achieved / peak, "traffic": bm_traffic, "peak_source": peak_kind,
-               "kernel": "bm25_score_kernel", "bytes_per_launch": bm_bytes,
-               "avg_launch_ms": bm_avg_ms, "launches": int(bm_n.value),
-               "share_of_step": bm_ms.value / ms_dev if ms_dev else None}
-    # BM25 runs on the library's side stream UNDER the dense pass: its in-step event time includes
-    # waiting for SMs the dense kernel holds, so it is also timed alone (same batch, same kernels)
-    bm_alone_ms = None
+                  "avg_launch_ms": scan_avg_ms, "launches": int(scan_n),
+                  "share_of_step": scan_ms / total_ms if total_ms else None,
+                  "frac_traffic": (traffic / (scan_avg_ms * 1e-3) / 1e9 / peak
+                                   if traffic and scan_avg_ms > 0 else None),
+                  "co_resident": "inside the step this kernel shares every SM with the BM25 scan "
+                                 "(4-stage ring): avg_launch_ms / achieved / frac are in-step; "
+                                 "alone_* is the same batch through a dense-only call"}
+    bm_roof = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peaks["source"],
+               "kernel": "bm25_run_kernel (pruned scan by runs)", "bytes_per_launch": bm_bytes,
+               "bytes_definition": "UNPRUNED algorithmic figure, 8 B x sum of df over every query-"
+                                   "term occurrence (SURVEY 8d); the pruned scan reads `traffic`",
+               "traffic": bm_traffic, "launches": int(bm_n), "in_step_ms": bm_avg_ms,
+               "in_step_share": bm_ms / total_ms if total_ms else None}
     if world == 1:
-        k_sc = torch.empty((B, TOPK), dtype=torch.float32, device=device)
-        k_id = torch.empty((B, TOPK), dtype=torch.int32, device=device)
-        k_ct = torch.empty((B,), dtype=torch.int32, device=device)
+        # both kernels again, each ALONE (same batch, same kernels, nothing beside them)
+        k_sc = torch.empty((B, TOPK), dtype=torch.float32, device=env.device)
+        k_id = torch.empty((B, TOPK), dtype=torch.int32, device=env.device)
+        k_ct = torch.empty((B,), dtype=torch.int32, device=env.device)
 
         def bm25_only():
-            native.call("anr_bm25_search", ctx.handle, bm25.handle, t_dev.data_ptr(),
-                        off_dev.data_ptr(), B, TOPK, None, None, 0, k_sc.data_ptr(), k_id.data_ptr(),
-                        k_ct.data_ptr(), engine.torch_stream_ptr())
-        native.call("anr_ctx_profile_enable", ctx.handle, 1)
-        for _ in range(3):
-            bm25_only()
-        native.call("anr_ctx_profile_read", ctx.handle, 1, None, None)
-        for _ in range(10):
-            bm25_only()
-        torch.cuda.synchronize()
-        a_ms, a_n = C.c_double(), C.c_int64()
-        native.call("anr_ctx_profile_read", ctx.handle, 1, C.byref(a_ms), C.byref(a_n))
-        native.call("anr_ctx_profile_enable", ctx.handle, 0)
-        bm_alone_ms = a_ms.value / max(a_n.value, 1)
-        # the roofline figures of the BM25 launch come from this pass; its in-step event time
-        # (which includes waiting for SMs the dense kernel holds) is kept beside them
-        bm_roof["overlapped"] = ("runs on a side stream under the dense pass: avg_launch_ms / achieved "
-                                 "/ frac are the same launch timed right after the timed region "
-                                 "without the dense pass; in_step_ms is its event time inside the step")
-        bm_roof["in_step_ms"] = bm_avg_ms
-        bm_roof["in_step_share"] = bm_roof["share_of_step"]
-        if bm_alone_ms:
-            bm_roof["share_of_step"] = bm_alone_ms * max(bm_n.value, 1) / ms_dev if ms_dev else None
-            bm_roof["avg_launch_ms"] = bm_alone_ms
-            bm_roof["achieved"] = bm_bytes / (bm_alone_ms * 1e-3) / 1e9
-            bm_roof["frac"] = bm_roof["achieved"] / peak
-    # Co-resident configuration (ANR_GEMM_BESIDE_STAGES / ANR_GEMM_MAX_STAGES: the dense main kernel
-    # shares every SM with the BM25 scan): its in-step time includes that sharing,
-    # so the same batch is also timed through a dense-only call, as is done for BM25 above.  Only
-    # active when one of the two knobs is set: the default run does not execute this block.
-    if world == 1 and (os.environ.get("ANR_GEMM_BESIDE_STAGES") or os.environ.get("ANR_GEMM_MAX_STAGES")):
-        try:
-            d_sc = torch.empty((B, TOPK), dtype=torch.float32, device=device)
-            d_id = torch.empty((B, TOPK), dtype=torch.int32, device=device)
-            d_ct = torch.empty((B,), dtype=torch.int32, device=device)
+            native.call("anr_bm25_search", env.ctx.handle, w.bm25.handle, qb.t_dev.data_ptr(),
+                        qb.off_dev.data_ptr(), B, TOPK, None, None, 0, k_sc.data_ptr(),
+                        k_id.data_ptr(), k_ct.data_ptr(), engine.torch_stream_ptr())
 
-            def dense_only():
-                native.call("anr_dense_search", ctx.handle, dense.handle, q_dev.data_ptr(), B, TOPK,
-                            None, 0, d_sc.data_ptr(), d_id.data_ptr(), d_ct.data_ptr(),
-                            engine.torch_stream_ptr())
-            native.call("anr_ctx_profile_enable", ctx.handle, 1)
+        def dense_only():
+            native.call("anr_dense_search", env.ctx.handle, w.dense.handle, qb.q_dev.data_ptr(), B,
+                        TOPK, None, 0, k_sc.data_ptr(), k_id.data_ptr(), k_ct.data_ptr(),
+                        engine.torch_stream_ptr())
+        for fn, kind, roof, nbytes in ((bm25_only, 1, bm_roof, bm_bytes),
+                                       (dense_only, 0, dense_roof, scan_bytes)):
+            native.call("anr_ctx_profile_enable", env.ctx.handle, 1)
             for _ in range(3):
-                dense_only()
-            native.call("anr_ctx_profile_read", ctx.handle, 0, None, None)
+                fn()
+            profile_reset(env)
             for _ in range(10):
-                dense_only()
-            torch.cuda.synchronize()
-            a_ms, a_n = C.c_double(), C.c_int64()
-            native.call("anr_ctx_profile_read", ctx.handle, 0, C.byref(a_ms), C.byref(a_n))
-            native.call("anr_ctx_profile_enable", ctx.handle, 0)
-            alone = a_ms.value / max(a_n.value, 1)
-            dense_roof["co_resident"] = ("shares every SM with the BM25 scan inside the step: "
-                                         "avg_launch_ms / achieved / frac are in-step; alone_* is the "
-                                         "same batch through a dense-only call")
-            dense_roof["alone_ms"] = alone
-            dense_roof["alone_achieved"] = scan_bytes / (alone * 1e-3) / 1e9 if alone > 0 else None
-            dense_roof["alone_frac"] = dense_roof["alone_achieved"] / peak if alone > 0 else None
-        except Exception as exc:
-            dense_roof["alone_error"] = repr(exc)[:200]
-    # dominant kernel = larger exclusive time (BM25 judged by its time alone when overlapped)
-    bm_cmp = bm_alone_ms * max(bm_n.value, 1) if bm_alone_ms else bm_ms.value
-    dominant = dense_roof if scan_ms.value >= bm_cmp else bm_roof
+                fn()
+            a_ms, a_n = profile_read(env, kind)
+            native.call("anr_ctx_profile_enable", env.ctx.handle, 0)
+            alone = a_ms / max(a_n, 1)
+            roof["alone_ms"] = alone
+            roof["alone_achieved"] = nbytes / (alone * 1e-3) / 1e9 if alone > 0 else None
+            roof["alone_frac"] = roof["alone_achieved"] / peak if alone > 0 else None
+    # BM25's headline figures are those of the launch timed alone (its in-step event time includes
+    # sharing the SMs with the dense kernel); the in-step time is kept beside them
+    bm_time = bm_roof.get("alone_ms") or bm_avg_ms
+    bm_roof["avg_launch_ms"] = bm_time
+    bm_roof["achieved"] = bm_bytes / (bm_time * 1e-3) / 1e9 if bm_time > 0 else 0.0
+    bm_roof["frac"] = bm_roof["achieved"] / peak
+    bm_roof["frac_traffic"] = (bm_traffic / (bm_time * 1e-3) / 1e9 / peak
+                               if bm_traffic and bm_time > 0 else None)
+    bm_roof["share_of_step"] = bm_time * max(bm_n, 1) / total_ms if total_ms else None
+    dominant = dense_roof if scan_ms >= bm_time * max(bm_n, 1) else bm_roof
 
-    # ---- the same step replayed from a CUDA graph (graph.HybridGraph) -----------------
-    # Reported beside the eager numbers, which stay the headline: one launch instead of ~20 plus
-    # the fork/join event traffic.  Results must equal the eager call's bit for bit.
+    # ---- the same step replayed from a CUDA graph (graph.HybridGraph) ----------------
     graph_rec = None
     if world == 1:
         try:
             graph_mod = importlib.import_module("a-nice-rag_b200.graph")
+            step_device, _ = step_fns(env, w, qb)
             graph_rec = {}
             n_it = max(args.steps, 50)
             for b_g in sorted({1, B}):
-                hg = graph_mod.HybridGraph(dense, bm25, b_g, N_TERMS * b_g, TOPK, TOPK, W_DENSE,
+                hg = graph_mod.HybridGraph(w.dense, w.bm25, b_g, N_TERMS * b_g, TOPK, TOPK, W_DENSE,
                                            W_BM25, WRRF_K, TOPK)
-                hg.load(q_dev[:b_g], t_dev[:N_TERMS * b_g], off_dev[:b_g + 1])
+                hg.load(qb.q_dev[:b_g], qb.t_dev[:N_TERMS * b_g], qb.off_dev[:b_g + 1])
                 for _ in range(5):
                     hg.replay()
                 step_device(b_g)
                 torch.cuda.synchronize()
-                same = bool(torch.equal(hg.ids, out_ids[:b_g]) and
-                            torch.equal(hg.scores, out_scores[:b_g]) and
-                            torch.equal(hg.counts, out_counts[:b_g]))
-                ms_g = timed(hg.replay, n_it) / n_it
+                same = bool(torch.equal(hg.ids, qb.out_ids[:b_g]) and
+                            torch.equal(hg.scores, qb.out_scores[:b_g]) and
+                            torch.equal(hg.counts, qb.out_counts[:b_g]))
+                ms_g = timed(env, hg.replay, n_it) / n_it
                 graph_rec[f"batch{b_g}"] = {"replay_ms": ms_g, "queries_per_s": 1e3 * b_g / ms_g,
                                             "identical_to_eager": same}
                 del hg
         except Exception as exc:   # never lose the headline line to the optional replay leg
             graph_rec = {"error": repr(exc)[:300]}
 
-    # ---- OPT-IN (ANR_BENCH_PIPELINE=1): host buffers in / out with two batches in flight
-    #      (graph.HybridPipeline, experimental until it has run on a B200) --------------------------
-    pipe_rec = None
-    if world == 1 and os.environ.get("ANR_BENCH_PIPELINE") == "1":
-        try:
-            graph_mod = importlib.import_module("a-nice-rag_b200.graph")
-            pipe = graph_mod.HybridPipeline(dense, bm25, B, N_TERMS * B, TOPK, TOPK, W_DENSE, W_BM25,
-                                            WRRF_K, TOPK, depth=2)
-            t_flat = t_host.reshape(-1)
-
-            def run_pipe(n_steps):
-                for i in range(n_steps):
-                    if i >= 2:
-                        pipe.collect()
-                    pipe.submit(q_host, t_flat, off_host)
-                last = None
-                for _ in range(min(2, n_steps)):
-                    last = pipe.collect()
-                return last
-            run_pipe(6)
-            step_device()
-            torch.cuda.synchronize()
-            last = run_pipe(3)
-            same = bool(np.array_equal(last[0], out_ids.cpu().numpy()) and
-                        np.array_equal(last[1], out_scores.cpu().numpy()))
-            n_it = max(args.steps, 50)
-            t0 = time.perf_counter()
-            run_pipe(n_it)
-            dt = time.perf_counter() - t0
-            pipe_rec = {"value": B * n_it / dt, "unit": "queries/s", "ms_per_step": 1e3 * dt / n_it,
-                        "depth": 2, "identical_to_eager": same,
-                        "timing": "host wall clock over the whole loop (every result read on the host)"}
-        except Exception as exc:
-            pipe_rec = {"error": repr(exc)[:300]}
-
-    # ---- CPU baseline + parity of this very batch (N = 1) --------------------------------------
-    cpu = None
-    checked = 0
-    if world == 1 and not args.no_cpu_baseline:
-        emb_host = emb.cpu().numpy()
-        post_host = {k: v.cpu().numpy() for k, v in post.items()}
-        emb_h, index = cpu_port_setup(emb_host, post_host, idf, avgdl)
+    # ---- CPU baseline + parity of EVERY query of this very batch --------------------------------
+    cpu, checked, parity_error = None, 0, None
+    if not args.no_cpu_baseline:
+        cores = set_cpu_threads()
+        shards = []
+        for r in range(world):   # rank 0 re-creates the other ranks' shards (seeded generators)
+            lo, hi = env.sharded.shard_range(args.chunks, r, world)
+            emb_r, post_r = (w.emb, w.post) if r == env.rank else make_shard(
+                env.synth, env.device, lo, hi, r, args.vocab)
+            post_host = {k: v.cpu().numpy() for k, v in post_r.items()}
+            shards.append((lo, emb_r.cpu().numpy(), cpu_index(post_host, w.idf, w.avgdl)))
+            del emb_r, post_r
         nq_cpu = min(args.cpu_queries, B)
-        cpu_port_run(emb_h, index, q_host, t_host, 1)                       # warm caches / BLAS
-        dt, results = cpu_port_run(emb_h, index, q_host, t_host, nq_cpu)
-        cpu = {"value": nq_cpu / dt, "unit": "queries/s", "cores": cpu_threads(), "kind": "port",
+        which = list(range(nq_cpu))
+        cpu_port_run(shards, qb.q_host, qb.t_host, [0])                      # warm caches / BLAS
+        dt, results = cpu_port_run(shards, qb.q_host, qb.t_host, which)
+        cpu = {"value": nq_cpu / dt, "unit": "queries/s", "cores": cores, "kind": "port",
                "sample": f"{nq_cpu} of the batch's {B} queries over the full {args.chunks}-chunk "
                          "corpus; numpy BLAS dot + CSR BM25 + Python RRF on a pre-stacked matrix "
                          "(the reference's per-query np.stack and pandas work NOT included)"}
-        # the WHOLE batch through the same kernels as the timed steps; the sampled queries are checked
-        got = engine.hybrid_search(dense, bm25, q_host, [list(map(int, t)) for t in t_host],
-                                   TOPK, TOPK, W_DENSE, W_BM25, WRRF_K, TOPK, want_lists=True)
-        for r in results:   # full dense score vector only where ids differ is costly: recompute lazily
-            r["dense_all"] = None
-        for q in range(nq_cpu):
-            if not np.array_equal(got["dense_rows"][q], results[q]["dense_ids"]):
-                results[q]["dense_all"] = emb_h @ q_host[q]
-        checked = check_against_cpu(results, got, nq_cpu)
+        try:
+            cpu["stock_path_config0"] = stock_path_config0()
+        except Exception as exc:
+            cpu["stock_path_config0"] = {"error": repr(exc)[:200]}
+        try:
+            checked = check_against_cpu(results, got, shards, qb.q_host)
+        except AssertionError as exc:
+            parity_error = str(exc)[:500]
+        del shards
 
+    steps = args.steps
     line = {
-        "metric": METRIC, "value": B * args.steps / (ms_dev * 1e-3), "unit": "queries/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "metric": METRIC, "value": B * steps / (ms_dev * 1e-3), "unit": "queries/s",
+        "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_dev / steps, "higher_is_better": True,
         "scaling": "weak" if args.chunks_per_gpu else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "batch": B, "sharding": f"chunks/{world}",
-                   "l2": "inputs larger than L2 (corpus shard >= 0.5 GB per GPU)",
-                   "bm25_postings_local": n_postings},
-        "e2e": {"value": B * args.steps / (ms_e2e * 1e-3), "unit": "queries/s",
-                "h2d_bytes_per_step": int(q_pin.numel() * 4 + t_pin.numel() * 4 + off_pin.numel() * 4),
-                "d2h_bytes_per_step": int(h_ids.numel() * 4 + h_scores.numel() * 8 + h_counts.numel() * 4)},
-        # kernels of this repo launched per step: dense (CUDA-core scan + final | tcgen05:
-        # pre-pass(es) + threshold + scan + rescore + flag compaction + flagged rescan + its merge),
-        # BM25 score + final, weights, WRRF; sharded: + the two merges of anr_sharded_fuse
-        # GEMM path: [query -> bf16] + sample pass + thresholds + GEMM + rescore + flag
-        # compaction + flagged rescan + its merge; BM25: [sample launch] + scan + final top-k;
-        # then the weight upload kernel and WRRF
-        "gpu_launches": int(args.steps * (
-            (7 + (1 if shadow else 0) if gemm else ((8 if B > 32 else 7) if B > 8 else 2))
-            + (3 if B >= 16 and (rows_local + 6143) // 6144 >= 32 else 2) + 2
-            + (2 if world > 1 else 0))),
-        # the kernel with the largest share of the step; the other one follows
+        "config": headline_config(args),
+        "shard": {"rows_local": rows_local, "bm25_postings_local": w.bm25.n_postings},
+        "blocks": {"n": len(t["block_ms"]), "steps_per_block": steps,
+                   "what": "value / ms_per_step are the median block; every block is exactly "
+                           "`steps` steps between two barriers, max over ranks",
+                   "ms_per_step_min": min(t["block_ms"]) / steps,
+                   "ms_per_step_max": max(t["block_ms"]) / steps,
+                   "ms_per_step_all": [m / steps for m in t["block_ms"]]},
+        "e2e": {"value": B * steps / (t["ms_e2e"] * 1e-3), "unit": "queries/s",
+                "h2d_bytes_per_step": int(qb.q_pin.numel() * 4 + qb.t_pin.numel() * 4 +
+                                          qb.off_pin.numel() * 4),
+                "d2h_bytes_per_step": int(qb.h_ids.numel() * 4 + qb.h_scores.numel() * 8 +
+                                          qb.h_counts.numel() * 4),
+                "ms_per_step_all": [m / steps for m in t["e2e_ms"]]},
+        # kernels of this repo launched per step.  GEMM path: query -> bf16, sample pass,
+        # thresholds, GEMM, rescore, flag compaction, flagged rescan, its merge (8; 7 with tf32
+        # operands); BM25: sample launch, main launch, final top-k, empty-query fix-up (4); weights
+        # + WRRF (2); sharded: the fusion side is weights + 2 merges + WRRF (4)
+        "gpu_launches": int(steps * len(t["block_ms"]) * (
+            ((8 if shadow else 7) if gemm else ((8 if B > 32 else 7) if B > 8 else 2)) + 4
+            + (4 if world > 1 else 2))),
         "roofline": dominant,
         "roofline_other": bm_roof if dominant is dense_roof else dense_roof,
+        "step_traffic": ({"dram_bytes": traffic + bm_traffic, "ms_at_peak": (traffic + bm_traffic) / peak / 1e6,
+                          "frac_of_peak": (traffic + bm_traffic) / peak / 1e6 / (ms_dev / steps)}
+                         if traffic and bm_traffic else None),
         "dense_operands": ("bf16 shadow copy" if shadow else "fp32 words as tf32") if (B > 8 or gemm) else "fp32",
         "dense_tc_pass": {"what": "sample pre-pass + threshold + scan + exact rescoring",
-                          "avg_ms": pass_ms.value / max(pass_n.value, 1), "passes": int(pass_n.value),
-                          "share_of_step": pass_ms.value / ms_dev if ms_dev else None},
-        "batch1": {"device_ms": ms_b1_dev, "device_qps": 1e3 / ms_b1_dev if ms_b1_dev else None,
-                   "e2e_p50_ms": statistics.median(lat) if lat else None,
-                   "e2e_p95_ms": (sorted(lat)[int(0.95 * len(lat))] if lat else None),
+                          "avg_ms": pass_ms / max(pass_n, 1), "passes": int(pass_n),
+                          "share_of_step": pass_ms / total_ms if total_ms else None},
+        "batch1": {"device_ms": t["ms_b1_dev"],
+                   "device_qps": 1e3 / t["ms_b1_dev"] if t["ms_b1_dev"] else None,
+                   "e2e_p50_ms": statistics.median(t["lat"]) if t["lat"] else None,
+                   "e2e_p95_ms": (sorted(t["lat"])[int(0.95 * len(t["lat"]))] if t["lat"] else None),
                    "dense_path": ("bf16 shadow GEMM pass + exact fp32 rescoring" if shadow
                                   else "fp32 CUDA-core scan")},
-        "batch1_fp32_scan": ({"device_ms": ms_b1_scan,
-                              "e2e_p50_ms": statistics.median(lat_scan) if lat_scan else None,
-                              "hbm_gbs": rows_local * D * 4 / (ms_b1_scan * 1e-3) / 1e9,
-                              "frac_of_peak": rows_local * D * 4 / (ms_b1_scan * 1e-3) / 1e9 / peak}
-                             if ms_b1_scan else None),
+        "batch1_fp32_scan": ({"device_ms": t["ms_b1_scan"],
+                              "e2e_p50_ms": statistics.median(t["lat_scan"]) if t["lat_scan"] else None,
+                              "hbm_gbs": rows_local * D * 4 / (t["ms_b1_scan"] * 1e-3) / 1e9,
+                              "frac_of_peak": rows_local * D * 4 / (t["ms_b1_scan"] * 1e-3) / 1e9 / peak}
+                             if t["ms_b1_scan"] else None),
         "filtered": ({"what": "same step with row / document masks keeping 2/3 of the corpus "
                               "(the reference's source-prefix filter)",
-                      "value": B * args.steps / (ms_filtered * 1e-3), "unit": "queries/s",
-                      "ms_per_step": ms_filtered / args.steps} if ms_filtered else None),
+                      "value": B * steps / (t["ms_filtered"] * 1e-3), "unit": "queries/s",
+                      "ms_per_step": t["ms_filtered"] / steps} if t["ms_filtered"] else None),
         "cuda_graph": graph_rec,
-        "e2e_pipelined": pipe_rec,
-        "clocks": clocks, "parity_checked_queries": checked,
+        "multi_gpu": t["multi"],
+        "clocks": t["clocks"], "parity_checked_queries": checked,
     }
+    if parity_error:
+        line["parity_error"] = parity_error
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    return line
+
+
+# ---------------------------------------------------------------------------------------
+# extra legs: the other BASELINE configs, bounded
+# ---------------------------------------------------------------------------------------
+def slab_iter(env, emb, slab_rows: int = 1 << 18):
+    """(first row, host fp32 [rows, D]) slabs of a device matrix through one pinned buffer."""
+    torch = env.torch
+    n = emb.shape[0]
+    pin = torch.empty((min(slab_rows, n), emb.shape[1]), dtype=torch.float32).pin_memory()
+    for r0 in range(0, n, slab_rows):
+        r1 = min(n, r0 + slab_rows)
+        pin[:r1 - r0].copy_(emb[r0:r1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        yield r0, pin[:r1 - r0].numpy()
+
+
+def bm25_term_fetcher(post):
+    tp = post["term_ptr"]
+
+    def fetch(t: int):
+        lo, hi = int(tp[t]), int(tp[t + 1])
+        return post["post_doc"][lo:hi].cpu().numpy(), post["post_tf"][lo:hi].cpu().numpy()
+    return fetch
+
+
+def measure_tf32_peak(env):
+    """cuBLAS tf32 throughput the way MEASURED_PEAKS.json measures bf16: 8192^3, best of 6."""
+    torch = env.torch
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn((8192, 8192), device=env.device)
+        b = torch.randn((8192, 8192), device=env.device)
+        best = 1e9
+        for _ in range(8):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            torch.matmul(a, b)
+            e.record()
+            torch.cuda.synchronize()
+            best = min(best, s.elapsed_time(e))
+        return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def run_big_legs(env, args, peaks, sampler):
+    """BASELINE configs[2], configs[3] and the batch-1 10M target on ONE GPU (rank 0, world 1)."""
+    from oracle import retrieval, slabs
+    torch, native, engine, synth = env.torch, env.native, env.engine, env.synth
+    n, vocab, steps = args.big_chunks, args.big_vocab, max(args.leg_steps, 3)
+    out = {}
+    stream = engine.torch_stream_ptr
+    emb = synth.unit_vectors_torch(n, D, EMB_SEED, env.device)
+    dense = engine.DenseIndex(emb, borrow=True)
+    dense.set_shadow(True)
+
+    # ---- configs[2]: 10M x 1024, batch 1024, dense-only top-100 ------------------------------
+    b3, k3 = 1024, 100
+    q3_host = synth.unit_vectors(b3, D, seed=Q_SEED)
+    q3 = torch.from_numpy(q3_host).to(env.device)
+    sc3 = torch.empty((b3, k3), dtype=torch.float32, device=env.device)
+    id3 = torch.empty((b3, k3), dtype=torch.int32, device=env.device)
+    ct3 = torch.empty((b3,), dtype=torch.int32, device=env.device)
+
+    def dense_step():
+        native.call("anr_dense_search", env.ctx.handle, dense.handle, q3.data_ptr(), b3, k3, None, 0,
+                    sc3.data_ptr(), id3.data_ptr(), ct3.data_ptr(), stream())
+    rec3 = {"workload": f"{n} chunks x {D}-d, batch {b3}, dense-only top-{k3} "
+                        "(tcgen05 GEMM nomination + exact fp32 rescoring)"}
+    flops = 2.0 * b3 * n * D
+    for operands in ("bf16", "tf32"):
+        dense.set_shadow(operands == "bf16")
+        mark = sampler.mark() if sampler else 0
+        for _ in range(3):
+            dense_step()
+        native.call("anr_ctx_profile_enable", env.ctx.handle, 1)
+        profile_reset(env)
+        ms = timed(env, dense_step, steps) / steps
+        k_ms, k_n = profile_read(env, 0)
+        native.call("anr_ctx_profile_enable", env.ctx.handle, 0)
+        kernel_ms = k_ms / max(k_n, 1)
+        r = {"ms_per_batch": ms, "queries_per_s": 1e3 * b3 / ms, "steps": steps,
+             "kernel_ms": kernel_ms, "tflops_kernel": flops / (kernel_ms * 1e-3) / 1e12,
+             "tflops_step": flops / (ms * 1e-3) / 1e12,
+             "clocks": sampler.summary(mark) if sampler else None}
+        if operands == "bf16":
+            r["roofline"] = {"bound": "tensor", "achieved": r["tflops_kernel"], "peak": peaks["bf16"],
+                             "unit": "TFLOP/s", "frac": r["tflops_kernel"] / peaks["bf16"],
+                             "peak_sustained": peaks["bf16_sustained"],
+                             "frac_sustained": r["tflops_kernel"] / peaks["bf16_sustained"],
+                             "peak_source": peaks["source"], "traffic": None,
+                             "kernel": "dense_gemm2_kernel<256, bf16> (cta_group::2)"}
+            if k3 == 100:
+                rec3["rows_bf16"] = id3.cpu().numpy()
+                rec3["scores_bf16"] = sc3.cpu().numpy()
+        else:
+            tf32_peak = measure_tf32_peak(env)
+            r["roofline"] = {"bound": "tensor", "achieved": r["tflops_kernel"], "peak": tf32_peak,
+                             "unit": "TFLOP/s", "frac": r["tflops_kernel"] / tf32_peak,
+                             "peak_source": "measured in this run: torch.matmul fp32 with "
+                                            "allow_tf32, 8192^3, best of 8", "traffic": None,
+                             "kernel": "dense_gemm2_kernel<256, tf32> (cta_group::2)"}
+            rec3["identical_to_bf16"] = bool(
+                np.array_equal(rec3["rows_bf16"], id3.cpu().numpy()) and
+                np.array_equal(rec3["scores_bf16"], sc3.cpu().numpy()))
+        rec3[operands] = r
+    dense.set_shadow(True)
+    rows3, scores3 = rec3.pop("rows_bf16"), rec3.pop("scores_bf16")
+
+    # ---- BM25 index over the same 10M documents (V = 500k) --------------------------------------
+    post = synth.zipf_postings_torch(n, vocab, ZIPF_S, POST_SEED, env.device)
+    nd = post["nd"].cpu().numpy()
+    idf = synth.idf_from_counts(n, nd, EPS)
+    avgdl = float(post["doc_len"].to(torch.int64).sum()) / n
+    bm25 = engine.Bm25Index(post["term_ptr"], post["post_doc"], post["post_tf"], post["doc_len"],
+                            idf, K1, B_PARAM, avgdl, n_terms=vocab, n_docs=n)
+
+    # ---- configs[3]: BM25-only, batch 256, top-10 --------------------------------------------
+    b4 = 256
+    tq4 = synth.zipf_queries(b4, N_TERMS, vocab, ZIPF_S, seed=T_SEED)
+    t4 = torch.from_numpy(tq4.reshape(-1).copy()).to(env.device)
+    o4 = torch.arange(0, (b4 + 1) * N_TERMS, N_TERMS, dtype=torch.int32, device=env.device)
+    sc4 = torch.empty((b4, TOPK), dtype=torch.float32, device=env.device)
+    id4 = torch.empty((b4, TOPK), dtype=torch.int32, device=env.device)
+    ct4 = torch.empty((b4,), dtype=torch.int32, device=env.device)
+
+    def bm25_step():
+        native.call("anr_bm25_search", env.ctx.handle, bm25.handle, t4.data_ptr(), o4.data_ptr(), b4,
+                    TOPK, None, None, 0, sc4.data_ptr(), id4.data_ptr(), ct4.data_ptr(), stream())
+    mark = sampler.mark() if sampler else 0
+    for _ in range(3):
+        bm25_step()
+    native.call("anr_ctx_profile_enable", env.ctx.handle, 1)
+    profile_reset(env)
+    ms4 = timed(env, bm25_step, steps) / steps
+    k_ms, k_n = profile_read(env, 1)
+    native.call("anr_ctx_profile_enable", env.ctx.handle, 0)
+    kernel4 = k_ms / max(k_n, 1)
+    bytes4 = 8 * int(nd[tq4.reshape(-1)].astype(np.int64).sum())
+    rec4 = {"workload": f"BM25-only, {n} docs, V={vocab}, Zipf {ZIPF_S}, {N_TERMS}-term queries, "
+                        f"batch {b4}, top-{TOPK}",
+            "postings": bm25.n_postings, "ms_per_batch": ms4, "queries_per_s": 1e3 * b4 / ms4,
+            "steps": steps, "sum_df_per_query": bytes4 / 8 / b4,
+            "roofline": {"bound": "hbm", "achieved": bytes4 / (kernel4 * 1e-3) / 1e9,
+                         "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": bytes4 / (kernel4 * 1e-3) / 1e9 / peaks["hbm"],
+                         "bytes_per_launch": bytes4, "avg_launch_ms": kernel4,
+                         "bytes_definition": "UNPRUNED algorithmic figure (8 B x sum of df); the "
+                                             "pruned scan skips most of it, so frac may exceed 1",
+                         "traffic": None, "peak_source": peaks["source"],
+                         "kernel": "bm25_run_kernel (pruned scan by runs)"},
+            "clocks": sampler.summary(mark) if sampler else None}
+
+    # ---- batch-1 hybrid at 10M (the >= 70 % of HBM roofline target) -----------------------------
+    qb = QueryBatch(env, 1, vocab)
+    rec1 = {"workload": workload_name(n, vocab) + ", batch 1"}
+
+    def hybrid1(want=False):
+        return engine.hybrid_search(dense, bm25, qb.q_host, [list(map(int, qb.t_host[0]))], TOPK,
+                                    TOPK, W_DENSE, W_BM25, WRRF_K, TOPK, want_lists=True)
+
+    def hybrid1_dev():
+        native.call("anr_hybrid_search", env.ctx.handle, dense.handle, bm25.handle,
+                    qb.q_dev.data_ptr(), qb.t_dev.data_ptr(), qb.off_dev.data_ptr(), 1, TOPK, TOPK,
+                    None, None, None, 0, W_DENSE, W_BM25, WRRF_K, TOPK, qb.out_ids.data_ptr(),
+                    qb.out_scores.data_ptr(), qb.out_counts.data_ptr(), None, None, None, None,
+                    stream())
+    got1 = {}
+    for path in ("bf16_shadow", "fp32_scan"):
+        dense.set_shadow(path == "bf16_shadow")
+        mark = sampler.mark() if sampler else 0
+        for _ in range(3):
+            hybrid1_dev()
+        native.call("anr_ctx_profile_enable", env.ctx.handle, 1)
+        profile_reset(env)
+        ms = timed(env, hybrid1_dev, steps) / steps
+        k_ms, k_n = profile_read(env, 0)
+        native.call("anr_ctx_profile_enable", env.ctx.handle, 0)
+        nbytes = n * D * (2 if path == "bf16_shadow" else 4)
+        kernel_ms = k_ms / max(k_n, 1)
+        rec1[path] = {"device_ms": ms, "steps": steps, "dense_kernel_ms": kernel_ms,
+                      "bytes_per_step": nbytes,
+                      "hbm_gbs_step": nbytes / (ms * 1e-3) / 1e9,
+                      "frac_of_hbm_peak_step": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm"],
+                      "frac_of_hbm_peak_kernel": (nbytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm"]
+                                                  if kernel_ms > 0 else None),
+                      "clocks": sampler.summary(mark) if sampler else None}
+        got1[path] = hybrid1()
+    dense.set_shadow(True)
+    rec1["target"] = ">= 0.70 of the measured HBM peak for the batch-1 hybrid step (north_star)"
+
+    # ---- parity: ONE slab sweep of the corpus serves configs[2] (4 sampled queries, top-100)
+    #      and the batch-1 query (= query 0, top-10); BM25 from the postings of the query terms ---
+    sample3 = [0, 341, 682, 1023]
+    try:
+        want_ids, want_sc = slabs.dense_topk_slabs(slab_iter(env, emb), q3_host[sample3], k3)
+
+        def score_of_factory(qv):
+            return lambda row: float(np.dot(emb[row].cpu().numpy(), qv))
+        for j, q in enumerate(sample3):
+            slabs.assert_topk_matches(rows3[q], scores3[q], want_ids[j], want_sc[j],
+                                      score_of_factory(q3_host[q]), what=f"config3 q{q}")
+        rec3["parity_checked_queries"] = len(sample3)
+        fetch = bm25_term_fetcher(post)
+        doc_len_host = post["doc_len"].cpu().numpy()
+        idf_of = lambda t: float(idf[t])   # noqa: E731
+        # batch-1 hybrid: both dense paths, same lists
+        b_all = slabs.bm25_scores_subindex(fetch, qb.t_host[0], doc_len_host, idf_of, avgdl, K1, B_PARAM)
+        b_docs = retrieval.bm25_topk(b_all, TOPK)
+        for path, g in got1.items():
+            slabs.assert_topk_matches(g["dense_rows"][0], g["dense_scores"][0], want_ids[0][:TOPK],
+                                      want_sc[0][:TOPK], score_of_factory(q3_host[0]),
+                                      what=f"batch1_10M dense {path}")
+            retrieval.assert_ranking_matches(g["bm25_ids"][0], g["bm25_scores"][0], b_docs,
+                                             b_all[b_docs], all_scores=b_all, rtol=1e-5, atol=1e-6,
+                                             what=f"batch1_10M bm25 {path}")
+            from oracle import pipeline
+            c = int(g["counts"][0])
+            pipeline.check_fused(g["ids"][0, :c], g["scores"][0, :c], g["dense_rows"][0],
+                                 g["bm25_ids"][0], (W_DENSE, W_BM25), WRRF_K, TOPK)
+        rec1["parity_checked_queries"] = 1
+        # configs[3]: 4 sampled queries of the batch
+        ids4, scs4 = id4.cpu().numpy(), sc4.cpu().numpy()
+        sample4 = [0, 85, 170, 255]
+        for q in sample4:
+            b_all = slabs.bm25_scores_subindex(fetch, tq4[q], doc_len_host, idf_of, avgdl, K1, B_PARAM)
+            b_docs = retrieval.bm25_topk(b_all, TOPK)
+            retrieval.assert_ranking_matches(ids4[q], scs4[q], b_docs, b_all[b_docs],
+                                             all_scores=b_all, rtol=1e-5, atol=1e-6,
+                                             what=f"config4 q{q}")
+        rec4["parity_checked_queries"] = len(sample4)
+    except AssertionError as exc:
+        out["parity_error"] = str(exc)[:500]
+    out["config3"], out["config4"], out["batch1_10M"] = rec3, rec4, rec1
+    del dense, bm25, emb, post
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_weak_leg(env, args, peaks, sampler):
+    """BASELINE configs[4] protocol (i): 12.5M chunks per GPU (100M on 8 GPUs), hybrid batch 64 and
+    batch 1; per-GPU bytes are constant, so the ideal latency is.  Parity: every rank scores the
+    sampled queries over ITS shard with the oracle (dense slab-wise, BM25 from the query terms'
+    postings, global idf), rank 0 merges those lists and compares with the all-gathered result."""
+    from oracle import pipeline, retrieval, slabs
+    torch, engine = env.torch, env.engine
+    rank, world = env.rank, env.world
+    per_gpu, steps = args.weak_chunks_per_gpu, max(args.leg_steps, 3)
+    n_total = per_gpu * world
+    free = engine.context(env.device.index).info()[2]
+    need = per_gpu * D * 6 + per_gpu * 160 * 14        # matrix + shadow + postings (+ build slack)
+    ok = torch.tensor([1 if free > need else 0], device=env.device)
+    if world > 1:
+        env.dist.all_reduce(ok, op=env.dist.ReduceOp.MIN)
+    if int(ok) == 0:
+        return {"skipped": f"needs ~{need / 1e9:.0f} GB free per GPU, {free / 1e9:.0f} GB available"}
+    w = Workload(env, n_total, args.vocab, True)
+    rec = {"workload": workload_name(n_total, args.vocab) + f", {per_gpu} chunks per GPU",
+           "n_gpus": world, "scaling": "weak", "rows_local": w.rows,
+           "bm25_postings_local": w.bm25.n_postings}
+    got = None
+    for B in (64, 1):
+        qb = QueryBatch(env, B, args.vocab) if B == 64 else qb64_view(env, qb64, 1)
+        if B == 64:
+            qb64 = qb
+        step_device, _ = step_fns(env, w, qb)
+        mark = sampler.mark() if sampler else 0
+        for _ in range(3):
+            step_device()
+        env.native.call("anr_ctx_profile_enable", env.ctx.handle, 1)
+        profile_reset(env)
+        ms = timed(env, step_device, steps) / steps
+        k_ms, k_n = profile_read(env, 0)
+        env.native.call("anr_ctx_profile_enable", env.ctx.handle, 0)
+        kernel_ms = k_ms / max(k_n, 1)
+        nbytes = w.rows * D * 2       # the bf16 shadow pass reads every local row once
+        rec[f"batch{B}"] = {
+            "ms_per_step": ms, "queries_per_s": 1e3 * B / ms, "steps": steps,
+            "dense_kernel_ms": kernel_ms, "bytes_per_gpu_per_step": nbytes,
+            "frac_of_hbm_peak_step": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm"],
+            "frac_of_hbm_peak_kernel": (nbytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm"]
+                                        if kernel_ms > 0 else None),
+            "clocks": sampler.summary(mark) if sampler and rank == 0 else None}
+        if B == 64:
+            got = (full_lists_sharded(env, w, qb) if world > 1 else
+                   full_lists_single_gpu(env, w, qb))
+    # ---- parity on sampled queries of the batch-64 result ------------------------------------
+    sample = [0, 21, 42, 63]
+    try:
+        set_cpu_threads()
+        ids_l, sc_l = slabs.dense_topk_slabs(slab_iter(env, w.emb), qb64.q_host[sample], TOPK)
+        fetch = bm25_term_fetcher(w.post)
+        doc_len_host = w.post["doc_len"].cpu().numpy()
+        idf_of = lambda t: float(w.idf[t])   # noqa: E731
+        local = []
+        for j, q in enumerate(sample):
+            b_all = slabs.bm25_scores_subindex(fetch, qb64.t_host[q], doc_len_host, idf_of, w.avgdl,
+                                               K1, B_PARAM)
+            b_docs = retrieval.bm25_topk(b_all, TOPK)
+            local.append(dict(dense_ids=ids_l[j] + w.lo, dense_scores=sc_l[j],
+                              bm25_ids=b_docs.astype(np.int64) + w.lo, bm25_scores=b_all[b_docs]))
+        gathered = [local]
+        if world > 1:
+            gathered = [None] * world
+            env.dist.all_gather_object(gathered, local)
+        if rank == 0:
+            for j, q in enumerate(sample):
+                merged = {}
+                for name in ("dense", "bm25"):
+                    ids = np.concatenate([g[j][name + "_ids"] for g in gathered])
+                    sc = np.concatenate([g[j][name + "_scores"] for g in gathered])
+                    # descending score, ties by ascending global id (the shards are in id order)
+                    order = np.lexsort((ids, -sc))[:TOPK]
+                    merged[name] = (ids[order], sc[order])
+                pool = {int(i): float(s) for g in gathered
+                        for i, s in zip(g[j]["dense_ids"], g[j]["dense_scores"])}
+                slabs.assert_topk_matches(got["dense_rows"][q, :TOPK], got["dense_scores"][q, :TOPK],
+                                          merged["dense"][0], merged["dense"][1],
+                                          lambda i: pool.get(i, -np.inf), what=f"weak dense q{q}")
+                poolb = {int(i): float(s) for g in gathered
+                         for i, s in zip(g[j]["bm25_ids"], g[j]["bm25_scores"])}
+                slabs.assert_topk_matches(got["bm25_ids"][q, :TOPK], got["bm25_scores"][q, :TOPK],
+                                          merged["bm25"][0], merged["bm25"][1],
+                                          lambda i: poolb.get(i, -np.inf), what=f"weak bm25 q{q}")
+                c = int(got["counts"][q])
+                pipeline.check_fused(got["ids"][q, :c], got["scores"][q, :c],
+                                     got["dense_rows"][q, :TOPK], got["bm25_ids"][q, :TOPK],
+                                     (W_DENSE, W_BM25), WRRF_K, TOPK)
+            rec["parity_checked_queries"] = len(sample)
+    except AssertionError as exc:
+        rec["parity_error"] = str(exc)[:500]
+    del w
+    torch.cuda.empty_cache()
+    return rec
+
+
+def qb64_view(env, qb64, b: int):
+    """A batch of the first b queries of an existing batch (same device buffers)."""
+    v = QueryBatch.__new__(QueryBatch)
+    v.__dict__.update(qb64.__dict__)
+    v.B = b
+    return v
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    env = Env()
+    env.torch, env.dist, env.rank, env.world = torch, dist, rank, world
+    env.device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=env.device)
+    pkg = importlib.import_module("a-nice-rag_b200")
+    env.engine, env.native = pkg.engine, pkg.native
+    env.synth = importlib.import_module("a-nice-rag_b200.synth")
+    env.sharded = importlib.import_module("a-nice-rag_b200.sharded")
+    env.ctx = env.engine.context(local_rank)
+    peaks = load_peaks()
+    legs = {x.strip() for x in args.legs.split(",") if x.strip()}
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    line = run_headline(env, args, peaks, sampler)
+    extra = {}
+    if "big" in legs and world == 1:
+        try:
+            extra.update(run_big_legs(env, args, peaks, sampler))
+        except Exception as exc:       # never lose the headline line to an extra leg
+            extra["big_error"] = repr(exc)[:400]
+            torch.cuda.empty_cache()
+    if "weak" in legs:
+        try:
+            weak = run_weak_leg(env, args, peaks, sampler)
+            if rank == 0:
+                extra["weak"] = weak
+        except Exception as exc:
+            extra["weak"] = {"error": repr(exc)[:400]}
+            torch.cuda.empty_cache()
+    if sampler:
+        sampler.stop()
+    if rank == 0:
+        line["legs"] = extra
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
-    global VOCAB
     args = parse_args()
-    VOCAB = args.vocab
     if args.chunks_per_gpu:
         args.chunks = args.chunks_per_gpu * dist_env()[2]
     if args.impl == "reference":

@@ -88,6 +88,12 @@ int anr_dense_shape(const anr_dense* index, int64_t* n, int32_t* d);
  * np.dot of src/search_engine.py:81.  Like anr_dense_upload and anr_bm25_reweight this MUTATES the
  * index: do not call it while another thread is searching the same index. */
 int anr_dense_set_shadow(anr_dense* index, int32_t enable);
+/* The rows of the index have been rewritten behind the library's back (a BORROWED index whose
+ * owner updated the tensor in place; anr_dense_upload does this itself for owned indices): drops
+ * the cached maximum row norm and the bf16 shadow copy, which the next search rebuilds.  Rows of
+ * an index must not change while a search on it is in flight.  The reference re-reads
+ * df["embedding"] on every call (src/search_engine.py:80); a resident copy needs this hook. */
+int anr_dense_invalidate(anr_dense* index);
 
 /* Inner-product top-k of each query against all (mask-eligible) rows, best
  * first.  Replaces np.dot + argpartition + argsort[::-1] of
@@ -131,7 +137,10 @@ int anr_bm25_shape(const anr_bm25* index, int32_t* n_terms, int32_t* n_docs, int
  * doc_mask as row_mask above over doc indices (the filtered branch :221-234).
  * doc_to_id (nullable, [n_docs]) maps doc index -> id written to out_docs
  * (the common id space used for fusion); NULL = doc index + id_base.
- * Zero-score documents are legitimate results when fewer than k documents match. */
+ * Zero-score documents are legitimate results when fewer than k documents match.
+ * A query with NO terms (q_offsets[q] == q_offsets[q+1]) returns nothing (out_counts[q] = 0, keys 0):
+ * `if not query_tokens: return []` at src/search_engine.py:216-217; in anr_hybrid_search such a
+ * query is fused from its dense list alone. */
 int anr_bm25_search(anr_ctx* ctx, const anr_bm25* index, const int32_t* q_terms,
                     const int32_t* q_offsets, int32_t n_queries, int32_t k,
                     const uint32_t* doc_mask, const int32_t* doc_to_id, int64_t id_base,

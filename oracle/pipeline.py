@@ -32,6 +32,26 @@ def hybrid_query(query: np.ndarray, emb: np.ndarray, index: csr.CsrIndex,
                 bm25_ids=b_ids, bm25_all=b_all)
 
 
+def hybrid_query_sharded(query: np.ndarray, shards: Sequence[Tuple[int, np.ndarray, csr.CsrIndex]],
+                         term_ids: Sequence[int], k_dense: int, k_bm25: int,
+                         weights: Dict[str, float], rrf_k: float, top_n: int,
+                         model_name: str = "voyage-3-large"):
+    """The same query over a corpus held as chunk shards ``(first row, emb, index)`` in row order:
+    the score vectors of the shards are concatenated (a dense score is per row; a BM25 score is
+    per document GIVEN corpus-wide idf / avgdl, which every shard's ``index`` must carry) and the
+    reference's top-k + fusion statements run on the concatenation -- what an unsharded reference
+    returns on the whole corpus."""
+    d_all = np.concatenate([retrieval.dense_scores(query, emb) for _, emb, _ in shards])
+    b_all = np.concatenate([csr.scores(ix, term_ids) for _, _, ix in shards])
+    d_rows = retrieval.topk_desc(d_all, k_dense)
+    b_docs = retrieval.bm25_topk(b_all, k_bm25)
+    fused = retrieval.weighted_rrf(
+        [([int(i) for i in d_rows], model_name), ([int(i) for i in b_docs], "BM25")],
+        weights, rrf_k)[:top_n]
+    return dict(fused=fused, dense_ids=d_rows, dense_scores=d_all[d_rows], bm25_docs=b_docs,
+                bm25_ids=b_docs, bm25_all=b_all, dense_all=d_all)
+
+
 def check_fused(got_ids: Sequence[int], got_scores: Sequence[float],
                 dense_ids: Sequence[int], bm25_ids: Sequence[int], weights: Tuple[float, float],
                 rrf_k: float, top_n: int) -> None:

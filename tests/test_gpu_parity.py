@@ -378,6 +378,26 @@ def test_dropin_config0_vs_reference_golden(config0_golden, tmp_path):
         want = retrieval.weighted_rrf([(res["id"].tolist(), "voyage-3-large"), (hits, "BM25")],
                                       WEIGHTS, WRRF_K)[:10]
         assert batch[j] == want
+    # An EMPTY token list has no BM25 list at all (search_engine.py:216-217 returns [] before any
+    # scoring: the query is fused from its dense list alone); a list of unknown tokens is scored
+    # (all zeros) and does contribute k zero-score documents, as in the reference.
+    odd_tokens = [[], ["zzz-not-in-the-vocabulary"], synth.token_strings(case["term_queries"][2])]
+    batch = se.hybrid_search_batch(case["queries"][:3], odd_tokens, df, bm25, sections, section_ids,
+                                   WEIGHTS, "voyage-3-large", 10, 10, WRRF_K)
+    for j, toks in enumerate(odd_tokens):
+        res = se.similarity_search_with_embedding(case["queries"][j], df, "voyage-3-large", 10)
+        hits = se.bm25_search_preprocessed(toks, bm25, sections, section_ids, 10)
+        assert len(hits) == (0 if not toks else 10)
+        want = retrieval.weighted_rrf([(res["id"].tolist(), "voyage-3-large"), (hits, "BM25")],
+                                      WEIGHTS, WRRF_K)[:10]
+        assert batch[j] == want, j
+    assert [i for i, _ in batch[0]] == se.similarity_search_with_embedding(
+        case["queries"][0], df, "voyage-3-large", 10)["id"].tolist()
+    # the same through the index classes: counts 0 / ids -1 for the query without terms
+    b_ix = importlib.import_module("a-nice-rag_b200.registry").resolve_bm25(bm25).index
+    sc, dc, ct = b_ix.search([[], [int(x) for x in case["term_queries"][2]], [-1]], 10)
+    assert ct.tolist() == [0, 10, 10] and (dc[0] == -1).all() and (sc[0] == 0).all()
+    assert (sc[2] == 0).all() and dc[2].tolist() == list(range(10))
 
 
 def test_wrrf_evaluator_sized_union_bit_exact():

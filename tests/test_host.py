@@ -102,6 +102,51 @@ def test_database_manager_contract_without_gpu(tmp_path, caplog):
     empty_db = str(tmp_path / "e.db")
     synth.write_chunks_db(empty_db, [], [], [], np.zeros((0, 4), dtype=np.float32))
     assert dm.load_embeddings_from_sql(empty_db).empty
+    # Same ids, OTHER vectors: the reference re-stacks df["embedding"] on every call
+    # (search_engine.py:80), so neither a copy with a new embedding column nor the loaded frame
+    # with its column replaced may resolve to the matrix that was uploaded at load time.
+    renorm = df.copy()
+    renorm["embedding"] = [2.0 * e for e in df["embedding"]]
+    e3, rows3 = registry.resolve_frame(renorm)
+    assert e3 is not entry and rows3 is None
+    assert np.array_equal(e3.packed, 2.0 * emb)
+    assert registry.resolve_frame(renorm)[0] is e3            # remembered by identity
+    renorm["embedding"] = [3.0 * e for e in df["embedding"]]   # ...until its vectors change again
+    e4, _ = registry.resolve_frame(renorm)
+    assert e4 is not e3 and np.array_equal(e4.packed, 3.0 * emb)
+    sub2 = df[df["source"].str.startswith("CG")].copy()
+    sub2["embedding"] = [-e for e in sub2["embedding"]]
+    e5, rows5 = registry.resolve_frame(sub2)
+    assert e5 is not entry and rows5 is None and np.array_equal(e5.packed, -emb[sub2.index])
+    assert registry.resolve_frame(df)[0] is entry               # the loaded frame is unaffected
+
+
+def test_bm25_entry_follows_parameter_changes(small_case, monkeypatch):
+    """A BM25Okapi whose k1 / b / idf table changed after its device index was built must get a
+    new index (the k1 / b / epsilon sweep of src/processing/bm25_test.py:180-315)."""
+    _, okapi = csr_from_case(small_case)
+    built = []
+
+    class FakeIndex:
+        def __init__(self, *a, **kw):
+            built.append(a[5:8])          # (k1, b, avgdl)
+            self.n_docs = len(a[3])
+    monkeypatch.setattr(engine, "Bm25Index", FakeIndex)
+    e1 = registry.resolve_bm25(okapi)
+    assert registry.resolve_bm25(okapi) is e1 and len(built) == 1
+    okapi.k1 = 1.2
+    e2 = registry.resolve_bm25(okapi)
+    assert e2 is not e1 and built[-1][0] == 1.2
+    okapi.idf = dict(okapi.idf)           # a recomputed idf table (new epsilon floor)
+    assert registry.resolve_bm25(okapi) is not e2 and len(built) == 3
+    # the filter-mask cache is keyed by content, not by id(sections)
+    srcs = list(small_case["sources"])
+    sections = [synth.Document("", {"id": str(i), "source": s}) for i, s in enumerate(srcs)]
+    monkeypatch.setattr(registry, "device_words", lambda w: None)
+    m1 = e2.filter_mask(sections, "CG")
+    assert e2.filter_mask(list(sections), "CG") is m1
+    other = [synth.Document("", {"id": str(i), "source": "NG1"}) for i in range(len(srcs))]
+    assert e2.filter_mask(other, "CG") is not m1 and e2.filter_mask(other, "CG")[2] == 0
 
 
 def test_bm25_pickle_roundtrip_with_shims(tmp_path, small_case):
@@ -463,3 +508,19 @@ def test_reference_arm_contract_under_torchrun(tmp_path):
     assert rec["e2e"] == {"value": rec["value"], "unit": "queries/s", "h2d_bytes_per_step": 0,
                           "d2h_bytes_per_step": 0}
     assert rec["config"]["batch"] == 64 and "4000 chunks" in rec["config"]["workload"]
+    # the arm pins the BLAS pool itself (torchrun exports OMP_NUM_THREADS=1), emits the config
+    # object of the CUDA arm key for key, and never maps the CUDA library
+    assert rec["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    sys.path.insert(0, ROOT)
+    import bench
+    ns = bench.argparse.Namespace(chunks=4000, vocab=50_000, batch=64, gpus=2)
+    assert rec["config"] == bench.headline_config(ns)
+    probe = subprocess.run(
+        [sys.executable, "-c",
+         "import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--chunks', '2000', "
+         "'--steps', '1', '--warmup', '0']; runpy.run_path(r'%s', run_name='__main__'); "
+         "print('LIBS', [l.split()[-1] for l in open('/proc/self/maps') if 'libanr_b200' in l])"
+         % os.path.join(ROOT, "bench.py")], capture_output=True, text=True, timeout=600,
+        cwd=str(tmp_path))
+    assert probe.returncode == 0, probe.stderr[-2000:]
+    assert "LIBS []" in probe.stdout, probe.stdout[-500:]

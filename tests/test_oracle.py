@@ -355,3 +355,47 @@ def test_committed_config0_golden_is_what_the_reference_produces_today(config0_g
             assert got.tolist() == want.tolist(), name
         else:
             np.testing.assert_array_equal(got, want, err_msg=name)
+
+
+# ---------------------------------------------------------------------------------------
+# the slab-wise / shard-wise forms used at 10M+ rows equal the whole-corpus statements
+# ---------------------------------------------------------------------------------------
+def test_slab_and_shard_forms_equal_the_whole_corpus_oracle(small_case):
+    from oracle import pipeline, slabs
+    case = small_case
+    ix, _ = csr_from_case(case)
+    emb, queries = case["emb"], case["queries"]
+    n = emb.shape[0]
+    bounds = [0, 300, 1100, n]
+    pieces = [(bounds[i], emb[bounds[i]:bounds[i + 1]]) for i in range(3)]
+    ids, sc = slabs.dense_topk_slabs(iter(pieces), queries[:4], 10)
+    for q in range(4):
+        w_ids, w_sc = retrieval.dense_topk(queries[q], emb, 10)
+        retrieval.assert_ranking_matches(ids[q], sc[q], w_ids, w_sc,
+                                         all_scores=retrieval.dense_scores(queries[q], emb))
+    fetch = lambda t: (ix.post_doc[ix.term_ptr[t]:ix.term_ptr[t + 1]],       # noqa: E731
+                       ix.post_tf[ix.term_ptr[t]:ix.term_ptr[t + 1]])
+    weights = {"voyage-3-large": 5.0, "BM25": 1.0}
+    for q in range(4):
+        terms = [int(t) if t < ix.idf.shape[0] else -1 for t in case["term_queries"][q]]
+        terms = terms + terms[:1] + [-1]          # a duplicate and an unknown term
+        want = csr.scores(ix, terms)
+        got = slabs.bm25_scores_subindex(fetch, terms, ix.doc_len, lambda t: float(ix.idf[t]),
+                                         ix.avgdl, ix.k1, ix.b)
+        assert np.array_equal(got, want)
+        # shards: the same documents' postings with GLOBAL idf / avgdl
+        shards = []
+        for i in range(3):
+            lo, hi = bounds[i], bounds[i + 1]
+            local = csr.from_token_ids(case["doc_ptr"][lo:hi + 1] - case["doc_ptr"][lo],
+                                       case["tokens"][case["doc_ptr"][lo]:case["doc_ptr"][hi]],
+                                       int(case["vocab"]), ix.k1, ix.b, 0.05)
+            local.idf, local.avgdl = ix.idf, ix.avgdl
+            shards.append((lo, emb[lo:hi], local))
+        whole = pipeline.hybrid_query(queries[q], emb, ix, terms, 10, 10, weights, 40.0, 10)
+        parts = pipeline.hybrid_query_sharded(queries[q], shards, terms, 10, 10, weights, 40.0, 10)
+        assert np.allclose(parts["bm25_all"], whole["bm25_all"], rtol=1e-12, atol=0)
+        retrieval.assert_ranking_matches(parts["dense_ids"], parts["dense_scores"],
+                                         whole["dense_ids"], whole["dense_scores"],
+                                         all_scores=retrieval.dense_scores(queries[q], emb))
+        assert [i for i, _ in parts["fused"]] == [i for i, _ in whole["fused"]]
