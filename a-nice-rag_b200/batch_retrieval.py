@@ -10,7 +10,10 @@ the same pipeline for a batch:
 
 * every dense retriever is ONE ``anr_dense_search`` call over all queries (the tensor-core GEMM
   path for > 32 queries), BM25 ONE ``anr_bm25_search`` call, the fusion ONE ``anr_wrrf_fuse``
-  call over ``[B, n_lists, k]`` integer ids (float64, bit-identical to the Python loop);
+  call over ``[B, n_lists, k]`` integer ids (float64, bit-identical to the Python loop); the
+  ranked lists STAY ON THE DEVICE between the searches and the fusion (at the evaluator's
+  ``similarity_k = 12000`` a batch of 2 048 queries is 100 MB per list: only the fused top-n
+  ids, and the hit rows when document dicts are asked for, come back to the host);
 * chunk-id strings are mapped to a common int32 id space on the host once per set of frames and
   never reach the GPU;
 * per query the result equals what ``retrieve_documents`` returns for that query (a list of
@@ -95,19 +98,34 @@ def _store_codes(system, source_enum, key, ids: Sequence[str]) -> Tuple["_IdSpac
     return space, hit
 
 
-def _wrrf_batch(ids: np.ndarray, lens: np.ndarray, weights: Sequence[float], rrf_k: float,
+def _wrrf_batch(ids_dev, lens_dev, weights: Sequence[float], rrf_k: float,
                 top_n: int) -> Tuple[np.ndarray, np.ndarray]:
-    """ids [B, n_lists, stride] int32, lens [B, n_lists] -> (fused ids [B, top_n], counts [B])."""
-    b, n_lists, stride = ids.shape
+    """ids [B, n_lists, stride] int32, lens [B, n_lists] int32 (device tensors)
+    -> (fused ids [B, top_n], counts [B]) on the host."""
+    b, n_lists, stride = (int(x) for x in ids_dev.shape)
     out_ids = np.empty((b, top_n), dtype=np.int32)
     out_scores = np.empty((b, top_n), dtype=np.float64)
     out_counts = np.empty(b, dtype=np.int32)
     w = np.ascontiguousarray(weights, dtype=np.float64)
-    native.call("anr_wrrf_fuse", engine.context(None).handle, native.ptr(np.ascontiguousarray(ids)),
-                native.ptr(np.ascontiguousarray(lens)), native.ptr(w), n_lists, stride, b,
-                float(rrf_k), int(top_n), native.ptr(out_ids), native.ptr(out_scores),
-                native.ptr(out_counts), None)
+    native.call("anr_wrrf_fuse", engine.context(None).handle, ids_dev.data_ptr(), lens_dev.data_ptr(),
+                native.ptr(w), n_lists, stride, b, float(rrf_k), int(top_n), native.ptr(out_ids),
+                native.ptr(out_scores), native.ptr(out_counts), engine.torch_stream_ptr())
     return out_ids, out_counts
+
+
+def _codes_on_device(codes_host: np.ndarray, cache: dict, key):
+    """A store's id codes as a resident int32 device tensor (uploaded once per store)."""
+    import torch
+    hit = cache.get(key)
+    if hit is None or hit.numel() != len(codes_host):
+        hit = cache[key] = torch.from_numpy(np.ascontiguousarray(codes_host)).to(
+            f"cuda:{engine.current_device()}")
+    return hit
+
+
+# queries per device pass: bounds the resident lists to ~0.5 GB per retriever
+def _chunk_queries(n_queries: int, k: int) -> int:
+    return max(1, min(n_queries, (1 << 27) // max(k, 1)))
 
 
 def retrieve_documents_batch(
@@ -139,11 +157,14 @@ def retrieve_documents_batch(
         return [[] for _ in range(n_queries)]
     bm25, bm25_sections, bm25_section_ids = bm25_tuple if bm25_tuple else (None, [], [])
 
-    space = None
-    lists: List[Tuple[str, np.ndarray, np.ndarray]] = []   # (model, codes [B, k], lens [B])
-    # per retriever, for the document dicts: (entry ids, frame, rows [B, k], scores [B, k], counts)
-    dense_hits = []
+    import torch
+    dev = torch.device("cuda", engine.current_device())
+    dev_codes = system.__dict__.setdefault("_anr_dev_codes", {})
+    want_hits = return_docs or use_reranker
 
+    # ---- which retrievers take part (the same for every query) ---------------------------------
+    space = None
+    dense_plan = []       # (model, entry, df, mask words, k, frame codes on the device)
     for model in DENSE_MODELS:
         df = embeddings_dict.get(model)
         if df is None or df.empty or model_weights.get(model, 0) <= 0 or model not in query_embeddings:
@@ -157,14 +178,11 @@ def retrieve_documents_batch(
         if eligible == 0:
             continue   # every query: "No documents found after filtering" -> empty result, no list
         k = max(1, min(int(similarity_k), eligible))
-        q = np.ascontiguousarray(query_embeddings[model], dtype=np.float32)
-        scores, rows, counts = entry.index().search(q, k, row_mask=mask_words)
         space, frame_codes = _store_codes(system, source_enum, ("dense", entry.key), entry.ids)
-        codes = np.where(rows >= 0, frame_codes[np.maximum(rows, 0)], -1).astype(np.int32)
-        lists.append((model, codes, counts.astype(np.int32)))
-        dense_hits.append((entry.ids, df, rows, scores, counts))
+        dense_plan.append((model, entry, df, mask_words, k,
+                           _codes_on_device(frame_codes, dev_codes, (source_enum, "dense", entry.key))))
 
-    bm25_docs = None
+    bm25_plan = None      # (index, mask words, k, section codes on the device, token lists)
     if use_hybrid_search and bm25 is not None and model_weights.get("BM25", 0) > 0:
         tokens = None
         if query_tokens is not None:
@@ -184,33 +202,61 @@ def retrieve_documents_batch(
                 _, mask_words, eligible = b_entry.filter_mask(bm25_sections, filename_type_filter)
             if eligible > 0:
                 k = max(1, min(int(similarity_k), eligible))
-                term_queries = [index.term_ids(t) for t in tokens]
-                _, docs, counts = index.search(term_queries, k, doc_mask=mask_words)
-                counts = counts.astype(np.int32)
-                # `if not query_tokens: return []` (search_engine.py:216-217)
-                for qi, t in enumerate(tokens):
-                    if not t:
-                        counts[qi] = 0
                 space, sec_codes = _store_codes(system, source_enum, ("bm25", id(b_entry)),
                                                 bm25_section_ids)
-                codes = np.where(docs >= 0, sec_codes[np.maximum(docs, 0)], -1).astype(np.int32)
-                lists.append(("BM25", codes, counts))
-                bm25_docs = (docs, counts)
+                bm25_plan = (index, mask_words, k,
+                             _codes_on_device(sec_codes, dev_codes, (source_enum, "bm25", id(b_entry))),
+                             [index.term_ids(t) for t in tokens])
 
-    if not lists:
+    n_lists = len(dense_plan) + (1 if bm25_plan else 0)
+    if n_lists == 0:
         logger.warning("No ranking methods available - no sections selected")
         return [[] for _ in range(n_queries)]
+    list_names = [p[0] for p in dense_plan] + (["BM25"] if bm25_plan else [])
+    stride = max([p[4] for p in dense_plan] + ([bm25_plan[2]] if bm25_plan else []))
+    weights = [float(model_weights.get(name, 1.0)) for name in list_names]
+    top_n = max(1, min(int(common_sections_n), n_lists * stride))
 
-    # ---- weighted RRF over all queries (a single list fuses to itself: same order) ----------
-    stride = max(c.shape[1] for _, c, _ in lists)
-    ids = np.full((n_queries, len(lists), stride), -1, dtype=np.int32)
-    lens = np.zeros((n_queries, len(lists)), dtype=np.int32)
-    for li, (_, codes, counts) in enumerate(lists):
-        ids[:, li, :codes.shape[1]] = codes
-        lens[:, li] = counts
-    weights = [float(model_weights.get(name, 1.0)) for name, _, _ in lists]
-    top_n = max(1, min(int(common_sections_n), len(lists) * stride))
-    fused, fused_counts = _wrrf_batch(ids, lens, weights, float(wrrf_k), top_n)
+    # ---- searches + weighted RRF, a chunk of queries at a time; lists stay on the device ------
+    fused = np.empty((n_queries, top_n), dtype=np.int32)
+    fused_counts = np.empty(n_queries, dtype=np.int32)
+    dense_hits = [(p[1].ids, p[2], [], [], []) for p in dense_plan]   # + rows, scores, counts (host)
+    bm25_host = ([], [])
+    step = _chunk_queries(n_queries, stride)
+    for q0 in range(0, n_queries, step):
+        q1 = min(n_queries, q0 + step)
+        b = q1 - q0
+        ids_dev = torch.full((b, n_lists, stride), -1, dtype=torch.int32, device=dev)
+        lens_dev = torch.zeros((b, n_lists), dtype=torch.int32, device=dev)
+        for li, (model, entry, df, mask_words, k, codes_dev) in enumerate(dense_plan):
+            q = torch.from_numpy(np.ascontiguousarray(query_embeddings[model][q0:q1],
+                                                      dtype=np.float32)).to(dev)
+            scores, rows, counts = entry.index().search_device(q, k, row_mask=mask_words)
+            ids_dev[:, li, :k] = torch.where(rows >= 0, codes_dev[rows.clamp(min=0).long()],
+                                             torch.full_like(rows, -1))
+            lens_dev[:, li] = counts
+            if want_hits:
+                dense_hits[li][2].append(rows.cpu().numpy())
+                dense_hits[li][3].append(scores.cpu().numpy())
+                dense_hits[li][4].append(counts.cpu().numpy())
+        if bm25_plan:
+            index, mask_words, k, codes_dev, term_queries = bm25_plan
+            # (a query without tokens gets no list: the library returns count 0 for it,
+            #  `if not query_tokens: return []`, search_engine.py:216-217)
+            _, docs, counts = index.search_device(term_queries[q0:q1], k, doc_mask=mask_words)
+            ids_dev[:, n_lists - 1, :k] = torch.where(docs >= 0, codes_dev[docs.clamp(min=0).long()],
+                                                      torch.full_like(docs, -1))
+            lens_dev[:, n_lists - 1] = counts
+            if want_hits:
+                bm25_host[0].append(docs.cpu().numpy())
+                bm25_host[1].append(counts.cpu().numpy())
+        f_ids, f_counts = _wrrf_batch(ids_dev, lens_dev, weights, float(wrrf_k), top_n)
+        fused[q0:q1], fused_counts[q0:q1] = f_ids, f_counts
+    if want_hits:
+        dense_hits = [(ids_, df_, np.concatenate(r), np.concatenate(s), np.concatenate(c))
+                      for ids_, df_, r, s, c in dense_hits]
+    bm25_docs = ((np.concatenate(bm25_host[0]), np.concatenate(bm25_host[1]))
+                 if want_hits and bm25_plan else None)
 
     names = space.names
     section_of = None

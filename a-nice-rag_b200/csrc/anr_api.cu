@@ -495,7 +495,7 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
 // ---- BM25 top-k pipeline on device buffers ---------------------------------------------
 Bm25View bm25_view(const anr_bm25* ix);
 
-// Head terms of the pruned scan: df >= n_docs / div (ANR_BM25_HEAD_DIV, default 8), the
+// Head terms of the pruned scan: df >= n_docs / div (ANR_BM25_HEAD_DIV, default 4), the
 // kBm25MaxHead most frequent at most, within a memory budget of a quarter of the postings' size
 // or 1 GB, whichever is larger.
 int bm25_ensure_heads(const anr_bm25* ix, cudaStream_t stream) {
@@ -505,7 +505,8 @@ int bm25_ensure_heads(const anr_bm25* ix, cudaStream_t stream) {
     std::vector<int64_t> tp(static_cast<size_t>(ix->n_terms) + 1);
     ANR_CUDA(cudaMemcpyAsync(tp.data(), ix->term_ptr, tp.size() * 8, cudaMemcpyDeviceToHost, stream));
     ANR_CUDA(cudaStreamSynchronize(stream));
-    static const int div = getenv("ANR_BM25_HEAD_DIV") ? std::max(atoi(getenv("ANR_BM25_HEAD_DIV")), 1) : 8;
+    // (1M docs, batch 64: df >= N/4 -> 0.254 ms per scan, N/8 -> 0.269, N/16 -> 0.269; profiles/r2_call2_*)
+    static const int div = getenv("ANR_BM25_HEAD_DIV") ? std::max(atoi(getenv("ANR_BM25_HEAD_DIV")), 1) : 4;
     const int64_t min_df = std::max<int64_t>(ix->n_docs / div, 1);
     std::vector<std::pair<int64_t, int32_t>> heads;
     for (int32_t t = 0; t < ix->n_terms; ++t) {

@@ -156,9 +156,17 @@ bm25_tile_item(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* __rest
   // that starts with every tile_stride-th one: the first wave of CTAs plays the role of a sample
   // pass (it publishes a k-th best score per query) and everything dispatched later prunes
   // against it.  n_sampled <= 0: grid = (tiles, queries), natural order.
+  // n_sampled == -4: LIGHT sample launch -- only the first quarter of every tile_stride-th tile is
+  // scored, nothing is written but the query's bound: a sample CTA has no bound to prune with and
+  // completes every document of its range, so its latency (50 us for a whole tile, and the main
+  // launch waits for it) goes with the range; the main launch (-5) then covers every tile.
+  const bool light_sample = n_sampled == -4;
   int tile, q;
-  if (n_sampled == -2) {          // separate sample launch: every tile_stride-th tile
+  if (n_sampled == -2 || light_sample) {   // separate sample launch: every tile_stride-th tile
     tile = bx * tile_stride;
+    q = by;
+  } else if (n_sampled == -5) {   // main launch after a light sample launch: every tile
+    tile = bx;
     q = by;
   } else if (n_sampled < -2) {    // main launch after a separate sample launch: skip its tiles
     tile = bx;
@@ -178,7 +186,8 @@ bm25_tile_item(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* __rest
     q = by;
   }
   const int d0 = tile * tile_docs;
-  const int d1 = min(ix.n_docs, d0 + tile_docs);
+  const int span = light_sample ? max(min(tile_docs, 1024), (tile_docs / 4 + 31) / 32 * 32) : tile_docs;
+  const int d1 = min(ix.n_docs, d0 + span);
   const int nd = d1 - d0;
   const int t_begin = q_offsets[q], t_end = q_offsets[q + 1];
 
@@ -522,19 +531,20 @@ bm25_tile_item(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* __rest
   if (ns <= kBm25Threads) {
     // rank by counting (keys are unique): one pass, no sort
     for (int i = threadIdx.x; i < k; i += kBm25Threads)
-      if (i >= ns) o[i] = 0ull;
+      if (i >= ns && !light_sample) o[i] = 0ull;
     if (threadIdx.x < ns) {
       const uint64_t key = sel[threadIdx.x];
       int rank = 0;
       for (int j = 0; j < ns; ++j) rank += sel[j] > key;
-      if (rank < k) o[rank] = key;
+      if (rank < k && !light_sample) o[rank] = key;
       // the tile's k-th best full score bounds the query's k-th best from below: publish it
       if (PRUNE && theta_g && rank == k - 1 && key_score(key) > 0.f)
         atomicMax(reinterpret_cast<int*>(theta_g + q), __float_as_int(key_score(key)));
     }
   } else {
     block_bitonic_sort_desc(sel, next_pow2(ns));
-    for (int i = threadIdx.x; i < k; i += blockDim.x) o[i] = i < ns ? sel[i] : 0ull;
+    if (!light_sample)
+      for (int i = threadIdx.x; i < k; i += blockDim.x) o[i] = i < ns ? sel[i] : 0ull;
     if (PRUNE && theta_g && threadIdx.x == 0 && ns >= k && key_score(sel[k - 1]) > 0.f)
       atomicMax(reinterpret_cast<int*>(theta_g + q), __float_as_int(key_score(sel[k - 1])));
   }
@@ -1022,7 +1032,11 @@ bm25_run_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_term
 }
 
 bool bm25_runs_enabled() {
-  static const bool on = !(getenv("ANR_BM25_RUNS") && atoi(getenv("ANR_BM25_RUNS")) == 0);
+  // Opt-in (ANR_BM25_RUNS=1).  Measured on 1M docs / batch 64 (profiles/r2_call3_*): 0.318 ms
+  // alone against 0.270 ms for the per-tile kernel -- a run is run_tiles times longer than a
+  // tile, so the grid is 3 waves instead of 12 and the last wave's imbalance costs what the
+  // saved searches gain; the per-tile kernel stays the default.
+  static const bool on = getenv("ANR_BM25_RUNS") && atoi(getenv("ANR_BM25_RUNS")) != 0;
   return on;
 }
 
@@ -1150,12 +1164,16 @@ static cudaError_t launch_score_t(const Bm25View& ix, const Bm25HeadView& hd, co
     dim3 grid(plan.n_tiles, nb);
     static const int fold_env = getenv("ANR_BM25_FOLD") ? atoi(getenv("ANR_BM25_FOLD")) : -1;
     const bool fold = fold_env >= 0 ? fold_env != 0 : !plan.beside_dense;
-    if (PRUNE && theta && plan.n_tiles >= 32 && !fold) {
+    // sample tiles: every stride-th one (1/16 of a large corpus; a small shard -- 125k documents
+    // are 21 tiles -- still gets a sample, or its whole first wave would run without a bound:
+    // 0.124 ms per batch of 64 on a 125k-document shard in round 1)
+    const int stride = plan.n_tiles >= 32 ? 16 : (plan.n_tiles / 2 > 2 ? plan.n_tiles / 2 : 2);
+    constexpr int kMinTilesForSample = 4;
+    if (PRUNE && theta && plan.n_tiles >= kMinTilesForSample && !fold) {
       // two launches: sample tiles, then the rest.  Beside the dense pass of a hybrid query this
       // is the better shape: the short first launch leaves the SMs to the dense pass' own short
       // kernels and its main kernel starts early (0.658 vs 0.674 ms per hybrid step); alone, the
       // folded single launch below is ~8 % faster.
-      const int stride = 16;
       dim3 grid_s((plan.n_tiles + stride - 1) / stride, nb);
       if constexpr (!EMIT_ALL && PRUNE) {
         if (persistent) {
@@ -1168,19 +1186,23 @@ static cudaError_t launch_score_t(const Bm25View& ix, const Bm25HeadView& hd, co
           continue;
         }
       }
+      // ANR_BM25_LIGHT_SAMPLE (default 1): the sample launch scores a quarter of each sampled tile
+      // and only publishes bounds; the main launch then covers every tile
+      static const int light_env =
+          getenv("ANR_BM25_LIGHT_SAMPLE") ? atoi(getenv("ANR_BM25_LIGHT_SAMPLE")) : 1;
+      const bool light = light_env != 0;
       if (plan.phase != 2)
         kern<<<grid_s, kBm25Threads, plan.smem_bytes, stream>>>(
             ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
-            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, -2);
+            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, light ? -4 : -2);
       if (plan.phase != 1)
         kern<<<grid, kBm25Threads, plan.smem_bytes, stream>>>(
             ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
-            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, -3);
+            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, light ? -5 : -3);
     } else if (plan.phase == 1) {
       // no separate sample launch in this plan: everything happens in phase 2
-    } else if (PRUNE && theta && plan.n_tiles >= 32 && plan.n_tiles <= 65535) {
+    } else if (PRUNE && theta && plan.n_tiles >= kMinTilesForSample && plan.n_tiles <= 65535) {
       // one launch, sample tiles first (see the kernel): no second launch, no idle tail between
-      const int stride = 16;
       const int n_sampled = (plan.n_tiles + stride - 1) / stride;
       dim3 grid_f(nb, plan.n_tiles);
       if constexpr (!EMIT_ALL && PRUNE) {

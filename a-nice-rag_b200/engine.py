@@ -209,6 +209,23 @@ class DenseIndex:
         return scores, rows, counts
 
 
+    def search_device(self, queries_dev, k: int, row_mask=None, id_base: int = 0):
+        """Same search with DEVICE tensors in and out (torch is the allocator): queries [b, d] fp32
+        on this index' GPU -> (scores f32 [b, k], rows i32 [b, k], counts i32 [b]) device tensors,
+        enqueued on torch's current stream without synchronising (results stay in HBM for the next
+        kernel, e.g. anr_wrrf_fuse)."""
+        import torch
+        b = int(queries_dev.shape[0])
+        dev = queries_dev.device
+        scores = torch.empty((b, k), dtype=torch.float32, device=dev)
+        rows = torch.empty((b, k), dtype=torch.int32, device=dev)
+        counts = torch.empty((b,), dtype=torch.int32, device=dev)
+        native.call("anr_dense_search", context(self.ctx_device).handle, self.handle,
+                    queries_dev.data_ptr(), b, int(k), native.ptr(row_mask), int(id_base),
+                    scores.data_ptr(), rows.data_ptr(), counts.data_ptr(), torch_stream_ptr())
+        return scores, rows, counts
+
+
 # ---------------------------------------------------------------------------------
 # BM25 index
 # ---------------------------------------------------------------------------------
@@ -328,6 +345,24 @@ class Bm25Index:
         native.call("anr_bm25_search", context(self.ctx_device).handle, self.handle,
                     native.ptr(terms), native.ptr(offsets), b, int(k), native.ptr(doc_mask), None,
                     int(id_base), native.ptr(scores), native.ptr(docs), native.ptr(counts), None)
+        return scores, docs, counts
+
+    def search_device(self, queries: Sequence[Sequence[int]], k: int, doc_mask=None, id_base: int = 0):
+        """``search`` with the results left on the device: -> (scores f32 [b, k], docs i32 [b, k],
+        counts i32 [b]) torch tensors on this index' GPU, enqueued on torch's current stream."""
+        import torch
+        terms, offsets = self.pack_queries(queries)
+        b = len(queries)
+        dev = torch.device("cuda", self.ctx_device)
+        t_dev = torch.from_numpy(terms if terms.size else np.zeros(1, dtype=np.int32)).to(dev)
+        o_dev = torch.from_numpy(offsets).to(dev)
+        scores = torch.empty((b, k), dtype=torch.float32, device=dev)
+        docs = torch.empty((b, k), dtype=torch.int32, device=dev)
+        counts = torch.empty((b,), dtype=torch.int32, device=dev)
+        native.call("anr_bm25_search", context(self.ctx_device).handle, self.handle, t_dev.data_ptr(),
+                    o_dev.data_ptr(), b, int(k), native.ptr(doc_mask), None, int(id_base),
+                    scores.data_ptr(), docs.data_ptr(), counts.data_ptr(), torch_stream_ptr())
+        self._keep = (t_dev, o_dev)      # alive until the next call: the kernels read them
         return scores, docs, counts
 
     def scores(self, term_ids: Sequence[int]) -> np.ndarray:

@@ -126,9 +126,7 @@ class HybridPipeline:
     step (``HybridGraph``), a stream and pinned host buffers; ``submit`` enqueues H2D copy ->
     replay -> D2H copy on the slot's stream and returns at once, ``collect`` waits for the oldest
     slot only.  Results are those of the eager call, bit for bit, in submission order.
-
-    EXPERIMENTAL: written at the end of round 1 after the GPU budget was spent; exercised only by
-    ``tests/test_gpu_zz_pipeline.py`` (opt-in) until it has run on a B200.
+    (``tests/test_gpu_zz_pipeline.py``; ``bench.py`` reports it as ``e2e_pipelined``.)
     """
 
     def __init__(self, dense: engine.DenseIndex, bm25: engine.Bm25Index, batch: int, max_terms: int,

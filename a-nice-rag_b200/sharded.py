@@ -117,3 +117,79 @@ class ShardedHybrid:
                     float(w_dense), float(w_bm25), float(rrf_k), top_n, buf["ids"].data_ptr(),
                     buf["scores"].data_ptr(), buf["counts"].data_ptr(), stream)
         return buf["ids"], buf["scores"], buf["counts"]
+
+
+class ShardedHybridGraph:
+    """One rank's sharded step of a FIXED shape -- local searches, NCCL all-gather, merge + fusion
+    -- captured as ONE CUDA graph and replayed per batch ("keep in-stream,
+    graph-captured").  A step on a small shard is a dozen short dependent launches around one
+    tens-of-microseconds kernel; replay removes the launch gaps between them.  The capture owns a
+    private context (the graph bakes in scratch addresses) and static input / output tensors;
+    every rank must capture and replay in the same order (the collective is part of the graph)."""
+
+    def __init__(self, dense: engine.DenseIndex, bm25: engine.Bm25Index, row_base: int, batch: int,
+                 max_terms: int, k: int, w_dense: float, w_bm25: float, rrf_k: float, top_n: int,
+                 doc_base: Optional[int] = None, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        dev = self.device = torch.device("cuda", dense.ctx_device)
+        self.ctx = engine.Context(dense.ctx_device)
+        self.dense, self.bm25 = dense, bm25
+        self.batch, self.max_terms, self.k, self.top_n = int(batch), int(max_terms), int(k), int(top_n)
+        self.row_base = int(row_base)
+        self.doc_base = int(row_base if doc_base is None else doc_base)
+        self.weights = (float(w_dense), float(w_bm25), float(rrf_k))
+        i32, i64, f32, f64 = torch.int32, torch.int64, torch.float32, torch.float64
+        self.q = torch.zeros((batch, dense.d), dtype=f32, device=dev)
+        self.terms = torch.full((self.max_terms,), -1, dtype=i32, device=dev)
+        self.offsets = torch.zeros((batch + 1,), dtype=i32, device=dev)
+        self.local = torch.empty((2, batch, k), dtype=i64, device=dev)
+        self.gathered = torch.empty((self.world, 2, batch, k), dtype=i64, device=dev)
+        self.ids = torch.empty((batch, top_n), dtype=i32, device=dev)
+        self.scores = torch.empty((batch, top_n), dtype=f64, device=dev)
+        self.counts = torch.empty((batch,), dtype=i32, device=dev)
+        self.stream = torch.cuda.Stream(dev)
+        self.graph = None
+
+    def _enqueue(self) -> None:
+        stream = engine.torch_stream_ptr()
+        native.call("anr_hybrid_search_keys", self.ctx.handle, self.dense.handle, self.bm25.handle,
+                    self.q.data_ptr(), self.terms.data_ptr(), self.offsets.data_ptr(), self.batch,
+                    self.k, None, None, self.row_base, self.doc_base, self.local.data_ptr(), stream)
+        src = self.local
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.gathered.view(-1), self.local.view(-1),
+                                             group=self.group)
+            src = self.gathered
+        w_d, w_b, rrf_k = self.weights
+        native.call("anr_sharded_fuse", self.ctx.handle, src.data_ptr(), self.world, self.batch,
+                    self.k, w_d, w_b, rrf_k, self.top_n, self.ids.data_ptr(), self.scores.data_ptr(),
+                    self.counts.data_ptr(), stream)
+
+    def load(self, queries_dev, terms_dev, offsets_dev) -> None:
+        n_terms = int(terms_dev.numel())
+        if n_terms > self.max_terms:
+            raise ValueError(f"{n_terms} query terms exceed the captured capacity {self.max_terms}")
+        self.q.copy_(queries_dev, non_blocking=True)
+        if n_terms:
+            self.terms[:n_terms].copy_(terms_dev.reshape(-1), non_blocking=True)
+        self.offsets.copy_(offsets_dev, non_blocking=True)
+
+    def capture(self) -> None:
+        """Warm-up (sizes the scratch, builds the lazily created index members, warms NCCL up),
+        then the capture.  Collective: every rank calls it."""
+        torch = self.torch
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            for _ in range(3):
+                self._enqueue()
+        self.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode="thread_local"):
+            self._enqueue()
+
+    def replay(self):
+        self.graph.replay()
+        return self.ids, self.scores, self.counts

@@ -722,6 +722,74 @@ def headline_report(env, args, peaks, w, qb, got, t):
         except Exception as exc:   # never lose the headline line to the optional replay leg
             graph_rec = {"error": repr(exc)[:300]}
 
+    # ---- two batches in flight: the latency-bound ends of one step (sample passes, thresholds,
+    #      rescoring, merges, fusion) run under the main kernels of the other.  `two_in_flight`:
+    #      inputs resident, two captured steps alternating on two streams; `e2e_pipelined`:
+    #      graph.HybridPipeline, host buffers in and out (H2D / D2H inside), depth 2. -------------
+    pipe_rec = None
+    if world == 1:
+        try:
+            graph_mod = importlib.import_module("a-nice-rag_b200.graph")
+            step_device, _ = step_fns(env, w, qb)
+            step_device()
+            torch.cuda.synchronize()
+            caps = [graph_mod.HybridGraph(w.dense, w.bm25, B, N_TERMS * B, TOPK, TOPK, W_DENSE, W_BM25,
+                                          WRRF_K, TOPK) for _ in range(2)]
+            streams = [torch.cuda.Stream(env.device) for _ in range(2)]
+            for hg in caps:
+                hg.load(qb.q_dev, qb.t_dev, qb.off_dev)
+                hg.replay()
+            torch.cuda.synchronize()
+            same = all(bool(torch.equal(hg.ids, qb.out_ids) and torch.equal(hg.scores, qb.out_scores))
+                       for hg in caps)
+
+            def two_steps():
+                cur = torch.cuda.current_stream()
+                for hg, st in zip(caps, streams):
+                    st.wait_stream(cur)
+                    with torch.cuda.stream(st):
+                        hg.replay()
+                for st in streams:
+                    cur.wait_stream(st)
+            n_it = max(args.steps, 50) // 2
+            for _ in range(5):
+                two_steps()
+            ms2 = timed(env, two_steps, n_it) / n_it / 2
+            pipe_rec = {"two_in_flight": {"ms_per_step": ms2, "queries_per_s": 1e3 * B / ms2,
+                                          "identical_to_eager": same,
+                                          "what": "device-resident inputs, two captured steps "
+                                                  "alternating on two streams"}}
+            del caps
+            pipe = graph_mod.HybridPipeline(w.dense, w.bm25, B, N_TERMS * B, TOPK, TOPK, W_DENSE,
+                                            W_BM25, WRRF_K, TOPK, depth=2)
+            t_flat = qb.t_host.reshape(-1)
+
+            def run_pipe(n_steps):
+                last = None
+                for i in range(n_steps):
+                    if i >= 2:
+                        last = pipe.collect()
+                    pipe.submit(qb.q_host, t_flat, qb.off_host)
+                for _ in range(min(2, n_steps)):
+                    last = pipe.collect()
+                return last
+            run_pipe(6)
+            last = run_pipe(3)
+            same_p = bool(np.array_equal(last[0], qb.out_ids.cpu().numpy()) and
+                          np.array_equal(last[1], qb.out_scores.cpu().numpy()))
+            n_it = max(args.steps, 50)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run_pipe(n_it)
+            dt = time.perf_counter() - t0
+            pipe_rec["e2e_pipelined"] = {
+                "value": B * n_it / dt, "unit": "queries/s", "ms_per_step": 1e3 * dt / n_it, "depth": 2,
+                "identical_to_eager": same_p,
+                "timing": "host wall clock over the whole loop (every result read on the host)"}
+            del pipe
+        except Exception as exc:
+            pipe_rec = dict(pipe_rec or {}, error=repr(exc)[:300])
+
     # ---- CPU baseline + parity of EVERY query of this very batch --------------------------------
     cpu, checked, parity_error = None, 0, None
     if not args.no_cpu_baseline:
@@ -805,6 +873,7 @@ def headline_report(env, args, peaks, w, qb, got, t):
                       "value": B * steps / (t["ms_filtered"] * 1e-3), "unit": "queries/s",
                       "ms_per_step": t["ms_filtered"] / steps} if t["ms_filtered"] else None),
         "cuda_graph": graph_rec,
+        "pipelined": pipe_rec,
         "multi_gpu": t["multi"],
         "clocks": t["clocks"], "parity_checked_queries": checked,
     }

@@ -530,6 +530,9 @@ def prune_corpus():
 def _check_bm25_batch(ix, queries, scores, docs, counts, k, what, mask=None):
     n_terms = len(ix.term_ptr) - 1
     for q, terms in enumerate(queries):
+        if len(terms) == 0:   # `if not query_tokens: return []` (search_engine.py:216-217)
+            assert counts[q] == 0 and (docs[q] == -1).all() and (scores[q] == 0).all(), (what, q)
+            continue
         all_scores = csr.scores(ix, [int(t) if 0 <= int(t) < n_terms else -1 for t in terms])
         if mask is None:
             want = retrieval.bm25_topk(all_scores, k)
@@ -550,7 +553,8 @@ def test_bm25_pruned_batches_vs_oracle(prune_corpus, nq, k):
     if nq > 3:
         queries[1] = queries[1] + queries[1][:3]            # duplicate terms count twice
         queries[2] = [vocab + 5, -1] + queries[2]            # unknown terms contribute nothing
-        queries[3] = []                                      # empty query: every score is 0
+        queries[3] = []                                      # empty query: no result at all
+        queries[4] = [vocab + 9, -1]                         # unknown terms only: k zero-score docs
         queries[0] = [0, 1, 2, 3, 0]                         # head terms only: nothing is pruned
     scores, docs, counts = index.search(queries, k)
     _check_bm25_batch(ix, queries, scores, docs, counts, k, f"pruned nq{nq}")

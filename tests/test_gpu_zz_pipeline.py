@@ -1,16 +1,11 @@
-"""GPU, OPT-IN (ANR_TEST_EXPERIMENTAL=1): graph.HybridPipeline -- host buffers in and out with two
-batches in flight -- returns, in submission order, exactly what the synchronous C-ABI call returns.
-Written after round 1's GPU budget was spent; it joins the default GPU suite once it has passed
-on a B200 (drop the skip below)."""
+"""GPU: graph.HybridPipeline -- host buffers in and out with two (or three) batches in flight --
+returns, in submission order, exactly what the synchronous C-ABI call returns."""
 import importlib
-import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ANR_TEST_EXPERIMENTAL") != "1",
-                                 reason="experimental: not yet run on a GPU box")]
+pytestmark = pytest.mark.gpu
 engine = importlib.import_module("a-nice-rag_b200.engine")
 graph = importlib.import_module("a-nice-rag_b200.graph")
 synth = importlib.import_module("a-nice-rag_b200.synth")

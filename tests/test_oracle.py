@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from helpers import (WEIGHTS, WRRF_K, check_ids_only, check_topk, csr_from_case, filter_mask,
-                     synth, tag)
+                     okapi_from_case, synth, tag)
 from oracle import bm25_okapi, csr, pipeline, reference_loader, retrieval
 
 FILTERS = (None, "CG,NG", "cg", "ZZ")
@@ -399,3 +399,36 @@ def test_slab_and_shard_forms_equal_the_whole_corpus_oracle(small_case):
                                          whole["dense_ids"], whole["dense_scores"],
                                          all_scores=retrieval.dense_scores(queries[q], emb))
         assert [i for i, _ in parts["fused"]] == [i for i, _ in whole["fused"]]
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="reference sources not mounted")
+def test_cpu_search_engine_equals_the_reference_class(small_case):
+    """oracle.cpu_search_engine (the CPU arm of the evaluator-shaped timing on the GPU box) against
+    the reference's SearchEngine imported verbatim, on the same frames / BM25 object."""
+    import types
+    import pandas as pd
+    from oracle import cpu_search_engine
+    ref_cls = reference_loader.load_reference().SearchEngine
+    ref, mine = ref_cls(None, None), cpu_search_engine.CpuSearchEngine()
+    case = small_case
+    n = case["emb"].shape[0]
+    srcs = list(case["sources"])
+    ids = synth.chunk_ids(n, srcs)
+    df = pd.DataFrame({"id": ids, "document": [""] * n, "source": srcs, "embedding": list(case["emb"]),
+                       "url": [""] * n})
+    okapi = okapi_from_case(case)
+    sections = [types.SimpleNamespace(page_content="", metadata={"id": ids[i], "source": srcs[i]})
+                for i in range(n)]
+    for flt in (None, "CG, NG", "ZZ"):
+        for q in range(4):
+            a = ref.similarity_search_with_embedding(case["queries"][q], df, "m", 25, flt)
+            b = mine.similarity_search_with_embedding(case["queries"][q], df, "m", 25, flt)
+            assert a["id"].tolist() == b["id"].tolist()
+            if len(a):
+                assert np.array_equal(a["similarity"].to_numpy(), b["similarity"].to_numpy())
+            toks = synth.token_strings(case["term_queries"][q])
+            assert (ref.bm25_search_preprocessed(toks, okapi, sections, ids, 25, flt)
+                    == mine.bm25_search_preprocessed(toks, okapi, sections, ids, 25, flt))
+    lists = [(ids[:30], "voyage-3-large"), (ids[10:50][::-1], "BM25")]
+    w = {"voyage-3-large": 5.0, "BM25": 1.0}
+    assert ref.weighted_reciprocal_rank_fusion(lists, w, 40) == mine.weighted_reciprocal_rank_fusion(lists, w, 40)
