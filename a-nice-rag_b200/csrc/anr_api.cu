@@ -65,6 +65,17 @@ struct anr_ctx {
   // (sample pre-pass + threshold + scan + rescoring)
   std::vector<EventPair> pool[3];  // created lazily, reused after every read
   size_t used[3] = {0, 0, 0};
+  // The scratch arena is shared by every call on this context, and calls are asynchronous on the
+  // CALLER's stream: a call issued on another stream than the previous one (torch's current
+  // stream, then NULL = the context's own non-blocking stream) would otherwise run beside it in
+  // the same scratch.  Every entry point waits on ev_last when the stream changes (StreamOrder).
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool last_valid = false;
+  // anr_ctx_timeline_*: where the parts of ONE hybrid step start and end (see the header)
+  bool timeline = false;
+  cudaEvent_t tl[ANR_TIMELINE_MARKS] = {};
+  bool tl_set[ANR_TIMELINE_MARKS] = {};
 };
 
 struct anr_dense {
@@ -187,6 +198,43 @@ EventPair* profile_take(anr_ctx* ctx, int kind) {
   }
   return &ctx->pool[kind][ctx->used[kind]++];
 }
+
+// Timeline mark `id` (include/anr_b200.h) on `stream`; a no-op unless anr_ctx_timeline_enable is on.
+void tl_mark(anr_ctx* ctx, int id, cudaStream_t stream) {
+  if (!ctx->timeline || id < 0 || id >= ANR_TIMELINE_MARKS) return;
+  if (!ctx->tl[id] && cudaEventCreate(&ctx->tl[id]) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  if (cudaEventRecord(ctx->tl[id], stream) == cudaSuccess) ctx->tl_set[id] = true;
+  else cudaGetLastError();
+}
+
+// Orders a call after the previous call of the same context when that one was enqueued on a
+// different stream (same stream: stream order already does it).  Nothing is recorded while the
+// stream is being captured into a graph: a captured step owns its context and its stream.
+struct StreamOrder {
+  anr_ctx* ctx;
+  cudaStream_t stream;
+  bool live = false;
+  StreamOrder(anr_ctx* c, cudaStream_t s) : ctx(c), stream(s) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) { cudaGetLastError(); return; }
+    if (st != cudaStreamCaptureStatusNone) return;
+    live = true;
+    if (ctx->last_valid && ctx->last_stream != stream && ctx->ev_last)
+      cudaStreamWaitEvent(stream, ctx->ev_last, 0);
+  }
+  ~StreamOrder() {
+    if (!live || !ctx->ev_last) return;
+    if (cudaEventRecord(ctx->ev_last, stream) == cudaSuccess) {
+      ctx->last_stream = stream;
+      ctx->last_valid = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
+};
 
 struct DeviceGuard {
   int prev = -1;
@@ -330,6 +378,19 @@ inline int dense_padded_queries(const anr_ctx* ctx, const anr_dense* ix, int nq,
   return pad_queries(nq, std::max(dense_group(ctx, ix, k), 1));
 }
 
+// Does a hybrid step of nq queries take the gated schedule?  Only the single-CTA 64-query GEMM
+// pass has a gate (the wider tiles fill the SM on their own).  OPT-IN (ANR_HYBRID_GATE=1).
+// Measured (profiles/r2_call10_*, 1M x 1024 + 1M docs, batch 64): the dense main kernel then
+// starts at 38 instead of 61 us into the step, but the folded BM25 launch runs 466 us beside it
+// (sample launch 60 + main launch 425 us in the default schedule): 0.532 against 0.539 ms per
+// step -- and a folded launch classifies head terms against a bound that moves while it runs, so
+// the last bit of a BM25 score is no longer repeatable.  Not worth it; the default stays the
+// two-launch schedule, whose main launch sees the sample launch's bounds.
+inline bool hybrid_gated(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
+  static const bool on = getenv("ANR_HYBRID_GATE") && atoi(getenv("ANR_HYBRID_GATE")) != 0;
+  return on && nq <= 64 && dense_use_gemm(ctx, ix, nq, k);
+}
+
 size_t dense_ws_bytes(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
   const int gmax = std::max(dense_group(ctx, ix, k), 1);
   const int nqp = pad_queries(nq, gmax);
@@ -350,7 +411,8 @@ size_t dense_ws_bytes(const anr_ctx* ctx, const anr_dense* ix, int nq, int k) {
 // ev_pre_main (nullable) is recorded when the pass' first long kernel is next in line on `stream`.
 int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq, int k,
                    const uint32_t* mask_dev, Arena& arena, const TopkOut& out,
-                   cudaStream_t stream, cudaEvent_t ev_pre_main = nullptr) {
+                   cudaStream_t stream, cudaEvent_t ev_pre_main = nullptr,
+                   DenseGate* gate = nullptr) {
   const int gmax = dense_group(ctx, ix, k);
   if (gmax < 1) return fail(ANR_ERR_UNSUPPORTED, "embedding rows too long for the scan kernel");
   const bool gemm = dense_use_gemm(ctx, ix, nq, k);
@@ -392,12 +454,24 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
       if (o.counts) o.counts += q0 * out.count_stride;
       ProfileScope prof(ctx, 2, stream);
       EventPair* ev = profile_take(ctx, 0);
+      EventPair tl_pair;   // timeline: the first group's main kernel
+      if (!ev && ctx->timeline && q0 == 0) {
+        for (int id : {4, 5})
+          if (!ctx->tl[id] && cudaEventCreate(&ctx->tl[id]) != cudaSuccess) cudaGetLastError();
+        if (ctx->tl[4] && ctx->tl[5]) {
+          tl_pair.start = ctx->tl[4];
+          tl_pair.stop = ctx->tl[5];
+          ctx->tl_set[4] = ctx->tl_set[5] = true;
+          ev = &tl_pair;
+        }
+      }
       ANR_CUDA(launch_dense_gemm(ctx->dp, ix->emb, ix->shadow, ix->n, ix->ld,
                                  q_dev + static_cast<size_t>(q0) * ix->ld, std::min(per, nq - q0), k,
                                  mask_dev, ix->norm_max, scratch, o, flags + q0,
                                  ev ? ev->start : nullptr, ev ? ev->stop : nullptr, stream,
-                                 q0 == 0 ? ev_pre_main : nullptr));
+                                 q0 == 0 ? ev_pre_main : nullptr, q0 == 0 ? gate : nullptr));
     }
+    tl_mark(ctx, 6, stream);
     const int fb_grid = dense_scan_flagged_grid(ctx->dp, ix->n, ix->ld, k);
     const int64_t fb_stride = static_cast<int64_t>(fb_grid) * k;
     int32_t* n_flagged = arena.take<int32_t>(1);
@@ -634,18 +708,23 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
     float* theta = r.theta;
     const int64_t stride = r.stride;
     if (phase == 1) {
+      tl_mark(ctx, 1, stream);
       ANR_CUDA(launch_bm25_score_topk(v, hd.n_head > 0 ? &hd : nullptr, terms_dev, offsets_dev, nq,
                                       k, mask_dev, plan, cand, stride, theta, stream));
+      tl_mark(ctx, 2, stream);
       return ANR_OK;
     }
+    tl_mark(ctx, 8, stream);
     {
       ProfileScope prof(ctx, 1, stream);
       ANR_CUDA(launch_bm25_score_topk(v, hd.n_head > 0 ? &hd : nullptr, terms_dev, offsets_dev, nq,
                                       k, mask_dev, plan, cand, stride, theta, stream));
     }
+    tl_mark(ctx, 9, stream);
     const int m = static_cast<int>(stride);
     ANR_CUDA(launch_topk_final(cand, stride, m, m, 0, nq, k, out, stream));
     ANR_CUDA(bm25_clear_empty_queries(offsets_dev, nq, k, out, stream));
+    tl_mark(ctx, 10, stream);
     return ANR_OK;
   }
   if (phase == 1) return ANR_OK;   // the full-ranking path has no sample launch
@@ -788,6 +867,7 @@ int anr_ctx_create(int device, anr_ctx** out) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_mid, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_last, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     anr_ctx_destroy(ctx);
     return fail_cuda("stream/event creation", e);
@@ -818,6 +898,27 @@ int anr_ctx_profile_read(anr_ctx* ctx, int32_t kind, double* total_ms, int64_t* 
   return ANR_OK;
 }
 
+int anr_ctx_timeline_enable(anr_ctx* ctx, int32_t on) {
+  if (!ctx) return fail(ANR_ERR_INVALID, "ctx is NULL");
+  ctx->timeline = on != 0;
+  for (bool& b : ctx->tl_set) b = false;
+  return ANR_OK;
+}
+
+int anr_ctx_timeline_read(anr_ctx* ctx, double* offsets_ms) {
+  if (!ctx || !offsets_ms) return fail(ANR_ERR_INVALID, "anr_ctx_timeline_read: NULL argument");
+  DeviceGuard guard(ctx->dp.device);
+  ANR_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < ANR_TIMELINE_MARKS; ++i) {
+    offsets_ms[i] = -1.0;
+    if (!ctx->tl_set[0] || !ctx->tl_set[i]) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->tl[0], ctx->tl[i]) == cudaSuccess) offsets_ms[i] = ms;
+    else cudaGetLastError();
+  }
+  return ANR_OK;
+}
+
 int anr_ctx_destroy(anr_ctx* ctx) {
   if (!ctx) return ANR_OK;
   DeviceGuard guard(ctx->dp.device);
@@ -832,6 +933,9 @@ int anr_ctx_destroy(anr_ctx* ctx) {
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
+  if (ctx->ev_last) cudaEventDestroy(ctx->ev_last);
+  for (cudaEvent_t e : ctx->tl)
+    if (e) cudaEventDestroy(e);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -979,6 +1083,7 @@ static int dense_search_impl(anr_ctx* ctx, const anr_dense* index, const float* 
   if (index->device != ctx->dp.device) return fail(ANR_ERR_INVALID, "index lives on another device");
   DeviceGuard guard(ctx->dp.device);
   cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  StreamOrder order(ctx, stream);
   const size_t cells = static_cast<size_t>(nq) * k;
   const size_t need = stage_queries_bytes(index, nq) + stage_mask_bytes(row_mask, index->n) +
                       dense_ws_bytes(ctx, index, nq, k) + out_need(out_keys, cells) +
@@ -1126,6 +1231,7 @@ int anr_bm25_reweight(anr_ctx* ctx, anr_bm25* index, const int32_t* post_tf, con
   if (index->device != ctx->dp.device) return fail(ANR_ERR_INVALID, "index lives on another device");
   DeviceGuard guard(ctx->dp.device);
   cudaStream_t stream = ctx->stream;
+  StreamOrder order(ctx, stream);
   const size_t pn = static_cast<size_t>(std::max<int64_t>(index->nnz, 1));
   const size_t need = padded(pn * 4) + padded(static_cast<size_t>(std::max(index->n_docs, 1)) * 4) +
                       padded(static_cast<size_t>(std::max(index->n_terms, 1)) * 8) + 2048;
@@ -1204,6 +1310,7 @@ static int bm25_search_impl(anr_ctx* ctx, const anr_bm25* index, const int32_t* 
     return fail(ANR_ERR_INVALID, "doc_to_id must be a device pointer (it is index-sized)");
   DeviceGuard guard(ctx->dp.device);
   cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  StreamOrder order(ctx, stream);
   const size_t cells = static_cast<size_t>(nq) * k;
   const size_t need = stage_terms_bytes(q_terms, q_offsets, nq) +
                       stage_mask_bytes(doc_mask, index->n_docs) +
@@ -1272,6 +1379,7 @@ int anr_bm25_scores(anr_ctx* ctx, const anr_bm25* index, const int32_t* q_terms,
   if (index->n_docs == 0) return ANR_OK;
   DeviceGuard guard(ctx->dp.device);
   cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  StreamOrder order(ctx, stream);
   const size_t n = static_cast<size_t>(index->n_docs);
   const size_t need = padded(n * 8) + padded(n * 4) +
                       padded(static_cast<size_t>(n_q_terms + 1) * 4) + 2048;
@@ -1309,6 +1417,7 @@ int anr_wrrf_fuse(anr_ctx* ctx, const int32_t* ids, const int32_t* lens, const d
     return fail(ANR_ERR_UNSUPPORTED, "anr_wrrf_fuse: more than 2^22 entries per query");
   DeviceGuard guard(ctx->dp.device);
   cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  StreamOrder order(ctx, stream);
   const size_t n_ids = static_cast<size_t>(n_queries) * n_lists * list_stride;
   const size_t n_lens = static_cast<size_t>(n_queries) * n_lists;
   const size_t cells = static_cast<size_t>(n_queries) * top_n;
@@ -1378,6 +1487,7 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
     return fail(ANR_ERR_UNSUPPORTED, "anr_hybrid_search: k_dense/k_bm25 above 4096");
   DeviceGuard guard(ctx->dp.device);
   cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  StreamOrder order(ctx, stream);
 
   const size_t fused_cells = static_cast<size_t>(nq) * top_n;
   const size_t list_cells = static_cast<size_t>(nq) * 2 * stride;
@@ -1436,6 +1546,9 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
   static const int overlap_env = getenv("ANR_HYBRID_OVERLAP") ? atoi(getenv("ANR_HYBRID_OVERLAP")) : -1;
   const bool overlap = overlap_env != 0;
   cudaStream_t bm25_stream = overlap ? ctx->side : stream;
+  if (ctx->timeline)
+    for (bool& b : ctx->tl_set) b = false;
+  tl_mark(ctx, 0, stream);
   if (overlap) {
     ANR_CUDA(cudaEventRecord(ctx->ev_fork, stream));
     ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
@@ -1445,16 +1558,25 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
     // the BM25 main launch, held back until the dense main kernel is next in line, so that the
     // persistent, bandwidth-bound dense kernel takes its SMs first (a BM25 main launch that got
     // there first stretched the dense kernel from 0.31 to 0.52 ms) | join
+    // Gated schedule (hybrid_gated): the BM25 scan is ONE launch (sample tiles first), held on the
+    // side stream until every CTA of the dense main kernel is resident (DenseGate).  A separate
+    // BM25 sample launch at the start of the step would sit in the SMs' shared memory while the
+    // dense sample pass wants it (the dense main kernel then started at 62 instead of 40 us).
+    const bool gated = hybrid_gated(ctx, dense, nq, k_dense);
+    DenseGate gate;
     Bm25Run run;
     if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k_bm25, doc_mask_dev, arena, ob,
-                               bm25_stream, true, 1, &run))
+                               bm25_stream, !gated, 1, &run))
       return rc;
+    tl_mark(ctx, 3, stream);
     if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k_dense, row_mask_dev, arena, od, stream,
-                                ctx->ev_mid))
+                                ctx->ev_mid, gated ? &gate : nullptr))
       return rc;
+    tl_mark(ctx, 7, stream);
     ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_mid, 0));
+    if (gated) ANR_CUDA(launch_gate_wait(gate.counter, gate.expected, ctx->side));
     if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k_bm25, doc_mask_dev, arena, ob,
-                               bm25_stream, true, 2, &run))
+                               bm25_stream, !gated, 2, &run))
       return rc;
     ANR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   } else {
@@ -1467,6 +1589,7 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
   if (overlap) ANR_CUDA(cudaStreamWaitEvent(stream, ctx->ev_join, 0));
   ANR_CUDA(launch_wrrf_fuse(lists, lens, w_dev, 2, stride, nq, rrf_k, top_n, nullptr, o_ids.dev,
                             o_scores.dev, o_counts.dev, stream));
+  tl_mark(ctx, 11, stream);
 
   // optional per-retriever outputs: strided device -> user layout [nq, k]
   auto copy_out = [&](void* user, const void* src, int k) -> cudaError_t {
@@ -1509,6 +1632,7 @@ int anr_hybrid_search_keys(anr_ctx* ctx, const anr_dense* dense, const anr_bm25*
     return fail(ANR_ERR_INVALID, "anr_hybrid_search_keys takes device pointers");
   DeviceGuard guard(ctx->dp.device);
   cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  StreamOrder order(ctx, stream);
   const size_t need = stage_queries_bytes(dense, nq) + stage_mask_bytes(row_mask, dense->n) +
                       stage_terms_bytes(q_terms, q_offsets, nq) +
                       stage_mask_bytes(doc_mask, bm25->n_docs) +
@@ -1534,15 +1658,19 @@ int anr_hybrid_search_keys(anr_ctx* ctx, const anr_dense* dense, const anr_bm25*
   ob.id_base = doc_base;
   ANR_CUDA(cudaEventRecord(ctx->ev_fork, stream));
   ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  const bool gated = hybrid_gated(ctx, dense, nq, k);
+  DenseGate gate;
   Bm25Run run;
   if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k, doc_mask_dev, arena, ob,
-                             ctx->side, true, 1, &run))
+                             ctx->side, !gated, 1, &run))
     return rc;
-  if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k, row_mask_dev, arena, od, stream, ctx->ev_mid))
+  if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k, row_mask_dev, arena, od, stream, ctx->ev_mid,
+                              gated ? &gate : nullptr))
     return rc;
   ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_mid, 0));
+  if (gated) ANR_CUDA(launch_gate_wait(gate.counter, gate.expected, ctx->side));
   if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k, doc_mask_dev, arena, ob,
-                             ctx->side, true, 2, &run))
+                             ctx->side, !gated, 2, &run))
     return rc;
   ANR_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   ANR_CUDA(cudaStreamWaitEvent(stream, ctx->ev_join, 0));
@@ -1558,6 +1686,7 @@ int anr_topk_merge(anr_ctx* ctx, const uint64_t* keys, int32_t n_parts, int32_t 
   if (k > kMaxFusedK) return fail(ANR_ERR_UNSUPPORTED, "anr_topk_merge: k above 128");
   DeviceGuard guard(ctx->dp.device);
   cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  StreamOrder order(ctx, stream);
   const size_t n_keys = static_cast<size_t>(n_parts) * n_queries * k;
   const size_t cells = static_cast<size_t>(n_queries) * k;
   const bool keys_host = !is_device_ptr(keys);
@@ -1599,6 +1728,7 @@ int anr_sharded_fuse(anr_ctx* ctx, const uint64_t* gathered, int32_t n_parts, in
   if (k > kMaxFusedK) return fail(ANR_ERR_UNSUPPORTED, "anr_sharded_fuse: k above 128");
   DeviceGuard guard(ctx->dp.device);
   cudaStream_t stream = stream_v ? static_cast<cudaStream_t>(stream_v) : ctx->stream;
+  StreamOrder order(ctx, stream);
   const size_t n_keys = static_cast<size_t>(n_parts) * 2 * nq * k;
   const size_t cells = static_cast<size_t>(nq) * top_n;
   const size_t list_cells = static_cast<size_t>(nq) * 2 * k;

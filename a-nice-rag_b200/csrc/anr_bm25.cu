@@ -1186,10 +1186,12 @@ static cudaError_t launch_score_t(const Bm25View& ix, const Bm25HeadView& hd, co
           continue;
         }
       }
-      // ANR_BM25_LIGHT_SAMPLE (default 1): the sample launch scores a quarter of each sampled tile
-      // and only publishes bounds; the main launch then covers every tile
+      // ANR_BM25_LIGHT_SAMPLE=1 (default 0): the sample launch scores a quarter of each sampled
+      // tile and only publishes bounds; the main launch then covers every tile.  Measured
+      // (profiles/r2_call5_*): the shorter sample launch does not pay for the weaker bounds --
+      // 0.595 against 0.543 ms per hybrid step, the main launch stretching from 0.425 to 0.495 ms.
       static const int light_env =
-          getenv("ANR_BM25_LIGHT_SAMPLE") ? atoi(getenv("ANR_BM25_LIGHT_SAMPLE")) : 1;
+          getenv("ANR_BM25_LIGHT_SAMPLE") ? atoi(getenv("ANR_BM25_LIGHT_SAMPLE")) : 0;
       const bool light = light_env != 0;
       if (plan.phase != 2)
         kern<<<grid_s, kBm25Threads, plan.smem_bytes, stream>>>(

@@ -160,9 +160,11 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                   int64_t n, int64_t n_row_tiles, int64_t tile_stride, int n_qblocks,
                   const uint32_t* __restrict__ mask, const float* __restrict__ thr,
                   uint64_t* __restrict__ cand, int32_t* __restrict__ cnt, int cap,
-                  float* __restrict__ gmax, int64_t gmax_stride, GemmLayout L) {
+                  float* __restrict__ gmax, int64_t gmax_stride, GemmLayout L,
+                  int32_t* __restrict__ gate) {
   using Cfg = GemmCfg<NQ, BF16>;
   extern __shared__ __align__(1024) unsigned char smem[];
+  if (gate && threadIdx.x == 0) atomicAdd(gate, 1);   // this CTA holds its shared memory now
   unsigned char* ring = smem;                                   // n_stages x [A slab | B slab]
   float* thr_s = reinterpret_cast<float*>(smem + L.thr_off);    // [n_qblocks * NQ]
   GemmStage* stages = reinterpret_cast<GemmStage*>(smem + L.stage_off);   // [4 epilogue warps]
@@ -536,9 +538,14 @@ dense_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 // rank-th best score of the corpus.  Queries >= n_real (zero padding) never nominate anything.
 __global__ void __launch_bounds__(kGmThrThreads)
 dense_gemm_thr_kernel(const float* __restrict__ gmax, int64_t gmax_stride, int m, int rank,
-                      int n_real, float* __restrict__ thr, uint64_t* __restrict__ thr_key) {
+                      int n_real, float* __restrict__ thr, uint64_t* __restrict__ thr_key,
+                      int32_t* __restrict__ cnt, int32_t* __restrict__ gate) {
   __shared__ uint64_t best[kGmThrThreads];
   const int q = blockIdx.x;
+  if (threadIdx.x == 0) {   // the main pass starts from empty candidate buffers and a closed gate
+    cnt[q] = 0;
+    if (q == 0 && gate) *gate = 0;
+  }
   if (q >= n_real) {
     if (threadIdx.x == 0) {
       thr[q] = INFINITY;
@@ -578,6 +585,21 @@ cudaError_t launch_f32_to_bf16(const float* in, void* out, int64_t count, cudaSt
   if (blocks > 148 * 16) blocks = 148 * 16;
   f32_to_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
       in, static_cast<__nv_bfloat16*>(out), n4);
+  return cudaGetLastError();
+}
+
+// One thread polls the gate (DenseGate, anr_internal.h); gives up after ~10 ms so that a dense
+// pass that never starts (an error upstream) cannot hang the BM25 stream.
+__global__ void gate_wait_kernel(const int32_t* __restrict__ counter, int expected) {
+  const long long t0 = clock64();
+  while (*reinterpret_cast<const volatile int32_t*>(counter) < expected) {
+    __nanosleep(200);
+    if (clock64() - t0 > 20000000ll) break;
+  }
+}
+cudaError_t launch_gate_wait(const int32_t* counter, int expected, cudaStream_t stream) {
+  if (!counter || expected < 1) return cudaSuccess;
+  gate_wait_kernel<<<1, 1, 0, stream>>>(counter, expected);
   return cudaGetLastError();
 }
 
@@ -662,7 +684,7 @@ size_t dense_gemm_scratch_bytes(const DeviceProps& dp, int64_t n, int ld, int nq
   const size_t nq_pad = static_cast<size_t>(dense_gemm_padded_queries(std::min(nq, dense_gemm_max_queries())));
   const size_t groups = static_cast<size_t>(gemm_sample_tiles(dp, n, k)) * 4;
   return nq_pad * kGmCap * 8 + nq_pad * groups * 4 + nq_pad * (4 + 4 + 8) +
-         nq_pad * static_cast<size_t>(ld) * 2 + 4096;
+         nq_pad * static_cast<size_t>(ld) * 2 + 4096 + 512;
 }
 
 // host-side only (GemmLayout is a kernel parameter and stays as it is): the launch group being
@@ -707,7 +729,7 @@ static cudaError_t gemm_launch_one(int grid, int threads, int smem, cudaStream_t
                                    int64_t n_row_tiles, int64_t tile_stride, int n_qblocks,
                                    const uint32_t* mask, const float* thr, uint64_t* cand,
                                    int32_t* cnt, int cap, float* gmax, int64_t gstride,
-                                   const GemmLayout& L) {
+                                   const GemmLayout& L, int32_t* gate = nullptr) {
   auto kern = dense_gemm_kernel<NQ, BF16, SAMPLE, PAIR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
@@ -729,7 +751,7 @@ static cudaError_t gemm_launch_one(int grid, int threads, int smem, cudaStream_t
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, map_a, map_b, n, n_row_tiles, tile_stride, n_qblocks, mask,
-                            thr, cand, cnt, cap, gmax, gstride, L);
+                            thr, cand, cnt, cap, gmax, gstride, L, gate);
 }
 
 template <int NQ, bool BF16, bool SAMPLE>
@@ -778,7 +800,8 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
                                     int64_t sample_tiles, int n_real, int k, float* gmax, float* thr,
                                     uint64_t* thr_key, uint64_t* cand, int32_t* cnt,
                                     const GemmLayout& L, cudaEvent_t ev_start, cudaEvent_t ev_stop,
-                                    cudaStream_t stream, cudaEvent_t ev_pre_main) {
+                                    cudaStream_t stream, cudaEvent_t ev_pre_main, int32_t* gate_ctr,
+                                    DenseGate* gate) {
   const int smem = L.total_bytes + 1024;  // room to align the dynamic base to 1024 bytes
   const int64_t n_tiles = (n + kGmRows - 1) / kGmRows;
   const int64_t stride = n_tiles / sample_tiles;
@@ -797,7 +820,7 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
     if (e != cudaSuccess) return e;
     dense_gemm_thr_kernel<<<nq_pad, kGmThrThreads, 0, stream>>>(
         gmax, gstride, static_cast<int>(gstride), gemm_thr_rank_for(n, sample_tiles, k), n_real, thr,
-        thr_key);
+        thr_key, cnt, nullptr);
     if (ev_pre_main) cudaEventRecord(ev_pre_main, stream);   // the main kernel is next in line
     if (ev_start) cudaEventRecord(ev_start, stream);
     e = gemm2_launch_one<NQ, BF16, false>(dp.sm_count, threads, smem, stream, map_a, map_b_half, n,
@@ -815,12 +838,17 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
                                                sample_tiles, stride, n_qblocks, mask, nullptr, nullptr,
                                                nullptr, 0, gmax, gstride, L);
   if (e != cudaSuccess) return e;
+  const int grid = static_cast<int>(std::min<int64_t>(dp.sm_count, n_tiles));
+  const bool gated = gate != nullptr && !pair;
   dense_gemm_thr_kernel<<<nq_pad, kGmThrThreads, 0, stream>>>(
       gmax, gstride, static_cast<int>(gstride), gemm_thr_rank_for(n, sample_tiles, k), n_real, thr,
-      thr_key);
+      thr_key, cnt, gated ? gate_ctr : nullptr);
+  if (gated) {
+    gate->counter = gate_ctr;
+    gate->expected = grid;
+  }
   if (ev_pre_main) cudaEventRecord(ev_pre_main, stream);   // the main kernel is next in line
   if (ev_start) cudaEventRecord(ev_start, stream);   // brackets the main GEMM kernel only
-  const int grid = static_cast<int>(std::min<int64_t>(dp.sm_count, n_tiles));
   if (pair)
     e = gemm_launch_one<NQ, BF16, false, true>(dp.sm_count, threads, smem, stream, map_a, map_b_half, n,
                                                n_tiles, 1, n_qblocks, mask, thr, cand, cnt, kGmCap,
@@ -828,7 +856,7 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
   else
     e = gemm_launch_one<NQ, BF16, false, false>(grid, threads, smem, stream, map_a, map_b, n, n_tiles,
                                                 1, n_qblocks, mask, thr, cand, cnt, kGmCap, nullptr,
-                                                0, L);
+                                                0, L, gated ? gate_ctr : nullptr);
   if (ev_stop) cudaEventRecord(ev_stop, stream);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -857,7 +885,7 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
                               int ld, const float* q_dev, int n_real, int k, const uint32_t* mask,
                               float emb_norm_max, unsigned char* scratch, const TopkOut& out,
                               int32_t* flags, cudaEvent_t ev_start, cudaEvent_t ev_stop,
-                              cudaStream_t stream, cudaEvent_t ev_pre_main) {
+                              cudaStream_t stream, cudaEvent_t ev_pre_main, DenseGate* gate) {
   const bool bf16 = shadow != nullptr;
   const int nqb_size = dense_gemm_block(n_real);
   const int nq_pad = dense_gemm_padded_queries(n_real);
@@ -883,6 +911,7 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
   float* thr = reinterpret_cast<float*>(take(static_cast<size_t>(nq_pad) * 4));
   int32_t* cnt = reinterpret_cast<int32_t*>(take(static_cast<size_t>(nq_pad) * 4));
   uint64_t* thr_key = reinterpret_cast<uint64_t*>(take(static_cast<size_t>(nq_pad) * 8));
+  int32_t* gate_ctr = reinterpret_cast<int32_t*>(take(256));
   const void* q_ops = q_dev;
   if (bf16) {
     void* q16 = take(static_cast<size_t>(nq_pad) * ld * 2);
@@ -890,8 +919,7 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
     if (e != cudaSuccess) return e;
     q_ops = q16;
   }
-  cudaError_t e = cudaMemsetAsync(cnt, 0, static_cast<size_t>(nq_pad) * 4, stream);
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;   // (cnt is zeroed by the threshold kernel, right before the main pass)
 
   CUtensorMap map_a, map_b, map_b_half;
   if (!gemm_encode_map(&map_a, bf16 ? shadow : static_cast<const void*>(emb), n, ld, kGmRows, bf16) ||
@@ -902,7 +930,7 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
 #define ANR_GEMM_CASE(NQV, BFV)                                                                   \
   e = gemm_launch_pair<NQV, BFV>(dp, map_a, map_b, map_b_half, n, n_qblocks, mask, sample_tiles,  \
                                  n_real, k, gmax, thr, thr_key, cand, cnt, L, ev_start, ev_stop,   \
-                                 stream, ev_pre_main)
+                                 stream, ev_pre_main, gate_ctr, gate)
   if (bf16) {
     if (nqb_size == 64) ANR_GEMM_CASE(64, true);
     else if (nqb_size == 128) ANR_GEMM_CASE(128, true);

@@ -93,11 +93,23 @@ int dense_gemm_max_queries();              // queries one launch group takes
 int dense_gemm_padded_queries(int nq);     // rows q_dev must hold for a group of nq queries
 size_t dense_gemm_scratch_bytes(const DeviceProps& dp, int64_t n, int ld, int nq, int k);
 cudaError_t launch_f32_to_bf16(const float* in, void* out, int64_t count, cudaStream_t stream);
+// "The main kernel is resident": every CTA of the persistent main GEMM kernel bumps *counter when
+// it starts; expected = its grid.  A hybrid step holds its BM25 launch behind that (a one-thread
+// kernel on the BM25 stream polls it, launch_gate_wait), so the dense CTAs own their shared
+// memory on every SM BEFORE the BM25 CTAs fill the rest -- an event can only say "the kernel
+// before it has finished", which lets a BM25 grid slip in first and starve the dense kernel
+// (0.63 instead of 0.41 ms, profiles/r2_call9_*).  counter stays null on paths without one.
+struct DenseGate {
+  int32_t* counter = nullptr;
+  int expected = 0;
+};
+cudaError_t launch_gate_wait(const int32_t* counter, int expected, cudaStream_t stream);
 cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const void* shadow, int64_t n,
                               int ld, const float* q_dev, int n_real, int k, const uint32_t* mask,
                               float emb_norm_max, unsigned char* scratch, const TopkOut& out,
                               int32_t* flags, cudaEvent_t ev_start, cudaEvent_t ev_stop,
-                              cudaStream_t stream, cudaEvent_t ev_pre_main = nullptr);
+                              cudaStream_t stream, cudaEvent_t ev_pre_main = nullptr,
+                              DenseGate* gate = nullptr);
 cudaError_t launch_dense_tc_rescore_append(const uint64_t* cand, const int32_t* cnt, int cap,
                                            const float* emb, int ld, const float* q_dev, int n_real,
                                            int k, float eps_scale, const uint64_t* thr_key,

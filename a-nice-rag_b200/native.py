@@ -37,6 +37,8 @@ SIGNATURES = {
     "anr_ctx_info": [_P, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_I64)],
     "anr_ctx_profile_enable": [_P, _I32],
     "anr_ctx_profile_read": [_P, _I32, C.POINTER(_F64), C.POINTER(_I64)],
+    "anr_ctx_timeline_enable": [_P, _I32],
+    "anr_ctx_timeline_read": [_P, C.POINTER(_F64)],
     "anr_dense_create": [_P, _P, _I64, _I32, _I32, C.POINTER(_P)],
     "anr_dense_upload": [_P, _P, _I64, _P, _I64],
     "anr_dense_destroy": [_P],

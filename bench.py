@@ -722,6 +722,30 @@ def headline_report(env, args, peaks, w, qb, got, t):
         except Exception as exc:   # never lose the headline line to the optional replay leg
             graph_rec = {"error": repr(exc)[:300]}
 
+    # ---- where the parts of ONE step start and end (events at fixed marks inside the call) -----
+    timeline = None
+    if world == 1:
+        try:
+            names = ["step_begin", "bm25_sample_begin", "bm25_sample_end", "dense_pass_begin",
+                     "dense_main_begin", "dense_main_end", "dense_rescore_end", "dense_pass_end",
+                     "bm25_main_begin", "bm25_main_end", "bm25_final_end", "fusion_end"]
+            step_device, _ = step_fns(env, w, qb)
+            native.call("anr_ctx_timeline_enable", env.ctx.handle, 1)
+            runs = []
+            for _ in range(9):
+                torch.cuda.synchronize()
+                step_device()
+                marks = (C.c_double * len(names))()
+                native.call("anr_ctx_timeline_read", env.ctx.handle, marks)
+                runs.append(list(marks))
+            native.call("anr_ctx_timeline_enable", env.ctx.handle, 0)
+            med = [statistics.median(r[i] for r in runs[2:]) for i in range(len(names))]
+            timeline = {"unit": "ms from step_begin, median of 7 single steps (one step in flight, "
+                                "the stream idle before it)",
+                        **{n: round(v, 4) for n, v in zip(names, med)}}
+        except Exception as exc:
+            timeline = {"error": repr(exc)[:200]}
+
     # ---- two batches in flight: the latency-bound ends of one step (sample passes, thresholds,
     #      rescoring, merges, fusion) run under the main kernels of the other.  `two_in_flight`:
     #      inputs resident, two captured steps alternating on two streams; `e2e_pipelined`:
@@ -873,6 +897,7 @@ def headline_report(env, args, peaks, w, qb, got, t):
                       "value": B * steps / (t["ms_filtered"] * 1e-3), "unit": "queries/s",
                       "ms_per_step": t["ms_filtered"] / steps} if t["ms_filtered"] else None),
         "cuda_graph": graph_rec,
+        "timeline": timeline,
         "pipelined": pipe_rec,
         "multi_gpu": t["multi"],
         "clocks": t["clocks"], "parity_checked_queries": checked,

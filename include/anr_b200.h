@@ -17,7 +17,9 @@
  *     lazily created index members, which synchronise.  A captured graph bakes in
  *     workspace addresses, so give it a context nothing else uses
  *     (a-nice-rag_b200/graph.py, tests/test_gpu_graph.py);
- *   - a context (workspace + streams) must not be used by two threads at once;
+ *   - a context (workspace + streams) must not be used by two threads at once; consecutive
+ *     calls on one context may use different streams: a call enqueued on another stream than
+ *     the previous one is ordered after it (the two share the context's scratch memory);
  *     index objects are immutable after creation and may be shared;
  *   - there is NO CPU implementation behind any of these: without a B200 (sm_100)
  *     device anr_ctx_create fails with ANR_ERR_NO_DEVICE.
@@ -67,6 +69,20 @@ int anr_ctx_info(anr_ctx* ctx, int32_t* sm_count, int64_t* hbm_total, int64_t* h
  * time (ms) and launch count per kind since the last read, and resets the counters. */
 int anr_ctx_profile_enable(anr_ctx* ctx, int32_t on);
 int anr_ctx_profile_read(anr_ctx* ctx, int32_t kind, double* total_ms, int64_t* launches);
+
+/* Timeline of ONE anr_hybrid_search step (the GEMM dense path): while enabled (and
+ * anr_ctx_profile_enable is off), the call records an event at each of the marks below on the stream
+ * that part runs on; anr_ctx_timeline_read synchronises and returns every mark's offset in ms
+ * from mark 0 (-1 = not reached).  For naming and timing the fixed costs of a step
+ * (bench.py `timeline`); no effect on results.
+ *   0 step begin             1 BM25 sample launch begin     2 BM25 sample launch end
+ *   3 dense pass begin       4 dense main kernel begin      5 dense main kernel end
+ *   6 dense rescoring end    7 dense pass end (flagged-query fallback launches included)
+ *   8 BM25 main launch begin 9 BM25 main launch end        10 BM25 final top-k end
+ *  11 fusion end */
+#define ANR_TIMELINE_MARKS 12
+int anr_ctx_timeline_enable(anr_ctx* ctx, int32_t on);
+int anr_ctx_timeline_read(anr_ctx* ctx, double* offsets_ms /* [ANR_TIMELINE_MARKS] */);
 
 /* ---- dense index: the chunk-embedding matrix ------------------------------
  * Replaces the per-query `np.stack(df["embedding"].values)` of
