@@ -275,21 +275,6 @@ __global__ void set_i32_pair_kernel(int32_t* out, int32_t a, int32_t b) {
   out[0] = a;
   out[1] = b;
 }
-// A query WITHOUT terms has no BM25 result at all: the reference returns [] for an empty token list
-// (src/search_engine.py:216-217) before any scoring, whereas scoring nothing would rank the first k
-// documents with score 0.  (A non-empty list of unknown tokens does get that zero-score ranking.)
-__global__ void bm25_clear_empty_queries_kernel(const int32_t* __restrict__ q_offsets, int nq, int k,
-                                                TopkOut out) {
-  const int q = blockIdx.x;
-  if (q >= nq || q_offsets[q + 1] != q_offsets[q]) return;
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    const int64_t at = q * out.stride_q + i;
-    if (out.keys) out.keys[at] = 0ull;
-    if (out.scores) out.scores[at] = 0.f;
-    if (out.ids) out.ids[at] = -1;
-  }
-  if (threadIdx.x == 0 && out.counts) out.counts[q * out.count_stride] = 0;
-}
 // BM25 results carry document ids in their own space: translate them to row ids of the
 // dense index' space before fusion (done by TopkOut::id_map), nothing else needed here.
 
@@ -649,12 +634,6 @@ Bm25View bm25_view(const anr_bm25* ix) {
   return v;
 }
 
-cudaError_t bm25_clear_empty_queries(const int32_t* offsets_dev, int nq, int k, const TopkOut& out,
-                                     cudaStream_t stream) {
-  bm25_clear_empty_queries_kernel<<<nq, 32, 0, stream>>>(offsets_dev, nq, k, out);
-  return cudaGetLastError();
-}
-
 // State of a BM25 top-k scan issued in two phases around the dense pass of a hybrid query.
 struct Bm25Run {
   bool active = false;
@@ -722,8 +701,9 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
     }
     tl_mark(ctx, 9, stream);
     const int m = static_cast<int>(stride);
-    ANR_CUDA(launch_topk_final(cand, stride, m, m, 0, nq, k, out, stream));
-    ANR_CUDA(bm25_clear_empty_queries(offsets_dev, nq, k, out, stream));
+    TopkOut live = out;
+    live.q_offsets = offsets_dev;   // a query without terms gets no result (search_engine.py:216-217)
+    ANR_CUDA(launch_topk_final(cand, stride, m, m, 0, nq, k, live, stream));
     tl_mark(ctx, 10, stream);
     return ANR_OK;
   }
@@ -744,9 +724,9 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
     if (o.scores) o.scores += q0 * out.stride_q;
     if (o.ids) o.ids += q0 * out.stride_q;
     if (o.counts) o.counts += q0 * out.count_stride;
+    o.q_offsets = offsets_dev + q0;   // a query without terms gets no result
     ANR_CUDA(launch_emit_sorted(keys, n_pow2, n_pow2, real, k, o, stream));
   }
-  ANR_CUDA(bm25_clear_empty_queries(offsets_dev, nq, k, out, stream));
   return ANR_OK;
 }
 
@@ -1750,6 +1730,18 @@ int anr_sharded_fuse(anr_ctx* ctx, const uint64_t* gathered, int32_t n_parts, in
   OutBuf<int32_t> o_ids = out_make(arena, out_ids, cells);
   OutBuf<double> o_scores = out_make(arena, out_scores, cells);
   OutBuf<int32_t> o_counts = out_make(arena, out_counts, nq);
+  static const bool one_launch = !(getenv("ANR_SHARDED_FUSE_SMALL") &&
+                                   atoi(getenv("ANR_SHARDED_FUSE_SMALL")) == 0);
+  if (one_launch && sharded_fuse_small_fits(n_parts, k)) {   // merge x 2 + fusion in ONE launch
+    ANR_CUDA(launch_sharded_fuse_small(keys_dev, n_parts, nq, k, w_dense, w_bm25, rrf_k, top_n,
+                                       o_ids.dev, o_scores.dev, o_counts.dev, stream));
+    bool any_host_small = false;
+    ANR_CUDA(out_flush(o_ids, stream, &any_host_small));
+    ANR_CUDA(out_flush(o_scores, stream, &any_host_small));
+    ANR_CUDA(out_flush(o_counts, stream, &any_host_small));
+    if (any_host_small) ANR_CUDA(cudaStreamSynchronize(stream));
+    return ANR_OK;
+  }
   set_f64_pair_kernel<<<1, 1, 0, stream>>>(w_dev, w_dense, w_bm25);
   ANR_CUDA(cudaGetLastError());
   const int64_t part_stride = 2ll * nq * k;

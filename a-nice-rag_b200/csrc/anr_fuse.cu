@@ -167,16 +167,13 @@ wrrf_fuse_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ le
 constexpr int kWrrfSmallCap = 64;
 constexpr int kWrrfSmallWarps = 8;
 
-__global__ void __launch_bounds__(kWrrfSmallWarps * 32)
-wrrf_fuse_small_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ lens,
-                       const double* __restrict__ weights, int n_lists, int list_stride,
-                       double rrf_k, int top_n, int nq, int32_t* __restrict__ out_ids,
-                       double* __restrict__ out_scores, int32_t* __restrict__ out_counts) {
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * kWrrfSmallWarps + (threadIdx.x >> 5);
-  if (q >= nq) return;   // whole warp
-  const int32_t* qids = ids + static_cast<int64_t>(q) * n_lists * list_stride;
-  const int32_t* qlens = lens + static_cast<int64_t>(q) * n_lists;
+// One warp, one query: qids [n_lists][list_stride] / qlens [n_lists] may live in global or shared
+// memory (the sharded merge below hands over lists it has just built in shared memory).
+__device__ __forceinline__ void
+wrrf_small_warp(const int32_t* qids, const int32_t* qlens, const double* weights, int n_lists,
+                int list_stride, double rrf_k, int top_n, int q, int lane,
+                int32_t* __restrict__ out_ids, double* __restrict__ out_scores,
+                int32_t* __restrict__ out_counts) {
   // my entries: insertion positions lane and lane + 32
   int id[2] = {0, 0};
   double term[2] = {0.0, 0.0};
@@ -236,6 +233,82 @@ wrrf_fuse_small_kernel(const int32_t* __restrict__ ids, const int32_t* __restric
     out_scores[base + i] = 0.0;
   }
   if (lane == 0 && out_counts) out_counts[q] = n_out;
+}
+
+__global__ void __launch_bounds__(kWrrfSmallWarps * 32)
+wrrf_fuse_small_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ lens,
+                       const double* __restrict__ weights, int n_lists, int list_stride,
+                       double rrf_k, int top_n, int nq, int32_t* __restrict__ out_ids,
+                       double* __restrict__ out_scores, int32_t* __restrict__ out_counts) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kWrrfSmallWarps + (threadIdx.x >> 5);
+  if (q >= nq) return;   // whole warp
+  wrrf_small_warp(ids + static_cast<int64_t>(q) * n_lists * list_stride,
+                  lens + static_cast<int64_t>(q) * n_lists, weights, n_lists, list_stride, rrf_k,
+                  top_n, q, lane, out_ids, out_scores, out_counts);
+}
+
+// ---- the consumer of a sharded step's all-gather, in ONE launch ---------------------------------
+// gathered: [n_parts][2][nq][k] sortable keys (per rank: dense plane, BM25 plane; ids global).  One
+// warp per query merges each retriever's n_parts lists to its global top-k (rank by counting:
+// keys are unique) in shared memory and runs the weighted RRF on the two merged lists -- what
+// launch_topk_final x 2 + launch_wrrf_fuse do in four launches; at 8 GPUs those launches were a
+// tenth of a 0.23 ms step.  Shapes: 2 k <= 64 and n_parts * k <= kShardMergeCap.
+constexpr int kShardMergeCap = 256;
+
+__global__ void __launch_bounds__(kWrrfSmallWarps * 32)
+sharded_fuse_small_kernel(const uint64_t* __restrict__ gathered, int n_parts, int nq, int k,
+                          double w_dense, double w_bm25, double rrf_k, int top_n,
+                          int32_t* __restrict__ out_ids, double* __restrict__ out_scores,
+                          int32_t* __restrict__ out_counts) {
+  __shared__ uint64_t s_keys[kWrrfSmallWarps][kShardMergeCap];
+  __shared__ int32_t s_ids[kWrrfSmallWarps][2][32];
+  __shared__ int32_t s_lens[kWrrfSmallWarps][2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kWrrfSmallWarps + warp;
+  if (q >= nq) return;   // whole warp
+  const int m = n_parts * k;
+  uint64_t* keys = s_keys[warp];
+  for (int which = 0; which < 2; ++which) {
+    int live = 0;
+    for (int i = lane; i < m; i += 32) {
+      const int part = i / k, j = i - part * k;
+      const uint64_t key =
+          gathered[((static_cast<int64_t>(part) * 2 + which) * nq + q) * k + j];
+      keys[i] = key;
+      live += key != 0ull;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) live += __shfl_xor_sync(kFullMask, live, o);
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) {
+      const uint64_t key = keys[i];
+      if (key == 0ull) continue;
+      int rank = 0;
+      for (int j = 0; j < m; ++j) rank += keys[j] > key;
+      if (rank < k) s_ids[warp][which][rank] = static_cast<int32_t>(key_id(key));
+    }
+    if (lane == 0) s_lens[warp][which] = live < k ? live : k;
+    __syncwarp();
+  }
+  const double weights[2] = {w_dense, w_bm25};
+  wrrf_small_warp(&s_ids[warp][0][0], s_lens[warp], weights, 2, 32, rrf_k, top_n, q, lane, out_ids,
+                  out_scores, out_counts);
+}
+
+bool sharded_fuse_small_fits(int n_parts, int k) {
+  return 2 * k <= kWrrfSmallCap && k <= 32 && n_parts * k <= kShardMergeCap;
+}
+
+cudaError_t launch_sharded_fuse_small(const uint64_t* gathered, int n_parts, int nq, int k,
+                                      double w_dense, double w_bm25, double rrf_k, int top_n,
+                                      int32_t* out_ids, double* out_scores, int32_t* out_counts,
+                                      cudaStream_t stream) {
+  if (!sharded_fuse_small_fits(n_parts, k) || nq < 1) return cudaErrorInvalidValue;
+  sharded_fuse_small_kernel<<<(nq + kWrrfSmallWarps - 1) / kWrrfSmallWarps, kWrrfSmallWarps * 32, 0,
+                              stream>>>(gathered, n_parts, nq, k, w_dense, w_bm25, rrf_k, top_n,
+                                        out_ids, out_scores, out_counts);
+  return cudaGetLastError();
 }
 
 size_t wrrf_scratch_keys(int n_lists, int list_stride, int nq) {

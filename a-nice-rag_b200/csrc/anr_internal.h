@@ -28,6 +28,10 @@ struct TopkOut {
   int64_t count_stride = 1;
   int64_t id_base = 0;
   const int32_t* id_map = nullptr;
+  // BM25 only (nullable): CSR offsets of the query terms, q_offsets[q] == q_offsets[q + 1] -> the
+  // query has NO result (count 0, empty slots): `if not query_tokens: return []`,
+  // src/search_engine.py:216-217
+  const int32_t* q_offsets = nullptr;
 };
 
 // ---- dense scan -------------------------------------------------------------
@@ -202,6 +206,12 @@ cudaError_t launch_wrrf_fuse(const int32_t* ids, const int32_t* lens, const doub
                              uint64_t* scratch, int32_t* out_ids, double* out_scores,
                              int32_t* out_counts, cudaStream_t stream);
 size_t wrrf_scratch_keys(int n_lists, int list_stride, int nq);
+// merge of the all-gathered [n_parts][2][nq][k] keys + weighted RRF in one launch (small shapes)
+bool sharded_fuse_small_fits(int n_parts, int k);
+cudaError_t launch_sharded_fuse_small(const uint64_t* gathered, int n_parts, int nq, int k,
+                                      double w_dense, double w_bm25, double rrf_k, int top_n,
+                                      int32_t* out_ids, double* out_scores, int32_t* out_counts,
+                                      cudaStream_t stream);
 int wrrf_max_entries();
 
 }  // namespace anr

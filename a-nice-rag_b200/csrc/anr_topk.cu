@@ -52,9 +52,10 @@ topk_final_kernel(const uint64_t* __restrict__ cand, int64_t stride_q, int m, in
     }
   }
   block_bitonic_sort_desc(keys, p2);
+  const bool dead = o.q_offsets && o.q_offsets[q + 1] == o.q_offsets[q];   // a query without terms
   uint64_t key = 0ull;
   if (threadIdx.x < k) {
-    key = threadIdx.x < p2 ? keys[threadIdx.x] : 0ull;
+    key = (threadIdx.x < p2 && !dead) ? keys[threadIdx.x] : 0ull;
     emit_entry(key, q * o.stride_q + threadIdx.x, o);
   }
   const int cnt = __syncthreads_count(key != 0ull);
@@ -102,12 +103,13 @@ topk_final_small_kernel(const uint64_t* __restrict__ cand, int64_t stride_q, int
   __syncthreads();
   const int ns = n_sel < cap ? n_sel : cap;
   block_bitonic_sort_desc(sel, next_pow2(ns < 2 ? 2 : ns));
+  const bool dead = o.q_offsets && o.q_offsets[q + 1] == o.q_offsets[q];   // a query without terms
   uint64_t key = 0ull;
   for (int i = threadIdx.x; i < k; i += kSmallThreads) {
-    key = i < ns ? sel[i] : 0ull;
+    key = (i < ns && !dead) ? sel[i] : 0ull;
     emit_entry(key, q * o.stride_q + i, o);
   }
-  if (threadIdx.x == 0 && o.counts) o.counts[q * o.count_stride] = ns < k ? ns : k;
+  if (threadIdx.x == 0 && o.counts) o.counts[q * o.count_stride] = dead ? 0 : (ns < k ? ns : k);
 }
 
 cudaError_t launch_topk_final(const uint64_t* cand, int64_t cand_stride_q, int m, int seg_len,
@@ -260,9 +262,10 @@ emit_sorted_kernel(const uint64_t* __restrict__ keys, int64_t stride_q, int64_t 
   if (threadIdx.x == 0) cnt = 0;
   __syncthreads();
   const int q = blockIdx.x;
+  const bool dead = o.q_offsets && o.q_offsets[q + 1] == o.q_offsets[q];   // a query without terms
   int mine = 0;
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    const uint64_t key = i < n_avail ? keys[q * stride_q + i] : 0ull;
+    const uint64_t key = (i < n_avail && !dead) ? keys[q * stride_q + i] : 0ull;
     emit_entry(key, q * o.stride_q + i, o);
     mine += key != 0ull;
   }

@@ -88,9 +88,12 @@ def main():
         out["graph_error"] = repr(exc)[:400]
     if env.rank == 0:
         print(json.dumps(out), flush=True)
-    if env.world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    # Captured graphs hold NCCL kernels of two communicators; tearing the process group down
+    # with them alive hung the first run of this probe until its time limit.  Everything is
+    # measured and printed: leave without running destructors.
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
