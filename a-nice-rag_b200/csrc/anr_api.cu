@@ -114,6 +114,13 @@ struct anr_bm25 {
   mutable int32_t n_head = 0;
   mutable bool head_built = false;         // slot map + allocation exist
   mutable bool head_filled = false;        // rows hold the current posting weights
+  // candidate-driven top-k (anr_bm25_ms.cu): largest posting weight per term, built on first use
+  mutable float* term_maxw = nullptr;      // [n_terms] (+ one int behind it: the negative-idf probe)
+  mutable int64_t* bkt_off = nullptr;      // [n_terms]
+  mutable uint8_t* bkt_shift = nullptr;    // [n_terms]
+  mutable int32_t* bkt = nullptr;          // bucket tables
+  mutable bool ms_ready = false;
+  mutable bool neg_idf = false;            // some idf < 0: the bounds do not hold, tiled scan only
   mutable std::mutex lazy;                 // guards the lazily built members (shared index)
 };
 
@@ -611,12 +618,60 @@ int bm25_ensure_heads(const anr_bm25* ix, cudaStream_t stream) {
   return ANR_OK;
 }
 
+// Candidate-driven top-k (anr_bm25_ms.cu) is the default for k <= 128; ANR_BM25_MAXSCORE=0 keeps
+// the tiled scan.  Tiny indices and batches beyond one grid dimension stay on the tiled scan.
+// (The two knobs are read on every call: the GPU tests switch paths inside one process.)
+bool bm25_ms_wanted(const anr_bm25* ix, int nq, int k) {
+  const char* e = getenv("ANR_BM25_MAXSCORE");
+  const bool on = !(e && atoi(e) == 0) && getenv("ANR_DISABLE_BM25_PRUNE") == nullptr;
+  return on && k <= kMaxFusedK && ix->n_docs >= 1024 && ix->nnz > 0 && nq <= 65535;
+}
+// Once per index (and after a reweighting): per-term largest weight + "is any idf negative".
+int bm25_ensure_ms(const anr_bm25* ix, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(ix->lazy);
+  if (ix->ms_ready) return ANR_OK;
+  const size_t nt = static_cast<size_t>(std::max(ix->n_terms, 1));
+  if (!ix->term_maxw) ANR_CUDA(cudaMalloc(&ix->term_maxw, nt * 4 + 16));
+  int32_t* neg_dev = reinterpret_cast<int32_t*>(ix->term_maxw + nt);
+  ANR_CUDA(launch_bm25_term_max(bm25_view(ix), ix->term_maxw, neg_dev, stream));
+  int32_t neg = 0;
+  ANR_CUDA(cudaMemcpyAsync(&neg, neg_dev, 4, cudaMemcpyDeviceToHost, stream));
+  if (!ix->bkt_off) {   // the tables follow the postings' positions only: built once per index
+    std::vector<int64_t> tp(static_cast<size_t>(ix->n_terms) + 1);
+    ANR_CUDA(cudaMemcpyAsync(tp.data(), ix->term_ptr, tp.size() * 8, cudaMemcpyDeviceToHost, stream));
+    ANR_CUDA(cudaStreamSynchronize(stream));
+    std::vector<int64_t> off(nt, 0);
+    std::vector<uint8_t> shift(nt, 0xff);
+    int64_t total = 0;
+    for (int32_t t = 0; t < ix->n_terms; ++t) {
+      const int sh = bm25_bucket_shift(tp[t + 1] - tp[t], ix->n_docs);
+      shift[t] = static_cast<uint8_t>(sh);
+      off[t] = total;
+      total += bm25_bucket_entries(sh, ix->n_docs);
+    }
+    ANR_CUDA(cudaMalloc(&ix->bkt_off, nt * 8));
+    ANR_CUDA(cudaMalloc(&ix->bkt_shift, nt));
+    ANR_CUDA(cudaMalloc(&ix->bkt, static_cast<size_t>(std::max<int64_t>(total, 1)) * 4));
+    ANR_CUDA(cudaMemcpyAsync(ix->bkt_off, off.data(), nt * 8, cudaMemcpyHostToDevice, stream));
+    ANR_CUDA(cudaMemcpyAsync(ix->bkt_shift, shift.data(), nt, cudaMemcpyHostToDevice, stream));
+    ANR_CUDA(launch_bm25_bucket_fill(bm25_view(ix), ix->bkt_off, ix->bkt_shift, ix->bkt, stream));
+  }
+  ANR_CUDA(cudaStreamSynchronize(stream));   // host vectors go out of scope; other streams may read
+  ix->neg_idf = neg != 0;
+  ix->ms_ready = true;
+  return ANR_OK;
+}
+
 size_t bm25_ws_bytes(const anr_ctx* ctx, const anr_bm25* ix, int nq, int k) {
   if (k <= kMaxFusedK) {
     const Bm25Plan plan = bm25_make_plan(ctx->dp, ix->n_docs, nq, k, false);
     const size_t slots = static_cast<size_t>(std::max(plan.n_tiles, plan.n_runs + plan.n_sampled));
+    size_t ms = 0;
+    if (bm25_ms_wanted(ix, nq, k))
+      ms = padded(bm25_ms_scratch_bytes(nq)) + padded(static_cast<size_t>(nq) * kMsSurvivors * 8) +
+           padded(static_cast<size_t>(nq) * 4) + 1024;
     return padded(static_cast<size_t>(nq) * slots * k * 8) +
-           padded((static_cast<size_t>(nq) + kBm25CounterSlots) * 4) + 512;
+           padded((static_cast<size_t>(nq) + kBm25CounterSlots) * 4) + 512 + ms;
   }
   const int64_t n_pow2 = next_pow2(std::max(ix->n_docs, 2));
   return padded(static_cast<size_t>(std::min(nq, 8)) * n_pow2 * 8) + 256;
@@ -637,6 +692,7 @@ Bm25View bm25_view(const anr_bm25* ix) {
 // State of a BM25 top-k scan issued in two phases around the dense pass of a hybrid query.
 struct Bm25Run {
   bool active = false;
+  bool ms_done = false;   // the candidate-driven path finished the whole search in phase 1
   Bm25Plan plan;
   Bm25HeadView hd;
   uint64_t* cand = nullptr;
@@ -652,6 +708,70 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
                   Arena& arena, const TopkOut& out, cudaStream_t stream,
                   bool beside_dense = false, int phase = 0, Bm25Run* run = nullptr) {
   const Bm25View v = bm25_view(ix);
+  if (phase == 2 && run && run->ms_done) return ANR_OK;
+  if (bm25_ms_wanted(ix, nq, k)) {
+    if (int rc = bm25_ensure_ms(ix, stream)) return rc;
+    if (!ix->neg_idf) {
+      // ---- candidate-driven top-k: plan | stage 1 | theta + required lists | stage 2 | final top-k,
+      //      then the exhaustive tiled scan for the (usually zero) flagged queries ----
+      Bm25HeadView hd;
+      if (ix->n_docs >= 8192) {
+        if (int rc = bm25_ensure_heads(ix, stream)) return rc;
+        hd.slot_of = ix->head_slot;
+        hd.head_w = ix->head_w;
+        hd.head_max = ix->head_max;
+        hd.head_ld = ix->head_ld;
+        hd.n_head = ix->n_head;
+      }
+      unsigned char* scratch = arena.take<unsigned char>(bm25_ms_scratch_bytes(nq));
+      uint64_t* surv = arena.take<uint64_t>(static_cast<size_t>(nq) * kMsSurvivors);
+      int32_t* flagged = arena.take<int32_t>(static_cast<size_t>(nq));
+      int32_t* n_flagged = arena.take<int32_t>(1);
+      const Bm25Plan plan = bm25_make_plan(ctx->dp, ix->n_docs, nq, k, false);
+      if (plan.smem_bytes > ctx->dp.max_smem_optin)
+        return fail(ANR_ERR_UNSUPPORTED, "bm25 tile does not fit in shared memory");
+      const int64_t fb_stride = static_cast<int64_t>(plan.n_tiles) * k;
+      uint64_t* fb_cand = arena.take<uint64_t>(static_cast<size_t>(nq) * fb_stride);
+      TopkOut live = out;
+      live.q_offsets = offsets_dev;   // a query without terms gets no result (search_engine.py:216-217)
+      tl_mark(ctx, 1, stream);
+      {
+        ProfileScope prof(ctx, 1, stream);
+        MsIndexView mx;
+        mx.term_maxw = ix->term_maxw;
+        mx.bkt_off = ix->bkt_off;
+        mx.bkt_shift = ix->bkt_shift;
+        mx.bkt = ix->bkt;
+        ANR_CUDA(launch_bm25_maxscore(ctx->dp, v, hd, mx, terms_dev, offsets_dev, nq, k, mask_dev,
+                                      scratch, surv, live, n_flagged, flagged, stream));
+      }
+      tl_mark(ctx, 2, stream);
+      tl_mark(ctx, 8, stream);
+      tl_mark(ctx, 9, stream);
+      if (getenv("ANR_MS_DEBUG")) {   // per-query statistics of the path (profiling runs only: synchronises)
+        struct Q { int64_t s2_total; int32_t n; float theta; int32_t s1_total, n_surv, flag; float tot; };
+        std::vector<Q> h(static_cast<size_t>(nq));
+        ANR_CUDA(cudaStreamSynchronize(stream));
+        ANR_CUDA(cudaMemcpy(h.data(), scratch, h.size() * sizeof(Q), cudaMemcpyDeviceToHost));
+        int64_t items = 0, surv_n = 0;
+        int flagged_n = 0;
+        for (const Q& x : h) { items += x.s2_total; surv_n += x.n_surv; flagged_n += x.flag != 0 || x.n_surv < k; }
+        fprintf(stderr, "[anr ms] nq %d k %d stage-2 postings %lld survivors %lld flagged %d\n", nq, k,
+                static_cast<long long>(items), static_cast<long long>(surv_n), flagged_n);
+        for (int i = 0; i < nq && i < 64; ++i)
+          fprintf(stderr, "[anr ms]   q%d terms %d theta %.3f tot %.2f s1 %d s2 %lld surv %d flag %d\n", i, h[i].n,
+                  h[i].theta, h[i].tot, h[i].s1_total, static_cast<long long>(h[i].s2_total), h[i].n_surv,
+                  h[i].flag);
+      }
+      ANR_CUDA(launch_bm25_score_listed(v, terms_dev, offsets_dev, nq, k, mask_dev, plan, fb_cand,
+                                        fb_stride, flagged, n_flagged, stream));
+      ANR_CUDA(launch_topk_final_flagged(fb_cand, fb_stride, static_cast<int>(fb_stride), nq, k, live,
+                                         n_flagged, flagged, stream));
+      tl_mark(ctx, 10, stream);
+      if (run) run->ms_done = true;
+      return ANR_OK;
+    }
+  }
   if (k <= kMaxFusedK) {
     Bm25Run local;
     Bm25Run& r = run ? *run : local;
@@ -1251,6 +1371,7 @@ int anr_bm25_reweight(anr_ctx* ctx, anr_bm25* index, const int32_t* post_tf, con
     index->n_head = 0;
   }
   index->head_filled = false;
+  index->ms_ready = false;   // per-term largest weights and the negative-idf check follow the new values
   ANR_CUDA(cudaStreamSynchronize(stream));   // host sources may be reused by the caller
   return ANR_OK;
 }
@@ -1266,6 +1387,10 @@ int anr_bm25_destroy(anr_bm25* index) {
   if (index->head_terms) cudaFree(index->head_terms);
   if (index->head_w) cudaFree(index->head_w);
   if (index->head_max) cudaFree(index->head_max);
+  if (index->term_maxw) cudaFree(index->term_maxw);
+  if (index->bkt_off) cudaFree(index->bkt_off);
+  if (index->bkt_shift) cudaFree(index->bkt_shift);
+  if (index->bkt) cudaFree(index->bkt);
   delete index;
   return ANR_OK;
 }
@@ -1549,12 +1674,16 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
                                bm25_stream, !gated, 1, &run))
       return rc;
     tl_mark(ctx, 3, stream);
+    // The candidate-driven BM25 path is done after phase 1 (short kernels with a few KB of shared
+    // memory each: they fit beside the dense CTA whatever its ring depth, so the dense pass keeps
+    // its full ring and nothing is held back); the tiled scan continues in phase 2.
+    const bool ms = run.ms_done;
     if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k_dense, row_mask_dev, arena, od, stream,
-                                ctx->ev_mid, gated ? &gate : nullptr))
+                                ms ? nullptr : ctx->ev_mid, gated && !ms ? &gate : nullptr))
       return rc;
     tl_mark(ctx, 7, stream);
-    ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_mid, 0));
-    if (gated) ANR_CUDA(launch_gate_wait(gate.counter, gate.expected, ctx->side));
+    if (!ms) ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_mid, 0));
+    if (gated && !ms) ANR_CUDA(launch_gate_wait(gate.counter, gate.expected, ctx->side));
     if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k_bm25, doc_mask_dev, arena, ob,
                                bm25_stream, !gated, 2, &run))
       return rc;
@@ -1644,11 +1773,12 @@ int anr_hybrid_search_keys(anr_ctx* ctx, const anr_dense* dense, const anr_bm25*
   if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k, doc_mask_dev, arena, ob,
                              ctx->side, !gated, 1, &run))
     return rc;
-  if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k, row_mask_dev, arena, od, stream, ctx->ev_mid,
-                              gated ? &gate : nullptr))
+  const bool ms = run.ms_done;   // (see anr_hybrid_search)
+  if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k, row_mask_dev, arena, od, stream,
+                              ms ? nullptr : ctx->ev_mid, gated && !ms ? &gate : nullptr))
     return rc;
-  ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_mid, 0));
-  if (gated) ANR_CUDA(launch_gate_wait(gate.counter, gate.expected, ctx->side));
+  if (!ms) ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_mid, 0));
+  if (gated && !ms) ANR_CUDA(launch_gate_wait(gate.counter, gate.expected, ctx->side));
   if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k, doc_mask_dev, arena, ob,
                              ctx->side, !gated, 2, &run))
     return rc;

@@ -136,7 +136,8 @@ __device__ __forceinline__ void
 bm25_tile_item(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* __restrict__ q_terms,
                const int32_t* __restrict__ q_offsets, int k, const uint32_t* __restrict__ doc_mask,
                int tile_docs, int list_cap, uint64_t* __restrict__ out, int64_t out_stride_q,
-               float* __restrict__ theta_g, int tile_stride, int n_sampled, int bx, int by) {
+               float* __restrict__ theta_g, int tile_stride, int n_sampled, int bx, int by,
+               const int32_t* __restrict__ q_list = nullptr) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* acc = reinterpret_cast<float*>(smem);
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(tile_docs) * 4);
@@ -185,6 +186,9 @@ bm25_tile_item(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* __rest
     tile = bx;
     q = by;
   }
+  // q_list (natural order only): block row `by` scores query q_list[by] into output row `by`
+  const int out_row = q;
+  if (q_list) q = q_list[by];
   const int d0 = tile * tile_docs;
   const int span = light_sample ? max(min(tile_docs, 1024), (tile_docs / 4 + 31) / 32 * 32) : tile_docs;
   const int d1 = min(ix.n_docs, d0 + span);
@@ -375,7 +379,7 @@ bm25_tile_item(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* __rest
       const int doc = d0 + i;
       bool ok = true;
       if (doc_mask) ok = (__ldg(doc_mask + (doc >> 5)) >> (doc & 31)) & 1u;
-      out[q * out_stride_q + doc] = ok ? make_key(acc[i], static_cast<uint32_t>(doc)) : 0ull;
+      out[out_row * out_stride_q + doc] = ok ? make_key(acc[i], static_cast<uint32_t>(doc)) : 0ull;
     }
     return;
   }
@@ -527,7 +531,7 @@ bm25_tile_item(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* __rest
   }
   __syncthreads();
   const int ns = n_sel < sel_cap ? n_sel : sel_cap;
-  uint64_t* o = out + q * out_stride_q + static_cast<int64_t>(tile) * k;
+  uint64_t* o = out + out_row * out_stride_q + static_cast<int64_t>(tile) * k;
   if (ns <= kBm25Threads) {
     // rank by counting (keys are unique): one pass, no sort
     for (int i = threadIdx.x; i < k; i += kBm25Threads)
@@ -556,10 +560,21 @@ bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_te
                   const int32_t* __restrict__ q_offsets, int k,
                   const uint32_t* __restrict__ doc_mask, int tile_docs, int list_cap,
                   uint64_t* __restrict__ out, int64_t out_stride_q, float* __restrict__ theta_g,
-                  int tile_stride, int n_sampled) {
+                  int tile_stride, int n_sampled, const int32_t* __restrict__ q_list,
+                  const int32_t* __restrict__ n_list) {
+  if (n_list) {   // device-side list of queries: block row y takes entries y, y + gridDim.y, ...
+    const int n = *n_list;
+    for (int by = blockIdx.y; by < n; by += gridDim.y) {
+      bm25_tile_item<EMIT_ALL, PRUNE>(ix, hd, q_terms, q_offsets, k, doc_mask, tile_docs, list_cap,
+                                      out, out_stride_q, theta_g, tile_stride, n_sampled, blockIdx.x,
+                                      by, q_list);
+      __syncthreads();   // the item's shared memory is no longer read
+    }
+    return;
+  }
   bm25_tile_item<EMIT_ALL, PRUNE>(ix, hd, q_terms, q_offsets, k, doc_mask, tile_docs, list_cap, out,
                                   out_stride_q, theta_g, tile_stride, n_sampled, blockIdx.x,
-                                  blockIdx.y);
+                                  blockIdx.y, q_list);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1196,11 +1211,11 @@ static cudaError_t launch_score_t(const Bm25View& ix, const Bm25HeadView& hd, co
       if (plan.phase != 2)
         kern<<<grid_s, kBm25Threads, plan.smem_bytes, stream>>>(
             ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
-            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, light ? -4 : -2);
+            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, light ? -4 : -2, nullptr, nullptr);
       if (plan.phase != 1)
         kern<<<grid, kBm25Threads, plan.smem_bytes, stream>>>(
             ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
-            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, light ? -5 : -3);
+            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, light ? -5 : -3, nullptr, nullptr);
     } else if (plan.phase == 1) {
       // no separate sample launch in this plan: everything happens in phase 2
     } else if (PRUNE && theta && plan.n_tiles >= kMinTilesForSample && plan.n_tiles <= 65535) {
@@ -1216,11 +1231,11 @@ static cudaError_t launch_score_t(const Bm25View& ix, const Bm25HeadView& hd, co
       }
       kern<<<grid_f, kBm25Threads, plan.smem_bytes, stream>>>(
           ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
-          out + q0 * out_stride_q, out_stride_q, theta + q0, stride, n_sampled);
+          out + q0 * out_stride_q, out_stride_q, theta + q0, stride, n_sampled, nullptr, nullptr);
     } else {
       kern<<<grid, kBm25Threads, plan.smem_bytes, stream>>>(
           ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
-          out + q0 * out_stride_q, out_stride_q, theta ? theta + q0 : nullptr, 1, -1);
+          out + q0 * out_stride_q, out_stride_q, theta ? theta + q0 : nullptr, 1, -1, nullptr, nullptr);
     }
   }
   return cudaGetLastError();
@@ -1246,6 +1261,27 @@ cudaError_t launch_bm25_score_topk(const Bm25View& ix, const Bm25HeadView* hd, c
   }
   return launch_score_t<false, false>(ix, Bm25HeadView(), q_terms, q_offsets, nq, k, doc_mask, plan,
                                       cand, cand_stride_q, nullptr, stream);
+}
+
+// Exhaustive tiled scan of the queries q_list[0 .. *n_list) (both on the device; at most nq): block
+// row b writes the candidates of query q_list[b] to cand[b * cand_stride_q + tile * k + i].  The
+// rerun of the queries the candidate-driven path flags (anr_bm25_ms.cu).
+cudaError_t launch_bm25_score_listed(const Bm25View& ix, const int32_t* q_terms,
+                                     const int32_t* q_offsets, int nq, int k,
+                                     const uint32_t* doc_mask, const Bm25Plan& plan, uint64_t* cand,
+                                     int64_t cand_stride_q, const int32_t* q_list,
+                                     const int32_t* n_list, cudaStream_t stream) {
+  if (k < 1 || k > kMaxFusedK) return cudaErrorInvalidValue;
+  if (plan.n_tiles < 1 || nq < 1) return cudaSuccess;
+  auto kern = bm25_score_kernel<false, false>;
+  cudaError_t e =
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
+  if (e != cudaSuccess) return e;
+  // few block rows: the list is usually empty and every CTA returns at once
+  kern<<<dim3(plan.n_tiles, nq < 16 ? nq : 16), kBm25Threads, plan.smem_bytes, stream>>>(
+      ix, Bm25HeadView(), q_terms, q_offsets, k, doc_mask, plan.tile_docs, plan.list_cap, cand,
+      cand_stride_q, nullptr, 1, -1, q_list, n_list);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_bm25_score_all(const Bm25View& ix, const int32_t* q_terms,

@@ -198,6 +198,44 @@ cudaError_t launch_bm25_score_all(const Bm25View& ix, const int32_t* q_terms,
                                   cudaStream_t stream);
 cudaError_t launch_keys_to_scores(const uint64_t* keys, int64_t n, float* scores,
                                   cudaStream_t stream);
+// Exhaustive tiled scan of the device-side list of queries q_list[0 .. *n_list): candidates of
+// q_list[b] go to cand[b * cand_stride_q + tile * k + i] (the rerun of flagged queries).
+cudaError_t launch_bm25_score_listed(const Bm25View& ix, const int32_t* q_terms,
+                                     const int32_t* q_offsets, int nq, int k,
+                                     const uint32_t* doc_mask, const Bm25Plan& plan, uint64_t* cand,
+                                     int64_t cand_stride_q, const int32_t* q_list,
+                                     const int32_t* n_list, cudaStream_t stream);
+
+// ---- BM25 top-k, candidate-driven (anr_bm25_ms.cu) ---------------------------------------------
+constexpr int kMsMaxTerms = 48;      // query terms the path takes (longer queries are flagged)
+constexpr int kMsSample = 4096;      // stage-1 candidates per query
+constexpr int kMsSurvivors = 4096;   // stage-2 survivors kept per query (more: flagged)
+constexpr int kMsBucketMin = 16;     // posting lists from this length on get a bucket table
+// Per-index data of the path (built once, rebuilt after a reweighting): the largest posting weight
+// of every term and the bucket tables that make "weight of document d in list t" a two-step lookup.
+struct MsIndexView {
+  const float* term_maxw = nullptr;    // [n_terms]
+  const int64_t* bkt_off = nullptr;    // [n_terms] first entry of the term's table in bkt
+  const uint8_t* bkt_shift = nullptr;  // [n_terms] bucket = doc >> shift; 0xff = no table
+  const int32_t* bkt = nullptr;        // positions (relative to the list) where the buckets start
+};
+size_t bm25_ms_scratch_bytes(int nq);
+// term_maxw[n_terms] <- largest posting weight of each term; *neg_idf <- 1 if some idf < 0
+cudaError_t launch_bm25_term_max(const Bm25View& ix, float* term_maxw, int32_t* neg_idf,
+                                 cudaStream_t stream);
+int bm25_bucket_shift(int64_t len, int n_docs);        // 0xff: the list gets no table
+int64_t bm25_bucket_entries(int shift, int n_docs);    // table entries of a list with that shift
+cudaError_t launch_bm25_bucket_fill(const Bm25View& ix, const int64_t* bkt_off, const uint8_t* bkt_shift,
+                                    int32_t* bkt, cudaStream_t stream);
+// surv: [nq][kMsSurvivors] keys of scratch; the ranked top-k of every query goes to `out`
+// (out.q_offsets set: a query without terms gets no result); flagged[0 .. *n_flagged) = the
+// queries that must be rerun through the exhaustive scan (ascending), whose rows in `out` are then
+// overwritten.  hd.n_head == 0: every lookup goes through the posting lists.
+cudaError_t launch_bm25_maxscore(const DeviceProps& dp, const Bm25View& ix, const Bm25HeadView& hd,
+                                 const MsIndexView& mx, const int32_t* q_terms,
+                                 const int32_t* q_offsets, int nq, int k, const uint32_t* doc_mask,
+                                 unsigned char* scratch, uint64_t* surv, const TopkOut& out,
+                                 int32_t* n_flagged, int32_t* flagged, cudaStream_t stream);
 
 // ---- fusion -------------------------------------------------------------------
 // scratch: wrrf_scratch_keys() 64-bit words (0 when the union fits in shared memory)

@@ -11,16 +11,6 @@
 
 namespace anr {
 
-__device__ __forceinline__ void emit_entry(uint64_t key, int64_t slot, const TopkOut& o) {
-  const bool valid = key != 0ull;
-  uint32_t id = key_id(key);
-  if (valid)
-    id = o.id_map ? static_cast<uint32_t>(o.id_map[id]) : static_cast<uint32_t>(id + o.id_base);
-  if (o.keys) o.keys[slot] = valid ? ((key & 0xffffffff00000000ull) | (0xffffffffu - id)) : 0ull;
-  if (o.scores) o.scores[slot] = valid ? key_score(key) : 0.f;
-  if (o.ids) o.ids[slot] = valid ? static_cast<int32_t>(id) : -1;
-}
-
 // Candidate i of a query lives at base[(i / seg_len) * seg_stride + (i % seg_len)]:
 // contiguous candidates use seg_len = m; the all-gathered [part][query][k] layout of
 // the sharded search uses seg_len = k, seg_stride = n_queries * k.

@@ -5,12 +5,24 @@
 //   * the final per-query selection kernel over a candidate array.
 #pragma once
 #include "anr_common.cuh"
+#include "anr_internal.h"
 
 namespace anr {
 
 constexpr int kMaxFusedK = 128;      // fused (threshold-list) top-k handles k <= this
 constexpr int kFinalThreads = 1024;  // topk_final_kernel block size
 constexpr int kFinalSortCap = 4096;  // keys the final kernel sorts in shared memory
+
+// One result entry (key 0 = empty slot) into whichever output arrays the caller asked for.
+__device__ __forceinline__ void emit_entry(uint64_t key, int64_t slot, const TopkOut& o) {
+  const bool valid = key != 0ull;
+  uint32_t id = key_id(key);
+  if (valid)
+    id = o.id_map ? static_cast<uint32_t>(o.id_map[id]) : static_cast<uint32_t>(id + o.id_base);
+  if (o.keys) o.keys[slot] = valid ? ((key & 0xffffffff00000000ull) | (0xffffffffu - id)) : 0ull;
+  if (o.scores) o.scores[slot] = valid ? key_score(key) : 0.f;
+  if (o.ids) o.ids[slot] = valid ? static_cast<int32_t>(id) : -1;
+}
 
 // Replace the minimum of list[0..k) by `key` (caller guarantees key > current
 // minimum or the list has empty slots) and return the new minimum = the warp's

@@ -516,7 +516,16 @@ def test_bm25_reweight_equals_rebuilt_index(small):
 
 
 # ---------------------------------------------------------------------------------------
-# BM25 pruned scan (anr_bm25.cu, PRUNE): dense head rows + MaxScore-style bound, 8192+ documents
+# BM25 top-k on 8192+ documents, both safe-pruning paths: the candidate-driven one
+# (anr_bm25_ms.cu, the default) and the tiled scan with dense head rows (anr_bm25.cu, PRUNE;
+# ANR_BM25_MAXSCORE=0 selects it, and it is the rerun path of flagged queries)
+@pytest.fixture(params=["candidates", "tiled"])
+def bm25_path(request, monkeypatch):
+    if request.param == "tiled":
+        monkeypatch.setenv("ANR_BM25_MAXSCORE", "0")
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def prune_corpus():
     n, vocab = 70_000, 4000
@@ -546,7 +555,7 @@ def _check_bm25_batch(ix, queries, scores, docs, counts, k, what, mask=None):
 
 
 @pytest.mark.parametrize("nq,k", [(1, 10), (8, 10), (16, 1), (17, 100), (64, 10), (70, 32), (33, 128)])
-def test_bm25_pruned_batches_vs_oracle(prune_corpus, nq, k):
+def test_bm25_pruned_batches_vs_oracle(prune_corpus, bm25_path, nq, k):
     ix, index, vocab = prune_corpus
     tq = synth.zipf_queries(nq, 8, vocab, 1.1, seed=60 + nq)
     queries = [list(map(int, t)) for t in tq]
@@ -560,7 +569,7 @@ def test_bm25_pruned_batches_vs_oracle(prune_corpus, nq, k):
     _check_bm25_batch(ix, queries, scores, docs, counts, k, f"pruned nq{nq}")
 
 
-def test_bm25_pruned_agrees_with_unpruned_scan(prune_corpus):
+def test_bm25_pruned_agrees_with_unpruned_scan(prune_corpus, bm25_path):
     ix, index, vocab = prune_corpus
     tq = synth.zipf_queries(40, 8, vocab, 1.1, seed=77)
     queries = [list(map(int, t)) for t in tq]
@@ -575,7 +584,7 @@ def test_bm25_pruned_agrees_with_unpruned_scan(prune_corpus):
     assert (d_g == d_o).mean() > 0.98
 
 
-def test_bm25_pruned_long_queries_take_the_unpruned_path(prune_corpus):
+def test_bm25_pruned_long_queries_take_the_unpruned_path(prune_corpus, bm25_path):
     """More than 64 terms in a query (one staged chunk): that query is scanned unpruned, next to
     pruned 3- and 33-term queries in the same launch."""
     ix, index, vocab = prune_corpus
@@ -587,7 +596,7 @@ def test_bm25_pruned_long_queries_take_the_unpruned_path(prune_corpus):
     _check_bm25_batch(ix, queries, scores, docs, counts, 10, "pruned long")
 
 
-def test_bm25_pruned_with_doc_mask(prune_corpus):
+def test_bm25_pruned_with_doc_mask(prune_corpus, bm25_path):
     ix, index, vocab = prune_corpus
     rng = np.random.default_rng(5)
     mask = rng.random(ix.doc_len.shape[0]) < 0.3
@@ -598,7 +607,7 @@ def test_bm25_pruned_with_doc_mask(prune_corpus):
     assert mask[docs].all()
 
 
-def test_bm25_pruned_after_reweight(prune_corpus):
+def test_bm25_pruned_after_reweight(prune_corpus, bm25_path):
     ix, index, vocab = prune_corpus
     other = csr.from_token_ids(*_prune_tokens(), vocab, 0.9, 0.7, 0.075)
     index2 = engine.Bm25Index(ix.term_ptr, ix.post_doc, ix.post_tf, ix.doc_len, ix.idf, ix.k1,
@@ -613,6 +622,37 @@ def test_bm25_pruned_after_reweight(prune_corpus):
 
 def _prune_tokens():
     return synth.zipf_corpus(70_000, 4000, 1.1, seed=51, len_lo=40, len_hi=120)
+
+
+def test_bm25_candidate_path_flag_conditions_and_repeatability(prune_corpus):
+    """The candidate-driven path (anr_bm25_ms.cu) next to the cases it hands to the exhaustive
+    scan on the device: fewer than k documents with a positive score (the reference ranks
+    zero-score documents too, search_engine.py:236-241), more survivors than its buffer holds
+    (one very frequent term, k = 128), more than 48 terms, a filter that keeps nothing; and its
+    scores do not depend on timing: two calls return identical bits."""
+    ix, index, vocab = prune_corpus
+    df = np.diff(ix.term_ptr)
+    rare = [int(t) for t in np.argsort(np.where(df > 0, df, 1 << 30), kind="stable")[:2]]   # shortest lists
+    tq = synth.zipf_queries(24, 8, vocab, 1.1, seed=123)
+    queries = [list(map(int, t)) for t in tq]
+    queries[0] = rare                         # (next to) no matching documents
+    queries[1] = [0]                          # the most frequent term alone
+    queries[2] = [int(t) for t in synth.zipf_queries(1, 60, vocab, 1.1, seed=5)[0]]
+    queries[3] = []
+    queries[4] = [rare[0]] * 3 + [0]          # duplicates of a rare term beside a head term
+    for k in (10, 128):
+        a = index.search(queries, k)
+        b = index.search(queries, k)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        _check_bm25_batch(ix, queries, *a, k, f"candidates k{k}")
+    nothing = np.zeros(ix.doc_len.shape[0], dtype=bool)
+    scores, docs, counts = index.search(queries, 10, doc_mask=engine.pack_mask(nothing))
+    assert (counts == 0).all() and (docs == -1).all()
+    few = nothing.copy()
+    few[[5, 77, 40_000]] = True
+    scores, docs, counts = index.search(queries, 10, doc_mask=engine.pack_mask(few))
+    _check_bm25_batch(ix, queries, scores, docs, counts, 10, "candidates 3 docs kept", mask=few)
 
 
 # ---------------------------------------------------------------------------------------

@@ -432,3 +432,52 @@ def test_cpu_search_engine_equals_the_reference_class(small_case):
     lists = [(ids[:30], "voyage-3-large"), (ids[10:50][::-1], "BM25")]
     w = {"voyage-3-large": 5.0, "BM25": 1.0}
     assert ref.weighted_reciprocal_rank_fusion(lists, w, 40) == mine.weighted_reciprocal_rank_fusion(lists, w, 40)
+
+
+# ---------------------------------------------------------------------------------------
+# The candidate-driven BM25 top-k (csrc/anr_bm25_ms.cu): its pruning decisions, restated in
+# oracle/maxscore_model.py, never lose a top-k document
+def test_maxscore_model_keeps_the_exact_topk():
+    from oracle import maxscore_model as mm
+    synth_mod = synth
+    n, vocab = 12_000, 2500
+    doc_ptr, tokens = synth_mod.zipf_corpus(n, vocab, 1.1, seed=5, len_lo=40, len_hi=120)
+    ix = csr.from_token_ids(doc_ptr, tokens, vocab, 1.7, 0.83, 0.05)
+    w = mm.posting_weights(ix)
+    idf32 = ix.idf.astype(np.float32)
+
+    def exhaustive(terms, k, allowed):
+        acc = np.zeros(n, np.float32)
+        for t in terms:                       # fp32 fma in query order, as the kernel sums
+            if 0 <= t < vocab and idf32[t] > 0:
+                a, b = int(ix.term_ptr[t]), int(ix.term_ptr[t + 1])
+                d = ix.post_doc[a:b]
+                acc[d] = (np.float64(idf32[t]) * w[a:b].astype(np.float64) + acc[d]).astype(np.float32)
+        if allowed is not None:
+            acc = np.where(allowed, acc, np.float32(-1))
+        order = np.lexsort((np.arange(n), -acc))[:k]
+        return [(float(acc[i]), int(i)) for i in order if acc[i] > 0]
+
+    tq = synth_mod.zipf_queries(6, 8, vocab, 1.1, seed=6)
+    allowed = np.random.default_rng(1).random(n) < 0.5
+    df = np.diff(ix.term_ptr)
+    rare = int(np.argmin(np.where(df > 0, df, 1 << 30)))      # the shortest posting list
+    k_rare = int(df[rare]) + 1                                # more than the documents that match
+    cases = [(list(map(int, t)), 10, None) for t in tq]
+    cases += [(list(map(int, tq[0])), 100, None), (list(map(int, tq[1])), 10, allowed),
+              ([int(tq[2][0])] * 3 + [-1, vocab + 5], 10, None), ([0, 1, 2], 10, None),
+              ([rare], k_rare, None), ([], 10, None)]
+    flagged_cases = 0
+    for terms, k, al in cases:
+        flagged, surv, stats = mm.topk(ix, w, terms, k, al)
+        want = exhaustive(terms, k, al)
+        if flagged:                           # handed to the exhaustive scan: nothing to prove
+            flagged_cases += 1
+            assert len(want) < k or stats["survivors"] > mm.SURVIVORS, (terms, k, stats)
+            continue
+        assert surv[:k] == want, (terms, k, stats)
+        # the pruning is real: far fewer postings are touched than the query's lists hold
+        if terms and k == 10 and al is None and len(terms) == 8:
+            sum_df = sum(int(df[t]) for t in terms if 0 <= t < vocab)
+            assert stats["streamed"] + stats["sampled"] < sum_df
+    assert flagged_cases == 1                 # the rare term alone: fewer than k matching documents
