@@ -370,6 +370,11 @@ inline int dense_padded_queries(const anr_ctx* ctx, const anr_dense* ix, int nq,
   return pad_queries(nq, std::max(dense_group(ctx, ix, k), 1));
 }
 
+// Shared memory the dense GEMM pass of a hybrid step leaves free on every SM for the kernels of the
+// BM25 path beside it: its stage kernels hold <= 4 KB of static shared memory, the rerun pair for
+// flagged queries (tiled scan + final top-k) 34 + 18 KB.
+constexpr int kBesideBm25Smem = 56 * 1024;
+
 // Does a hybrid step of nq queries take the gated schedule?  Only the single-CTA 64-query GEMM
 // pass has a gate (the wider tiles fill the SM on their own).  OPT-IN (ANR_HYBRID_GATE=1).
 // Measured (profiles/r2_call10_*, 1M x 1024 + 1M docs, batch 64): the dense main kernel then
@@ -742,8 +747,17 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
         mx.bkt_off = ix->bkt_off;
         mx.bkt_shift = ix->bkt_shift;
         mx.bkt = ix->bkt;
+        cudaEvent_t marks[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (ctx->timeline)
+          for (int i = 0; i < 4; ++i) {
+            const int id = 12 + i;
+            if (!ctx->tl[id] && cudaEventCreate(&ctx->tl[id]) != cudaSuccess) cudaGetLastError();
+            marks[i] = ctx->tl[id];
+            ctx->tl_set[id] = marks[i] != nullptr;
+          }
         ANR_CUDA(launch_bm25_maxscore(ctx->dp, v, hd, mx, terms_dev, offsets_dev, nq, k, mask_dev,
-                                      scratch, surv, live, n_flagged, flagged, stream));
+                                      scratch, surv, live, n_flagged, flagged, stream,
+                                      beside_dense || ctx->beside_dense, marks));
       }
       tl_mark(ctx, 2, stream);
       tl_mark(ctx, 8, stream);
@@ -1678,9 +1692,11 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
     // memory each: they fit beside the dense CTA whatever its ring depth, so the dense pass keeps
     // its full ring and nothing is held back); the tiled scan continues in phase 2.
     const bool ms = run.ms_done;
-    if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k_dense, row_mask_dev, arena, od, stream,
-                                ms ? nullptr : ctx->ev_mid, gated && !ms ? &gate : nullptr))
-      return rc;
+    if (ms) dense_gemm_set_leave_smem(kBesideBm25Smem);
+    const int rc_dense = dense_pipeline(ctx, dense, q_dev, nq, k_dense, row_mask_dev, arena, od, stream,
+                                        ms ? nullptr : ctx->ev_mid, gated && !ms ? &gate : nullptr);
+    dense_gemm_set_leave_smem(0);
+    if (rc_dense) return rc_dense;
     tl_mark(ctx, 7, stream);
     if (!ms) ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_mid, 0));
     if (gated && !ms) ANR_CUDA(launch_gate_wait(gate.counter, gate.expected, ctx->side));
@@ -1774,9 +1790,11 @@ int anr_hybrid_search_keys(anr_ctx* ctx, const anr_dense* dense, const anr_bm25*
                              ctx->side, !gated, 1, &run))
     return rc;
   const bool ms = run.ms_done;   // (see anr_hybrid_search)
-  if (int rc = dense_pipeline(ctx, dense, q_dev, nq, k, row_mask_dev, arena, od, stream,
-                              ms ? nullptr : ctx->ev_mid, gated && !ms ? &gate : nullptr))
-    return rc;
+  if (ms) dense_gemm_set_leave_smem(kBesideBm25Smem);
+  const int rc_dense = dense_pipeline(ctx, dense, q_dev, nq, k, row_mask_dev, arena, od, stream,
+                                      ms ? nullptr : ctx->ev_mid, gated && !ms ? &gate : nullptr);
+  dense_gemm_set_leave_smem(0);
+  if (rc_dense) return rc_dense;
   if (!ms) ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_mid, 0));
   if (gated && !ms) ANR_CUDA(launch_gate_wait(gate.counter, gate.expected, ctx->side));
   if (int rc = bm25_pipeline(ctx, bm25, qt.terms, qt.offsets, nq, k, doc_mask_dev, arena, ob,

@@ -1276,6 +1276,9 @@ cudaError_t launch_bm25_score_listed(const Bm25View& ix, const int32_t* q_terms,
   auto kern = bm25_score_kernel<false, false>;
   cudaError_t e =
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
+  if (e == cudaSuccess)   // (the dense kernels' L1 / shared-memory split: CTAs of both may share an SM)
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
   // few block rows: the list is usually empty and every CTA returns at once
   kern<<<dim3(plan.n_tiles, nq < 16 ? nq : 16), kBm25Threads, plan.smem_bytes, stream>>>(

@@ -34,6 +34,7 @@
 // Needs every idf >= 0 (BM25Okapi's epsilon floor guarantees it unless the average idf itself is
 // negative; such an index takes the tiled scan).
 #include <algorithm>
+#include <cstdlib>
 
 #include "anr_internal.h"
 #include "anr_topk.cuh"
@@ -158,10 +159,12 @@ int64_t bm25_bucket_entries(int shift, int n_docs) {
 }
 
 // ---- 1. plan: one warp per query --------------------------------------------------------------
+template <int VARIANT>
 __global__ void __launch_bounds__(kMsThreads)
 ms_plan_kernel(Bm25View ix, Bm25HeadView hd, MsIndexView mx, const int32_t* __restrict__ q_terms,
-               const int32_t* __restrict__ q_offsets, int nq, MsQuery* __restrict__ queries,
-               MsTerm* __restrict__ terms, int32_t* __restrict__ ticket) {
+               const int32_t* __restrict__ q_offsets, int nq, int sample,
+               MsQuery* __restrict__ queries, MsTerm* __restrict__ terms,
+               int32_t* __restrict__ ticket) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * (kMsThreads / 32) + warp;
   if (blockIdx.x == 0 && threadIdx.x == 0) { ticket[0] = 0; ticket[1] = 0; }
@@ -232,8 +235,8 @@ ms_plan_kernel(Bm25View ix, Bm25HeadView hd, MsIndexView mx, const int32_t* __re
   for (int e = 0; e < 2; ++e) {
     const int j = lane + 32 * e;
     int s1 = 0;
-    if (len[e] > 0 && before[e] < kMsSample)
-      s1 = static_cast<int>(min(static_cast<int64_t>(len[e]), kMsSample - before[e]));
+    if (len[e] > 0 && before[e] < sample)
+      s1 = static_cast<int>(min(static_cast<int64_t>(len[e]), sample - before[e]));
     s1_sum += s1;
     if (j < n) {
       MsTerm& t = T[j];
@@ -320,6 +323,7 @@ __device__ __forceinline__ bool ms_allowed(const uint32_t* __restrict__ mask, in
 }
 
 // ---- 2. stage 1: full score of every sample posting ---------------------------------------------
+template <int VARIANT>
 __global__ void __launch_bounds__(kMsThreads)
 ms_stage1_kernel(Bm25View ix, Bm25HeadView hd, const uint32_t* __restrict__ doc_mask,
                  const MsQuery* __restrict__ queries, const MsTerm* __restrict__ terms,
@@ -355,6 +359,7 @@ ms_stage1_kernel(Bm25View ix, Bm25HeadView hd, const uint32_t* __restrict__ doc_
 
 // ---- 3. theta + required set: one CTA per query; the last CTA to finish lays the queries' -------
 //         stage-2 postings end to end (q_base = exclusive prefix of s2_total)
+template <int VARIANT>
 __global__ void __launch_bounds__(kMsThreads)
 ms_theta_kernel(int k, int nq, MsQuery* __restrict__ queries, MsTerm* __restrict__ terms,
                 const uint64_t* __restrict__ s1keys, int64_t* __restrict__ q_base,
@@ -461,7 +466,8 @@ ms_theta_kernel(int k, int nq, MsQuery* __restrict__ queries, MsTerm* __restrict
 // once: every trip of the loop is one lookup per lane, whatever stage each lane's candidate is in
 // (bounds / ownership / exact sum).  With lock-step rounds of 32 candidates a warp waited for its
 // longest-lived candidate in every round (ncu: 33 % of the warp slots active, 115 us).
-__global__ void __launch_bounds__(kMsThreads, 6)
+template <int VARIANT>
+__global__ void __launch_bounds__(kMsThreads, 5)
 ms_stage2_kernel(Bm25View ix, Bm25HeadView hd, const uint32_t* __restrict__ doc_mask, int nq, int cap,
                  MsQuery* __restrict__ queries, const MsTerm* __restrict__ terms,
                  const int64_t* __restrict__ q_base, uint64_t* __restrict__ surv) {
@@ -476,6 +482,8 @@ ms_stage2_kernel(Bm25View ix, Bm25HeadView hd, const uint32_t* __restrict__ doc_
   bool have = false;
   int q = -1, j = 0, n = 0, doc = 0, phase = 0, idx = 0, self_s2 = 0;
   int64_t q_lo = 0, q_hi = 0;                              // items of query q: [q_lo, q_hi)
+  int64_t seg_lo = 0, seg_hi = 0, self_lo = 0;             // items of its list j: [seg_lo, seg_hi)
+  float self_idf = 0.f, self_rem = 0.f;
   const MsTerm* T = terms;
   float c_self = 0.f, partial = 0.f, remaining = 0.f, theta = 0.f, slack = 0.f, tot = 0.f, full = 0.f;
 
@@ -484,12 +492,12 @@ ms_stage2_kernel(Bm25View ix, Bm25HeadView hd, const uint32_t* __restrict__ doc_
   };
 
   for (;;) {
-    // ---- lanes without a candidate take the next postings (two attempts: most of the postings
-    //      that fail die on the first compare)
+    // ---- lanes without a candidate take the next postings (up to four attempts while half the warp
+    //      is free: most postings die on the first compare, before any lookup)
 #pragma unroll 1
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 4; ++attempt) {
       const unsigned want = __ballot_sync(kFullMask, !have);
-      if (want == 0u) break;
+      if (want == 0u || (attempt >= 2 && __popc(want) < 16)) break;
       if (cursor >= cend) {   // next chunk of this warp
         chunk += n_warps * kMsWarpItems;
         cursor = chunk;
@@ -502,34 +510,40 @@ ms_stage2_kernel(Bm25View ix, Bm25HeadView hd, const uint32_t* __restrict__ doc_
       const int64_t item = cursor + mine_rank;
       cursor += min(__popc(want), avail);
       if (take) {
-        if (item >= q_hi || item < q_lo) {   // the query that holds the item: last q with q_base[q] <= item
-          int l = 0, h = nq;
-          while (h - l > 1) {
-            const int mid = (l + h) >> 1;
-            if (q_base[mid] <= item) l = mid; else h = mid;
+        if (item >= seg_hi || item < seg_lo) {   // (usually the list my last posting came from)
+          if (item >= q_hi || item < q_lo) {     // the query that holds the item: last q with q_base[q] <= item
+            int l = 0, h = nq;
+            while (h - l > 1) {
+              const int mid = (l + h) >> 1;
+              if (q_base[mid] <= item) l = mid; else h = mid;
+            }
+            q = l;
+            q_lo = q_base[q];
+            q_hi = q_base[q + 1];
+            T = terms + static_cast<size_t>(q) * kMsMaxTerms;
+            n = queries[q].n;
+            theta = queries[q].theta;
+            tot = queries[q].tot;
+            slack = 2e-5f * tot;
           }
-          q = l;
-          q_lo = q_base[q];
-          q_hi = q_base[q + 1];
-          T = terms + static_cast<size_t>(q) * kMsMaxTerms;
-          n = queries[q].n;
-          theta = queries[q].theta;
-          tot = queries[q].tot;
-          slack = 2e-5f * tot;
+          int64_t r = item - q_lo;
+          j = 0;
+          while (r >= T[j].s2) { r -= T[j].s2; ++j; }
+          seg_lo = item - r;
+          seg_hi = seg_lo + T[j].s2;
+          self_s2 = T[j].s2;
+          self_lo = T[j].lo;
+          self_idf = T[j].idf;
+          self_rem = tot - T[j].ub - T[j].sub;
         }
-        int64_t r = item - q_lo;
-        j = 0;
-        while (r >= T[j].s2) { r -= T[j].s2; ++j; }
-        const MsTerm& self = T[j];
-        const int64_t p_self = self.lo + r;
+        const int64_t p_self = self_lo + (item - seg_lo);
         doc = __ldg(ix.post_doc + p_self);
         c_self = __ldg(ix.post_w + p_self);
         // What a document that is MINE to score can reach at most: its own posting + the bounds
         // of the other terms, the required lists ordered before mine excluded (a document found
         // there is that list's candidate).
-        partial = self.idf * c_self;
-        remaining = tot - self.ub - self.sub;
-        self_s2 = self.s2;
+        partial = self_idf * c_self;
+        remaining = self_rem;
         if (ms_allowed(doc_mask, doc) && !(partial + remaining + slack < theta)) {
           have = true;
           phase = 0;
@@ -633,6 +647,7 @@ __device__ __forceinline__ void ms_collect_flags(const MsQuery* __restrict__ que
 }
 
 // ---- 5. the survivors of a query, ranked by counting (keys are unique): one CTA per query -------
+template <int VARIANT>
 __global__ void __launch_bounds__(kMsThreads)
 ms_final_kernel(const MsQuery* __restrict__ queries, const uint64_t* __restrict__ surv, int cap, int k,
                 int nq, TopkOut o, int32_t* __restrict__ ticket, int32_t* __restrict__ n_flagged,
@@ -667,11 +682,37 @@ ms_final_kernel(const MsQuery* __restrict__ queries, const uint64_t* __restrict_
   if (last) ms_collect_flags(queries, o.q_offsets, nq, k, cap, n_flagged, flagged);
 }
 
+// plan | stage 1 | theta + required lists | stage 2 | ranking + flagged list, one instantiation
+template <int VARIANT>
+static void ms_launch_chain(const DeviceProps& dp, const Bm25View& ix, const Bm25HeadView& hd,
+                            const MsIndexView& mx, const int32_t* q_terms, const int32_t* q_offsets,
+                            int nq, int k, const uint32_t* doc_mask, int sample, MsQuery* queries,
+                            MsTerm* terms, uint64_t* s1keys, int64_t* q_base, int32_t* ticket,
+                            uint64_t* surv, const TopkOut& out, int32_t* n_flagged, int32_t* flagged,
+                            cudaStream_t stream, const cudaEvent_t* marks) {
+  auto mark = [&](int i) { if (marks && marks[i]) cudaEventRecord(marks[i], stream); };
+  const int wpb = kMsThreads / 32;
+  ms_plan_kernel<VARIANT><<<(nq + wpb - 1) / wpb, kMsThreads, 0, stream>>>(
+      ix, hd, mx, q_terms, q_offsets, nq, sample, queries, terms, ticket);
+  mark(0);
+  ms_stage1_kernel<VARIANT><<<dim3(sample / kMsThreads, nq), kMsThreads, 0, stream>>>(
+      ix, hd, doc_mask, queries, terms, s1keys);
+  mark(1);
+  ms_theta_kernel<VARIANT><<<nq, kMsThreads, 0, stream>>>(k, nq, queries, terms, s1keys, q_base, ticket);
+  mark(2);
+  ms_stage2_kernel<VARIANT><<<dp.sm_count * 5, kMsThreads, 0, stream>>>(
+      ix, hd, doc_mask, nq, kMsSurvivors, queries, terms, q_base, surv);
+  mark(3);
+  ms_final_kernel<VARIANT><<<nq, kMsThreads, 0, stream>>>(queries, surv, kMsSurvivors, k, nq, out,
+                                                          ticket + 1, n_flagged, flagged);
+}
+
 cudaError_t launch_bm25_maxscore(const DeviceProps& dp, const Bm25View& ix, const Bm25HeadView& hd,
                                  const MsIndexView& mx, const int32_t* q_terms,
                                  const int32_t* q_offsets, int nq, int k, const uint32_t* doc_mask,
                                  unsigned char* scratch, uint64_t* surv, const TopkOut& out,
-                                 int32_t* n_flagged, int32_t* flagged, cudaStream_t stream) {
+                                 int32_t* n_flagged, int32_t* flagged, cudaStream_t stream,
+                                 bool beside_dense, const cudaEvent_t* marks) {
   if (nq < 1) return cudaSuccess;
   auto pad = [](size_t b) { return (b + 255) / 256 * 256; };
   MsQuery* queries = reinterpret_cast<MsQuery*>(scratch);
@@ -683,16 +724,35 @@ cudaError_t launch_bm25_maxscore(const DeviceProps& dp, const Bm25View& ix, cons
   int64_t* q_base = reinterpret_cast<int64_t*>(scratch);
   scratch += pad((static_cast<size_t>(nq) + 1) * 8);
   int32_t* ticket = reinterpret_cast<int32_t*>(scratch);
-  const int wpb = kMsThreads / 32;
-  ms_plan_kernel<<<(nq + wpb - 1) / wpb, kMsThreads, 0, stream>>>(ix, hd, mx, q_terms, q_offsets, nq,
-                                                                 queries, terms, ticket);
-  ms_stage1_kernel<<<dim3(kMsSample / kMsThreads, nq), kMsThreads, 0, stream>>>(ix, hd, doc_mask, queries,
-                                                                                terms, s1keys);
-  ms_theta_kernel<<<nq, kMsThreads, 0, stream>>>(k, nq, queries, terms, s1keys, q_base, ticket);
-  ms_stage2_kernel<<<dp.sm_count * 6, kMsThreads, 0, stream>>>(ix, hd, doc_mask, nq, kMsSurvivors, queries,
-                                                              terms, q_base, surv);
-  ms_final_kernel<<<nq, kMsThreads, 0, stream>>>(queries, surv, kMsSurvivors, k, nq, out, ticket + 1,
-                                                 n_flagged, flagged);
+  // Two instantiations of every kernel.  VARIANT 1 runs beside the dense pass of a hybrid step and
+  // asks for the dense kernels' L1 / shared-memory split (all shared): CTAs that ask for different
+  // splits cannot share an SM -- without it the stage kernels took the SMs first and the dense CTAs
+  // waited for them to drain (0.487 against 0.460 ms per step, profiles/r2_call24/25).  VARIANT 0
+  // runs alone with the default split: the lookups live on L1 hits (72 %), and the all-shared
+  // split costs them 40 % (0.133 -> 0.190 ms per batch of 64).
+  if (beside_dense) {
+    static const bool set = [] {
+      auto prefer = [](const void* f) {
+        cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      };
+      prefer(reinterpret_cast<const void*>(ms_plan_kernel<1>));
+      prefer(reinterpret_cast<const void*>(ms_stage1_kernel<1>));
+      prefer(reinterpret_cast<const void*>(ms_theta_kernel<1>));
+      prefer(reinterpret_cast<const void*>(ms_stage2_kernel<1>));
+      prefer(reinterpret_cast<const void*>(ms_final_kernel<1>));
+      return true;
+    }();
+    (void)set;
+  }
+  // stage-1 candidates per query (ANR_MS_SAMPLE, a profiling knob; at most kMsSample)
+  static const int sample_env = getenv("ANR_MS_SAMPLE") ? atoi(getenv("ANR_MS_SAMPLE")) : kMsSample;
+  const int sample = std::min(std::max(sample_env, kMsThreads), kMsSample) / kMsThreads * kMsThreads;
+  if (beside_dense)
+    ms_launch_chain<1>(dp, ix, hd, mx, q_terms, q_offsets, nq, k, doc_mask, sample, queries, terms, s1keys,
+                       q_base, ticket, surv, out, n_flagged, flagged, stream, marks);
+  else
+    ms_launch_chain<0>(dp, ix, hd, mx, q_terms, q_offsets, nq, k, doc_mask, sample, queries, terms, s1keys,
+                       q_base, ticket, surv, out, n_flagged, flagged, stream, marks);
   return cudaGetLastError();
 }
 

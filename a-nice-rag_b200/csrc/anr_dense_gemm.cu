@@ -645,6 +645,14 @@ static int gemm_epi_warps(int nq_block) {
   return epi_env == 4 || epi_env == 8 ? epi_env : (nq_block >= 128 ? 8 : 4);
 }
 
+// Shared memory (bytes) the GEMM launches issued by this thread leave free on every SM: the short
+// kernels of the BM25 path that runs beside the dense pass of a hybrid step (anr_api.cu) hold a few
+// KB of static shared memory each -- its rerun kernels 34 + 18 KB -- and a dense CTA that takes the
+// whole SM makes them wait until it exits (measured: the 2 KB ranking kernel of the BM25 path sat
+// 218 us behind the 9-stage ring of the 64-query pass, profiles/r2_call24_*).
+static thread_local int t_leave_smem = 0;
+void dense_gemm_set_leave_smem(int bytes) { t_leave_smem = bytes > 0 ? bytes : 0; }
+
 static bool make_gemm_layout(const DeviceProps& dp, int ld, bool bf16, int b_rows, int nq_pad,
                              GemmLayout* L, int ring_cap = 0, int n_epi = kGmEpiWarps) {
   const int slab = bf16 ? 64 : 32;
@@ -659,6 +667,10 @@ static bool make_gemm_layout(const DeviceProps& dp, int ld, bool bf16, int b_row
   int n_stages = avail / L->stage_bytes;
   if (n_stages < 3) return false;
   if (n_stages > kGmMaxStages) n_stages = kGmMaxStages;
+  if (t_leave_smem > 0) {   // (never below 4 stages: the ring has to cover the HBM latency)
+    const int fit = (avail - t_leave_smem) / L->stage_bytes;
+    n_stages = std::min(n_stages, std::max(fit, std::min(n_stages, 4)));
+  }
   // a shorter ring leaves shared memory to the BM25 CTAs of a hybrid step (gemm_ring_cap)
   if (ring_cap >= 3 && n_stages > ring_cap) n_stages = ring_cap;
   L->n_stages = n_stages;
@@ -893,7 +905,7 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
   GemmLayout L;
   const int mode = gemm_mode(dp, nqb_size, (n + kGmRows - 1) / kGmRows);
   const int ring_cap = gemm_ring_cap(ev_pre_main != nullptr, bf16, nqb_size, n_real);
-  t_ring_capped = ring_cap >= 3;
+  t_ring_capped = ring_cap >= 3 || t_leave_smem > 0;   // (both keep the max-shared L1 split)
   if (!make_gemm_layout(dp, ld, bf16, mode == 2 ? nqb_size / 2 : nqb_size, nq_pad, &L, ring_cap,
                         gemm_epi_warps(nqb_size)))
     return cudaErrorInvalidConfiguration;

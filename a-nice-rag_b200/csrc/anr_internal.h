@@ -108,6 +108,8 @@ struct DenseGate {
   int expected = 0;
 };
 cudaError_t launch_gate_wait(const int32_t* counter, int expected, cudaStream_t stream);
+// GEMM launches issued by the calling thread leave this much shared memory free per SM (0 = none)
+void dense_gemm_set_leave_smem(int bytes);
 cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const void* shadow, int64_t n,
                               int ld, const float* q_dev, int n_real, int k, const uint32_t* mask,
                               float emb_norm_max, unsigned char* scratch, const TopkOut& out,
@@ -235,7 +237,10 @@ cudaError_t launch_bm25_maxscore(const DeviceProps& dp, const Bm25View& ix, cons
                                  const MsIndexView& mx, const int32_t* q_terms,
                                  const int32_t* q_offsets, int nq, int k, const uint32_t* doc_mask,
                                  unsigned char* scratch, uint64_t* surv, const TopkOut& out,
-                                 int32_t* n_flagged, int32_t* flagged, cudaStream_t stream);
+                                 int32_t* n_flagged, int32_t* flagged, cudaStream_t stream,
+                                 bool beside_dense /* the kernels share the SMs with a dense pass */,
+                                 const cudaEvent_t* marks = nullptr /* [4], nullable entries: recorded
+                                 after plan / stage 1 / theta / stage 2 */);
 
 // ---- fusion -------------------------------------------------------------------
 // scratch: wrrf_scratch_keys() 64-bit words (0 when the union fits in shared memory)

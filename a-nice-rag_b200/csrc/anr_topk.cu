@@ -157,6 +157,16 @@ cudaError_t launch_topk_final_flagged(const uint64_t* cand, int64_t cand_stride,
                                       int k, const TopkOut& out, const int32_t* n_flagged,
                                       const int32_t* flagged, cudaStream_t stream) {
   if (k < 1 || k > kMaxFusedK || m < 1) return cudaErrorInvalidValue;
+  // (these launches usually find an empty list and run beside another pass' main kernel: the same
+  // L1 / shared-memory split as the dense kernels, so that their CTAs can share an SM with it)
+  static const bool carveout_set = [] {
+    cudaFuncSetAttribute(topk_final_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(topk_final_small_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    return true;
+  }();
+  (void)carveout_set;
   if (static_cast<int64_t>(k) * ((m + kSmallThreads - 1) / kSmallThreads) > kSmallCap)
     topk_final_kernel<<<nq, kFinalThreads, 0, stream>>>(cand, cand_stride, m, m, 0, k, out,
                                                         n_flagged, flagged);

@@ -639,7 +639,7 @@ def headline_report(env, args, peaks, w, qb, got, t):
     nd_local = w.post["nd"].cpu().numpy()
     bm_bytes = 8 * int(nd_local[qb.t_host.reshape(-1)].astype(np.int64).sum())
     traffic = traffic_tbl.get(dense_kernel + " co-resident") if at_default else None
-    bm_traffic = traffic_tbl.get("bm25_score_kernel<0, 1> main launch, batch 64, co-resident") if at_default else None
+    bm_traffic = traffic_tbl.get("bm25 candidate-driven top-k, batch 64") if at_default else None
     dense_roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                   "frac": achieved / peak, "traffic": traffic, "peak_source": peaks["source"],
                   "kernel": dense_kernel, "bytes_per_launch": scan_bytes,
@@ -647,13 +647,20 @@ def headline_report(env, args, peaks, w, qb, got, t):
                   "share_of_step": scan_ms / total_ms if total_ms else None,
                   "frac_traffic": (traffic / (scan_avg_ms * 1e-3) / 1e9 / peak
                                    if traffic and scan_avg_ms > 0 else None),
-                  "co_resident": "inside the step this kernel shares every SM with the BM25 scan "
-                                 "(4-stage ring): avg_launch_ms / achieved / frac are in-step; "
-                                 "alone_* is the same batch through a dense-only call"}
+                  "co_resident": "inside the step this kernel shares every SM with the BM25 kernels "
+                                 "(its ring leaves them 56 KB of shared memory): avg_launch_ms / "
+                                 "achieved / frac are in-step; alone_* is the same batch through a "
+                                 "dense-only call"}
     bm_roof = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peaks["source"],
-               "kernel": "bm25_score_kernel<0, 1> (pruned scan, main launch)", "bytes_per_launch": bm_bytes,
+               "kernel": "BM25 candidate-driven top-k (ms_plan / ms_stage1 / ms_theta / ms_stage2 / "
+                         "ms_final kernels, anr_bm25_ms.cu; one `launch` = the whole chain)",
+               "bytes_per_launch": bm_bytes,
                "bytes_definition": "UNPRUNED algorithmic figure, 8 B x sum of df over every query-"
-                                   "term occurrence (SURVEY 8d); the pruned scan reads `traffic`",
+                                   "term occurrence (SURVEY 8d): what an exhaustive scan would read. "
+                                   "The path touches `traffic` bytes and is bound by the latency "
+                                   "of dependent random DRAM accesses, not by bandwidth: frac says "
+                                   "how fast an exhaustive scan would have to be to keep up, "
+                                   "frac_traffic is the DRAM share it actually uses",
                "traffic": bm_traffic, "launches": int(bm_n), "in_step_ms": bm_avg_ms,
                "in_step_share": bm_ms / total_ms if total_ms else None}
     if world == 1:
@@ -726,9 +733,10 @@ def headline_report(env, args, peaks, w, qb, got, t):
     timeline = None
     if world == 1:
         try:
-            names = ["step_begin", "bm25_sample_begin", "bm25_sample_end", "dense_pass_begin",
+            names = ["step_begin", "bm25_begin", "bm25_topk_end", "dense_pass_begin",
                      "dense_main_begin", "dense_main_end", "dense_rescore_end", "dense_pass_end",
-                     "bm25_main_begin", "bm25_main_end", "bm25_final_end", "fusion_end"]
+                     "bm25_rerun_begin", "bm25_rerun_begin_", "bm25_end", "fusion_end",
+                     "bm25_plan_end", "bm25_stage1_end", "bm25_theta_end", "bm25_stage2_end"]
             step_device, _ = step_fns(env, w, qb)
             native.call("anr_ctx_timeline_enable", env.ctx.handle, 1)
             runs = []
@@ -742,7 +750,7 @@ def headline_report(env, args, peaks, w, qb, got, t):
             med = [statistics.median(r[i] for r in runs[2:]) for i in range(len(names))]
             timeline = {"unit": "ms from step_begin, median of 7 single steps (one step in flight, "
                                 "the stream idle before it)",
-                        **{n: round(v, 4) for n, v in zip(names, med)}}
+                        **{n: round(v, 4) for n, v in zip(names, med) if not n.endswith("_")}}
         except Exception as exc:
             timeline = {"error": repr(exc)[:200]}
 
@@ -1074,10 +1082,12 @@ def run_big_legs(env, args, peaks, sampler):
                          "peak": peaks["hbm"], "unit": "GB/s",
                          "frac": bytes4 / (kernel4 * 1e-3) / 1e9 / peaks["hbm"],
                          "bytes_per_launch": bytes4, "avg_launch_ms": kernel4,
-                         "bytes_definition": "UNPRUNED algorithmic figure (8 B x sum of df); the "
-                                             "pruned scan skips most of it, so frac may exceed 1",
+                         "bytes_definition": "UNPRUNED algorithmic figure (8 B x sum of df): what an "
+                                             "exhaustive scan would read; the candidate-driven "
+                                             "path touches a small part of it (latency-bound "
+                                             "lookups), so frac exceeds 1",
                          "traffic": None, "peak_source": peaks["source"],
-                         "kernel": "bm25_score_kernel<0, 1> (pruned scan, one folded launch)"},
+                         "kernel": "BM25 candidate-driven top-k (anr_bm25_ms.cu, the whole chain)"},
             "clocks": sampler.summary(mark) if sampler else None}
 
     # ---- batch-1 hybrid at 10M (the >= 70 % of HBM roofline target) -----------------------------

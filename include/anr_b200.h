@@ -75,12 +75,16 @@ int anr_ctx_profile_read(anr_ctx* ctx, int32_t kind, double* total_ms, int64_t* 
  * that part runs on; anr_ctx_timeline_read synchronises and returns every mark's offset in ms
  * from mark 0 (-1 = not reached).  For naming and timing the fixed costs of a step
  * (bench.py `timeline`); no effect on results.
- *   0 step begin             1 BM25 sample launch begin     2 BM25 sample launch end
+ *   0 step begin             1 BM25 begin                   2 BM25 candidate-driven top-k end
  *   3 dense pass begin       4 dense main kernel begin      5 dense main kernel end
  *   6 dense rescoring end    7 dense pass end (flagged-query fallback launches included)
- *   8 BM25 main launch begin 9 BM25 main launch end        10 BM25 final top-k end
- *  11 fusion end */
-#define ANR_TIMELINE_MARKS 12
+ *   8 BM25 rerun begin       9 (same)                      10 BM25 end (rerun of flagged queries)
+ *  11 fusion end
+ *  12 BM25 plan end         13 BM25 stage 1 end            14 BM25 theta / required lists end
+ *  15 BM25 stage 2 end      (2 = the ranking of the survivors' end)
+ * (With the tiled BM25 scan, ANR_BM25_MAXSCORE=0: 1-2 = its sample launch, 8-9 = its main launch,
+ * 10 = its final top-k; 12-15 are not reached.) */
+#define ANR_TIMELINE_MARKS 16
 int anr_ctx_timeline_enable(anr_ctx* ctx, int32_t on);
 int anr_ctx_timeline_read(anr_ctx* ctx, double* offsets_ms /* [ANR_TIMELINE_MARKS] */);
 
