@@ -683,7 +683,7 @@ ms_final_kernel(const MsQuery* __restrict__ queries, const uint64_t* __restrict_
 }
 
 // plan | stage 1 | theta + required lists | stage 2 | ranking + flagged list, one instantiation
-template <int VARIANT>
+template <int VARIANT, int EARLY>
 static void ms_launch_chain(const DeviceProps& dp, const Bm25View& ix, const Bm25HeadView& hd,
                             const MsIndexView& mx, const int32_t* q_terms, const int32_t* q_offsets,
                             int nq, int k, const uint32_t* doc_mask, int sample, MsQuery* queries,
@@ -692,13 +692,13 @@ static void ms_launch_chain(const DeviceProps& dp, const Bm25View& ix, const Bm2
                             cudaStream_t stream, const cudaEvent_t* marks) {
   auto mark = [&](int i) { if (marks && marks[i]) cudaEventRecord(marks[i], stream); };
   const int wpb = kMsThreads / 32;
-  ms_plan_kernel<VARIANT><<<(nq + wpb - 1) / wpb, kMsThreads, 0, stream>>>(
+  ms_plan_kernel<EARLY><<<(nq + wpb - 1) / wpb, kMsThreads, 0, stream>>>(
       ix, hd, mx, q_terms, q_offsets, nq, sample, queries, terms, ticket);
   mark(0);
-  ms_stage1_kernel<VARIANT><<<dim3(sample / kMsThreads, nq), kMsThreads, 0, stream>>>(
+  ms_stage1_kernel<EARLY><<<dim3(sample / kMsThreads, nq), kMsThreads, 0, stream>>>(
       ix, hd, doc_mask, queries, terms, s1keys);
   mark(1);
-  ms_theta_kernel<VARIANT><<<nq, kMsThreads, 0, stream>>>(k, nq, queries, terms, s1keys, q_base, ticket);
+  ms_theta_kernel<EARLY><<<nq, kMsThreads, 0, stream>>>(k, nq, queries, terms, s1keys, q_base, ticket);
   mark(2);
   ms_stage2_kernel<VARIANT><<<dp.sm_count * 5, kMsThreads, 0, stream>>>(
       ix, hd, doc_mask, nq, kMsSurvivors, queries, terms, q_base, surv);
@@ -747,11 +747,15 @@ cudaError_t launch_bm25_maxscore(const DeviceProps& dp, const Bm25View& ix, cons
   // stage-1 candidates per query (ANR_MS_SAMPLE, a profiling knob; at most kMsSample)
   static const int sample_env = getenv("ANR_MS_SAMPLE") ? atoi(getenv("ANR_MS_SAMPLE")) : kMsSample;
   const int sample = std::min(std::max(sample_env, kMsThreads), kMsSample) / kMsThreads * kMsThreads;
-  if (beside_dense)
-    ms_launch_chain<1>(dp, ix, hd, mx, q_terms, q_offsets, nq, k, doc_mask, sample, queries, terms, s1keys,
+  static const bool early_default = getenv("ANR_MS_EARLY_SPLIT") && atoi(getenv("ANR_MS_EARLY_SPLIT")) == 0;
+  if (beside_dense && early_default)
+    ms_launch_chain<1, 0>(dp, ix, hd, mx, q_terms, q_offsets, nq, k, doc_mask, sample, queries, terms, s1keys,
+                          q_base, ticket, surv, out, n_flagged, flagged, stream, marks);
+  else if (beside_dense)
+    ms_launch_chain<1, 1>(dp, ix, hd, mx, q_terms, q_offsets, nq, k, doc_mask, sample, queries, terms, s1keys,
                        q_base, ticket, surv, out, n_flagged, flagged, stream, marks);
   else
-    ms_launch_chain<0>(dp, ix, hd, mx, q_terms, q_offsets, nq, k, doc_mask, sample, queries, terms, s1keys,
+    ms_launch_chain<0, 0>(dp, ix, hd, mx, q_terms, q_offsets, nq, k, doc_mask, sample, queries, terms, s1keys,
                        q_base, ticket, surv, out, n_flagged, flagged, stream, marks);
   return cudaGetLastError();
 }

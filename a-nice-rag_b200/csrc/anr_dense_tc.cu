@@ -380,7 +380,7 @@ dense_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a,
 // a relevant row, or more than kTcRescoreCap candidates fall inside the margin): the caller
 // then reruns that query through the exact scan.
 constexpr int kTcRescoreCap = 2048;
-constexpr int kTcRescoreThreads = 512;
+constexpr int kTcRescoreThreads = 1024;
 
 // Sample pre-pass: thr0[q] = key that rejects every score <= the kl-th best tf32 score among the
 // sample's candidates.  The kl-th best of a subset never exceeds the kl-th best of the whole
@@ -388,8 +388,8 @@ constexpr int kTcRescoreThreads = 512;
 __global__ void __launch_bounds__(kTcRescoreThreads)
 dense_tc_thr_kernel(const uint64_t* __restrict__ cand, int m, int kl,
                     uint64_t* __restrict__ thr0) {
-  // (kl = the rank asked for, <= 512)
-  // kl-th largest of the 512 per-thread bests: kl distinct rows reach it, so it is a lower
+  // (kl = the rank asked for, <= kTcRescoreThreads)
+  // kl-th largest of the per-thread bests: kl distinct rows reach it, so it is a lower
   // bound of the sample's (hence the corpus') kl-th best -- all a starting threshold needs
   __shared__ uint64_t best[kTcRescoreThreads];
   const int q = blockIdx.x;
@@ -433,15 +433,16 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
   for (int i = threadIdx.x; i < ld; i += blockDim.x) part = fmaf(qv[i], qv[i], part);
   part = warp_sum(part);
   if (lane == 0) atomicAdd(&q_norm2, part);
-  // T = k-th largest of the 512 per-thread bests: a lower bound of the k-th best tf32 score
+  // T = k-th largest of the per-thread bests: a lower bound of the k-th best tf32 score
   // (k distinct candidates reach it).  A lower T only widens the rescored margin, so exactness
   // is unaffected and no list of candidates has to be maintained here.
   __shared__ uint64_t s_kth;
   uint64_t kth;
   {
     uint64_t b = 0ull;
-    for (int i = threadIdx.x; i < m; i += kTcRescoreThreads) {
-      const uint64_t v = c[i];
+#pragma unroll 8
+    for (int i = threadIdx.x; i < m; i += kTcRescoreThreads) {   // (independent loads: one round trip)
+      const uint64_t v = __ldg(c + i);
       b = v > b ? v : b;
     }
     kth = block_kth_of_thread_bests<kTcRescoreThreads / 32>(b, k, top, &s_kth);
@@ -462,8 +463,9 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
     }
     if (mn != 0ull && key_score(mn) >= cut) bad = 1;
   }
-  for (int i = threadIdx.x; i < m; i += blockDim.x) {
-    const uint64_t v = c[i];
+#pragma unroll 8
+  for (int i = threadIdx.x; i < m; i += kTcRescoreThreads) {
+    const uint64_t v = __ldg(c + i);
     if (v != 0ull && key_score(v) >= cut) {
       const int slot = atomicAdd(&n_sel, 1);
       if (slot < kTcRescoreCap) sel[slot] = v;
@@ -475,35 +477,41 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
     if (threadIdx.x == 0) bad = 1;
     ns = kTcRescoreCap;
   }
-  // exact fp32 inner products, one warp per candidate, two candidates in flight per warp (the
+  // exact fp32 inner products, one warp per candidate, four candidates in flight per warp (the
   // rows are random 4 KB reads: latency, not bytes).  The summation order per row is fixed.
-  for (int i = warp; i < ns; i += 2 * n_warps) {
-    const int i2 = i + n_warps;
-    const bool two = i2 < ns;
-    const uint32_t row_a = key_id(sel[i]);
-    const uint32_t row_b = two ? key_id(sel[i2]) : row_a;
-    const float* ea = emb + static_cast<size_t>(row_a) * ld;
-    const float* eb = emb + static_cast<size_t>(row_b) * ld;
-    float acc_a = 0.f, acc_b = 0.f;
-    for (int col = lane * 4; col < ld; col += 128) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(ea + col));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(eb + col));
-      const float4 qq = __ldg(reinterpret_cast<const float4*>(qv + col));
-      acc_a = fmaf(a.x, qq.x, acc_a);
-      acc_a = fmaf(a.y, qq.y, acc_a);
-      acc_a = fmaf(a.z, qq.z, acc_a);
-      acc_a = fmaf(a.w, qq.w, acc_a);
-      acc_b = fmaf(b.x, qq.x, acc_b);
-      acc_b = fmaf(b.y, qq.y, acc_b);
-      acc_b = fmaf(b.z, qq.z, acc_b);
-      acc_b = fmaf(b.w, qq.w, acc_b);
+  for (int i = warp; i < ns; i += 4 * n_warps) {
+    uint32_t row[4];
+    const float* e[4];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int iu = i + u * n_warps;
+      row[u] = key_id(sel[iu < ns ? iu : i]);
+      e[u] = emb + static_cast<size_t>(row[u]) * ld;
     }
-    acc_a = warp_sum(acc_a);
-    acc_b = warp_sum(acc_b);
+#pragma unroll 2
+    for (int col = lane * 4; col < ld; col += 128) {
+      const float4 qq = __ldg(reinterpret_cast<const float4*>(qv + col));
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(e[u] + col));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[u] = fmaf(v[u].x, qq.x, acc[u]);
+        acc[u] = fmaf(v[u].y, qq.y, acc[u]);
+        acc[u] = fmaf(v[u].z, qq.z, acc[u]);
+        acc[u] = fmaf(v[u].w, qq.w, acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
     __syncwarp();
     if (lane == 0) {
-      sel[i] = make_key(acc_a, row_a);
-      if (two) sel[i2] = make_key(acc_b, row_b);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int iu = i + u * n_warps;
+        if (iu < ns) sel[iu] = make_key(acc[u], row[u]);
+      }
     }
   }
   __syncthreads();
