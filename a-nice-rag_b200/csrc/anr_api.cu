@@ -670,13 +670,13 @@ int bm25_ensure_ms(const anr_bm25* ix, cudaStream_t stream) {
 size_t bm25_ws_bytes(const anr_ctx* ctx, const anr_bm25* ix, int nq, int k) {
   if (k <= kMaxFusedK) {
     const Bm25Plan plan = bm25_make_plan(ctx->dp, ix->n_docs, nq, k, false);
-    const size_t slots = static_cast<size_t>(std::max(plan.n_tiles, plan.n_runs + plan.n_sampled));
+    const size_t slots = static_cast<size_t>(plan.n_tiles);
     size_t ms = 0;
     if (bm25_ms_wanted(ix, nq, k))
       ms = padded(bm25_ms_scratch_bytes(nq)) + padded(static_cast<size_t>(nq) * kMsSurvivors * 8) +
            padded(static_cast<size_t>(nq) * 4) + 1024;
     return padded(static_cast<size_t>(nq) * slots * k * 8) +
-           padded((static_cast<size_t>(nq) + kBm25CounterSlots) * 4) + 512 + ms;
+           padded(static_cast<size_t>(nq) * 4) + 512 + ms;
   }
   const int64_t n_pow2 = next_pow2(std::max(ix->n_docs, 2));
   return padded(static_cast<size_t>(std::min(nq, 8)) * n_pow2 * 8) + 256;
@@ -805,13 +805,9 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
         r.hd.head_ld = ix->head_ld;
         r.hd.n_head = ix->n_head;
       }
-      // pruned scans go run by run (one candidate slot per run and per sample tile)
-      r.plan.use_runs = r.hd.n_head > 0 && bm25_runs_enabled() &&
-                        r.plan.run_smem_bytes <= ctx->dp.max_smem_optin;
-      r.stride = static_cast<int64_t>(r.plan.use_runs ? r.plan.n_runs + r.plan.n_sampled
-                                                      : r.plan.n_tiles) * k;
+      r.stride = static_cast<int64_t>(r.plan.n_tiles) * k;
       r.cand = arena.take<uint64_t>(static_cast<size_t>(nq) * r.stride);
-      r.theta = arena.take<float>(static_cast<size_t>(nq) + kBm25CounterSlots);   // + work counters
+      r.theta = arena.take<float>(static_cast<size_t>(nq));
       r.active = true;
     }
     Bm25Plan plan = r.plan;

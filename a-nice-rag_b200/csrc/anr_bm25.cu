@@ -39,8 +39,6 @@ namespace anr {
 constexpr int kBm25Threads = 256;
 constexpr int kBm25TermChunk = 64;  // query terms whose slice bounds are staged at once
 constexpr int kBm25CandCap = 2048;  // pruned scan: documents of a tile whose score is completed
-constexpr int kBm25ResCap = 512;    // run kernel: keys a run keeps; compacted to its k best beyond 256
-constexpr int kBm25RunCand = 1024;  // run kernel: documents of a tile listed for completion
 
 // weight[p] = tf*(k1+1) / (tf + k1*(1 - b + b*doc_len/avgdl)), evaluated in float64 in the
 // operation order of BM25Okapi.get_scores, rounded once to fp32.
@@ -99,27 +97,6 @@ Bm25Plan bm25_make_plan(const DeviceProps& dp, int n_docs, int nq, int k, bool e
                                                                                  : k * per_thread);
   p.smem_bytes = p.tile_docs * 4 + p.list_cap * 8 + kBm25TermChunk * (8 + 8 + 4) +
                  (emit_all ? 0 : kBm25CandCap * 2);
-  // runs of the pruned scan (bm25_run_kernel): long enough to amortise the per-run set-up, short
-  // enough that (runs x queries) still fills the SMs three times over; about every 16th tile
-  // is scored ahead as a sample
-  if (!emit_all && p.n_tiles > 0) {
-    const int64_t slots = 6LL * dp.sm_count;
-    int64_t run = static_cast<int64_t>(p.n_tiles) * nq / (3 * slots);
-    if (run < 1) run = 1;
-    if (run > 8) run = 8;
-    if (const char* e = getenv("ANR_BM25_RUN_TILES")) {
-      const int64_t v = atoll(e);
-      if (v >= 1 && v <= 64) run = v;
-    }
-    p.run_tiles = static_cast<int>(run);
-    p.n_runs = (p.n_tiles + p.run_tiles - 1) / p.run_tiles;
-    int every = 16 / p.run_tiles > 1 ? 16 / p.run_tiles : 1;
-    if (every > p.n_runs / 2) every = p.n_runs / 2 > 1 ? p.n_runs / 2 : 1;
-    p.sample_every = every;
-    p.n_sampled = (p.n_runs + every - 1) / every;
-    p.run_smem_bytes = p.tile_docs * 4 + p.list_cap * 8 + kBm25ResCap * 8 +
-                       kBm25TermChunk * (8 + 8 + 4 + 4) + kBm25RunCand * 2;
-  }
   return p;
 }
 
@@ -128,9 +105,7 @@ __device__ __forceinline__ uint64_t kth_of_thread_bests(uint64_t best, int k, ui
   return block_kth_of_thread_bests<kBm25Threads / 32>(best, k, tbest, s_out);
 }
 
-// One (tile, query) work item.  bx / by are the block coordinates of the item in the grid the
-// classic kernel would have been launched with (bx fastest): the classic kernel passes blockIdx,
-// the persistent one the coordinates of the item it pulled from the work counter.
+// One (tile, query) work item; bx / by = its block coordinates in the launch grid.
 template <bool EMIT_ALL, bool PRUNE>
 __device__ __forceinline__ void
 bm25_tile_item(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* __restrict__ q_terms,
@@ -157,17 +132,9 @@ bm25_tile_item(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* __rest
   // that starts with every tile_stride-th one: the first wave of CTAs plays the role of a sample
   // pass (it publishes a k-th best score per query) and everything dispatched later prunes
   // against it.  n_sampled <= 0: grid = (tiles, queries), natural order.
-  // n_sampled == -4: LIGHT sample launch -- only the first quarter of every tile_stride-th tile is
-  // scored, nothing is written but the query's bound: a sample CTA has no bound to prune with and
-  // completes every document of its range, so its latency (50 us for a whole tile, and the main
-  // launch waits for it) goes with the range; the main launch (-5) then covers every tile.
-  const bool light_sample = n_sampled == -4;
   int tile, q;
-  if (n_sampled == -2 || light_sample) {   // separate sample launch: every tile_stride-th tile
+  if (n_sampled == -2) {   // separate sample launch: every tile_stride-th tile
     tile = bx * tile_stride;
-    q = by;
-  } else if (n_sampled == -5) {   // main launch after a light sample launch: every tile
-    tile = bx;
     q = by;
   } else if (n_sampled < -2) {    // main launch after a separate sample launch: skip its tiles
     tile = bx;
@@ -190,8 +157,7 @@ bm25_tile_item(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* __rest
   const int out_row = q;
   if (q_list) q = q_list[by];
   const int d0 = tile * tile_docs;
-  const int span = light_sample ? max(min(tile_docs, 1024), (tile_docs / 4 + 31) / 32 * 32) : tile_docs;
-  const int d1 = min(ix.n_docs, d0 + span);
+  const int d1 = min(ix.n_docs, d0 + tile_docs);
   const int nd = d1 - d0;
   const int t_begin = q_offsets[q], t_end = q_offsets[q + 1];
 
@@ -535,20 +501,19 @@ bm25_tile_item(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* __rest
   if (ns <= kBm25Threads) {
     // rank by counting (keys are unique): one pass, no sort
     for (int i = threadIdx.x; i < k; i += kBm25Threads)
-      if (i >= ns && !light_sample) o[i] = 0ull;
+      if (i >= ns) o[i] = 0ull;
     if (threadIdx.x < ns) {
       const uint64_t key = sel[threadIdx.x];
       int rank = 0;
       for (int j = 0; j < ns; ++j) rank += sel[j] > key;
-      if (rank < k && !light_sample) o[rank] = key;
+      if (rank < k) o[rank] = key;
       // the tile's k-th best full score bounds the query's k-th best from below: publish it
       if (PRUNE && theta_g && rank == k - 1 && key_score(key) > 0.f)
         atomicMax(reinterpret_cast<int*>(theta_g + q), __float_as_int(key_score(key)));
     }
   } else {
     block_bitonic_sort_desc(sel, next_pow2(ns));
-    if (!light_sample)
-      for (int i = threadIdx.x; i < k; i += blockDim.x) o[i] = i < ns ? sel[i] : 0ull;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) o[i] = i < ns ? sel[i] : 0ull;
     if (PRUNE && theta_g && threadIdx.x == 0 && ns >= k && key_score(sel[k - 1]) > 0.f)
       atomicMax(reinterpret_cast<int*>(theta_g + q), __float_as_int(key_score(sel[k - 1])));
   }
@@ -577,594 +542,12 @@ bm25_score_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_te
                                   blockIdx.y, q_list);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Pruned scan by RUNS.  Half of the time of the per-tile kernel above is per-(tile, query) set-up:
-// term classification, the 32-ary searches for every term's first posting in the tile (five
-// dependent loads), the thread-best / k-th selection and the output of k keys per tile (measured:
-// halving the tile doubled that share, profiles/r2_call2).  Here ONE CTA scores run_tiles
-// consecutive tiles of one query:
-//   * classification and the posting searches happen once per run; every streamed term keeps a
-//     CURSOR that the scatter loop itself advances (the smallest position whose document lies
-//     beyond the tile, a warp min + one shared atomicMin per warp and term);
-//   * with a bound theta for the query (published by the sample tiles, raised by every finished
-//     run) the documents whose partial score reaches cut = theta - ub are noted WHILE their
-//     postings are scattered (the accumulator crosses cut at most once), so there is no sweep over
-//     the tile; their scores are completed from the dense head rows and only full scores >= theta
-//     enter the run's candidate list -- no per-tile selection at all;
-//   * the run's list is ranked once, at its end (k keys per RUN go to the final top-k kernel).
-// A tile without a usable bound (theta <= ub: the sample tiles) takes the per-tile procedure of the
-// kernel above and adds its k best to the list.  Scores and results are those of the kernel above
-// (same accumulation order); tests/test_gpu_parity.py::test_bm25_pruned_*.
-__global__ void __launch_bounds__(kBm25Threads, 6)
-bm25_run_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_terms,
-                const int32_t* __restrict__ q_offsets, int k, const uint32_t* __restrict__ doc_mask,
-                int tile_docs, int list_cap, uint64_t* __restrict__ out, int64_t out_stride_q,
-                float* __restrict__ theta_g, int n_tiles, int run_tiles, int sample_every, int n_runs,
-                int n_sampled, int phase) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  float* acc = reinterpret_cast<float*>(smem);
-  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(tile_docs) * 4);
-  uint64_t* res = lists + list_cap;                                  // [kBm25ResCap]
-  int64_t* s_cur = reinterpret_cast<int64_t*>(res + kBm25ResCap);    // next posting of a streamed term
-  int64_t* s_end = s_cur + kBm25TermChunk;
-  float* s_idf = reinterpret_cast<float*>(s_end + kBm25TermChunk);
-  uint32_t* s_next = reinterpret_cast<uint32_t*>(s_idf + kBm25TermChunk);   // cursor advance of the tile
-  uint16_t* cand_idx = reinterpret_cast<uint16_t*>(s_next + kBm25TermChunk);  // [kBm25RunCand]
-  __shared__ int n_stream, n_cand, n_res, n_sel, n_h;
-  __shared__ int s_slot[kBm25TermChunk], h_slot[kBm25TermChunk];
-  __shared__ float h_idf[kBm25TermChunk];
-  __shared__ float h_ub, s_theta, s_kth_score;
-  __shared__ uint64_t s_thr;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // ---- which run / tiles / output slot ----
-  int q, run;
-  bool sample;
-  if (phase == 1) {          // sample launch: grid (n_sampled, queries)
-    run = blockIdx.x * sample_every; q = blockIdx.y; sample = true;
-  } else if (phase == 2) {   // main launch after a sample launch: grid (n_runs, queries)
-    run = blockIdx.x; q = blockIdx.y; sample = false;
-  } else {                   // one launch, sample tiles dispatched first: grid (queries, n_sampled + n_runs)
-    q = blockIdx.x;
-    const int y = blockIdx.y;
-    sample = y < n_sampled;
-    run = sample ? y * sample_every : y - n_sampled;
-  }
-  int t0 = run * run_tiles, t1 = min(n_tiles, t0 + run_tiles), slot = run;
-  if (sample) { t1 = t0 + 1; slot = n_runs + run / sample_every; }
-  else if (run % sample_every == 0) ++t0;   // that tile went ahead as a sample
-  uint64_t* o = out + q * out_stride_q + static_cast<int64_t>(slot) * k;
-  if (t0 >= t1) {
-    for (int i = tid; i < k; i += kBm25Threads) o[i] = 0ull;
-    return;
-  }
-  const int t_begin = q_offsets[q], t_end = q_offsets[q + 1];
-  const int n_terms_q = t_end - t_begin;
-  const bool long_q = n_terms_q > kBm25TermChunk;   // scored chunk by chunk, nothing left to head rows
-  if (tid == 0) { n_h = 0; h_ub = 0.f; n_res = 0; n_stream = 0; }
-  float theta_run = 0.f;   // block-uniform: best bound this run has established itself
-
-  // ---- set-up of a chunk of terms for the tile starting at document d0: classification (head
-  //      terms left to the dense rows), first posting at or beyond d0 of every streamed term ----
-  auto locate = [&](int c0, int nc, int d0, bool classify) {
-    __syncthreads();
-    if (classify) {
-      if (warp == 0) {
-        const float theta0 = __ldcg(theta_g + q);
-        int slot_e[2] = {-1, -1};
-        float ub_e[2] = {0.f, 0.f};
-        float tail_idf = 0.f;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = lane + 32 * e;
-          if (j < nc) {
-            const int term = q_terms[c0 + j];
-            if (term >= 0 && term < ix.n_terms) {
-              const float idf = ix.idf[term];
-              const int sl = hd.slot_of[term];
-              if (idf > 0.f && sl != 0xff) {
-                slot_e[e] = sl;
-                ub_e[e] = idf * hd.head_max[sl];
-              } else {
-                tail_idf = fmaxf(tail_idf, idf);
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int of = 16; of > 0; of >>= 1)
-          tail_idf = fmaxf(tail_idf, __shfl_xor_sync(kFullMask, tail_idf, of));
-        const float theta_cls = theta0 > 0.f ? theta0 : tail_idf;
-        if (theta_cls > 0.f) {
-          float cum[2] = {0.f, 0.f};
-          for (int jj = 0; jj < nc; ++jj) {
-            const int owner = jj & 31, sl2 = jj >> 5;
-            const int s_jj = __shfl_sync(kFullMask, sl2 ? slot_e[1] : slot_e[0], owner);
-            const float u_jj = __shfl_sync(kFullMask, sl2 ? ub_e[1] : ub_e[0], owner);
-            if (s_jj < 0) continue;   // warp-uniform
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int j = lane + 32 * e;
-              if (slot_e[e] >= 0 && (u_jj < ub_e[e] || (u_jj == ub_e[e] && jj <= j))) cum[e] += u_jj;
-            }
-          }
-#pragma unroll
-          for (int e = 0; e < 2; ++e)
-            if (slot_e[e] >= 0 && !(cum[e] * (1.f + 1e-4f) < theta_cls)) slot_e[e] = -1;   // essential
-        }
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-          if (lane + 32 * e < nc) s_slot[lane + 32 * e] = slot_e[e];
-      }
-      __syncthreads();
-    }
-    for (int j = warp; j < nc; j += kBm25Threads / 32) {
-      const int term = q_terms[c0 + j];
-      int64_t lo = 0, hi = 0;
-      float idf = 0.f;
-      const int slot_j = classify ? s_slot[j] : -1;
-      if (term >= 0 && term < ix.n_terms) {
-        idf = ix.idf[term];
-        if (idf != 0.f && slot_j < 0) {
-          lo = ix.term_ptr[term];
-          hi = ix.term_ptr[term + 1];
-        }
-      }
-      if (!classify && lane == 0) s_slot[j] = -1;
-      const int64_t term_end = hi;
-      while (hi > lo) {   // invariant: the answer (first index with doc >= d0) lies in [lo, hi]
-        const int64_t len = hi - lo;
-        if (len <= 32) {
-          const int64_t pos = lo + lane;
-          const bool below = pos < hi && __ldg(ix.post_doc + pos) < d0;
-          lo += __popc(__ballot_sync(kFullMask, below));
-          break;
-        }
-        const int64_t step = (len + 32) / 33;
-        const int64_t pos = lo + (lane + 1) * step - 1;
-        const bool below = pos < hi && __ldg(ix.post_doc + pos) < d0;
-        const int cnt = __popc(__ballot_sync(kFullMask, below));
-        const int64_t nhi = lo + (cnt + 1) * step - 1;
-        if (cnt < 32 && nhi < hi) hi = nhi;
-        lo += cnt * step;
-      }
-      if (lane == 0) { s_cur[j] = lo; s_end[j] = term_end; s_idf[j] = idf; }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      if (classify) {   // head terms in query order (deterministic summation order)
-        int n = 0;
-        float ub = 0.f;
-        for (int j = 0; j < nc; ++j)
-          if (s_slot[j] >= 0) {
-            h_slot[n] = s_slot[j];
-            h_idf[n] = s_idf[j];
-            ub += s_idf[j] * hd.head_max[s_slot[j]];
-            ++n;
-          }
-        n_h = n;
-        h_ub = ub;
-      }
-      int m = 0;   // only terms with postings left take a turn (and a barrier) in the scatter
-      for (int j = 0; j < nc; ++j)
-        if (s_end[j] > s_cur[j]) {
-          s_cur[m] = s_cur[j];
-          s_end[m] = s_end[j];
-          s_idf[m] = s_idf[j];
-          ++m;
-        }
-      n_stream = m;
-    }
-    __syncthreads();
-  };
-
-  // the run's candidate list: room for one key per thread is kept at every push site
-  auto compact_res = [&]() {   // whole block, after a barrier; keeps the k best
-    const int n = n_res < kBm25ResCap ? n_res : kBm25ResCap;
-    const int np2 = next_pow2(n > 2 ? n : 2);
-    for (int i = n + tid; i < np2; i += kBm25Threads) res[i] = 0ull;
-    block_bitonic_sort_desc(res, np2);
-    if (n >= k) {
-      const float s = key_score(res[k - 1]);
-      if (s > theta_run) theta_run = s;
-      if (tid == 0 && s > 0.f) atomicMax(reinterpret_cast<int*>(theta_g + q), __float_as_int(s));
-    }
-    __syncthreads();
-    if (tid == 0) n_res = n < k ? n : k;
-    __syncthreads();
-  };
-  auto ensure_room = [&]() {   // block-uniform (n_res is read after a barrier)
-    if (n_res > kBm25ResCap - kBm25Threads) compact_res();
-  };
-
-  for (int t = t0; t < t1; ++t) {
-    const int d0 = t * tile_docs;
-    const int d1 = min(ix.n_docs, d0 + tile_docs);
-    const int nd = d1 - d0;
-    {
-      float4* a4 = reinterpret_cast<float4*>(acc);
-      const int n4 = (nd + 3) >> 2;
-      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-      for (int i = tid; i < n4; i += kBm25Threads) a4[i] = z;
-    }
-    if (tid == 0) { n_cand = 0; s_theta = __ldcg(theta_g + q); }
-    if (!long_q && t == t0) locate(t_begin, n_terms_q, d0, true);
-    if (tid < kBm25TermChunk) s_next[tid] = 0xffffffffu;
-    __syncthreads();
-    const float theta = fmaxf(s_theta, theta_run);
-    const float ub = h_ub * (1.f + 1e-5f);   // slack for the rounding of the completed sum
-    const bool bounded = theta > ub;
-    // a document can still reach theta only if its partial score reaches cut
-    const float cut = bounded ? theta - ub - 1e-6f * theta : INFINITY;
-
-    // ---- scatter-accumulate the streamed terms, one after another (see the kernel above) ----
-    struct Item { int d[4]; float w[4]; };
-    const int kInvalid = 0x7fffffff;
-    auto load_item = [&](int64_t p, int64_t end) {
-      Item it;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t pp = p + u * kBm25Threads;
-        const bool in = pp < end;
-        it.d[u] = in ? __ldg(ix.post_doc + pp) : kInvalid;
-        it.w[u] = in ? __ldg(ix.post_w + pp) : 0.f;
-      }
-      return it;
-    };
-    auto scatter = [&](int ns_terms, bool keep_cursor) {
-      if (ns_terms <= 0) return;
-      Item pre = load_item(s_cur[0] + tid, s_end[0]);
-      for (int j = 0; j < ns_terms; ++j) {
-        const int64_t end = s_end[j], base = s_cur[j];
-        const float idf = s_idf[j];
-        int64_t p = base + tid;
-        Item cur = pre;
-        while (true) {
-          const bool more = cur.d[3] < d1;
-          Item nxt;
-          if (more) { p += 4 * kBm25Threads; nxt = load_item(p, end); }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (cur.d[u] < d1) {
-              const int i = cur.d[u] - d0;
-              const float before = acc[i];
-              const float after = fmaf(idf, cur.w[u], before);
-              acc[i] = after;
-              if (after >= cut && before < cut) {   // crosses the bar once: note it for completion
-                const int c = atomicAdd(&n_cand, 1);
-                if (c < kBm25RunCand) cand_idx[c] = static_cast<uint16_t>(i);
-              }
-            }
-          if (!more) break;
-          cur = nxt;
-        }
-        if (keep_cursor) {   // first posting beyond the tile = where the next tile starts
-          int64_t pos = end;
-#pragma unroll
-          for (int u = 3; u >= 0; --u)
-            if (cur.d[u] >= d1) pos = p + u * kBm25Threads;
-          if (pos > end) pos = end;
-          const uint32_t rel = __reduce_min_sync(kFullMask, static_cast<uint32_t>(pos - base));
-          if (lane == 0) atomicMin(&s_next[j], rel);
-        }
-        if (j + 1 < ns_terms) pre = load_item(s_cur[j + 1] + tid, s_end[j + 1]);
-        __syncthreads();
-      }
-    };
-    if (!long_q) {
-      scatter(n_stream, true);
-    } else {
-      for (int c0 = t_begin; c0 < t_end; c0 += kBm25TermChunk) {
-        locate(c0, min(kBm25TermChunk, t_end - c0), d0, false);
-        scatter(n_stream, false);
-      }
-    }
-    __syncthreads();
-    const int nh = n_h;
-    auto completed = [&](int i) -> float {   // partial -> full score: one load per head term
-      float full = acc[i];
-      const float* col = hd.head_w + (d0 + i);
-      for (int h = 0; h < nh; ++h)
-        full = fmaf(h_idf[h], __ldg(col + static_cast<int64_t>(h_slot[h]) * hd.head_ld), full);
-      return full;
-    };
-    auto allowed = [&](int doc) -> bool {
-      return !doc_mask || ((__ldg(doc_mask + (doc >> 5)) >> (doc & 31)) & 1u);
-    };
-
-    if (bounded) {
-      // ---- the noted documents: complete, keep what reaches theta ----
-      const int nc_tile = n_cand;
-      if (nc_tile <= kBm25RunCand) {
-        for (int c0 = 0; c0 < nc_tile; c0 += kBm25Threads) {
-          ensure_room();
-          const int c = c0 + tid;
-          if (c < nc_tile) {
-            const int i = cand_idx[c];
-            const float full = completed(i);
-            if (full >= theta && allowed(d0 + i)) res[atomicAdd(&n_res, 1)] = make_key(full, static_cast<uint32_t>(d0 + i));
-          }
-          __syncthreads();
-        }
-      } else {   // more than the list holds: walk the tile
-        for (int i0 = 0; i0 < nd; i0 += kBm25Threads) {
-          ensure_room();
-          const int i = i0 + tid;
-          if (i < nd && acc[i] >= cut) {
-            const float full = completed(i);
-            if (full >= theta && allowed(d0 + i)) res[atomicAdd(&n_res, 1)] = make_key(full, static_cast<uint32_t>(d0 + i));
-          }
-          __syncthreads();
-        }
-      }
-    } else {
-      // ---- no usable bound (sample tiles): the per-tile selection of the kernel above ----
-      uint64_t* tbest = lists;
-      uint64_t* sel = lists + kBm25Threads;
-      const int sel_cap = list_cap - kBm25Threads;
-      float cutu = -INFINITY;
-      auto key_of = [&](int i) -> uint64_t {
-        const int doc = d0 + i;
-        if (!allowed(doc)) return 0ull;
-        const float a = acc[i];
-        if (a < cutu) return 0ull;
-        return make_key(a, static_cast<uint32_t>(doc));
-      };
-      uint64_t best = 0ull;
-      bool listed = false, have_best = false;
-      if (nh > 0) {
-        // documents that hold a streamed term first: the k-th best of their full scores bounds the
-        // tile's k-th best; the others are completed only if the head terms alone could reach it
-        if (tid == 0) n_cand = 0;
-        __syncthreads();
-        {
-          const float4* a4 = reinterpret_cast<const float4*>(acc);
-          for (int b0 = 0; b0 < nd; b0 += kBm25Threads * 4) {
-            const int i0 = b0 + tid * 4;
-            const float4 v = i0 < nd ? a4[i0 >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float e[4] = {v.x, v.y, v.z, v.w};
-            unsigned mine = 0u;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) mine |= ((i0 + u < nd && e[u] != 0.f) ? 1u : 0u) << u;
-            if (__any_sync(kFullMask, mine != 0u)) {
-              const int cnt = __popc(mine);
-              int incl = cnt;
-#pragma unroll
-              for (int of = 1; of < 32; of <<= 1) {
-                const int tt = __shfl_up_sync(kFullMask, incl, of);
-                if (lane >= of) incl += tt;
-              }
-              int base = 0;
-              if (lane == 31) base = atomicAdd(&n_cand, incl);
-              base = __shfl_sync(kFullMask, base, 31);
-              int sl = base + incl - cnt;
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if ((mine >> u) & 1u) {
-                  if (sl < kBm25RunCand) cand_idx[sl] = static_cast<uint16_t>(i0 + u);
-                  ++sl;
-                }
-            }
-          }
-        }
-        __syncthreads();
-        bool rest = n_cand > kBm25RunCand;
-        if (!rest) {
-          for (int c = tid; c < n_cand; c += kBm25Threads) {
-            const int i = cand_idx[c];
-            acc[i] = completed(i);
-            const uint64_t key = key_of(i);
-            best = key > best ? key : best;
-          }
-          const uint64_t kth1 = kth_of_thread_bests(best, k, tbest, &s_thr);
-          if (kth1 != 0ull && key_score(kth1) > ub) {
-            listed = true;   // untouched documents score at most ub: they cannot reach the k-th best
-            have_best = true;
-            cutu = key_score(kth1) - 1e-6f * fabsf(key_score(kth1));
-            if (!(cutu > ub)) { listed = false; have_best = false; cutu = -INFINITY; rest = true; }
-          } else {
-            rest = true;
-          }
-          if (rest)   // complete everything that has not been completed (accumulator still 0)
-            for (int i = tid; i < nd; i += kBm25Threads)
-              if (acc[i] == 0.f) acc[i] = completed(i);
-        } else {
-          for (int i = tid; i < nd; i += kBm25Threads) acc[i] = completed(i);
-        }
-        __syncthreads();
-      }
-      if (!have_best) {
-        best = 0ull;
-        if (listed) {
-          for (int c = tid; c < n_cand; c += kBm25Threads) {
-            const uint64_t key = key_of(cand_idx[c]);
-            best = key > best ? key : best;
-          }
-        } else {
-          for (int i = tid; i < nd; i += kBm25Threads) {
-            const uint64_t key = key_of(i);
-            best = key > best ? key : best;
-          }
-        }
-      }
-      if (tid == 0) { n_sel = 0; s_kth_score = 0.f; }
-      for (int i = tid; i < sel_cap; i += kBm25Threads) sel[i] = 0ull;
-      uint64_t thr = 0ull;
-      const bool small = listed && n_cand <= 64;
-      if (!small) thr = kth_of_thread_bests(best, k, tbest, &s_thr);
-      else __syncthreads();
-      const int n_sweep = listed ? n_cand : nd;
-      for (int c = tid; c < n_sweep; c += kBm25Threads) {
-        const uint64_t key = key_of(listed ? cand_idx[c] : c);
-        if (key != 0ull && key >= thr) {
-          const int sl = atomicAdd(&n_sel, 1);
-          if (sl < sel_cap) sel[sl] = key;   // cannot overflow: <= k threads x ceil(tile / 256) docs
-        }
-      }
-      __syncthreads();
-      ensure_room();
-      const int ns = n_sel < sel_cap ? n_sel : sel_cap;
-      if (ns <= kBm25Threads) {   // rank by counting (keys are unique)
-        if (tid < ns) {
-          const uint64_t key = sel[tid];
-          int rank = 0;
-          for (int j = 0; j < ns; ++j) rank += sel[j] > key;
-          if (rank < k) res[atomicAdd(&n_res, 1)] = key;
-          if (rank == k - 1) s_kth_score = key_score(key);
-        }
-      } else {
-        block_bitonic_sort_desc(sel, next_pow2(ns));
-        if (tid < k) res[atomicAdd(&n_res, 1)] = sel[tid];
-        if (tid == 0 && ns >= k) s_kth_score = key_score(sel[k - 1]);
-      }
-      __syncthreads();
-      // the tile's k-th best full score bounds the query's k-th best from below
-      const float tk = s_kth_score;
-      if (tk > 0.f) {
-        if (tk > theta_run) theta_run = tk;
-        if (tid == 0) atomicMax(reinterpret_cast<int*>(theta_g + q), __float_as_int(tk));
-      }
-    }
-    // cursors of the streamed terms move to the first posting beyond this tile
-    if (!long_q && tid < n_stream && s_next[tid] != 0xffffffffu) s_cur[tid] += s_next[tid];
-    __syncthreads();
-  }
-
-  // ---- the run's k best, ranked ----
-  if (n_res > kBm25Threads) compact_res();
-  const int n = n_res;
-  for (int i = tid; i < k; i += kBm25Threads)
-    if (i >= n) o[i] = 0ull;
-  if (tid < n) {
-    const uint64_t key = res[tid];
-    int rank = 0;
-    for (int j = 0; j < n; ++j) rank += res[j] > key;
-    if (rank < k) o[rank] = key;
-    if (rank == k - 1 && key_score(key) > 0.f)
-      atomicMax(reinterpret_cast<int*>(theta_g + q), __float_as_int(key_score(key)));
-  }
-}
-
-bool bm25_runs_enabled() {
-  // Opt-in (ANR_BM25_RUNS=1).  Measured on 1M docs / batch 64 (profiles/r2_call3_*): 0.318 ms
-  // alone against 0.270 ms for the per-tile kernel -- a run is run_tiles times longer than a
-  // tile, so the grid is 3 waves instead of 12 and the last wave's imbalance costs what the
-  // saved searches gain; the per-tile kernel stays the default.
-  static const bool on = getenv("ANR_BM25_RUNS") && atoi(getenv("ANR_BM25_RUNS")) != 0;
-  return on;
-}
-
-static cudaError_t launch_bm25_runs(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* q_terms,
-                                    const int32_t* q_offsets, int nq, int k, const uint32_t* doc_mask,
-                                    const Bm25Plan& plan, uint64_t* out, int64_t out_stride_q,
-                                    float* theta, cudaStream_t stream) {
-  if (plan.n_tiles < 1 || nq < 1) return cudaSuccess;
-  auto kern = bm25_run_kernel;
-  cudaError_t e =
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.run_smem_bytes);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-  if (e != cudaSuccess) return e;
-  static const int fold_env = getenv("ANR_BM25_FOLD") ? atoi(getenv("ANR_BM25_FOLD")) : -1;
-  const bool fold = (fold_env >= 0 ? fold_env != 0 : !plan.beside_dense) &&
-                    plan.n_runs + plan.n_sampled <= 65535;
-  for (int q0 = 0; q0 < nq; q0 += 65535) {
-    const int nb = nq - q0 < 65535 ? nq - q0 : 65535;
-    uint64_t* o = out + q0 * out_stride_q;
-    if (fold) {
-      if (plan.phase == 1) continue;   // nothing separate to launch ahead
-      kern<<<dim3(nb, plan.n_sampled + plan.n_runs), kBm25Threads, plan.run_smem_bytes, stream>>>(
-          ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap, o, out_stride_q,
-          theta + q0, plan.n_tiles, plan.run_tiles, plan.sample_every, plan.n_runs, plan.n_sampled, 0);
-    } else {
-      if (plan.phase != 2)
-        kern<<<dim3(plan.n_sampled, nb), kBm25Threads, plan.run_smem_bytes, stream>>>(
-            ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap, o,
-            out_stride_q, theta + q0, plan.n_tiles, plan.run_tiles, plan.sample_every, plan.n_runs,
-            plan.n_sampled, 1);
-      if (plan.phase != 1)
-        kern<<<dim3(plan.n_runs, nb), kBm25Threads, plan.run_smem_bytes, stream>>>(
-            ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap, o,
-            out_stride_q, theta + q0, plan.n_tiles, plan.run_tiles, plan.sample_every, plan.n_runs,
-            plan.n_sampled, 2);
-    }
-  }
-  return cudaGetLastError();
-}
-
-// EXPERIMENTAL (ANR_BM25_PERSISTENT=<CTAs per SM>, not yet run on a GPU): the same items pulled
-// from a work counter by a grid that is resident from its first cycle.  Nothing is launched
-// behind another kernel's back, so the scan can share SMs with the dense main kernel whatever the
-// launch order, and two batches can be in flight.  Items are
-// taken in the order the hardware would have dispatched the classic grid (bx fastest).
-template <bool PRUNE>
-__global__ void __launch_bounds__(kBm25Threads)
-bm25_score_persistent_kernel(Bm25View ix, Bm25HeadView hd, const int32_t* __restrict__ q_terms,
-                             const int32_t* __restrict__ q_offsets, int k,
-                             const uint32_t* __restrict__ doc_mask, int tile_docs, int list_cap,
-                             uint64_t* __restrict__ out, int64_t out_stride_q,
-                             float* __restrict__ theta_g, int tile_stride, int n_sampled, int gx,
-                             int gy, int* __restrict__ work_counter) {
-  __shared__ int s_item;
-  const int n_items = gx * gy;
-  for (;;) {
-    __syncthreads();   // the previous item's shared memory is no longer read
-    if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
-    __syncthreads();
-    const int item = s_item;
-    if (item >= n_items) return;
-    bm25_tile_item<false, PRUNE>(ix, hd, q_terms, q_offsets, k, doc_mask, tile_docs, list_cap, out,
-                                 out_stride_q, theta_g, tile_stride, n_sampled, item % gx, item / gx);
-  }
-}
-
-// CTAs per SM of the experimental persistent grid (0 = classic launches)
-static int bm25_persistent_ctas() {
-  static const int v = getenv("ANR_BM25_PERSISTENT") ? atoi(getenv("ANR_BM25_PERSISTENT")) : 0;
-  return v > 0 && v <= 16 ? v : 0;
-}
-static int bm25_sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
-      n = 148;
-  }
-  return n;
-}
-
-// One classic grid (gx, gy) of items through the persistent kernel.
-template <bool PRUNE>
-static void launch_persistent(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* q_terms,
-                              const int32_t* q_offsets, int k, const uint32_t* doc_mask,
-                              const Bm25Plan& plan, uint64_t* out, int64_t out_stride_q, float* theta,
-                              int tile_stride, int n_sampled, int gx, int gy, int* counter,
-                              cudaStream_t stream) {
-  auto kern = bm25_score_persistent_kernel<PRUNE>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
-  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                       cudaSharedmemCarveoutMaxShared);
-  const long long items = static_cast<long long>(gx) * gy;
-  const long long resident = static_cast<long long>(bm25_sm_count()) * bm25_persistent_ctas();
-  const unsigned grid = static_cast<unsigned>(items < resident ? items : resident);
-  kern<<<grid, kBm25Threads, plan.smem_bytes, stream>>>(ix, hd, q_terms, q_offsets, k, doc_mask,
-                                                        plan.tile_docs, plan.list_cap, out,
-                                                        out_stride_q, theta, tile_stride, n_sampled,
-                                                        gx, gy, counter);
-}
-
-// counters: two zeroed ints behind the theta array (sample launch, main launch), or null.
 template <bool EMIT_ALL, bool PRUNE>
 static cudaError_t launch_score_t(const Bm25View& ix, const Bm25HeadView& hd, const int32_t* q_terms,
                                   const int32_t* q_offsets, int nq, int k,
                                   const uint32_t* doc_mask, const Bm25Plan& plan, uint64_t* out,
-                                  int64_t out_stride_q, float* theta, cudaStream_t stream,
-                                  int* counters = nullptr) {
+                                  int64_t out_stride_q, float* theta, cudaStream_t stream) {
   if (plan.n_tiles < 1 || nq < 1) return cudaSuccess;
-  const bool persistent = !EMIT_ALL && PRUNE && counters && bm25_persistent_ctas() > 0 && nq <= 65535;
   auto kern = bm25_score_kernel<EMIT_ALL, PRUNE>;
   cudaError_t e =
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
@@ -1190,45 +573,20 @@ static cudaError_t launch_score_t(const Bm25View& ix, const Bm25HeadView& hd, co
       // kernels and its main kernel starts early (0.658 vs 0.674 ms per hybrid step); alone, the
       // folded single launch below is ~8 % faster.
       dim3 grid_s((plan.n_tiles + stride - 1) / stride, nb);
-      if constexpr (!EMIT_ALL && PRUNE) {
-        if (persistent) {
-          if (plan.phase != 2)
-            launch_persistent<true>(ix, hd, q_terms, q_offsets, k, doc_mask, plan, out, out_stride_q,
-                                    theta, stride, -2, grid_s.x, nb, counters, stream);
-          if (plan.phase != 1)
-            launch_persistent<true>(ix, hd, q_terms, q_offsets, k, doc_mask, plan, out, out_stride_q,
-                                    theta, stride, -3, grid.x, nb, counters + 1, stream);
-          continue;
-        }
-      }
-      // ANR_BM25_LIGHT_SAMPLE=1 (default 0): the sample launch scores a quarter of each sampled
-      // tile and only publishes bounds; the main launch then covers every tile.  Measured
-      // (profiles/r2_call5_*): the shorter sample launch does not pay for the weaker bounds --
-      // 0.595 against 0.543 ms per hybrid step, the main launch stretching from 0.425 to 0.495 ms.
-      static const int light_env =
-          getenv("ANR_BM25_LIGHT_SAMPLE") ? atoi(getenv("ANR_BM25_LIGHT_SAMPLE")) : 0;
-      const bool light = light_env != 0;
       if (plan.phase != 2)
         kern<<<grid_s, kBm25Threads, plan.smem_bytes, stream>>>(
             ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
-            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, light ? -4 : -2, nullptr, nullptr);
+            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, -2, nullptr, nullptr);
       if (plan.phase != 1)
         kern<<<grid, kBm25Threads, plan.smem_bytes, stream>>>(
             ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
-            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, light ? -5 : -3, nullptr, nullptr);
+            out + q0 * out_stride_q, out_stride_q, theta + q0, stride, -3, nullptr, nullptr);
     } else if (plan.phase == 1) {
       // no separate sample launch in this plan: everything happens in phase 2
     } else if (PRUNE && theta && plan.n_tiles >= kMinTilesForSample && plan.n_tiles <= 65535) {
       // one launch, sample tiles first (see the kernel): no second launch, no idle tail between
       const int n_sampled = (plan.n_tiles + stride - 1) / stride;
       dim3 grid_f(nb, plan.n_tiles);
-      if constexpr (!EMIT_ALL && PRUNE) {
-        if (persistent) {
-          launch_persistent<true>(ix, hd, q_terms, q_offsets, k, doc_mask, plan, out, out_stride_q,
-                                  theta, stride, n_sampled, nb, plan.n_tiles, counters, stream);
-          continue;
-        }
-      }
       kern<<<grid_f, kBm25Threads, plan.smem_bytes, stream>>>(
           ix, hd, q_terms, q_offsets + q0, k, doc_mask, plan.tile_docs, plan.list_cap,
           out + q0 * out_stride_q, out_stride_q, theta + q0, stride, n_sampled, nullptr, nullptr);
@@ -1247,17 +605,12 @@ cudaError_t launch_bm25_score_topk(const Bm25View& ix, const Bm25HeadView* hd, c
                                    int64_t cand_stride_q, float* theta, cudaStream_t stream) {
   if (k < 1 || k > kMaxFusedK) return cudaErrorInvalidValue;
   if (hd && hd->n_head > 0) {
-    // theta is [nq] floats followed by kBm25CounterSlots ints of work counters (anr_api.cu)
     if (theta && plan.phase != 2) {
-      cudaError_t e = cudaMemsetAsync(theta, 0, static_cast<size_t>(nq + kBm25CounterSlots) * 4, stream);
+      cudaError_t e = cudaMemsetAsync(theta, 0, static_cast<size_t>(nq) * 4, stream);
       if (e != cudaSuccess) return e;
     }
-    if (plan.use_runs && theta)
-      return launch_bm25_runs(ix, *hd, q_terms, q_offsets, nq, k, doc_mask, plan, cand, cand_stride_q,
-                              theta, stream);
     return launch_score_t<false, true>(ix, *hd, q_terms, q_offsets, nq, k, doc_mask, plan, cand,
-                                       cand_stride_q, theta, stream,
-                                       theta ? reinterpret_cast<int*>(theta + nq) : nullptr);
+                                       cand_stride_q, theta, stream);
   }
   return launch_score_t<false, false>(ix, Bm25HeadView(), q_terms, q_offsets, nq, k, doc_mask, plan,
                                       cand, cand_stride_q, nullptr, stream);

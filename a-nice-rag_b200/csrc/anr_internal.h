@@ -152,7 +152,6 @@ struct Bm25View {
 // bounds what the head terms can still add, and completes the score of the few documents that
 // can still reach the tile's k-th best (MaxScore-style pruning; results are unchanged).
 constexpr int kBm25MaxHead = 128;
-constexpr int kBm25CounterSlots = 8;   // ints of work counters kept behind a search's theta array
 struct Bm25HeadView {
   const uint8_t* slot_of = nullptr;   // [n_terms] head slot of a term, 0xff = not a head term
   const float* head_w = nullptr;      // [n_head][head_ld]
@@ -177,15 +176,7 @@ struct Bm25Plan {
   bool beside_dense = false;   // the scan runs on a side stream next to the dense pass (hybrid)
   int phase = 0;               // 0 = whole scan; 1 = only the separate sample launch (if the plan
                                // has one); 2 = everything after it
-  // Pruned scan by RUNS (bm25_run_kernel): one CTA scores run_tiles consecutive tiles of one query
-  // and keeps its posting cursors, classification and candidate list across them; the first tile
-  // of every sample_every-th run is scored ahead of the rest (it publishes the query's first
-  // bound).  Candidate slots per query: n_runs (one per run) + n_sampled (one per sample tile).
-  int run_tiles = 1, n_runs = 0, sample_every = 1, n_sampled = 0;
-  int run_smem_bytes = 0;
-  bool use_runs = false;       // set by the caller once it knows that head rows exist
 };
-bool bm25_runs_enabled();
 Bm25Plan bm25_make_plan(const DeviceProps& dp, int n_docs, int nq, int k, bool emit_all);
 // cand[q * cand_stride_q + tile * k + i] candidate keys (ids = doc index)
 // hd (nullable) + theta (nq floats of scratch, nullable) enable the pruned scan.

@@ -190,10 +190,10 @@ def test_config1_two_shards_replay_equals_unsharded(config1):
 
 def test_config3_bm25_10M_docs_batch256_properties():
     """BASELINE.json configs[3] at full size: BM25-only over a 10M-document CSR index (V = 500k,
-    Zipf 1.1), 8-term queries, batch 256, top-10 -- the pruned scan (dense head rows, runs with
-    cursors).  Sampled queries against a float64 scatter of the same postings on the device
-    (rank_bm25 get_scores' formula, src/search_engine.py:219); the unpruned scan of the same
-    batch returns the same documents."""
+    Zipf 1.1), 8-term queries, batch 256, top-10 -- the candidate-driven path (anr_bm25_ms.cu).
+    Sampled queries against a float64 scatter of the same postings on the device (rank_bm25
+    get_scores' formula, src/search_engine.py:219); the unpruned tiled scan of the same batch
+    returns the same documents."""
     import os
     import torch
     free, _ = torch.cuda.mem_get_info()
