@@ -655,6 +655,53 @@ def test_bm25_candidate_path_flag_conditions_and_repeatability(prune_corpus):
     _check_bm25_batch(ix, queries, scores, docs, counts, 10, "candidates 3 docs kept", mask=few)
 
 
+def test_bm25_negative_average_idf_takes_the_exhaustive_scan():
+    """Every term in more than half of the documents: BM25Okapi's raw idf values are all negative,
+    so is their average, and the epsilon floor (epsilon * average_idf, rank_bm25 _calc_idf) is
+    NEGATIVE too.  Term bounds mean nothing then: the candidate-driven path must hand the whole
+    index to the exhaustive scan, which ranks documents that lack the terms (score 0) first."""
+    rng = np.random.default_rng(7)
+    n, vocab = 3000, 6
+    doc_len = rng.integers(10, 16, n)
+    doc_ptr = np.concatenate([[0], np.cumsum(doc_len)]).astype(np.int64)
+    tokens = rng.integers(0, vocab, int(doc_ptr[-1])).astype(np.int32)
+    ix = csr.from_token_ids(doc_ptr, tokens, vocab, 1.5, 0.75, 0.25)
+    assert (ix.idf < 0).all()
+    index = engine.Bm25Index(ix.term_ptr, ix.post_doc, ix.post_tf, ix.doc_len, ix.idf, ix.k1,
+                             ix.b, ix.avgdl)
+    queries = [[0, 1], [2], [3, 3, 4], [5, 0, 1, 2]] * 5
+    for k in (10, 100):
+        scores, docs, counts = index.search(queries, k)
+        _check_bm25_batch(ix, queries, scores, docs, counts, k, f"negative idf k{k}")
+
+
+def test_bm25_candidate_path_ties_duplicates_and_term_count_limits():
+    """A corpus of 60 distinct documents, each stored 100 times (every score occurs 100 times: the
+    k-th best is always inside a run of equal scores, and far more than k documents reach theta),
+    and queries of exactly 48 terms (the most the candidate-driven path takes), 49 (flagged and
+    rerun) and 1."""
+    rng = np.random.default_rng(11)
+    vocab, distinct, copies = 400, 60, 100
+    base_docs = [rng.integers(0, vocab, rng.integers(20, 60)).astype(np.int32) for _ in range(distinct)]
+    order = rng.permutation(distinct * copies) % distinct
+    docs_tok = [base_docs[i] for i in order]
+    doc_ptr = np.concatenate([[0], np.cumsum([len(d) for d in docs_tok])]).astype(np.int64)
+    tokens = np.concatenate(docs_tok)
+    ix = csr.from_token_ids(doc_ptr, tokens, vocab, 1.7, 0.83, 0.05)
+    index = engine.Bm25Index(ix.term_ptr, ix.post_doc, ix.post_tf, ix.doc_len, ix.idf, ix.k1,
+                             ix.b, ix.avgdl)
+    q48 = [int(t) for t in rng.integers(0, vocab, 48)]
+    queries = [q48, q48 + [int(q48[0])], [int(base_docs[0][0])],
+               [int(t) for t in base_docs[3][:6]], [int(t) for t in base_docs[7][:3]] * 2]
+    for k in (1, 10, 100, 128):
+        scores, docs, counts = index.search(queries, k)
+        _check_bm25_batch(ix, queries, scores, docs, counts, k, f"ties k{k}")
+        for q in range(len(queries)):   # one total order everywhere: equal scores -> lower document first
+            sc, dd = scores[q, :counts[q]], docs[q, :counts[q]]
+            same = sc[1:] == sc[:-1]
+            assert (dd[1:][same] > dd[:-1][same]).all(), (k, q)
+
+
 # ---------------------------------------------------------------------------------------
 # batched orchestrator (SURVEY 8 f4): retrieve_documents for B queries == the per-query pipeline
 def test_retrieve_documents_batch_equals_per_query_orchestrator(small):
