@@ -72,6 +72,10 @@ struct anr_ctx {
   cudaEvent_t ev_last = nullptr;
   cudaStream_t last_stream = nullptr;
   bool last_valid = false;
+  // anr_ctx_last_rerun: device counters of the last call's rerun lists (in the scratch buffer: valid
+  // until the next call on this context), null when that call had no such list
+  const int32_t* last_dense_flagged = nullptr;
+  const int32_t* last_bm25_flagged = nullptr;
   // anr_ctx_timeline_*: where the parts of ONE hybrid step start and end (see the header)
   bool timeline = false;
   cudaEvent_t tl[ANR_TIMELINE_MARKS] = {};
@@ -152,6 +156,8 @@ struct Arena {
 inline size_t padded(size_t bytes) { return (bytes + 255) & ~static_cast<size_t>(255); }
 
 int ws_reserve(anr_ctx* ctx, size_t bytes) {
+  ctx->last_dense_flagged = nullptr;   // (a new call: the previous call's rerun counters are gone)
+  ctx->last_bm25_flagged = nullptr;
   bytes += 4096;
   if (bytes <= ctx->ws_bytes) return ANR_OK;
   // earlier work (on the context's stream or a caller's) may still be using the old buffer
@@ -475,6 +481,7 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
     int32_t* flagged = arena.take<int32_t>(static_cast<size_t>(nq));
     uint64_t* fb_cand = arena.take<uint64_t>(static_cast<size_t>(nq) * fb_stride);
     ANR_CUDA(launch_compact_flags(flags, nq, n_flagged, flagged, stream));
+    ctx->last_dense_flagged = n_flagged;
     ANR_CUDA(launch_dense_scan_flagged(ctx->dp, ix->emb, ix->n, ix->ld, q_dev, n_flagged, flagged, k,
                                        mask_dev, fb_cand, fb_stride, stream));
     ANR_CUDA(launch_topk_final_flagged(fb_cand, fb_stride, static_cast<int>(fb_stride), nq, k, out,
@@ -519,6 +526,7 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
     int32_t* flagged = arena.take<int32_t>(static_cast<size_t>(nq));
     uint64_t* fb_cand = arena.take<uint64_t>(static_cast<size_t>(nq) * fb_stride);
     ANR_CUDA(launch_compact_flags(flags, nq, n_flagged, flagged, stream));
+    ctx->last_dense_flagged = n_flagged;
     ANR_CUDA(launch_dense_scan_flagged(ctx->dp, ix->emb, ix->n, ix->ld, q_dev, n_flagged, flagged, k,
                                        mask_dev, fb_cand, fb_stride, stream));
     ANR_CUDA(launch_topk_final_flagged(fb_cand, fb_stride, static_cast<int>(fb_stride), nq, k, out,
@@ -777,6 +785,7 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
                   h[i].theta, h[i].tot, h[i].s1_total, static_cast<long long>(h[i].s2_total), h[i].n_surv,
                   h[i].flag);
       }
+      ctx->last_bm25_flagged = n_flagged;
       ANR_CUDA(launch_bm25_score_listed(v, terms_dev, offsets_dev, nq, k, mask_dev, plan, fb_cand,
                                         fb_stride, flagged, n_flagged, stream));
       ANR_CUDA(launch_topk_final_flagged(fb_cand, fb_stride, static_cast<int>(fb_stride), nq, k, live,
@@ -1062,6 +1071,20 @@ int anr_ctx_sync(anr_ctx* ctx) {
   if (!ctx) return fail(ANR_ERR_INVALID, "ctx is NULL");
   DeviceGuard guard(ctx->dp.device);
   ANR_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ANR_OK;
+}
+
+int anr_ctx_last_rerun(anr_ctx* ctx, int32_t* dense_queries, int32_t* bm25_queries) {
+  if (!ctx) return fail(ANR_ERR_INVALID, "anr_ctx_last_rerun: ctx is NULL");
+  DeviceGuard guard(ctx->dp.device);
+  ANR_CUDA(cudaDeviceSynchronize());
+  int32_t d = -1, b = -1;
+  if (ctx->last_dense_flagged)
+    ANR_CUDA(cudaMemcpy(&d, ctx->last_dense_flagged, 4, cudaMemcpyDeviceToHost));
+  if (ctx->last_bm25_flagged)
+    ANR_CUDA(cudaMemcpy(&b, ctx->last_bm25_flagged, 4, cudaMemcpyDeviceToHost));
+  if (dense_queries) *dense_queries = d;
+  if (bm25_queries) *bm25_queries = b;
   return ANR_OK;
 }
 

@@ -35,6 +35,13 @@ class Context:
     def sync(self) -> None:
         native.call("anr_ctx_sync", self.handle)
 
+    def last_rerun(self) -> Tuple[int, int]:
+        """(dense queries, BM25 queries) of the last search call on this context that left the fast
+        paths and were rerun exactly on the device; -1 = the call had no such path (anr_b200.h)."""
+        d, b = C.c_int32(), C.c_int32()
+        native.call("anr_ctx_last_rerun", self.handle, C.byref(d), C.byref(b))
+        return d.value, b.value
+
     def info(self) -> Tuple[int, int, int]:
         sm, total, free = C.c_int32(), C.c_int64(), C.c_int64()
         native.call("anr_ctx_info", self.handle, C.byref(sm), C.byref(total), C.byref(free))

@@ -596,6 +596,13 @@ def run_headline(env, args, peaks, sampler):
     # ---- the whole batch with its per-retriever lists (what the parity check reads) -----------
     got = full_lists_sharded(env, w, qb) if world > 1 else (
         full_lists_single_gpu(env, w, qb) if rank == 0 else None)
+    # queries of the benchmark batch that left the fast paths (bf16 nomination margin -> exact fp32
+    # rescan; candidate-driven BM25 -> exhaustive scan): both reruns cost several times the step
+    reruns = None
+    if world == 1:
+        d_rr, b_rr = env.ctx.last_rerun()
+        reruns = {"dense_queries": d_rr, "bm25_queries": b_rr, "of": B,
+                  "what": "queries of the benchmark batch rerun exactly on the device (-1: no such path)"}
 
     # ---- rank 0 alone from here: rooflines, graph replay, CPU port + parity ---------------------
     res = None
@@ -604,7 +611,7 @@ def run_headline(env, args, peaks, sampler):
             block_ms=block_ms, ms_dev=ms_dev, total_ms=total_ms, ms_e2e=ms_e2e, e2e_ms=e2e_ms,
             scan=(scan_ms, scan_n), bm=(bm_ms, bm_n), tc_pass=(pass_ms, pass_n), multi=multi,
             ms_filtered=ms_filtered, lat=lat, ms_b1_dev=ms_b1_dev, ms_b1_scan=ms_b1_scan,
-            lat_scan=lat_scan, clocks=clocks, shadow=shadow))
+            lat_scan=lat_scan, clocks=clocks, shadow=shadow, reruns=reruns))
     del w, qb
     torch.cuda.empty_cache()
     return res
@@ -901,6 +908,7 @@ def headline_report(env, args, peaks, w, qb, got, t):
                       "ms_per_step": t["ms_filtered"] / steps} if t["ms_filtered"] else None),
         "cuda_graph": graph_rec,
         "timeline": timeline,
+        "reruns": t.get("reruns"),
         "pipelined": pipe_rec,
         "multi_gpu": t["multi"],
         "clocks": t["clocks"], "parity_checked_queries": checked,

@@ -62,6 +62,15 @@ int anr_ctx_sync(anr_ctx* ctx);
 /* sm count, total/free HBM bytes of the context's device (any pointer may be NULL) */
 int anr_ctx_info(anr_ctx* ctx, int32_t* sm_count, int64_t* hbm_total, int64_t* hbm_free);
 
+/* How many queries of the LAST search call on this context left the fast paths and were rerun on
+ * the device: dense = queries whose tensor-core nomination could not prove exactness (bf16 / tf32
+ * margin, overflowing candidate buffers) and went through the exact fp32 scan; bm25 = queries the
+ * candidate-driven top-k handed to the exhaustive scan (fewer than k scoring documents, too many
+ * survivors, more than 48 terms).  -1 = the call had no such path.  Synchronises the device; valid
+ * until the next call on the context.  Both reruns return the same results at a higher cost, so
+ * this is the number to watch on production-shaped data. */
+int anr_ctx_last_rerun(anr_ctx* ctx, int32_t* dense_queries, int32_t* bm25_queries);
+
 /* Per-kernel timing for roofline reports.  While enabled, every launch of the dominant
  * kernels (kind 0 = dense scan kernel -- CUDA-core, tcgen05 or tcgen05 CTA-pair variant --,
  * kind 1 = BM25 score kernel, kind 2 = a whole tensor-core pass: sample pre-pass + threshold +

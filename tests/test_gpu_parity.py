@@ -640,12 +640,18 @@ def test_bm25_candidate_path_flag_conditions_and_repeatability(prune_corpus):
     queries[2] = [int(t) for t in synth.zipf_queries(1, 60, vocab, 1.1, seed=5)[0]]
     queries[3] = []
     queries[4] = [rare[0]] * 3 + [0]          # duplicates of a rare term beside a head term
+    ctx = engine.context(index.ctx_device)
     for k in (10, 128):
         a = index.search(queries, k)
+        reran = ctx.last_rerun()[1]
         b = index.search(queries, k)
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
         _check_bm25_batch(ix, queries, *a, k, f"candidates k{k}")
+        # the 60-term query always goes through the exhaustive scan; the empty one never does
+        assert 1 <= reran < len(queries), reran
+    index.search(queries[5:], 10)
+    assert ctx.last_rerun() == (-1, 0)        # ordinary queries: nothing left the candidate path
     nothing = np.zeros(ix.doc_len.shape[0], dtype=bool)
     scores, docs, counts = index.search(queries, 10, doc_mask=engine.pack_mask(nothing))
     assert (counts == 0).all() and (docs == -1).all()
