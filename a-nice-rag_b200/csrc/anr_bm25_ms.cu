@@ -12,8 +12,8 @@
 //   1. PLAN      terms ranked by document frequency; the shortest lists, up to kMsSample postings
 //                in all (the last one cut to a prefix), form the sample S1.
 //   2. STAGE 1   every S1 posting is a candidate document whose FULL score is computed (below);
-//                theta = the k-th largest of 256 per-thread bests of those scores: a lower bound
-//                of the query's k-th best score, because the candidates are distinct documents.
+//                theta = the k-th best of those scores: a lower bound of the query's k-th best
+//                score, because the candidates are distinct documents.
 //   3. REQUIRED  terms are set aside, longest list first, while the sum of their bounds stays
 //                below theta: a document that holds none of the remaining ("required") terms
 //                scores below theta and cannot enter the top-k.
@@ -42,6 +42,7 @@
 namespace anr {
 
 constexpr int kMsThreads = 256;
+constexpr int kMsThetaSel = 2048;   // theta kernel: sample keys at or above the per-thread-best bound (<= 128 x 16)
 constexpr int kMsWarpItems = 64;    // stage 2: consecutive postings a warp's lanes share out at a time
 
 struct __align__(8) MsTerm {
@@ -365,8 +366,10 @@ ms_theta_kernel(int k, int nq, MsQuery* __restrict__ queries, MsTerm* __restrict
                 const uint64_t* __restrict__ s1keys, int64_t* __restrict__ q_base,
                 int32_t* __restrict__ ticket) {
   __shared__ uint64_t tbest[kMsThreads];
+  __shared__ uint64_t sel[kMsThetaSel];
   __shared__ uint64_t s_kth;
   __shared__ int64_t part[kMsThreads];
+  __shared__ int n_sel;
   __shared__ bool last;
   const int q = blockIdx.x, lane = threadIdx.x & 31;
   MsQuery* Q = queries + q;
@@ -376,7 +379,28 @@ ms_theta_kernel(int k, int nq, MsQuery* __restrict__ queries, MsTerm* __restrict
     const uint64_t v = s1keys[static_cast<size_t>(q) * kMsSample + i];
     best = v > best ? v : best;
   }
-  const uint64_t kth = block_kth_of_thread_bests<kMsThreads / 32>(best, k, tbest, &s_kth);
+  uint64_t kth = block_kth_of_thread_bests<kMsThreads / 32>(best, k, tbest, &s_kth);
+  // kth bounds the sample's k-th best from below; the exact k-th best (a higher theta: fewer
+  // required lists, earlier rejections) is among the <= k * ceil(n1 / 256) keys at or above it
+  if (kth != 0ull && n1 > kMsThreads) {
+    if (threadIdx.x == 0) n_sel = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n1; i += kMsThreads) {
+      const uint64_t v = s1keys[static_cast<size_t>(q) * kMsSample + i];
+      if (v >= kth) {
+        const int slot = atomicAdd(&n_sel, 1);
+        if (slot < kMsThetaSel) sel[slot] = v;
+      }
+    }
+    __syncthreads();
+    const int m = min(n_sel, kMsThetaSel);
+    if (n_sel <= kMsThetaSel && m >= k) {   // (always, by the bound above; else keep the lower bound)
+      const int p2 = next_pow2(m);
+      for (int i = m + threadIdx.x; i < p2; i += kMsThreads) sel[i] = 0ull;
+      block_bitonic_sort_desc(sel, p2);
+      kth = sel[k - 1];
+    }
+  }
   const float theta = kth != 0ull ? key_score(kth) : 0.f;
   if (threadIdx.x < 32) {
     MsTerm* T = terms + static_cast<size_t>(q) * kMsMaxTerms;
@@ -646,32 +670,56 @@ __device__ __forceinline__ void ms_collect_flags(const MsQuery* __restrict__ que
   if (threadIdx.x == 0) *n_flagged = count;
 }
 
-// ---- 5. the survivors of a query, ranked by counting (keys are unique): one CTA per query -------
+// ---- 5. the survivors of a query, ranked: one CTA per query --------------------------------------
+// Usually a few dozen keys: one key per thread, rank by counting (keys are unique).  More than 256
+// (a weak theta: up to kMsSurvivors): the k-th largest of the per-thread bests bounds the k-th best
+// from below, the keys at or above it -- at most k * ceil(ns / 256) <= 2048 -- are collected and
+// sorted.  (Ranking 4000 survivors by counting took 0.6 ms per launch at 256 queries.)
+constexpr int kMsFinalSel = 2048;
 template <int VARIANT>
 __global__ void __launch_bounds__(kMsThreads)
 ms_final_kernel(const MsQuery* __restrict__ queries, const uint64_t* __restrict__ surv, int cap, int k,
                 int nq, TopkOut o, int32_t* __restrict__ ticket, int32_t* __restrict__ n_flagged,
                 int32_t* __restrict__ flagged) {
   __shared__ uint64_t keys[kMsThreads];
+  __shared__ uint64_t sel[kMsFinalSel];
+  __shared__ uint64_t s_kth;
+  __shared__ int n_sel;
   __shared__ bool last;
   const int q = blockIdx.x;
   const int ns = min(queries[q].n_surv, cap);
   const uint64_t* sv = surv + static_cast<size_t>(q) * cap;
   const bool dead = o.q_offsets && o.q_offsets[q + 1] == o.q_offsets[q];   // a query without terms
-  for (int i = ns + threadIdx.x; i < k; i += kMsThreads) emit_entry(0ull, q * o.stride_q + i, o);
-  // (usually ns is a few dozen: one tile, one key per thread)
-  for (int base = 0; base < ns; base += kMsThreads) {
-    const int mine = base + threadIdx.x;
-    const uint64_t key = mine < ns ? sv[mine] : 0ull;
+  if (ns <= kMsThreads) {
+    const uint64_t key = static_cast<int>(threadIdx.x) < ns ? sv[threadIdx.x] : 0ull;
+    keys[threadIdx.x] = key;
+    __syncthreads();
     int rank = 0;
-    for (int t0 = 0; t0 < ns; t0 += kMsThreads) {
-      __syncthreads();
-      keys[threadIdx.x] = t0 + static_cast<int>(threadIdx.x) < ns ? sv[t0 + threadIdx.x] : 0ull;
-      __syncthreads();
-      const int m = min(kMsThreads, ns - t0);
-      for (int i = 0; i < m; ++i) rank += keys[i] > key;
-    }
+    for (int i = 0; i < ns; ++i) rank += keys[i] > key;
+    for (int i = ns + threadIdx.x; i < k; i += kMsThreads) emit_entry(0ull, q * o.stride_q + i, o);
     if (key != 0ull && rank < k) emit_entry(dead ? 0ull : key, q * o.stride_q + rank, o);
+  } else {
+    uint64_t best = 0ull;
+    for (int i = threadIdx.x; i < ns; i += kMsThreads) {
+      const uint64_t v = sv[i];
+      best = v > best ? v : best;
+    }
+    if (threadIdx.x == 0) n_sel = 0;
+    const uint64_t thr = block_kth_of_thread_bests<kMsThreads / 32>(best, k, keys, &s_kth);
+    for (int i = threadIdx.x; i < ns; i += kMsThreads) {
+      const uint64_t v = sv[i];
+      if (v >= thr) {
+        const int slot = atomicAdd(&n_sel, 1);
+        if (slot < kMsFinalSel) sel[slot] = v;   // cannot overflow: <= k threads x ceil(ns / 256) keys
+      }
+    }
+    __syncthreads();
+    const int m = min(n_sel, kMsFinalSel);
+    const int p2 = next_pow2(m < 2 ? 2 : m);
+    for (int i = m + threadIdx.x; i < p2; i += kMsThreads) sel[i] = 0ull;
+    block_bitonic_sort_desc(sel, p2);
+    for (int i = threadIdx.x; i < k; i += kMsThreads)
+      emit_entry((i < m && !dead) ? sel[i] : 0ull, q * o.stride_q + i, o);
   }
   if (threadIdx.x == 0) {
     if (o.counts) o.counts[q * o.count_stride] = dead ? 0 : min(ns, k);

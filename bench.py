@@ -88,6 +88,9 @@ def parse_args():
     ap.add_argument("--big-vocab", type=int, default=500_000)
     ap.add_argument("--weak-chunks-per-gpu", type=int, default=12_500_000)
     ap.add_argument("--leg-steps", type=int, default=10, help="timed steps of each extra leg")
+    ap.add_argument("--leg-budget-s", type=float, default=420.0,
+                    help="wall-clock budget of the extra legs; past it the headline line is "
+                         "printed without them")
     return ap.parse_args()
 
 
@@ -1310,6 +1313,18 @@ def run_ours(args):
 
     line = run_headline(env, args, peaks, sampler)
     extra = {}
+    # The extra legs are bounded (~30 s on one GPU) but collective at N > 1: if one of them ever
+    # hung (a rank lost, a wedged collective) the driver would kill the run and lose the headline
+    # with it.  Past the budget rank 0 prints the headline line with what it has and every rank
+    # leaves.
+    def _give_up():
+        if rank == 0:
+            line["legs"] = dict(extra, aborted=f"extra legs exceeded --leg-budget-s {args.leg_budget_s}")
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+    watchdog = threading.Timer(args.leg_budget_s, _give_up)
+    watchdog.daemon = True
+    watchdog.start()
     if "big" in legs and world == 1:
         try:
             extra.update(run_big_legs(env, args, peaks, sampler))
@@ -1324,6 +1339,7 @@ def run_ours(args):
         except Exception as exc:
             extra["weak"] = {"error": repr(exc)[:400]}
             torch.cuda.empty_cache()
+    watchdog.cancel()
     if sampler:
         sampler.stop()
     if rank == 0:

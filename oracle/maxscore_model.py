@@ -2,7 +2,7 @@
 TEST INFRASTRUCTURE ONLY.
 
 It restates, step by step, the decisions the CUDA path takes for ONE query -- sample selection,
-theta from per-thread bests, the required set, the quick and progressive bound tests, the
+theta from the sample, the required set, the quick and progressive bound tests, the
 ownership rule (shortest required list first) that keeps a document from being listed twice, the conditions that flag a query
 for the exhaustive scan -- with fp32 arithmetic, so that ``tests/test_oracle.py`` can prove on the
 CPU that the pruning is SAFE: whenever the model does not flag a query, its survivors contain the
@@ -118,16 +118,17 @@ def topk(ix, post_w: np.ndarray, term_ids: Sequence[int], k: int,
                 return None
         return exact(j_self, c_self, doc)
 
-    # ---- stage 1 + theta (k-th largest of the 256 per-thread bests)
+    # ---- stage 1 + theta (k-th best full score of the sample)
     s2 = np.zeros(n, np.int64)
     keys: List[Tuple[float, int]] = []
     for j in range(n):
         for p in range(int(s1[j])):
             s = full_score(j, p, 1, f32(0))
             keys.append((float(s), -int(ix.post_doc[lo[j] + p])) if s is not None and s > 0 else (0.0, 0))
-    best = [max(keys[t::THREADS], default=(0.0, 0)) for t in range(THREADS)]
-    best.sort(reverse=True)
-    theta = f32(best[k - 1][0]) if k <= THREADS and best[k - 1][0] > 0 else f32(0)
+    # (the kernel: k-th largest of the 256 per-thread bests as a first bound, then the exact k-th
+    #  best among the keys at or above it -- the k-th best of the sample)
+    ranked = sorted(keys, reverse=True)
+    theta = f32(ranked[k - 1][0]) if len(ranked) >= k and ranked[k - 1][0] > 0 else f32(0)
     # ---- required set: set aside, longest list first, while the bounds stay below theta
     cum = f32(0)
     aside = set()
