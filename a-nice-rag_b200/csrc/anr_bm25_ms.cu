@@ -488,7 +488,7 @@ ms_theta_kernel(int k, int nq, MsQuery* __restrict__ queries, MsTerm* __restrict
 // ---- 4. stage 2: every posting of the required lists --------------------------------------------
 // One candidate per LANE, and a lane that is done with its candidate takes the next posting at
 // once: every trip of the loop is one lookup per lane, whatever stage each lane's candidate is in
-// (bounds / ownership / exact sum).  With lock-step rounds of 32 candidates a warp waited for its
+// (bounds / ownership).  With lock-step rounds of 32 candidates a warp waited for its
 // longest-lived candidate in every round (ncu: 33 % of the warp slots active, 115 us).
 template <int VARIANT>
 __global__ void __launch_bounds__(kMsThreads, 5)
@@ -509,7 +509,8 @@ ms_stage2_kernel(Bm25View ix, Bm25HeadView hd, const uint32_t* __restrict__ doc_
   int64_t seg_lo = 0, seg_hi = 0, self_lo = 0;             // items of its list j: [seg_lo, seg_hi)
   float self_idf = 0.f, self_rem = 0.f;
   const MsTerm* T = terms;
-  float c_self = 0.f, partial = 0.f, remaining = 0.f, theta = 0.f, slack = 0.f, tot = 0.f, full = 0.f;
+  float c_self = 0.f, partial = 0.f, remaining = 0.f, theta = 0.f, slack = 0.f, tot = 0.f;
+  float wv[kMsMaxTerms];   // weights of my candidate's terms as they are looked up (local memory)
 
   auto before = [&](const MsTerm& t, int jj) {   // required list ordered before mine: it owns shared documents
     return t.s2 > 0 && (t.s2 < self_s2 || (t.s2 == self_s2 && jj < j));
@@ -594,18 +595,19 @@ ms_stage2_kernel(Bm25View ix, Bm25HeadView hd, const uint32_t* __restrict__ doc_
       }
       if (phase == 1) {   // does a required list ordered before mine hold the document?
         while (idx < n && !(idx != j && before(T[idx], idx))) ++idx;
-        if (idx < n) look = idx; else { phase = 2; idx = 0; full = 0.f; }
-      }
-      if (phase == 2 && look < 0) {   // the reference's sum: query order, duplicates repeat, fp32 fma
-        while (idx < n) {
-          const MsTerm& t = T[idx];
-          if (t.len != 0) {
-            if (idx != j) { look = idx; break; }
-            full = fmaf(t.idf, c_self, full);
+        if (idx < n) {
+          look = idx;
+        } else {
+          // every term is resolved (the weights of the terms that can add were kept as they were
+          // looked up; a list ordered before mine does not hold the document): the reference's
+          // sum -- query order, duplicates repeat, fp32 fma -- and a survivor if it reaches theta
+          float full = 0.f;
+          for (int jj = 0; jj < n; ++jj) {
+            const MsTerm& t = T[jj];
+            if (t.len == 0) continue;
+            const float w = jj == j ? c_self : (before(t, jj) ? 0.f : wv[jj]);
+            if (w > 0.f) full = fmaf(t.idf, w, full);
           }
-          ++idx;
-        }
-        if (look < 0) {   // every term is in: a survivor if it reaches theta
           if (full >= theta && full > 0.f) {
             const int s = atomicAdd(&queries[q].n_surv, 1);
             if (s < cap) surv[static_cast<size_t>(q) * cap + s] = make_key(full, static_cast<uint32_t>(doc));
@@ -623,13 +625,12 @@ ms_stage2_kernel(Bm25View ix, Bm25HeadView hd, const uint32_t* __restrict__ doc_
       if (phase != 1) w = ms_weight(ix, hd, t, doc);
       else found = ms_find(ix.post_doc + t.lo, t.len, t.bkt, t.shift, doc) >= 0;
       if (phase == 0) {
+        wv[look] = w;
         remaining -= t.ub;
         if (w > 0.f) partial = fmaf(t.idf, w, partial);
         if (partial + fmaxf(remaining, 0.f) + slack < theta) have = false;
-      } else if (phase == 1) {
-        if (found) have = false;   // that list owns the document
       } else {
-        if (w > 0.f) full = fmaf(t.idf, w, full);
+        if (found) have = false;   // that list owns the document
       }
       ++idx;
     }
