@@ -1674,13 +1674,14 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
   ob.scores = list_scores + stride;
   ob.counts = lens + 1;
   ob.id_map = doc_to_id;
-  // BM25 always runs on the side stream next to the dense pass.  The CUDA-core scan leaves ~90 KB
-  // of shared memory per SM free, so BM25 CTAs co-reside with it; the 64-query GEMM pass of a
-  // hybrid step runs with a 4-stage ring for the same reason (gemm_ring_cap, anr_dense_gemm.cu):
-  // three BM25 CTAs share every SM with the dense CTA.  The wider tensor-core passes fill the SM;
-  // there the gain is that the latency-bound ends of one pipeline (BM25's sample launch, the dense
-  // pass' threshold / rescoring / fallback kernels) run under the other's main kernel.
-  // ANR_HYBRID_OVERLAP=0 serialises the two pipelines.
+  // BM25 always runs on the side stream next to the dense pass (ANR_HYBRID_OVERLAP=0 serialises the
+  // two).  Default (k_bm25 <= 128): the candidate-driven path -- a chain of short kernels, all of it
+  // issued up front -- runs beside the whole dense chain; its kernels ask for the dense kernels' L1
+  // split and the GEMM ring leaves them shared memory (kBesideBm25Smem), so the CTAs of both chains
+  // truly share the SMs.  With the tiled scan (ANR_BM25_MAXSCORE=0, k_bm25 > 128, negative idf) the
+  // older two-phase schedule below applies: sample launch | dense pre-pass | dense main kernel |
+  // BM25 main launch, with the GEMM ring capped so that BM25 CTAs of 34 KB fit beside the dense CTA
+  // (gemm_ring_cap, anr_dense_gemm.cu).
   static const int overlap_env = getenv("ANR_HYBRID_OVERLAP") ? atoi(getenv("ANR_HYBRID_OVERLAP")) : -1;
   const bool overlap = overlap_env != 0;
   cudaStream_t bm25_stream = overlap ? ctx->side : stream;
@@ -1692,14 +1693,11 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
     ANR_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
   }
   if (overlap) {
-    // side: BM25 sample launch | main: dense pre-pass kernels, then the dense main kernel | side:
-    // the BM25 main launch, held back until the dense main kernel is next in line, so that the
-    // persistent, bandwidth-bound dense kernel takes its SMs first (a BM25 main launch that got
-    // there first stretched the dense kernel from 0.31 to 0.52 ms) | join
-    // Gated schedule (hybrid_gated): the BM25 scan is ONE launch (sample tiles first), held on the
-    // side stream until every CTA of the dense main kernel is resident (DenseGate).  A separate
-    // BM25 sample launch at the start of the step would sit in the SMs' shared memory while the
-    // dense sample pass wants it (the dense main kernel then started at 62 instead of 40 us).
+    // Tiled scan only: side: BM25 sample launch | main: dense pre-pass kernels, then the dense main
+    // kernel | side: the BM25 main launch, held back until the dense main kernel is next in line,
+    // so that the persistent, bandwidth-bound dense kernel takes its SMs first (a BM25 main launch
+    // that got there first stretched the dense kernel from 0.31 to 0.52 ms) | join.  Gated variant
+    // (hybrid_gated, opt-in): ONE BM25 launch held until every dense CTA is resident (DenseGate).
     const bool gated = hybrid_gated(ctx, dense, nq, k_dense);
     DenseGate gate;
     Bm25Run run;
@@ -1707,9 +1705,8 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
                                bm25_stream, !gated, 1, &run))
       return rc;
     tl_mark(ctx, 3, stream);
-    // The candidate-driven BM25 path is done after phase 1 (short kernels with a few KB of shared
-    // memory each: they fit beside the dense CTA whatever its ring depth, so the dense pass keeps
-    // its full ring and nothing is held back); the tiled scan continues in phase 2.
+    // The candidate-driven BM25 path has issued its whole chain in phase 1: nothing is held back,
+    // and the dense pass leaves its kernels shared memory; the tiled scan continues in phase 2.
     const bool ms = run.ms_done;
     if (ms) dense_gemm_set_leave_smem(kBesideBm25Smem);
     const int rc_dense = dense_pipeline(ctx, dense, q_dev, nq, k_dense, row_mask_dev, arena, od, stream,
@@ -1759,8 +1756,8 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
 
 // Both local searches of ONE shard in one call, as sortable keys with global ids (what the
 // sharded merge consumes): out_keys is [2, n_queries, k], plane 0 = dense, plane 1 = BM25.  Same
-// two-stream schedule as anr_hybrid_search (BM25 sample launch | dense pre-pass | dense main kernel
-// | BM25 main launch | join); device pointers only.
+// two-stream schedule as anr_hybrid_search (the BM25 chain beside the dense chain); device pointers
+// only.
 int anr_hybrid_search_keys(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25,
                            const float* queries, const int32_t* q_terms, const int32_t* q_offsets,
                            int32_t nq, int32_t k, const uint32_t* row_mask, const uint32_t* doc_mask,

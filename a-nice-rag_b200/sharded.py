@@ -104,8 +104,8 @@ class ShardedHybrid:
         stream = engine.torch_stream_ptr()
         buf = self._buffers(b, k, top_n)
         local, gathered = buf["local"], buf["gathered"]
-        # both local searches in one library call: BM25 on the context's side stream around the
-        # dense pass (sample launch | dense pre-pass | dense main kernel | BM25 main launch | join)
+        # both local searches in one library call: the BM25 chain on the context's side stream beside
+        # the dense chain, joined before the call's last kernel
         native.call("anr_hybrid_search_keys", ctx.handle, self.dense.handle, self.bm25.handle,
                     queries_dev.data_ptr(), terms_dev.data_ptr(), offsets_dev.data_ptr(), b, k, None,
                     None, self.row_base, self.doc_base, local.data_ptr(), stream)
