@@ -434,8 +434,8 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
       std::lock_guard<std::mutex> lock(ix->lazy);
       if (!ix->shadow) {
         void* sh = nullptr;
-        ANR_CUDA(cudaMalloc(&sh, static_cast<size_t>(ix->n) * ix->ld * 2));
-        cudaError_t e = launch_f32_to_bf16(ix->emb, sh, ix->n * ix->ld, stream);
+        ANR_CUDA(cudaMalloc(&sh, dense_shadow_bytes(ix->n, ix->ld)));
+        cudaError_t e = launch_dense_shadow_fill(ix->emb, sh, ix->n, ix->ld, stream);
         // other streams may use the copy as soon as the pointer is published
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) {
@@ -448,7 +448,11 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
     unsigned char* scratch =
         arena.take<unsigned char>(dense_gemm_scratch_bytes(ctx->dp, ix->n, ix->ld, nq, k));
     int32_t* flags = arena.take<int32_t>(static_cast<size_t>(nq));
+    int32_t* n_flagged = arena.take<int32_t>(1);
+    int32_t* flagged = arena.take<int32_t>(static_cast<size_t>(nq));
     const int per = dense_gemm_max_queries();
+    // one launch group: its rescoring kernel lists the flagged queries itself (no compaction launch)
+    const bool fold_flags = nq <= per;
     for (int q0 = 0; q0 < nq; q0 += per) {
       TopkOut o = out;
       if (o.keys) o.keys += q0 * out.stride_q;
@@ -472,15 +476,14 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
                                  q_dev + static_cast<size_t>(q0) * ix->ld, std::min(per, nq - q0), k,
                                  mask_dev, ix->norm_max, scratch, o, flags + q0,
                                  ev ? ev->start : nullptr, ev ? ev->stop : nullptr, stream,
-                                 q0 == 0 ? ev_pre_main : nullptr, q0 == 0 ? gate : nullptr));
+                                 q0 == 0 ? ev_pre_main : nullptr, q0 == 0 ? gate : nullptr,
+                                 fold_flags ? n_flagged : nullptr, fold_flags ? flagged : nullptr));
     }
     tl_mark(ctx, 6, stream);
     const int fb_grid = dense_scan_flagged_grid(ctx->dp, ix->n, ix->ld, k);
     const int64_t fb_stride = static_cast<int64_t>(fb_grid) * k;
-    int32_t* n_flagged = arena.take<int32_t>(1);
-    int32_t* flagged = arena.take<int32_t>(static_cast<size_t>(nq));
     uint64_t* fb_cand = arena.take<uint64_t>(static_cast<size_t>(nq) * fb_stride);
-    ANR_CUDA(launch_compact_flags(flags, nq, n_flagged, flagged, stream));
+    if (!fold_flags) ANR_CUDA(launch_compact_flags(flags, nq, n_flagged, flagged, stream));
     ctx->last_dense_flagged = n_flagged;
     ANR_CUDA(launch_dense_scan_flagged(ctx->dp, ix->emb, ix->n, ix->ld, q_dev, n_flagged, flagged, k,
                                        mask_dev, fb_cand, fb_stride, stream));
@@ -872,6 +875,12 @@ int bm25_pipeline(anr_ctx* ctx, const anr_bm25* ix, const int32_t* terms_dev,
 // Stage the query matrix: returns a device [pad_queries(nq), ld] zero-padded copy.
 int stage_queries(const anr_dense* ix, const float* queries, int nq, int nqp, Arena& arena,
                   cudaStream_t stream, const float** q_dev) {
+  // device-resident queries that need no padding are read in place
+  if (nqp == nq && ix->ld == ix->d && reinterpret_cast<uintptr_t>(queries) % 16 == 0 &&
+      is_device_ptr(queries)) {
+    *q_dev = queries;
+    return ANR_OK;
+  }
   float* q = arena.take<float>(static_cast<size_t>(nqp) * ix->ld);
   if (nqp != nq || ix->ld != ix->d)
     ANR_CUDA(cudaMemsetAsync(q, 0, static_cast<size_t>(nqp) * ix->ld * 4, stream));
@@ -1659,8 +1668,11 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
   if (int rc = stage_mask(row_mask, dense->n, arena, stream, &row_mask_dev)) return rc;
   if (int rc = stage_terms(q_terms, q_offsets, nq, arena, stream, &qt)) return rc;
   if (int rc = stage_mask(doc_mask, bm25->n_docs, arena, stream, &doc_mask_dev)) return rc;
-  set_f64_pair_kernel<<<1, 1, 0, stream>>>(w_dev, w_dense, w_bm25);
-  ANR_CUDA(cudaGetLastError());
+  const bool fuse_pair = wrrf_fuse_pair_fits(stride);   // weights travel as kernel arguments
+  if (!fuse_pair) {
+    set_f64_pair_kernel<<<1, 1, 0, stream>>>(w_dev, w_dense, w_bm25);
+    ANR_CUDA(cudaGetLastError());
+  }
 
   TopkOut od;
   od.ids = lists;
@@ -1728,8 +1740,12 @@ int anr_hybrid_search(anr_ctx* ctx, const anr_dense* dense, const anr_bm25* bm25
       return rc;
   }
   if (overlap) ANR_CUDA(cudaStreamWaitEvent(stream, ctx->ev_join, 0));
-  ANR_CUDA(launch_wrrf_fuse(lists, lens, w_dev, 2, stride, nq, rrf_k, top_n, nullptr, o_ids.dev,
-                            o_scores.dev, o_counts.dev, stream));
+  if (fuse_pair)
+    ANR_CUDA(launch_wrrf_fuse_pair(lists, lens, w_dense, w_bm25, stride, nq, rrf_k, top_n, o_ids.dev,
+                                   o_scores.dev, o_counts.dev, stream));
+  else
+    ANR_CUDA(launch_wrrf_fuse(lists, lens, w_dev, 2, stride, nq, rrf_k, top_n, nullptr, o_ids.dev,
+                              o_scores.dev, o_counts.dev, stream));
   tl_mark(ctx, 11, stream);
 
   // optional per-retriever outputs: strided device -> user layout [nq, k]

@@ -166,6 +166,8 @@ ms_plan_kernel(Bm25View ix, Bm25HeadView hd, MsIndexView mx, const int32_t* __re
                const int32_t* __restrict__ q_offsets, int nq, int sample,
                MsQuery* __restrict__ queries, MsTerm* __restrict__ terms,
                int32_t* __restrict__ ticket) {
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * (kMsThreads / 32) + warp;
   if (blockIdx.x == 0 && threadIdx.x == 0) { ticket[0] = 0; ticket[1] = 0; }
@@ -329,6 +331,8 @@ __global__ void __launch_bounds__(kMsThreads)
 ms_stage1_kernel(Bm25View ix, Bm25HeadView hd, const uint32_t* __restrict__ doc_mask,
                  const MsQuery* __restrict__ queries, const MsTerm* __restrict__ terms,
                  uint64_t* __restrict__ s1keys) {
+  pdl_wait();
+  pdl_trigger();
   const int q = blockIdx.y;
   const int i0 = blockIdx.x * kMsThreads + threadIdx.x;
   const int n1 = queries[q].s1_total;
@@ -371,6 +375,8 @@ ms_theta_kernel(int k, int nq, MsQuery* __restrict__ queries, MsTerm* __restrict
   __shared__ int64_t part[kMsThreads];
   __shared__ int n_sel;
   __shared__ bool last;
+  pdl_wait();
+  pdl_trigger();
   const int q = blockIdx.x, lane = threadIdx.x & 31;
   MsQuery* Q = queries + q;
   const int n1 = Q->s1_total, n = Q->n;
@@ -495,6 +501,7 @@ __global__ void __launch_bounds__(kMsThreads, 5)
 ms_stage2_kernel(Bm25View ix, Bm25HeadView hd, const uint32_t* __restrict__ doc_mask, int nq, int cap,
                  MsQuery* __restrict__ queries, const MsTerm* __restrict__ terms,
                  const int64_t* __restrict__ q_base, uint64_t* __restrict__ surv) {
+  pdl_wait();   // (no early trigger: the ranking kernel need not park beside this long one)
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int64_t total = q_base[nq];
@@ -687,6 +694,8 @@ ms_final_kernel(const MsQuery* __restrict__ queries, const uint64_t* __restrict_
   __shared__ uint64_t s_kth;
   __shared__ int n_sel;
   __shared__ bool last;
+  pdl_wait();
+  pdl_trigger();
   const int q = blockIdx.x;
   const int ns = min(queries[q].n_surv, cap);
   const uint64_t* sv = surv + static_cast<size_t>(q) * cap;
@@ -741,19 +750,20 @@ static void ms_launch_chain(const DeviceProps& dp, const Bm25View& ix, const Bm2
                             cudaStream_t stream, const cudaEvent_t* marks) {
   auto mark = [&](int i) { if (marks && marks[i]) cudaEventRecord(marks[i], stream); };
   const int wpb = kMsThreads / 32;
-  ms_plan_kernel<EARLY><<<(nq + wpb - 1) / wpb, kMsThreads, 0, stream>>>(
-      ix, hd, mx, q_terms, q_offsets, nq, sample, queries, terms, ticket);
+  launch_chain(ms_plan_kernel<EARLY>, dim3((nq + wpb - 1) / wpb), dim3(kMsThreads), 0, stream, ix, hd,
+               mx, q_terms, q_offsets, nq, sample, queries, terms, ticket);
   mark(0);
-  ms_stage1_kernel<EARLY><<<dim3(sample / kMsThreads, nq), kMsThreads, 0, stream>>>(
-      ix, hd, doc_mask, queries, terms, s1keys);
+  launch_chain(ms_stage1_kernel<EARLY>, dim3(sample / kMsThreads, nq), dim3(kMsThreads), 0, stream, ix,
+               hd, doc_mask, queries, terms, s1keys);
   mark(1);
-  ms_theta_kernel<EARLY><<<nq, kMsThreads, 0, stream>>>(k, nq, queries, terms, s1keys, q_base, ticket);
+  launch_chain(ms_theta_kernel<EARLY>, dim3(nq), dim3(kMsThreads), 0, stream, k, nq, queries, terms,
+               s1keys, q_base, ticket);
   mark(2);
-  ms_stage2_kernel<VARIANT><<<dp.sm_count * 5, kMsThreads, 0, stream>>>(
-      ix, hd, doc_mask, nq, kMsSurvivors, queries, terms, q_base, surv);
+  launch_chain(ms_stage2_kernel<VARIANT>, dim3(dp.sm_count * 5), dim3(kMsThreads), 0, stream, ix, hd,
+               doc_mask, nq, static_cast<int>(kMsSurvivors), queries, terms, q_base, surv);
   mark(3);
-  ms_final_kernel<VARIANT><<<nq, kMsThreads, 0, stream>>>(queries, surv, kMsSurvivors, k, nq, out,
-                                                          ticket + 1, n_flagged, flagged);
+  launch_chain(ms_final_kernel<VARIANT>, dim3(nq), dim3(kMsThreads), 0, stream, queries, surv,
+               static_cast<int>(kMsSurvivors), k, nq, out, ticket + 1, n_flagged, flagged);
 }
 
 cudaError_t launch_bm25_maxscore(const DeviceProps& dp, const Bm25View& ix, const Bm25HeadView& hd,

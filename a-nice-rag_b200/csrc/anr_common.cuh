@@ -95,6 +95,21 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
+// ---- programmatic dependent launch (chains of short kernels on one stream) ----
+// A step is ~10 dependent kernels per chain, most of them a few microseconds long: what separates
+// them (drain, flush, launch, CTA scheduling) costs as much as they do.  Kernels launched through
+// launch_chain() may become resident while their predecessor still runs; pdl_wait() -- the FIRST
+// statement of every such kernel -- then blocks until the predecessor grid has completed and its
+// writes are visible, so the stream order of all memory effects is unchanged.  pdl_trigger()
+// lets the successor be scheduled (it fires once every CTA of the grid has called it or exited);
+// placed after pdl_wait(), at most one successor waits on the SMs at a time.  Long kernels call
+// it at their end, so that nothing parks beside them.  Without the launch attribute both are
+// no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ float4 lds128(const float* p) {
   return *reinterpret_cast<const float4*>(p);
 }

@@ -197,6 +197,8 @@ dense_scan_flagged_kernel(const float* __restrict__ emb, int64_t n, int ld,
                           const uint32_t* __restrict__ mask, uint64_t* __restrict__ cand,
                           int64_t cand_stride, ScanLayout L) {
   extern __shared__ __align__(128) unsigned char smem[];
+  pdl_wait();
+  pdl_trigger();
   const int nf = *n_flagged;
   for (int f = 0; f < nf; ++f) {
     dense_scan_body<1, RW, false>(emb, n, ld, q_all + static_cast<size_t>(flagged[f]) * ld, k, mask,
@@ -338,9 +340,8 @@ static cudaError_t launch_flagged_t(const DeviceProps& dp, const float* emb, int
   const int64_t n_tiles = (n + RW - 1) / RW;
   int grid = static_cast<int>(n_tiles < dp.sm_count ? n_tiles : dp.sm_count);
   if (grid < 1) grid = 1;
-  kern<<<grid, kScanThreads, L.total_bytes, stream>>>(emb, n, ld, q_all, n_flagged, flagged, k, mask,
-                                                      cand, cand_stride, L);
-  return cudaGetLastError();
+  return launch_chain(kern, dim3(grid), dim3(kScanThreads), static_cast<size_t>(L.total_bytes), stream,
+                      emb, n, ld, q_all, n_flagged, flagged, k, mask, cand, cand_stride, L);
 }
 
 // grid the flagged rescan uses = candidates per flagged query / k

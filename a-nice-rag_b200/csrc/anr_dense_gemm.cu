@@ -40,6 +40,7 @@ constexpr int kGmThrThreads = 512;
 struct GemmLayout {
   int thr_off, stage_off, bar_off, total_bytes;
   int n_stages, n_slabs, stage_bytes;
+  int a_tiled;   // the corpus operand is the TILED bf16 shadow copy (see f32_to_bf16_tiled_kernel)
 };
 
 template <int NQ, bool BF16>
@@ -164,6 +165,8 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                   int32_t* __restrict__ gate) {
   using Cfg = GemmCfg<NQ, BF16>;
   extern __shared__ __align__(1024) unsigned char smem[];
+  pdl_wait();
+  if (SAMPLE) pdl_trigger();   // (the long main pass triggers at its end: nothing parks beside it)
   if (gate && threadIdx.x == 0) atomicAdd(gate, 1);   // this CTA holds its shared memory now
   unsigned char* ring = smem;                                   // n_stages x [A slab | B slab]
   float* thr_s = reinterpret_cast<float*>(smem + L.thr_off);    // [n_qblocks * NQ]
@@ -219,13 +222,17 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       int s = 0;
       uint32_t ph = 0;
       for (int64_t it = 0; it < my_row_tiles; ++it) {
-        const int row0 = static_cast<int>(tile_of(it) * tile_stride * kGmRows);
+        const int64_t tile_a = tile_of(it) * tile_stride;
+        const int row0 = static_cast<int>(tile_a * kGmRows);
+        // tiled shadow: slab kb of row tile t is the 16 KB block (t * n_slabs + kb)
+        const int blk0 = static_cast<int>(tile_a * L.n_slabs * kGmRows);
         for (int qb = 0; qb < n_qblocks; ++qb) {
           for (int kb = 0; kb < L.n_slabs; ++kb) {
             mbar_wait(&empty[s], ph ^ 1u);
             unsigned char* st = ring + static_cast<size_t>(s) * Cfg::kStageBytes;
             mbar_arrive_expect_tx(&full[s], Cfg::kStageBytes);
-            tma_load_2d(st, &map_a, kb * Cfg::kSlabElems, row0, &full[s]);
+            if (L.a_tiled) tma_load_2d(st, &map_a, 0, blk0 + kb * kGmRows, &full[s]);
+            else tma_load_2d(st, &map_a, kb * Cfg::kSlabElems, row0, &full[s]);
             if (PAIR)   // my half of the query slab, into both CTAs
               tma_load_2d_mcast(st + kGmABytes + rank * (Cfg::kBBytes / 2), &map_b,
                                 kb * Cfg::kSlabElems, qb * NQ + rank * (NQ / 2), &full[s], 0x3);
@@ -332,6 +339,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (!SAMPLE) pdl_trigger();
   if (PAIR) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
@@ -366,6 +374,8 @@ dense_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   constexpr uint32_t kIdesc2 = (1u << 4) | (Cfg::kFmt << 7) | (Cfg::kFmt << 10) |
                                (static_cast<uint32_t>(NQ >> 3) << 17) | (16u << 24);
   extern __shared__ __align__(1024) unsigned char smem[];
+  pdl_wait();
+  if (SAMPLE) pdl_trigger();
   unsigned char* ring = smem;
   float* thr_s = reinterpret_cast<float*>(smem + L.thr_off);
   GemmStage* stages = reinterpret_cast<GemmStage*>(smem + L.stage_off);
@@ -415,14 +425,17 @@ dense_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       int s = 0;
       uint32_t ph = 0;
       for (int64_t it = 0; it < my_units; ++it) {
-        const int row0 = static_cast<int>(tile_of(it) * tile_stride * kGmRows);
+        const int64_t tile_a = tile_of(it) * tile_stride;
+        const int row0 = static_cast<int>(tile_a * kGmRows);
+        const int blk0 = static_cast<int>(tile_a * L.n_slabs * kGmRows);   // (tiled shadow)
         for (int qb = 0; qb < n_qblocks; ++qb) {
           for (int kb = 0; kb < L.n_slabs; ++kb) {
             mbar_wait(&empty[s], ph ^ 1u);
             unsigned char* st = ring + static_cast<size_t>(s) * kStage2;
             if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kStage2);
             const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), 0);
-            tma_load_2d_cg2(st, &map_a, kb * Cfg::kSlabElems, row0, lead_full);
+            if (L.a_tiled) tma_load_2d_cg2(st, &map_a, 0, blk0 + kb * kGmRows, lead_full);
+            else tma_load_2d_cg2(st, &map_a, kb * Cfg::kSlabElems, row0, lead_full);
             tma_load_2d_cg2(st + kGmABytes, &map_b, kb * Cfg::kSlabElems, qb * NQ + rank * (NQ / 2),
                             lead_full);
             if (++s == L.n_stages) { s = 0; ph ^= 1u; }
@@ -524,6 +537,7 @@ dense_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (!SAMPLE) pdl_trigger();
   cluster_sync_all();   // both CTAs are done with each other's shared memory, barriers and TMEM
   if (warp == 1) {
     tc_fence_after();
@@ -539,12 +553,16 @@ dense_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 __global__ void __launch_bounds__(kGmThrThreads)
 dense_gemm_thr_kernel(const float* __restrict__ gmax, int64_t gmax_stride, int m, int rank,
                       int n_real, float* __restrict__ thr, uint64_t* __restrict__ thr_key,
-                      int32_t* __restrict__ cnt, int32_t* __restrict__ gate) {
+                      int32_t* __restrict__ cnt, int32_t* __restrict__ gate,
+                      int32_t* __restrict__ ticket) {
   __shared__ uint64_t best[kGmThrThreads];
+  pdl_wait();
+  pdl_trigger();
   const int q = blockIdx.x;
   if (threadIdx.x == 0) {   // the main pass starts from empty candidate buffers and a closed gate
     cnt[q] = 0;
     if (q == 0 && gate) *gate = 0;
+    if (q == 0 && ticket) *ticket = 0;   // (the rescoring kernel's last-CTA ticket)
   }
   if (q >= n_real) {
     if (threadIdx.x == 0) {
@@ -567,6 +585,8 @@ dense_gemm_thr_kernel(const float* __restrict__ gmax, int64_t gmax_stride, int m
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                    int64_t n4) {
+  pdl_wait();
+  pdl_trigger();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(in) + i);
@@ -583,8 +603,63 @@ cudaError_t launch_f32_to_bf16(const float* in, void* out, int64_t count, cudaSt
   const int64_t n4 = count / 4;  // callers pass multiples of 4 (ld % 4 == 0)
   int64_t blocks = (n4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  f32_to_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
-      in, static_cast<__nv_bfloat16*>(out), n4);
+  return launch_chain(f32_to_bf16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream,
+                      in, static_cast<__nv_bfloat16*>(out), n4);
+}
+
+// The bf16 shadow copy of the corpus in TILED order: the 128-row x 64-column block (t, kb) --
+// what one ring stage of the GEMM pass holds -- is one contiguous 16 KB run at block index
+// t * n_slabs + kb, rows of 128 bytes.  A stage is then ONE sequential 16 KB read instead of 128
+// pieces of 128 bytes 2 KB apart (the row-major copy: 6.25-6.7 TB/s for the 64-query pass against
+// 7.4 TB/s for the fp32 scan's sequential 16 KB bulk copies).  Rows >= n of the last tile are zero.
+__global__ void f32_to_bf16_tiled_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                         int64_t n, int ld4, int n_slabs, int64_t total4) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / ld4;
+    const int col = static_cast<int>(i - row * ld4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n) v = __ldg(reinterpret_cast<const float4*>(in) + i);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 p;
+    p.x = *reinterpret_cast<uint32_t*>(&lo);
+    p.y = *reinterpret_cast<uint32_t*>(&hi);
+    const int64_t t = row / kGmRows;
+    const int r = static_cast<int>(row - t * kGmRows);
+    const int64_t blk = t * n_slabs + (col >> 6);
+    const int64_t dst = (blk * kGmRows + r) * 64 + (col & 63);   // in elements
+    reinterpret_cast<uint2*>(out)[dst >> 2] = p;
+  }
+}
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("ANR_PDL") && atoi(getenv("ANR_PDL")) == 0);
+  return on;
+}
+
+static bool shadow_tiled_env() {
+  static const bool on = !(getenv("ANR_SHADOW_TILED") && atoi(getenv("ANR_SHADOW_TILED")) == 0);
+  return on;
+}
+// Layout of the shadow copy of an [n, ld] corpus (ld % 64 == 0): tiled unless ANR_SHADOW_TILED=0 or
+// the block rows would overflow the TMA's 32-bit coordinates.
+bool dense_shadow_tiled(int64_t n, int ld) {
+  const int64_t n_tiles = (n + kGmRows - 1) / kGmRows;
+  return shadow_tiled_env() && ld % 64 == 0 && (n_tiles + 1) * (ld / 64) * kGmRows < (1ll << 31);
+}
+size_t dense_shadow_bytes(int64_t n, int ld) {
+  const int64_t rows = dense_shadow_tiled(n, ld) ? (n + kGmRows - 1) / kGmRows * kGmRows : n;
+  return static_cast<size_t>(rows) * ld * 2;
+}
+cudaError_t launch_dense_shadow_fill(const float* emb, void* shadow, int64_t n, int ld,
+                                     cudaStream_t stream) {
+  if (!dense_shadow_tiled(n, ld)) return launch_f32_to_bf16(emb, shadow, n * ld, stream);
+  const int64_t rows = (n + kGmRows - 1) / kGmRows * kGmRows;
+  const int64_t total4 = rows * (ld / 4);
+  int64_t blocks = (total4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f32_to_bf16_tiled_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      emb, static_cast<__nv_bfloat16*>(shadow), n, ld / 4, ld / 64, total4);
   return cudaGetLastError();
 }
 
@@ -735,6 +810,20 @@ static bool gemm_encode_map(CUtensorMap* map, const void* base, int64_t rows, in
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// the tiled shadow copy as a 2-D tensor of 128-byte rows: box = one 16 KB block
+static bool gemm_encode_map_tiled(CUtensorMap* map, const void* base, int64_t n, int ld) {
+  EncodeTiledFn fn = gemm_encode_fn();
+  if (!fn) return false;
+  const int64_t n_tiles = (n + kGmRows - 1) / kGmRows;
+  const cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(n_tiles * (ld / 64) * kGmRows)};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(kGmRows)};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NQ, bool BF16, bool SAMPLE, bool PAIR>
 static cudaError_t gemm_launch_one(int grid, int threads, int smem, cudaStream_t stream,
                                    const CUtensorMap& map_a, const CUtensorMap& map_b, int64_t n,
@@ -755,13 +844,15 @@ static cudaError_t gemm_launch_one(int grid, int threads, int smem, cudaStream_t
   cfg.blockDim = dim3(static_cast<unsigned>(threads));
   cfg.dynamicSmemBytes = static_cast<size_t>(smem);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, map_a, map_b, n, n_row_tiles, tile_stride, n_qblocks, mask,
                             thr, cand, cnt, cap, gmax, gstride, L, gate);
 }
@@ -784,13 +875,15 @@ static cudaError_t gemm2_launch_one(int grid, int threads, int smem, cudaStream_
   cfg.blockDim = dim3(static_cast<unsigned>(threads));
   cfg.dynamicSmemBytes = static_cast<size_t>(smem);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, map_a, map_b_half, n, n_row_tiles, tile_stride, n_qblocks,
                             mask, thr, cand, cnt, cap, gmax, gstride, L);
 }
@@ -830,9 +923,10 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
                                          sample_tiles, stride, n_qblocks, mask, nullptr, nullptr,
                                          nullptr, 0, gmax, gstride, L);
     if (e != cudaSuccess) return e;
-    dense_gemm_thr_kernel<<<nq_pad, kGmThrThreads, 0, stream>>>(
-        gmax, gstride, static_cast<int>(gstride), gemm_thr_rank_for(n, sample_tiles, k), n_real, thr,
-        thr_key, cnt, nullptr);
+    e = launch_chain(dense_gemm_thr_kernel, dim3(nq_pad), dim3(kGmThrThreads), 0, stream, gmax, gstride,
+                     static_cast<int>(gstride), gemm_thr_rank_for(n, sample_tiles, k), n_real, thr,
+                     thr_key, cnt, static_cast<int32_t*>(nullptr), gate_ctr + 8);
+    if (e != cudaSuccess) return e;
     if (ev_pre_main) cudaEventRecord(ev_pre_main, stream);   // the main kernel is next in line
     if (ev_start) cudaEventRecord(ev_start, stream);
     e = gemm2_launch_one<NQ, BF16, false>(dp.sm_count, threads, smem, stream, map_a, map_b_half, n,
@@ -852,9 +946,10 @@ static cudaError_t gemm_launch_pair(const DeviceProps& dp, const CUtensorMap& ma
   if (e != cudaSuccess) return e;
   const int grid = static_cast<int>(std::min<int64_t>(dp.sm_count, n_tiles));
   const bool gated = gate != nullptr && !pair;
-  dense_gemm_thr_kernel<<<nq_pad, kGmThrThreads, 0, stream>>>(
-      gmax, gstride, static_cast<int>(gstride), gemm_thr_rank_for(n, sample_tiles, k), n_real, thr,
-      thr_key, cnt, gated ? gate_ctr : nullptr);
+  e = launch_chain(dense_gemm_thr_kernel, dim3(nq_pad), dim3(kGmThrThreads), 0, stream, gmax, gstride,
+                   static_cast<int>(gstride), gemm_thr_rank_for(n, sample_tiles, k), n_real, thr,
+                   thr_key, cnt, gated ? gate_ctr : static_cast<int32_t*>(nullptr), gate_ctr + 8);
+  if (e != cudaSuccess) return e;
   if (gated) {
     gate->counter = gate_ctr;
     gate->expected = grid;
@@ -897,7 +992,8 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
                               int ld, const float* q_dev, int n_real, int k, const uint32_t* mask,
                               float emb_norm_max, unsigned char* scratch, const TopkOut& out,
                               int32_t* flags, cudaEvent_t ev_start, cudaEvent_t ev_stop,
-                              cudaStream_t stream, cudaEvent_t ev_pre_main, DenseGate* gate) {
+                              cudaStream_t stream, cudaEvent_t ev_pre_main, DenseGate* gate,
+                              int32_t* n_flagged, int32_t* flagged) {
   const bool bf16 = shadow != nullptr;
   const int nqb_size = dense_gemm_block(n_real);
   const int nq_pad = dense_gemm_padded_queries(n_real);
@@ -909,6 +1005,7 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
   if (!make_gemm_layout(dp, ld, bf16, mode == 2 ? nqb_size / 2 : nqb_size, nq_pad, &L, ring_cap,
                         gemm_epi_warps(nqb_size)))
     return cudaErrorInvalidConfiguration;
+  L.a_tiled = bf16 && dense_shadow_tiled(n, ld) ? 1 : 0;
   const int64_t sample_tiles = gemm_sample_tiles(dp, n, k);
 
   // carve the scratch
@@ -934,7 +1031,9 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
   cudaError_t e = cudaSuccess;   // (cnt is zeroed by the threshold kernel, right before the main pass)
 
   CUtensorMap map_a, map_b, map_b_half;
-  if (!gemm_encode_map(&map_a, bf16 ? shadow : static_cast<const void*>(emb), n, ld, kGmRows, bf16) ||
+  if (!(L.a_tiled ? gemm_encode_map_tiled(&map_a, shadow, n, ld)
+                  : gemm_encode_map(&map_a, bf16 ? shadow : static_cast<const void*>(emb), n, ld,
+                                    kGmRows, bf16)) ||
       !gemm_encode_map(&map_b, q_ops, nq_pad, ld, nqb_size, bf16) ||
       !gemm_encode_map(&map_b_half, q_ops, nq_pad, ld, nqb_size / 2, bf16))
     return cudaErrorInvalidValue;
@@ -958,8 +1057,11 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
   // operand by < 2^-10 relative; bf16 rounds to nearest, <= 2^-8 relative per operand; plus
   // fp32 accumulation noise
   const float eps_rel = bf16 ? 8.1e-3f : 2.5e-3f;
+  // n_flagged != nullptr: this launch group is the whole batch, and the rescoring kernel's last CTA
+  // lists the flagged queries itself (ticket zeroed by the threshold kernel)
   return launch_dense_tc_rescore_append(cand, cnt, kGmCap, emb, ld, q_dev, n_real, k,
-                                        emb_norm_max * eps_rel, thr_key, out, flags, stream);
+                                        emb_norm_max * eps_rel, thr_key, out, flags, stream,
+                                        n_flagged ? gate_ctr + 8 : nullptr, n_flagged, flagged);
 }
 
 }  // namespace anr

@@ -411,11 +411,15 @@ __global__ void __launch_bounds__(kTcRescoreThreads)
 dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
                         const float* __restrict__ emb, int ld, const float* __restrict__ q_dev,
                         int k, float eps_scale, const uint64_t* __restrict__ thr0, TopkOut o,
-                        int32_t* __restrict__ flags, const int32_t* __restrict__ cnt, int cap) {
+                        int32_t* __restrict__ flags, const int32_t* __restrict__ cnt, int cap,
+                        int32_t* __restrict__ ticket, int32_t* __restrict__ n_flagged,
+                        int32_t* __restrict__ flagged) {
   __shared__ uint64_t top[kTcRescoreThreads];    // per-thread best tf32 keys
   __shared__ uint64_t sel[kTcRescoreCap];        // candidates inside the margin, then exact keys
   __shared__ int n_sel, bad;
   __shared__ float q_norm2;
+  pdl_wait();
+  pdl_trigger();
   const int q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_warps = kTcRescoreThreads / 32;
@@ -550,6 +554,33 @@ dense_tc_rescore_kernel(const uint64_t* __restrict__ cand, int n_lists, int kl,
   if (threadIdx.x == 0) {
     if (o.counts) o.counts[q * o.count_stride] = n_out;
     flags[q] = bad;
+  }
+  // ticket != nullptr (one launch covers the whole batch, <= 1024 queries): the last CTA to finish
+  // lists the flagged queries in ascending order -- what compact_flags_kernel does in a launch of
+  // its own (~4 us of every step, for a list that is almost always empty)
+  if (ticket) {
+    __shared__ bool s_last;
+    __shared__ int s_off[kTcRescoreThreads / 32];
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(ticket, 1) == static_cast<int>(gridDim.x) - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+      const int t = threadIdx.x;
+      const bool f = t < static_cast<int>(gridDim.x) &&
+                     *reinterpret_cast<const volatile int32_t*>(flags + t) != 0;
+      const unsigned ballot = __ballot_sync(kFullMask, f);
+      if (lane == 0) s_off[warp] = __popc(ballot);
+      __syncthreads();
+      int off = 0, total = 0;
+      for (int w = 0; w < kTcRescoreThreads / 32; ++w) {
+        if (w < warp) off += s_off[w];
+        total += s_off[w];
+      }
+      if (f) flagged[off + __popc(ballot & ((1u << lane) - 1u))] = t;
+      if (t == 0) *n_flagged = total;
+    }
   }
 }
 
@@ -720,7 +751,7 @@ cudaError_t launch_dense_tc(const DeviceProps& dp, const float* emb, int64_t n, 
   if (e != cudaSuccess) return e;
   dense_tc_rescore_kernel<<<n_real, kTcRescoreThreads, 0, stream>>>(
       cand, grid * kTcEpiWarps, L.kl, emb, ld, q_dev, k, 2.5e-3f * emb_norm_max, thr0, out, flags,
-      nullptr, 0);
+      nullptr, 0, nullptr, nullptr, nullptr);
   return cudaGetLastError();
 }
 
@@ -769,7 +800,7 @@ cudaError_t launch_dense_tc_pair(const DeviceProps& dp, const float* emb, int64_
   if (e != cudaSuccess) return e;
   dense_tc_rescore_kernel<<<n_real, kTcRescoreThreads, 0, stream>>>(
       cand, n_clusters * kTcEpiWarps, L.kl, emb, ld, q_dev, k, 2.5e-3f * emb_norm_max, thr0, out,
-      flags, nullptr, 0);
+      flags, nullptr, 0, nullptr, nullptr, nullptr);
   return cudaGetLastError();
 }
 
@@ -777,10 +808,12 @@ cudaError_t launch_dense_tc_pair(const DeviceProps& dp, const float* emb, int64_
 cudaError_t launch_dense_tc_rescore_append(const uint64_t* cand, const int32_t* cnt, int cap,
                                            const float* emb, int ld, const float* q_dev, int n_real,
                                            int k, float eps_scale, const uint64_t* thr_key,
-                                           const TopkOut& out, int32_t* flags, cudaStream_t stream) {
-  dense_tc_rescore_kernel<<<n_real, kTcRescoreThreads, 0, stream>>>(
-      cand, 0, 0, emb, ld, q_dev, k, eps_scale, thr_key, out, flags, cnt, cap);
-  return cudaGetLastError();
+                                           const TopkOut& out, int32_t* flags, cudaStream_t stream,
+                                           int32_t* ticket, int32_t* n_flagged, int32_t* flagged) {
+  if (n_real > kTcRescoreThreads) ticket = nullptr;   // (the last CTA lists one flag per thread)
+  return launch_chain(dense_tc_rescore_kernel, dim3(n_real), dim3(kTcRescoreThreads), 0, stream, cand,
+                      0, 0, emb, ld, q_dev, k, eps_scale, thr_key, out, flags, cnt, cap, ticket,
+                      n_flagged, flagged);
 }
 
 bool dense_tc_pair_enabled() { return getenv("ANR_DISABLE_TC_PAIR") == nullptr; }

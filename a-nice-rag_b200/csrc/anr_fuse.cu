@@ -248,6 +248,34 @@ wrrf_fuse_small_kernel(const int32_t* __restrict__ ids, const int32_t* __restric
                   top_n, q, lane, out_ids, out_scores, out_counts);
 }
 
+// The hybrid step's two lists with the weights as kernel arguments: no device-side weight array to
+// fill first (that was a 1-thread launch at the head of every step, in front of BOTH chains).
+__global__ void __launch_bounds__(kWrrfSmallWarps * 32)
+wrrf_fuse_pair_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ lens,
+                      double w0, double w1, int list_stride, double rrf_k, int top_n, int nq,
+                      int32_t* __restrict__ out_ids, double* __restrict__ out_scores,
+                      int32_t* __restrict__ out_counts) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kWrrfSmallWarps + (threadIdx.x >> 5);
+  if (q >= nq) return;   // whole warp
+  const double weights[2] = {w0, w1};
+  wrrf_small_warp(ids + static_cast<int64_t>(q) * 2 * list_stride, lens + static_cast<int64_t>(q) * 2,
+                  weights, 2, list_stride, rrf_k, top_n, q, lane, out_ids, out_scores, out_counts);
+}
+
+bool wrrf_fuse_pair_fits(int list_stride) { return list_stride >= 1 && 2 * list_stride <= kWrrfSmallCap; }
+
+cudaError_t launch_wrrf_fuse_pair(const int32_t* ids, const int32_t* lens, double w0, double w1,
+                                  int list_stride, int nq, double rrf_k, int top_n, int32_t* out_ids,
+                                  double* out_scores, int32_t* out_counts, cudaStream_t stream) {
+  if (!wrrf_fuse_pair_fits(list_stride) || top_n < 1) return cudaErrorInvalidValue;
+  if (nq < 1) return cudaSuccess;
+  wrrf_fuse_pair_kernel<<<(nq + kWrrfSmallWarps - 1) / kWrrfSmallWarps, kWrrfSmallWarps * 32, 0,
+                          stream>>>(ids, lens, w0, w1, list_stride, rrf_k, top_n, nq, out_ids,
+                                    out_scores, out_counts);
+  return cudaGetLastError();
+}
+
 // ---- the consumer of a sharded step's all-gather, in ONE launch ---------------------------------
 // gathered: [n_parts][2][nq][k] sortable keys (per rank: dense plane, BM25 plane; ids global).  One
 // warp per query merges each retriever's n_parts lists to its global top-k (rank by counting:

@@ -5,6 +5,26 @@
 
 namespace anr {
 
+// Programmatic dependent launch for the kernel chains of a step (anr_common.cuh: pdl_wait /
+// pdl_trigger).  ANR_PDL=0 launches them fully serialised, as plain <<<>>> would.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+
 // Records the calling thread's anr_last_error() message and returns `code` (anr_api.cu); for the
 // translation units that implement ABI entry points of their own.
 int set_error(int code, const char* what, const char* detail = nullptr);
@@ -97,6 +117,10 @@ int dense_gemm_max_queries();              // queries one launch group takes
 int dense_gemm_padded_queries(int nq);     // rows q_dev must hold for a group of nq queries
 size_t dense_gemm_scratch_bytes(const DeviceProps& dp, int64_t n, int ld, int nq, int k);
 cudaError_t launch_f32_to_bf16(const float* in, void* out, int64_t count, cudaStream_t stream);
+// the corpus' bf16 shadow copy (tiled 16 KB blocks, anr_dense_gemm.cu): size and fill
+size_t dense_shadow_bytes(int64_t n, int ld);
+cudaError_t launch_dense_shadow_fill(const float* emb, void* shadow, int64_t n, int ld,
+                                     cudaStream_t stream);
 // "The main kernel is resident": every CTA of the persistent main GEMM kernel bumps *counter when
 // it starts; expected = its grid.  A hybrid step holds its BM25 launch behind that (a one-thread
 // kernel on the BM25 stream polls it, launch_gate_wait), so the dense CTAs own their shared
@@ -115,11 +139,14 @@ cudaError_t launch_dense_gemm(const DeviceProps& dp, const float* emb, const voi
                               float emb_norm_max, unsigned char* scratch, const TopkOut& out,
                               int32_t* flags, cudaEvent_t ev_start, cudaEvent_t ev_stop,
                               cudaStream_t stream, cudaEvent_t ev_pre_main = nullptr,
-                              DenseGate* gate = nullptr);
+                              DenseGate* gate = nullptr, int32_t* n_flagged = nullptr,
+                              int32_t* flagged = nullptr);
 cudaError_t launch_dense_tc_rescore_append(const uint64_t* cand, const int32_t* cnt, int cap,
                                            const float* emb, int ld, const float* q_dev, int n_real,
                                            int k, float eps_scale, const uint64_t* thr_key,
-                                           const TopkOut& out, int32_t* flags, cudaStream_t stream);
+                                           const TopkOut& out, int32_t* flags, cudaStream_t stream,
+                                           int32_t* ticket = nullptr, int32_t* n_flagged = nullptr,
+                                           int32_t* flagged = nullptr);
 
 // ---- top-k ------------------------------------------------------------------
 // Per query: select the best k (<= kMaxFusedK) of m candidate keys, sorted best first.
@@ -235,6 +262,11 @@ cudaError_t launch_bm25_maxscore(const DeviceProps& dp, const Bm25View& ix, cons
 
 // ---- fusion -------------------------------------------------------------------
 // scratch: wrrf_scratch_keys() 64-bit words (0 when the union fits in shared memory)
+// two lists (the hybrid step), weights by value; 2 * list_stride <= 64
+bool wrrf_fuse_pair_fits(int list_stride);
+cudaError_t launch_wrrf_fuse_pair(const int32_t* ids, const int32_t* lens, double w0, double w1,
+                                  int list_stride, int nq, double rrf_k, int top_n, int32_t* out_ids,
+                                  double* out_scores, int32_t* out_counts, cudaStream_t stream);
 cudaError_t launch_wrrf_fuse(const int32_t* ids, const int32_t* lens, const double* weights,
                              int n_lists, int list_stride, int nq, double rrf_k, int top_n,
                              uint64_t* scratch, int32_t* out_ids, double* out_scores,

@@ -19,6 +19,8 @@ topk_final_kernel(const uint64_t* __restrict__ cand, int64_t stride_q, int m, in
                   int64_t seg_stride, int k, TopkOut o, const int32_t* __restrict__ n_active,
                   const int32_t* __restrict__ row_map) {
   __shared__ uint64_t keys[kFinalSortCap];
+  pdl_wait();
+  pdl_trigger();
   if (n_active && static_cast<int>(blockIdx.x) >= *n_active) return;
   const uint64_t* c = cand + blockIdx.x * stride_q;
   const int q = row_map ? row_map[blockIdx.x] : blockIdx.x;
@@ -67,6 +69,8 @@ topk_final_small_kernel(const uint64_t* __restrict__ cand, int64_t stride_q, int
   __shared__ uint64_t best[kSmallThreads];
   __shared__ uint64_t sel[kSmallCap];
   __shared__ int n_sel;
+  pdl_wait();
+  pdl_trigger();
   if (n_active && static_cast<int>(blockIdx.x) >= *n_active) return;
   const uint64_t* c = cand + blockIdx.x * stride_q;
   const int q = row_map ? row_map[blockIdx.x] : blockIdx.x;
@@ -122,6 +126,8 @@ __global__ void __launch_bounds__(256)
 compact_flags_kernel(const int32_t* __restrict__ flags, int nq, int32_t* __restrict__ n_flagged,
                      int32_t* __restrict__ flagged) {
   __shared__ int count;
+  pdl_wait();
+  pdl_trigger();
   if (threadIdx.x == 0) count = 0;
   __syncthreads();
   for (int base = 0; base < nq; base += 256) {   // ordered: one chunk of 256 queries at a time
@@ -148,8 +154,8 @@ compact_flags_kernel(const int32_t* __restrict__ flags, int nq, int32_t* __restr
 
 cudaError_t launch_compact_flags(const int32_t* flags, int nq, int32_t* n_flagged, int32_t* flagged,
                                  cudaStream_t stream) {
-  compact_flags_kernel<<<1, 256, 0, stream>>>(flags, nq, n_flagged, flagged);
-  return cudaGetLastError();
+  return launch_chain(compact_flags_kernel, dim3(1), dim3(256), 0, stream, flags, nq, n_flagged,
+                      flagged);
 }
 
 // Merge of the flagged rescan: block b < *n_flagged ranks cand[b] into result row flagged[b].
@@ -168,12 +174,10 @@ cudaError_t launch_topk_final_flagged(const uint64_t* cand, int64_t cand_stride,
   }();
   (void)carveout_set;
   if (static_cast<int64_t>(k) * ((m + kSmallThreads - 1) / kSmallThreads) > kSmallCap)
-    topk_final_kernel<<<nq, kFinalThreads, 0, stream>>>(cand, cand_stride, m, m, 0, k, out,
-                                                        n_flagged, flagged);
-  else
-    topk_final_small_kernel<<<nq, kSmallThreads, 0, stream>>>(cand, cand_stride, m, m, 0, k, out,
-                                                              n_flagged, flagged);
-  return cudaGetLastError();
+    return launch_chain(topk_final_kernel, dim3(nq), dim3(kFinalThreads), 0, stream, cand, cand_stride,
+                        m, m, 0, k, out, n_flagged, flagged);
+  return launch_chain(topk_final_small_kernel, dim3(nq), dim3(kSmallThreads), 0, stream, cand,
+                      cand_stride, m, m, 0, k, out, n_flagged, flagged);
 }
 
 // ---- large-k path: global bitonic sort, descending --------------------------------
