@@ -1004,6 +1004,15 @@ int anr_ctx_create(int device, anr_ctx** out) {
   return ANR_OK;
 }
 
+int anr_set_option(const char* key, int32_t value) {
+  if (!key) return fail(ANR_ERR_INVALID, "anr_set_option: key is NULL");
+  if (strcmp(key, "pdl") == 0) {
+    pdl_set_mask(value);
+    return ANR_OK;
+  }
+  return fail(ANR_ERR_INVALID, "anr_set_option: unknown key");
+}
+
 int anr_ctx_profile_enable(anr_ctx* ctx, int32_t on) {
   if (!ctx) return fail(ANR_ERR_INVALID, "ctx is NULL");
   ctx->profiling = on != 0;

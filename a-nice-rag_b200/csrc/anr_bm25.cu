@@ -637,7 +637,7 @@ cudaError_t launch_bm25_score_listed(const Bm25View& ix, const int32_t* q_terms,
   if (e != cudaSuccess) return e;
   // few block rows: the list is usually empty and every CTA returns at once (16 rows of 82 tiles
   // took ~5 us to schedule and exit at the end of the BM25 chain of every step)
-  return launch_chain(kern, dim3(plan.n_tiles, nq < 4 ? nq : 4), dim3(kBm25Threads),
+  return launch_chain_on(kPdlBm25, kern, dim3(plan.n_tiles, nq < 4 ? nq : 4), dim3(kBm25Threads),
                       static_cast<size_t>(plan.smem_bytes), stream, ix, Bm25HeadView(), q_terms,
                       q_offsets, k, doc_mask, plan.tile_docs, plan.list_cap, cand, cand_stride_q,
                       static_cast<float*>(nullptr), 1, -1, q_list, n_list);

@@ -375,8 +375,10 @@ ms_theta_kernel(int k, int nq, MsQuery* __restrict__ queries, MsTerm* __restrict
   __shared__ int64_t part[kMsThreads];
   __shared__ int n_sel;
   __shared__ bool last;
+  // no early trigger: stage 2 is next, and its 5 CTAs per SM hold every register of an SM -- made
+  // resident while this kernel runs they took SMs ahead of the dense main kernel of the step, whose
+  // CTAs then waited for them (the dense kernel's span in a step: 0.32 -> 0.35 ms)
   pdl_wait();
-  pdl_trigger();
   const int q = blockIdx.x, lane = threadIdx.x & 31;
   MsQuery* Q = queries + q;
   const int n1 = Q->s1_total, n = Q->n;
@@ -750,19 +752,19 @@ static void ms_launch_chain(const DeviceProps& dp, const Bm25View& ix, const Bm2
                             cudaStream_t stream, const cudaEvent_t* marks) {
   auto mark = [&](int i) { if (marks && marks[i]) cudaEventRecord(marks[i], stream); };
   const int wpb = kMsThreads / 32;
-  launch_chain(ms_plan_kernel<EARLY>, dim3((nq + wpb - 1) / wpb), dim3(kMsThreads), 0, stream, ix, hd,
+  launch_chain_on(kPdlBm25, ms_plan_kernel<EARLY>, dim3((nq + wpb - 1) / wpb), dim3(kMsThreads), 0, stream, ix, hd,
                mx, q_terms, q_offsets, nq, sample, queries, terms, ticket);
   mark(0);
-  launch_chain(ms_stage1_kernel<EARLY>, dim3(sample / kMsThreads, nq), dim3(kMsThreads), 0, stream, ix,
+  launch_chain_on(kPdlBm25, ms_stage1_kernel<EARLY>, dim3(sample / kMsThreads, nq), dim3(kMsThreads), 0, stream, ix,
                hd, doc_mask, queries, terms, s1keys);
   mark(1);
-  launch_chain(ms_theta_kernel<EARLY>, dim3(nq), dim3(kMsThreads), 0, stream, k, nq, queries, terms,
+  launch_chain_on(kPdlBm25, ms_theta_kernel<EARLY>, dim3(nq), dim3(kMsThreads), 0, stream, k, nq, queries, terms,
                s1keys, q_base, ticket);
   mark(2);
-  launch_chain(ms_stage2_kernel<VARIANT>, dim3(dp.sm_count * 5), dim3(kMsThreads), 0, stream, ix, hd,
+  launch_chain_on(kPdlBm25, ms_stage2_kernel<VARIANT>, dim3(dp.sm_count * 5), dim3(kMsThreads), 0, stream, ix, hd,
                doc_mask, nq, static_cast<int>(kMsSurvivors), queries, terms, q_base, surv);
   mark(3);
-  launch_chain(ms_final_kernel<VARIANT>, dim3(nq), dim3(kMsThreads), 0, stream, queries, surv,
+  launch_chain_on(kPdlBm25, ms_final_kernel<VARIANT>, dim3(nq), dim3(kMsThreads), 0, stream, queries, surv,
                static_cast<int>(kMsSurvivors), k, nq, out, ticket + 1, n_flagged, flagged);
 }
 

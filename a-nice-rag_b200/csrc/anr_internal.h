@@ -6,11 +6,15 @@
 namespace anr {
 
 // Programmatic dependent launch for the kernel chains of a step (anr_common.cuh: pdl_wait /
-// pdl_trigger).  ANR_PDL=0 launches them fully serialised, as plain <<<>>> would.
-bool pdl_enabled();
+// pdl_trigger).  The mask (ANR_PDL, default 7; anr_set_option("pdl", mask)) selects who launches
+// that way: bit 0 the dense chain, bit 1 the BM25 chain, bit 2 the dense MAIN kernel (made resident
+// while the threshold kernel runs); a cleared bit = fully serialised launches, as plain <<<>>>.
+constexpr int kPdlDense = 1, kPdlBm25 = 2, kPdlDenseMain = 4;
+bool pdl_enabled(int which = kPdlDense);
+void pdl_set_mask(int mask);
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                                cudaStream_t stream, Args... args) {
+inline cudaError_t launch_chain_on(int which, void (*kern)(KArgs...), dim3 grid, dim3 block,
+                                   size_t smem, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -20,8 +24,13 @@ inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl_enabled(which) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                cudaStream_t stream, Args... args) {
+  return launch_chain_on(kPdlDense, kern, grid, block, smem, stream, args...);
 }
 
 

@@ -19,8 +19,8 @@ topk_final_kernel(const uint64_t* __restrict__ cand, int64_t stride_q, int m, in
                   int64_t seg_stride, int k, TopkOut o, const int32_t* __restrict__ n_active,
                   const int32_t* __restrict__ row_map) {
   __shared__ uint64_t keys[kFinalSortCap];
-  pdl_wait();
-  pdl_trigger();
+  pdl_wait();   // (no early trigger: the last kernel of a chain; what follows it -- the fusion, an
+                // event record, a copy to the host -- must see it complete)
   if (n_active && static_cast<int>(blockIdx.x) >= *n_active) return;
   const uint64_t* c = cand + blockIdx.x * stride_q;
   const int q = row_map ? row_map[blockIdx.x] : blockIdx.x;
@@ -69,8 +69,8 @@ topk_final_small_kernel(const uint64_t* __restrict__ cand, int64_t stride_q, int
   __shared__ uint64_t best[kSmallThreads];
   __shared__ uint64_t sel[kSmallCap];
   __shared__ int n_sel;
-  pdl_wait();
-  pdl_trigger();
+  pdl_wait();   // (no early trigger: the last kernel of a chain; what follows it -- the fusion, an
+                // event record, a copy to the host -- must see it complete)
   if (n_active && static_cast<int>(blockIdx.x) >= *n_active) return;
   const uint64_t* c = cand + blockIdx.x * stride_q;
   const int q = row_map ? row_map[blockIdx.x] : blockIdx.x;

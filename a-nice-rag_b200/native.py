@@ -36,6 +36,7 @@ SIGNATURES = {
     "anr_ctx_set_beside_dense": [_P, _I32],
     "anr_ctx_info": [_P, C.POINTER(_I32), C.POINTER(_I64), C.POINTER(_I64)],
     "anr_ctx_last_rerun": [_P, C.POINTER(_I32), C.POINTER(_I32)],
+    "anr_set_option": [C.c_char_p, _I32],
     "anr_ctx_profile_enable": [_P, _I32],
     "anr_ctx_profile_read": [_P, _I32, C.POINTER(_F64), C.POINTER(_I64)],
     "anr_ctx_timeline_enable": [_P, _I32],

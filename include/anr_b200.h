@@ -71,6 +71,15 @@ int anr_ctx_info(anr_ctx* ctx, int32_t* sm_count, int64_t* hbm_total, int64_t* h
  * this is the number to watch on production-shaped data. */
 int anr_ctx_last_rerun(anr_ctx* ctx, int32_t* dense_queries, int32_t* bm25_queries);
 
+/* Process-wide tuning knobs that can change between calls (measurement scripts; every knob also has
+ * an environment variable read at load time).  Known keys:
+ *   "pdl"  (ANR_PDL, default 7)  who launches its kernel chain programmatically (each kernel may
+ *          become resident while its predecessor runs and waits for it with griddepcontrol.wait):
+ *          bit 0 the dense chain, bit 1 the BM25 chain, bit 2 the dense main kernel; 0 = every
+ *          launch fully serialised.  No effect on results.
+ * Unknown key: ANR_ERR_INVALID.  Not for use while another thread is inside a search call. */
+int anr_set_option(const char* key, int32_t value);
+
 /* Per-kernel timing for roofline reports.  While enabled, every launch of the dominant
  * kernels (kind 0 = dense scan kernel -- CUDA-core, tcgen05 or tcgen05 CTA-pair variant --,
  * kind 1 = BM25 score kernel, kind 2 = a whole tensor-core pass: sample pre-pass + threshold +

@@ -201,3 +201,55 @@ def test_gemm_and_scan_paths_agree(big_corpus):
     assert (r_g == r_sc).mean() > 0.99 and (r_b == r_sc).mean() > 0.99
     np.testing.assert_allclose(s_g, s_sc, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(s_b, s_sc, rtol=1e-5, atol=1e-6)
+
+
+def test_hybrid_step_with_reruns_on_both_chains_equals_the_separate_searches(big_corpus):
+    """One hybrid call whose dense chain AND BM25 chain both end in a device-side rerun (a query
+    whose append buffer overflows on 20 000 duplicate rows; a 60-term query and a query with fewer
+    than k matching documents) must return exactly what the dense-only call, the BM25-only call
+    and anr_wrrf_fuse return one after the other: the kernels of a chain are launched
+    programmatically (each may become resident while its predecessor runs), and the fusion waits
+    for the LAST kernel of both chains (search_engine.py:21-34 on query_rag_retrieval.py:357-362's
+    two lists).  Repeated, so that a kernel started too early would show."""
+    from oracle import csr
+    emb, _ = big_corpus
+    n, k, nq = 120_000, 10, 64
+    emb = emb[:n].copy()
+    emb[5000:25000] = emb[5000]
+    dense = engine.DenseIndex(emb)
+    dense.set_shadow(True)
+    vocab = 4000
+    ix = csr.from_token_ids(*synth.zipf_corpus(n, vocab, 1.1, seed=51, len_lo=40, len_hi=120),
+                            vocab, 1.7, 0.83, 0.05)
+    bm25 = engine.Bm25Index(ix.term_ptr, ix.post_doc, ix.post_tf, ix.doc_len, ix.idf, ix.k1, ix.b,
+                            ix.avgdl)
+    queries = synth.unit_vectors(nq, 1024, seed=12)
+    queries[5] = emb[5000]
+    queries[61] = emb[7000]
+    df = np.diff(ix.term_ptr)
+    rare = [int(t) for t in np.argsort(np.where(df > 0, df, 1 << 30), kind="stable")[:2]]
+    terms = [list(map(int, t)) for t in synth.zipf_queries(nq, 8, vocab, 1.1, seed=77)]
+    terms[3] = rare                                                    # fewer than k matches
+    terms[40] = [int(t) for t in synth.zipf_queries(1, 60, vocab, 1.1, seed=5)[0]]   # > 48 terms
+    terms[41] = []                                                     # no terms: dense list alone
+    d_scores, d_rows, d_counts = dense.search(queries, k)
+    b_scores, b_docs, b_counts = bm25.search(terms, k)
+    assert d_rows[5].tolist() == list(range(5000, 5010))
+    ctx = engine.context(dense.ctx_device)
+    for rep in range(6):
+        got = engine.hybrid_search(dense, bm25, queries, terms, k, k, 5.0, 1.0, 40.0, k,
+                                   want_lists=True)
+        d_rr, b_rr = ctx.last_rerun()
+        assert d_rr >= 2 and b_rr >= 1, (d_rr, b_rr)
+        assert np.array_equal(got["dense_rows"], d_rows), rep
+        assert np.array_equal(got["dense_scores"], d_scores), rep
+        for q in range(nq):
+            nb = int(b_counts[q])
+            assert np.array_equal(got["bm25_ids"][q, :nb], b_docs[q, :nb]), (rep, q)
+            assert np.array_equal(got["bm25_scores"][q, :nb], b_scores[q, :nb]), (rep, q)
+            ids, sc = engine.wrrf_fuse([d_rows[q, :int(d_counts[q])].tolist(), b_docs[q, :nb].tolist()],
+                                       [5.0, 1.0], 40.0, k)
+            c = int(got["counts"][q])
+            assert c == len(ids), (rep, q)
+            assert np.array_equal(got["ids"][q, :c], ids), (rep, q)
+            assert np.array_equal(got["scores"][q, :c], sc), (rep, q)
