@@ -27,6 +27,18 @@ def test_library_exports_every_declared_symbol():
     assert lib.anr_abi_version() == 1
 
 
+def test_set_option_knows_its_keys():
+    """anr_set_option is host-only state (no device call): the launch mask is accepted, an unknown
+    key is ANR_ERR_INVALID with a message, NULL is rejected."""
+    native.call("anr_set_option", b"pdl", 0)
+    native.call("anr_set_option", b"pdl", 7)
+    with pytest.raises(native.AnrError) as err:
+        native.call("anr_set_option", b"no_such_knob", 1)
+    assert "unknown key" in str(err.value)
+    with pytest.raises(native.AnrError):
+        native.call("anr_set_option", None, 1)
+
+
 def test_no_device_is_a_loud_error_not_a_fallback():
     import torch
     if torch.cuda.is_available():
