@@ -452,7 +452,7 @@ int dense_pipeline(anr_ctx* ctx, const anr_dense* ix, const float* q_dev, int nq
     int32_t* flagged = arena.take<int32_t>(static_cast<size_t>(nq));
     const int per = dense_gemm_max_queries();
     // one launch group: its rescoring kernel lists the flagged queries itself (no compaction launch)
-    const bool fold_flags = nq <= per;
+    const bool fold_flags = nq <= per && nq <= 1024;   // (one flag per thread of that last CTA)
     for (int q0 = 0; q0 < nq; q0 += per) {
       TopkOut o = out;
       if (o.keys) o.keys += q0 * out.stride_q;
