@@ -620,6 +620,19 @@ def test_bm25_pruned_after_reweight(prune_corpus, bm25_path):
     _check_bm25_batch(other, queries, scores, docs, counts, 10, "pruned reweight")
 
 
+def test_bm25_content_word_queries(prune_corpus, bm25_path):
+    """Stop-word-free queries (SURVEY 8d's "content-word" variant: terms resampled within Zipf ranks
+    > 27, what preprocess_bm25.py:41-46 leaves of a real query): eight terms of similar idf give the
+    candidate-driven path a weak bound -- few lists set aside, nearly every posting a candidate --
+    which is the distribution where its pruning decisions are exercised most."""
+    ix, index, vocab = prune_corpus
+    tq = synth.zipf_queries(48, 8, vocab, 1.1, seed=131, skip_head=27)
+    queries = [list(map(int, t)) for t in tq]
+    for k in (10, 100):
+        scores, docs, counts = index.search(queries, k)
+        _check_bm25_batch(ix, queries, scores, docs, counts, k, f"content words k{k}")
+
+
 def _prune_tokens():
     return synth.zipf_corpus(70_000, 4000, 1.1, seed=51, len_lo=40, len_hi=120)
 
