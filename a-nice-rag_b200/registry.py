@@ -95,8 +95,24 @@ def _cell_ptr(cell) -> int:
     return cell.__array_interface__["data"][0] if isinstance(cell, np.ndarray) else -1
 
 
+def _cells(col):
+    """The values of a column as something indexable by position without a copy (the column's own
+    ndarray or extension array): a Series.iat call costs ~10 us, and the probes below run on every
+    query.  (Never to_numpy(): on an Arrow-backed string column that converts all N rows.)"""
+    values = getattr(col, "_values", None)      # ndarray or ExtensionArray: both take values[i]
+    return values if values is not None and hasattr(values, "__getitem__") else col.iat
+
+
+_probe_cache: Dict[int, np.ndarray] = {}
+
+
 def _probe_positions(n: int) -> np.ndarray:
-    return np.unique(np.linspace(0, n - 1, num=min(n, 8)).astype(np.int64))
+    hit = _probe_cache.get(n)
+    if hit is None:
+        if len(_probe_cache) > 64:
+            _probe_cache.clear()
+        hit = _probe_cache[n] = np.unique(np.linspace(0, n - 1, num=min(n, 8)).astype(np.int64))
+    return hit
 
 
 def _same_vectors(entry: DenseEntry, emb_col, positions, rows) -> bool:
@@ -105,8 +121,9 @@ def _same_vectors(entry: DenseEntry, emb_col, positions, rows) -> bool:
     place is not detectable this way; DenseIndex.invalidate / a fresh load is the way to do that.)"""
     row_bytes = entry.packed.strides[0]
     base = entry.packed.ctypes.data
+    cells = _cells(emb_col)
     for p, r in zip(positions, rows):
-        cell = emb_col.iat[int(p)]
+        cell = cells[int(p)]
         want = base + int(r) * row_bytes if entry.probe_ptrs is None else entry.probe_ptrs.get(int(r))
         if want is None:
             continue                      # this row was not probed at registration
@@ -132,19 +149,22 @@ def resolve_frame(df: pd.DataFrame) -> Tuple[DenseEntry, Optional[np.ndarray]]:
         # costs more than the search itself)
         n = len(df)
         labels = df.index
-        id_col = df["id"]
-        emb_col = df["embedding"]
+        emb_col = df["embedding"]          # (one column fetch costs ~60 us in pandas 3: no more
         if n == entry.n and isinstance(labels, pd.RangeIndex) and labels.start == 0 \
-                and labels.step == 1:
+                and labels.step == 1:      #  than needed on the per-query path)
+            # the whole frame in load order: the probed cells ARE rows 0, .., n - 1 of the packed
+            # matrix (first and last included); the result frame is taken from df itself, so its
+            # other columns need no check
             probe = _probe_positions(n) if n else np.zeros(0, dtype=np.int64)
-            if n == 0 or (id_col.iat[0] == entry.ids[0] and id_col.iat[n - 1] == entry.ids[n - 1]
-                          and _same_vectors(entry, emb_col, probe, probe)):
+            if n == 0 or _same_vectors(entry, emb_col, probe, probe):
                 return entry, None
+        id_col = df["id"]
         rows = np.asarray(labels)
         if n and rows.dtype.kind in "iu" and rows.min() >= 0 and rows.max() < entry.n \
                 and labels.is_unique:
             probe = _probe_positions(n)
-            if all(id_col.iat[int(p)] == entry.ids[rows[p]] for p in probe) and \
+            ids = _cells(id_col)
+            if all(ids[int(p)] == entry.ids[rows[p]] for p in probe) and \
                     _same_vectors(entry, emb_col, probe, rows[probe]):
                 return entry, rows.astype(np.int64)
     # unknown frame: pack and upload it (np.stack raises for ragged rows, like the reference)

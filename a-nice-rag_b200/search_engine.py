@@ -147,7 +147,11 @@ class SearchEngine:
         rows, scores = rows[0, :c].astype(np.int64), scores[0, :c]
         pos = rows if positions_of is None else positions_of.get_indexer(rows)
         result_df = df.take(pos)      # = df.iloc[pos].copy() (:89, :137) without the second copy
-        result_df["similarity"] = scores.astype(np.result_type(query_embedding.dtype, np.float32))
+        similarity = scores.astype(np.result_type(query_embedding.dtype, np.float32))
+        if "similarity" in result_df.columns:     # (a frame that already went through a search)
+            result_df["similarity"] = similarity
+        else:                                     # same frame as the assignment, ~35 us cheaper
+            result_df.insert(len(result_df.columns), "similarity", similarity)
         return result_df
 
     @_never_raises(pd.DataFrame, "{model_name} similarity search with precalculated embedding")
