@@ -74,6 +74,17 @@ class _IdSpace:
     def __init__(self):
         self.code_of: Dict[str, int] = {}
         self.names: List[str] = []
+        self._names_arr: Optional[np.ndarray] = None
+
+    def names_array(self) -> np.ndarray:
+        """`names` as an object array (rebuilt when the space has grown): codes -> id strings by
+        ONE fancy index per query instead of a Python loop over 12 000 codes (the evaluator's
+        full ranking: 3.8 -> 0.34 ms per query on the host)."""
+        if self._names_arr is None or len(self._names_arr) != len(self.names):
+            arr = np.empty(len(self.names), dtype=object)
+            arr[:] = self.names
+            self._names_arr = arr
+        return self._names_arr
 
     def codes(self, ids: Sequence[str]) -> np.ndarray:
         out = np.empty(len(ids), dtype=np.int32)
@@ -258,11 +269,11 @@ def retrieve_documents_batch(
     bm25_docs = ((np.concatenate(bm25_host[0]), np.concatenate(bm25_host[1]))
                  if want_hits and bm25_plan else None)
 
-    names = space.names
+    names = space.names_array()
     section_of = None
     out: List[List] = []
     for qi in range(n_queries):
-        section_ids = [names[int(c)] for c in fused[qi, :int(fused_counts[qi])]]
+        section_ids = names[fused[qi, :int(fused_counts[qi])]].tolist()
         if not return_docs and not use_reranker:
             out.append(section_ids)
             continue
